@@ -1,0 +1,188 @@
+/*
+ * mdgrad_b200.h - C ABI of libmdgrad_b200.so: the sm_100a (B200) implementation of
+ * torchmd/mdgrad's MD hot path (periodic neighbor list, pair distance / force, fused
+ * Velocity-Verlet / Nose-Hoover-chain step, RDF).
+ *
+ * The reference (torchmd/mdgrad @ cea2332e) is pure Python/PyTorch and has no FFI; the
+ * boundary it exposes for this path is its Python API.  Every entry point below therefore
+ * cites the reference Python function whose work it replaces (file:line relative to the
+ * reference tree); the binding a reference maintainer would add is the ctypes stub shown
+ * in INTEGRATION.md (and shipped as mdgrad_b200/_lib.py).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - every function returns an int status: MDG_OK or a negative MDG_E_* code;
+ *    mdg_last_error() returns a thread-local message for the last failure. Nothing throws.
+ *  - pointers named d_* are DEVICE pointers (e.g. tensor.data_ptr()); h_* are HOST pointers.
+ *  - all work is enqueued on the cudaStream_t passed as `stream` (void*; pass PyTorch's
+ *    current stream). Calls are asynchronous except where "SYNC" is stated (a count
+ *    read-back that sizes a caller allocation).
+ *  - a context (mdg_ctx) owns all scratch / internal lists for one device and one box;
+ *    it is thread-compatible (one thread at a time), not re-entrant.
+ *  - fp32 on device throughout, like the reference (torch.Tensor default dtype).
+ *  - cells are orthorhombic: h_cell3 = (Lx, Ly, Lz). (The reference accepts a general 3x3
+ *    cell, topology.py:55-59; every config of the path is cubic.  The Python layer raises
+ *    for non-diagonal cells instead of silently falling back.)
+ */
+#ifndef MDGRAD_B200_H
+#define MDGRAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDG_OK            0
+#define MDG_E_BADARG     -1
+#define MDG_E_CUDA       -2
+#define MDG_E_CAPACITY   -3   /* a fixed-capacity internal table overflowed; grow and retry */
+#define MDG_E_STATE      -4   /* call order violated (e.g. export before build) */
+#define MDG_E_SKIN       -5   /* an atom moved more than skin/2 between list rebuilds */
+#define MDG_E_NCCL       -6
+
+/* pair potential kinds: reference torchmd/potentials.py */
+#define MDG_POT_LJ        0   /* LennardJones   :317-327  params (sigma, epsilon)            */
+#define MDG_POT_LJFAM     1   /* LJFamily       :61-73    params (sigma, epsilon, rep, attr) */
+#define MDG_POT_LJ69      2   /* LennardJones69 :329-339  params (sigma, epsilon)            */
+#define MDG_POT_EXV       3   /* ExcludedVolume :341-352  params (sigma, epsilon, power)     */
+#define MDG_POT_BUCK      4   /* Buck           :354-365  params (A, B, C)                   */
+#define MDG_POT_MORSE     5   /* ModifiedMorse  :75-93    params (a, phi)                    */
+#define MDG_MAX_POT_PARAMS 4
+
+/* integrators: reference torchmd/md.py + torchmd/sovlers.py */
+#define MDG_INT_NVE       0   /* NVE.forward md.py:131-148 + verlet_update sovlers.py:25-40   */
+#define MDG_INT_NHC       1   /* NoseHooverChain.forward md.py:210-240 + NHverlet_update
+                                 sovlers.py:110-127                                          */
+#define MDG_MAX_CHAINS    16
+
+typedef struct mdg_ctx mdg_ctx;
+
+int         mdg_version(void);
+const char* mdg_last_error(void);
+
+/* Create / destroy a context on CUDA device `device`. */
+int mdg_create(int device, mdg_ctx** out);
+int mdg_destroy(mdg_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  neighbor list - replaces generate_nbr_list(xyz, cutoff, cell, index_tuple, ex_pairs,
+ *     get_dis)  torchmd/topology.py:30-73 (and PairPotentials._reset_topology,
+ *     torchmd/interface.py:263-282).
+ *
+ * mdg_nbr_build: bins the N atoms of d_xyz (N x 3 fp32, any order, need not be wrapped) into
+ * cells by a device-wide counting sort and finds, for every atom, all neighbors with
+ * d2 < fl32(cutoff^2) and d2 != 0 using the reference's exact fp32 arithmetic
+ * (d = x_j - x_i; image = -(d/L > 0.5) + (d/L < -0.5); d += image*L; d2 = (dx^2+dy^2)+dz^2,
+ * no FMA contraction; topology.py:35,59-67).  Systems with fewer than 3 cells on an axis (or
+ * N <= small) use an all-pairs tiled search with identical single-image semantics.
+ *   d_sel_a / d_sel_b : optional per-atom 0/1 flags = membership in index_tuple[0] / [1]
+ *                       (generate_pair_index, topology.py:15-27); both NULL = all pairs.
+ *   d_ex_keys, n_ex   : optional exclusions (ex_pairs, topology.py:44-53) as SORTED unique
+ *                       int64 keys min(i,j)*N + max(i,j).
+ * SYNC: returns in *h_npairs the number P of undirected pairs (i<j) so the caller can size
+ * the export buffers.
+ *
+ * mdg_nbr_export: writes the list in the reference's exact layout and ORDER (row-major
+ * (i, j) with i<j, torch.nonzero order, topology.py:68): d_nbr P x 2 int64, d_offsets P x 3
+ * fp32 in {-1,0,1} (topology.py:60-62,73), d_dis P fp32 = sqrt(d2) or NULL (topology.py:71).
+ * ------------------------------------------------------------------------------------------ */
+int mdg_nbr_build(mdg_ctx* ctx, const float* d_xyz, int n, const float* h_cell3, double cutoff,
+                  const uint8_t* d_sel_a, const uint8_t* d_sel_b,
+                  const int64_t* d_ex_keys, int n_ex,
+                  void* stream, int64_t* h_npairs);
+int mdg_nbr_export(mdg_ctx* ctx, int64_t* d_nbr, float* d_offsets, float* d_dis, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2+K3  listed-pair energy and forces - replaces PairPotentials.forward
+ *     (torchmd/interface.py:284-300: compute_dis topology.py:5-12 -> u(r).sum()) together
+ *     with the autograd force F = -dE/dxyz (torchmd/md.py:227-228, nff/utils/scatter.py:5-21).
+ *
+ * Evaluates E = sum over the pairs of the list held by ctx (last mdg_nbr_build) with the
+ * CURRENT d_xyz and the stored image offsets - no cutoff re-test, exactly as the reference
+ * evaluates a (possibly stale) stored list.  Outputs (any may be NULL):
+ *   d_energy  : 1 fp32 (total energy)
+ *   d_force   : N x 3 fp32, F = -dE/dxyz
+ *   d_dparams : MDG_MAX_POT_PARAMS fp32, dE/dparam for the differentiable parameters of the
+ *               kind (sigma, epsilon | A, B, C)
+ *   d_dis     : not provided here - use mdg_pair_dis_*.
+ * ------------------------------------------------------------------------------------------ */
+int mdg_pair_force(mdg_ctx* ctx, int kind, const float* h_params, int n_params,
+                   const float* d_xyz, int n,
+                   float* d_energy, float* d_force, float* d_dparams, void* stream);
+
+/* Generic listed-pair distance op for learned u(r) (pairMLP etc.): replaces compute_dis
+ * (torchmd/topology.py:5-12) and its autograd backward.  The list is given explicitly in the
+ * reference layout (d_nbr P x 2 int64, d_offsets P x 3 fp32).
+ *   fwd: d_dis[p] = | x_i - x_j - offsets_p * cell |
+ *   bwd: d_grad_xyz (N x 3, zero-initialised by the callee) += scatter of d_grad_dis[p] * unit vector */
+int mdg_pair_dis_fwd(const float* d_xyz, int n, const int64_t* d_nbr, const float* d_offsets,
+                     int64_t n_pairs, const float* h_cell3, float* d_dis, void* stream);
+int mdg_pair_dis_bwd(const float* d_xyz, int n, const int64_t* d_nbr, const float* d_offsets,
+                     int64_t n_pairs, const float* h_cell3, const float* d_dis,
+                     const float* d_grad_dis, float* d_grad_xyz, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  RDF - replaces rdf.forward (torchmd/observable.py:62-76) + generate_vol_bins (:10-21):
+ * Gaussian-smeared pair-distance histogram over all pairs with d < end + 0.5 of ONE frame
+ * (call once per frame and sum counts for a batch): d_count[k] += sum_p exp(-0.5/w^2 (d_p - mu_k)^2),
+ * mu = linspace(start, end, nbins), w = `width` (<=0: mu_1 - mu_0).  Normalisation
+ * (count/sum, / (vol_bins/V)) is nbins-sized host-side algebra in the Python layer.
+ * d_count must be zero-initialised by the caller (accumulates).
+ * ------------------------------------------------------------------------------------------ */
+int mdg_rdf_accumulate(mdg_ctx* ctx, const float* d_xyz, int n, const float* h_cell3,
+                       double start, double end, int nbins, double width,
+                       const uint8_t* d_sel_a, const uint8_t* d_sel_b,
+                       float* d_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 + driver  fused MD epoch - replaces the hot loop of Simulations.simulate
+ *     (torchmd/md.py:73-96) -> odeint (torchmd/sovlers.py:171-193) ->
+ *     FixedGridODESolver.integrate (torchmd/tinydiffeq.py:56-76) -> NHverlet_update /
+ *     verlet_update (sovlers.py:110-127 / :25-40) -> NoseHooverChain.forward / NVE.forward
+ *     (md.py:210-240 / :131-148) with a PairPotentials model whose list is rebuilt at every
+ *     evaluation (topology_update_freq = 1).
+ *
+ * Integrates n_grid-1 steps over the fp32 time grid h_tgrid (n_grid points; per-step dt is
+ * t[i+1]-t[i] in fp32 exactly as tinydiffeq.py:67-68) starting from (d_v0, d_q0, h_pv0) and
+ * writes the stacked trajectory like the reference: d_traj_v / d_traj_q  (n_grid x N x 3,
+ * frame 0 = initial state), h_traj_pv (n_grid x n_chains; NULL for NVE).  One force
+ * evaluation per step (bitwise-equivalent to the reference's two).
+ * The pair set contributing at every evaluation equals a freshly built reference list: a
+ * Verlet list with `skin` is re-tested against fl32(cutoff^2) with the exact arithmetic of
+ * mdg_nbr_build; it is rebuilt every `rebuild_every` steps and a device-side check raises
+ * MDG_E_SKIN (state untouched) if any atom moved > skin/2 in between.
+ * traj_stride > 1 keeps only every traj_stride-th grid point (extension; reference = 1).
+ * SYNC at the end (h_traj_pv, error flags).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mdg_md_params {
+    int    integrator;            /* MDG_INT_NVE | MDG_INT_NHC                                  */
+    int    pot_kind;              /* MDG_POT_*                                                  */
+    float  pot_params[MDG_MAX_POT_PARAMS];
+    double cutoff;                /* as passed to PairPotentials(cutoff=)                       */
+    float  cell[3];
+    int    n_chains;              /* NHC: number of bath variables M                            */
+    float  Q[MDG_MAX_CHAINS];     /* NHC bath masses (md.py:191-193), fp32 as the reference     */
+    double T;                     /* target temperature in energy units (md.py:186), python float */
+    int    ndof;                  /* N * dim (md.py:187)                                        */
+    float  skin;                  /* Verlet skin (0 = rebuild every step, no re-test needed)    */
+    int    rebuild_every;         /* steps between list rebuilds (>=1)                          */
+    int    traj_stride;           /* 1 = every grid point (reference behaviour)                 */
+} mdg_md_params;
+
+int mdg_md_run(mdg_ctx* ctx, const mdg_md_params* p, int n, const float* d_mass,
+               const float* d_v0, const float* d_q0, const float* h_pv0,
+               const float* h_tgrid, int n_grid,
+               float* d_traj_v, float* d_traj_q, float* h_traj_pv,
+               float* h_last_energy, void* stream);
+
+/* Statistics of the last mdg_md_run / mdg_nbr_build on this context (for bench / tests):
+ * out[0]=kernels launched, out[1]=list rebuilds, out[2]=directed list entries (last build),
+ * out[3]=max row length, out[4]=ncell_x, out[5]=ncell_y, out[6]=ncell_z, out[7]=path
+ * (0 = cell list, 1 = all-pairs). */
+int mdg_get_stats(mdg_ctx* ctx, int64_t* h_out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDGRAD_B200_H */

@@ -1,0 +1,230 @@
+"""ctypes binding of libmdgrad_b200.so (the C ABI declared in include/mdgrad_b200.h).
+
+This is the stub a reference maintainer would add: raw `tensor.data_ptr()`
+device pointers and PyTorch's current CUDA stream go straight into the `extern "C"` entry
+points.  There is NO fallback: if the shared library is missing or a tensor is not on a CUDA
+device the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmdgrad_b200.so")
+
+MDG_OK, MDG_E_BADARG, MDG_E_CUDA, MDG_E_CAPACITY, MDG_E_STATE, MDG_E_SKIN, MDG_E_NCCL = 0, -1, -2, -3, -4, -5, -6
+POT_LJ, POT_LJFAM, POT_LJ69, POT_EXV, POT_BUCK, POT_MORSE = range(6)
+INT_NVE, INT_NHC = 0, 1
+MAX_POT_PARAMS = 4
+MAX_CHAINS = 16
+
+# every symbol include/mdgrad_b200.h declares (checked by tests/test_cabi_symbols.py)
+SYMBOLS = [
+    "mdg_version", "mdg_last_error", "mdg_create", "mdg_destroy", "mdg_nbr_build", "mdg_nbr_export",
+    "mdg_pair_force", "mdg_pair_dis_fwd", "mdg_pair_dis_bwd", "mdg_rdf_accumulate", "mdg_md_run",
+    "mdg_get_stats",
+]
+
+
+class MdParams(ctypes.Structure):
+    """mirror of struct mdg_md_params"""
+    _fields_ = [
+        ("integrator", ctypes.c_int),
+        ("pot_kind", ctypes.c_int),
+        ("pot_params", ctypes.c_float * MAX_POT_PARAMS),
+        ("cutoff", ctypes.c_double),
+        ("cell", ctypes.c_float * 3),
+        ("n_chains", ctypes.c_int),
+        ("Q", ctypes.c_float * MAX_CHAINS),
+        ("T", ctypes.c_double),
+        ("ndof", ctypes.c_int),
+        ("skin", ctypes.c_float),
+        ("rebuild_every", ctypes.c_int),
+        ("traj_stride", ctypes.c_int),
+    ]
+
+
+class MdgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmdgrad_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; raises (never falls back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libmdgrad_b200.so not found at %s - build it with `python -m mdgrad_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback for the MD hot path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ip, dbl, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.mdg_version.restype = ip
+    lib.mdg_last_error.restype = ctypes.c_char_p
+    lib.mdg_create.argtypes = [ip, ctypes.POINTER(vp)]
+    lib.mdg_destroy.argtypes = [vp]
+    lib.mdg_nbr_build.argtypes = [vp, vp, ip, fp, dbl, vp, vp, vp, ip, vp, ctypes.POINTER(i64)]
+    lib.mdg_nbr_export.argtypes = [vp, vp, vp, vp, vp]
+    lib.mdg_pair_force.argtypes = [vp, ip, fp, ip, vp, ip, vp, vp, vp, vp]
+    lib.mdg_pair_dis_fwd.argtypes = [vp, ip, vp, vp, i64, fp, vp, vp]
+    lib.mdg_pair_dis_bwd.argtypes = [vp, ip, vp, vp, i64, fp, vp, vp, vp, vp]
+    lib.mdg_rdf_accumulate.argtypes = [vp, vp, ip, fp, dbl, dbl, ip, dbl, vp, vp, vp, vp]
+    lib.mdg_md_run.argtypes = [vp, ctypes.POINTER(MdParams), ip, vp, vp, vp, fp, fp, ip, vp, vp, fp, fp, vp]
+    lib.mdg_get_stats.argtypes = [vp, ctypes.POINTER(i64)]
+    for name in SYMBOLS:
+        if name not in ("mdg_last_error",):
+            getattr(lib, name).restype = ip
+    lib.mdg_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != MDG_OK:
+        raise MdgError(status, load().mdg_last_error().decode("utf-8", "replace"))
+
+
+def _farr(vals, n=None):
+    vals = [float(v) for v in vals]
+    n = len(vals) if n is None else n
+    return (ctypes.c_float * n)(*(vals + [0.0] * (n - len(vals))))
+
+
+def require_cuda(t, name="tensor"):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(
+            "mdgrad_b200: %s must live on a CUDA device (got %s); the MD hot path is sm_100a CUDA "
+            "only and has no CPU fallback" % (name, getattr(t, "device", type(t))))
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class Context:
+    """One mdg_ctx per (device, use).  Not thread-safe."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("mdgrad_b200.Context needs a CUDA device, got %s" % device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self._h = ctypes.c_void_p()
+        check(load().mdg_create(idx, ctypes.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                load().mdg_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    # -- K1 ---------------------------------------------------------------------------------
+    def nbr_list(self, xyz, cell3, cutoff, sel_a=None, sel_b=None, ex_keys=None, get_dis=False):
+        """generate_nbr_list for one frame: returns (nbr int64 (P,2), offsets fp32 (P,3)[, dis (P,)])."""
+        require_cuda(xyz, "xyz")
+        xyz = xyz.detach().to(torch.float32).contiguous()
+        n = xyz.shape[0]
+        dev = xyz.device
+        npairs = ctypes.c_int64(0)
+        with torch.cuda.device(dev):
+            check(load().mdg_nbr_build(self._h, _ptr(xyz), n, _farr(cell3, 3), float(cutoff), _ptr(sel_a), _ptr(sel_b),
+                                       _ptr(ex_keys), 0 if ex_keys is None else int(ex_keys.numel()), _stream(dev),
+                                       ctypes.byref(npairs)))
+            P = npairs.value
+            nbr = torch.empty((P, 2), dtype=torch.int64, device=dev)
+            off = torch.empty((P, 3), dtype=torch.float32, device=dev)
+            dis = torch.empty((P,), dtype=torch.float32, device=dev) if get_dis else None
+            check(load().mdg_nbr_export(self._h, _ptr(nbr), _ptr(off), _ptr(dis), _stream(dev)))
+        self._keepalive = (xyz, sel_a, sel_b, ex_keys)
+        return (nbr, off, dis) if get_dis else (nbr, off)
+
+    # -- K2+K3 ------------------------------------------------------------------------------
+    def pair_force(self, kind, params, xyz, want_force=True, want_dparams=False):
+        """E (0-d), F (N,3) or None, dE/dparams (4,) or None over the list of the last nbr_list()."""
+        require_cuda(xyz, "xyz")
+        xyz = xyz.detach().to(torch.float32).contiguous()
+        n = xyz.shape[0]
+        dev = xyz.device
+        e = torch.empty((), dtype=torch.float32, device=dev)
+        f = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_force else None
+        dp = torch.empty((MAX_POT_PARAMS,), dtype=torch.float32, device=dev) if want_dparams else None
+        with torch.cuda.device(dev):
+            check(load().mdg_pair_force(self._h, int(kind), _farr(params, MAX_POT_PARAMS), len(params), _ptr(xyz), n,
+                                        _ptr(e), _ptr(f), _ptr(dp), _stream(dev)))
+        return e, f, dp
+
+    # -- K6 ---------------------------------------------------------------------------------
+    def rdf_accumulate(self, xyz, cell3, start, end, nbins, width, count, sel_a=None, sel_b=None):
+        require_cuda(xyz, "xyz")
+        xyz = xyz.detach().to(torch.float32).contiguous()
+        dev = xyz.device
+        with torch.cuda.device(dev):
+            check(load().mdg_rdf_accumulate(self._h, _ptr(xyz), xyz.shape[0], _farr(cell3, 3), float(start), float(end),
+                                            int(nbins), float(width) if width else 0.0, _ptr(sel_a), _ptr(sel_b),
+                                            _ptr(count), _stream(dev)))
+        self._keepalive = (xyz, sel_a, sel_b)
+
+    # -- K4 + driver ------------------------------------------------------------------------
+    def md_run(self, params, mass, v0, q0, pv0, tgrid, want_energy=False):
+        """Runs one epoch; returns (traj_v, traj_q, traj_pv or None, last_energy or None)."""
+        for t, nm in ((mass, "mass"), (v0, "v0"), (q0, "q0")):
+            require_cuda(t, nm)
+        dev = q0.device
+        n = q0.shape[0]
+        n_grid = len(tgrid)
+        stride = max(1, params.traj_stride)
+        n_frames = (n_grid - 1) // stride + 1
+        tv = torch.empty((n_frames, n, 3), dtype=torch.float32, device=dev)
+        tq = torch.empty((n_frames, n, 3), dtype=torch.float32, device=dev)
+        M = params.n_chains if params.integrator == INT_NHC else 0
+        hpv = (ctypes.c_float * max(1, n_frames * M))()
+        hpv0 = _farr(pv0 if M else [0.0], max(1, M))
+        tg = _farr(tgrid)
+        e = ctypes.c_float(0.0)
+        with torch.cuda.device(dev):
+            check(load().mdg_md_run(self._h, ctypes.byref(params), n, _ptr(mass), _ptr(v0), _ptr(q0), hpv0, tg, n_grid,
+                                    _ptr(tv), _ptr(tq), hpv if M else None,
+                                    ctypes.byref(e) if want_energy else None, _stream(dev)))
+        tpv = None
+        if M:
+            tpv = torch.tensor(list(hpv), dtype=torch.float32).reshape(n_frames, M).to(dev)
+        return tv, tq, tpv, (e.value if want_energy else None)
+
+    def stats(self):
+        out = (ctypes.c_int64 * 8)()
+        check(load().mdg_get_stats(self._h, out))
+        keys = ["launches", "rebuilds", "entries", "maxrow_or_K", "ncx", "ncy", "ncz", "path"]
+        return dict(zip(keys, list(out)))
+
+
+def pair_dis_fwd(xyz, nbr, offsets, cell3):
+    require_cuda(xyz, "xyz")
+    P = nbr.shape[0]
+    dis = torch.empty((P,), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        check(load().mdg_pair_dis_fwd(_ptr(xyz), xyz.shape[0], _ptr(nbr), _ptr(offsets), P, _farr(cell3, 3), _ptr(dis),
+                                      _stream(xyz.device)))
+    return dis
+
+
+def pair_dis_bwd(xyz, nbr, offsets, cell3, dis, grad_dis):
+    require_cuda(xyz, "xyz")
+    g = torch.empty_like(xyz)
+    with torch.cuda.device(xyz.device):
+        check(load().mdg_pair_dis_bwd(_ptr(xyz), xyz.shape[0], _ptr(nbr), _ptr(offsets), nbr.shape[0], _farr(cell3, 3),
+                                      _ptr(dis), _ptr(grad_dis), _ptr(g), _stream(xyz.device)))
+    return g

@@ -1,0 +1,102 @@
+"""Builds libmdgrad_b200.so (sm_100a) and the C oracle in-tree with nvcc / gcc.
+
+`python -m mdgrad_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles without a GPU.
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import concurrent.futures as cf
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libmdgrad_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+          "-Xptxas", "-v"]
+# per-file extra flags
+EXTRA = {"engine.cu": ["-fmad=false"]}
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stamp(path, flags):
+    h = hashlib.sha1()
+    for p in [path, os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "mdgrad_b200.h")]:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(flags).encode())
+    return h.hexdigest()
+
+
+def _compile(src, verbose):
+    flags = ARCH + COMMON + EXTRA.get(src, [])
+    path = os.path.join(CSRC, src)
+    obj = os.path.join(OBJ, src[:-3] + ".o")
+    stamp_file = obj + ".stamp"
+    stamp = _stamp(path, flags)
+    if os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return obj, False, ""
+    cmd = [NVCC] + flags + ["-c", path, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    with open(obj + ".ptxas.txt", "w") as f:
+        f.write(r.stderr)
+    return obj, True, r.stderr
+
+
+def build(verbose=False, force=False):
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+    srcs = _sources()
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(lambda s: _compile(s, verbose), srcs))
+    objs = [r[0] for r in results]
+    rebuilt = any(r[1] for r in results)
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if verbose:
+        for r in results:
+            if r[2]:
+                print(r[2])
+    return LIB
+
+
+def build_oracle():
+    """Compile oracle/oracle_c.c -> oracle/_ref/liboracle.so (test infrastructure)."""
+    src = os.path.join(ROOT, "oracle", "oracle_c.c")
+    if not os.path.exists(src):
+        return None
+    outdir = os.path.join(ROOT, "oracle", "_ref")
+    os.makedirs(outdir, exist_ok=True)
+    out = os.path.join(outdir, "liboracle_c.so")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", src, "-o", out, "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed for oracle_c.c:\n%s" % r.stderr)
+    return out
+
+
+if __name__ == "__main__":
+    lib = build(verbose="-v" in sys.argv, force="--force" in sys.argv)
+    print("built", lib)
+    o = build_oracle()
+    if o:
+        print("built", o)

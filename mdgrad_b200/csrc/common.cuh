@@ -1,0 +1,253 @@
+// common.cuh - context, error plumbing, exact-arithmetic helpers and analytic pair potentials
+// shared by the kernels of libmdgrad_b200.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/mdgrad_b200.h"
+
+#define MDG_VERSION 100
+
+// ---------------------------------------------------------------------------------------------
+// error handling (thread-local message, never throws)
+// ---------------------------------------------------------------------------------------------
+void mdg_set_error(const char* fmt, ...);
+
+#define MDG_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            mdg_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return MDG_E_CUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+#define MDG_TRY(call)                \
+    do {                             \
+        int _s = (call);             \
+        if (_s != MDG_OK) return _s; \
+    } while (0)
+
+#define MDG_KERNEL_CHECK() MDG_CUDA(cudaGetLastError())
+
+// grow-only device buffer
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return MDG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cap = 0;
+            mdg_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return MDG_E_CUDA;
+        }
+        cap = want;
+        return MDG_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// list entry encoding: bits 0..25 = neighbor index (sorted order), bits 26..31 = image code,
+// 2 bits per axis holding off_k + 1 in {0,1,2} (off = reference `offsets` row-relative:
+// computed from d = x_j - x_i of the row atom i, topology.py:35,59-62)
+// ---------------------------------------------------------------------------------------------
+#define MDG_IDX_BITS 26
+#define MDG_IDX_MASK ((1u << MDG_IDX_BITS) - 1u)
+#define MDG_MAX_ATOMS (1 << MDG_IDX_BITS)
+
+struct Box {
+    float L[3];
+    float invL[3];  // fl32(1/L): torch `.inverse()` of a diagonal cell is the correctly rounded reciprocal
+};
+
+// Exact restatement of the reference membership arithmetic (SURVEY Appendix A1,
+// reference torchmd/topology.py:35,59-67) for ONE axis: returns d + off*L and the off code.
+// No FMA contraction anywhere: every product and sum is individually rounded like the
+// reference's separate ATen ops.
+__device__ __forceinline__ float mdg_min_image_axis(float xi, float xj, float L, float invL, int& code) {
+    float d = __fsub_rn(xj, xi);
+    float red = __fmul_rn(d, invL);
+    float off = 0.0f;
+    code = 1;
+    if (red > 0.5f) { off = -1.0f; code = 0; }
+    else if (red < -0.5f) { off = 1.0f; code = 2; }
+    return __fadd_rn(d, __fmul_rn(off, L));
+}
+
+// d2 = (dx*dx + dy*dy) + dz*dz, left to right, each op rounded (torch .pow(2).sum(-1) on CPU)
+__device__ __forceinline__ float mdg_d2_exact(float dx, float dy, float dz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ uint32_t mdg_pack_entry(int j, int cx, int cy, int cz) {
+    return (uint32_t)j | ((uint32_t)(cx | (cy << 2) | (cz << 4)) << MDG_IDX_BITS);
+}
+
+// image shift (off*L) for a packed code, per axis
+__device__ __forceinline__ float mdg_code_shift(uint32_t code2, float L) {
+    // code2 in {0,1,2} -> off in {-1,0,+1}
+    return code2 == 1u ? 0.0f : (code2 == 0u ? -L : L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// analytic pair potentials (reference torchmd/potentials.py). pair_eval returns
+//   e = u(r),  g = -u'(r)/r  (so that F_i = -g * (x_j - x_i + off*L)),
+// and optionally the parameter derivatives du/dparam in dp[0..3].
+// ---------------------------------------------------------------------------------------------
+struct PotParams {
+    int   kind;
+    float p[MDG_MAX_POT_PARAMS];
+    float aux;  // Morse: A0
+};
+
+__device__ __forceinline__ float mdg_ipow(float x, int n) {
+    float r = 1.0f;
+    float b = x;
+    while (n > 0) {
+        if (n & 1) r *= b;
+        b *= b;
+        n >>= 1;
+    }
+    return r;
+}
+
+template <int KIND, bool WITH_DP>
+__device__ __forceinline__ void pair_eval(const PotParams& P, float d2, float& e, float& g, float* dp) {
+    if (KIND == MDG_POT_LJ) {
+        float sigma = P.p[0], eps = P.p[1];
+        float r2i = 1.0f / d2;
+        float s2 = sigma * sigma * r2i;
+        float s6 = s2 * s2 * s2;
+        float s12 = s6 * s6;
+        e = 4.0f * eps * (s12 - s6);
+        g = 24.0f * eps * (2.0f * s12 - s6) * r2i;
+        if (WITH_DP) {
+            dp[0] = 24.0f * eps * (2.0f * s12 - s6) / sigma;
+            dp[1] = 4.0f * (s12 - s6);
+        }
+    } else if (KIND == MDG_POT_LJFAM || KIND == MDG_POT_LJ69) {
+        float sigma = P.p[0], eps = P.p[1];
+        float rp = (KIND == MDG_POT_LJ69) ? 9.0f : P.p[2];
+        float ap = (KIND == MDG_POT_LJ69) ? 6.0f : P.p[3];
+        float r = sqrtf(d2);
+        float s = sigma / r;
+        float srp, sap;
+        if (rp == floorf(rp) && ap == floorf(ap) && rp >= 0.f && ap >= 0.f && rp < 64.f && ap < 64.f) {
+            srp = mdg_ipow(s, (int)rp);
+            sap = mdg_ipow(s, (int)ap);
+        } else {
+            srp = powf(s, rp);
+            sap = powf(s, ap);
+        }
+        e = 4.0f * eps * (srp - sap);
+        float w = 4.0f * eps * (rp * srp - ap * sap);
+        g = w / d2;
+        if (WITH_DP) {
+            dp[0] = w / sigma;
+            dp[1] = 4.0f * (srp - sap);
+        }
+    } else if (KIND == MDG_POT_EXV) {
+        float sigma = P.p[0], eps = P.p[1], pw = P.p[2];
+        float r = sqrtf(d2);
+        float s = sigma / r;
+        float sp = (pw == floorf(pw) && pw >= 0.f && pw < 64.f) ? mdg_ipow(s, (int)pw) : powf(s, pw);
+        e = 4.0f * eps * sp;
+        float w = 4.0f * eps * pw * sp;
+        g = w / d2;
+        if (WITH_DP) {
+            dp[0] = w / sigma;
+            dp[1] = 4.0f * sp;
+        }
+    } else if (KIND == MDG_POT_BUCK) {
+        float A = P.p[0], B = P.p[1], C = P.p[2];
+        float r = sqrtf(d2);
+        float ex = expf(-B * r);
+        float r2i = 1.0f / d2;
+        float r6i = r2i * r2i * r2i;
+        e = A * ex - C * r6i;
+        g = A * B * ex / r - 6.0f * C * r6i * r2i;
+        if (WITH_DP) {
+            dp[0] = ex;
+            dp[1] = -A * r * ex;
+            dp[2] = -r6i;
+        }
+    } else {  // MDG_POT_MORSE
+        float a = P.p[0], phi = P.p[1], A0 = P.aux;
+        float r = sqrtf(d2);
+        float rphi = powf(r, phi);
+        float x = a * (1.0f - rphi) / phi;
+        float ex = expf(x);
+        float inv = 1.0f / (1.0f + A0);
+        e = (ex * ex - 2.0f * ex - A0) * inv;
+        // du/dr = (2 e^{2x} - 2 e^{x}) * dx/dr / (1+A0), dx/dr = -a r^{phi-1} = -a rphi / r
+        float dudr = (2.0f * ex * ex - 2.0f * ex) * (-a * rphi / r) * inv;
+        g = -dudr / r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the context
+// ---------------------------------------------------------------------------------------------
+struct mdg_ctx {
+    int device = 0;
+    int sm_count = 148;
+
+    // geometry of the current build
+    int    n = 0;
+    Box    box;
+    int    nc[3] = {1, 1, 1};
+    int    ncell = 0;
+    int    path = 1;          // 0 = cell list, 1 = all-pairs
+    float  rlist2 = 0.f;      // fl32(double(rlist)^2): list membership threshold
+    float  rc2 = 0.f;         // fl32(double(cutoff)^2): force re-test threshold
+    int    cap = 0;           // row capacity (entries), multiple of 32
+    bool   built = false;
+    bool   has_sel = false;
+    bool   rows_wanted = true; // false: sort into cells only (RDF traversal needs no stored rows)
+
+    // cell / sort tables
+    DevBuf cell_of, slot_of, cell_count, cell_start, perm, perm_tmp, stencil;
+    DevBuf qs_buf[2];         // float4 sorted positions (double-buffered: the sorter's input may be
+    float4* qs_ptr = nullptr; //   the previous output), w = original index (int bits)
+    // list
+    DevBuf rows, row_len;     // uint32 [n*cap], int [n]
+    DevBuf flags;             // int[8]: 0 = capacity overflow, 1 = skin violation
+    // export scratch
+    DevBuf up_cnt, up_off, scan_tmp;
+    int64_t npairs = 0;
+    // force scratch
+    DevBuf fs;                // float4 sorted force+energy
+    DevBuf partials;          // double partial sums
+    // masks (kept for the build)
+    const uint8_t* sel_a = nullptr;
+    const uint8_t* sel_b = nullptr;
+    const int64_t* ex_keys = nullptr;
+    int n_ex = 0;
+
+    // engine state (sorted order)
+    DevBuf v4, vh4, q4b, f4b, qref, mass_sorted, pvbuf, kebuf, dtbuf;
+
+    // stats
+    int64_t stat_launches = 0, stat_rebuilds = 0, stat_entries = 0, stat_maxrow = 0;
+    int* h_pinned = nullptr;  // pinned int[16] for read-backs
+};
+
+// internal entry points shared across translation units ------------------------------------
+int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_sorted_in, int n,
+                     const float* h_cell3, double rlist, double cutoff, cudaStream_t st);
+int mdg_i_scan_exclusive(mdg_ctx* c, const int* d_in, int* d_out, int n, int* d_total, cudaStream_t st);
+int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest,
+                       bool with_dp, double* d_dp_partials, cudaStream_t st);
+PotParams mdg_make_pot(int kind, const float* h_params, int n_params);
+int mdg_i_check_flags(mdg_ctx* c, cudaStream_t st, bool sync);

@@ -1,0 +1,385 @@
+// engine.cu - fused Velocity-Verlet / Nose-Hoover-chain integrator kernels (K4 in SURVEY.md 2c)
+// and the device-resident MD epoch driver.
+//
+// Replaces the hot loop of Simulations.simulate (reference torchmd/md.py:73-96) ->
+// FixedGridODESolver.integrate (torchmd/tinydiffeq.py:56-76) -> NHverlet_update / verlet_update
+// (torchmd/sovlers.py:110-127 / :25-40) -> NoseHooverChain.forward / NVE.forward
+// (torchmd/md.py:210-240 / :131-148).
+//
+// This translation unit is compiled with -fmad=false: the integrator algebra is memory-bound,
+// and keeping every product/sum individually rounded reproduces the reference's separate
+// elementwise ATen ops (only the global kinetic-energy reduction order differs).
+#include "common.cuh"
+
+int mdg_i_force_blocks(mdg_ctx* c);
+
+#define INT_THREADS 256
+#define INT_MAX_BLOCKS 592   // 148 SMs x 4 resident CTAs; grid-stride beyond that
+
+struct IntArgs {
+    int    n;
+    int    integrator;
+    int    M;                      // chains
+    float  Q[MDG_MAX_CHAINS];
+    float  T;                      // fl32(T)
+    float  target;                 // fl32(T * ndof * 0.5) computed in double like the python expression
+    float  half_skin2;             // (skin/2)^2
+};
+
+// scalar state on device ----------------------------------------------------------------------
+//   pv[2][MDG_MAX_CHAINS] ping-pong bath momenta, ph[MDG_MAX_CHAINS] half-step increments
+struct Scalars {
+    float pv[2][MDG_MAX_CHAINS];
+    float ph[MDG_MAX_CHAINS];
+};
+
+__device__ __forceinline__ double block_sum_double(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    return t;  // valid in thread 0
+}
+
+// fixed-order sum of per-block partials, identical in every block -> deterministic broadcast
+__device__ __forceinline__ float sum_partials(const double* __restrict__ part, int np, double* sm, float* bc) {
+    double v = 0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) v += part[i];
+    double t = block_sum_double(v, sm);
+    if (threadIdx.x == 0) *bc = (float)t;
+    __syncthreads();
+    return *bc;
+}
+
+// NHC bath derivative (reference torchmd/md.py:234-236)
+__device__ __forceinline__ void nhc_dpv(const IntArgs& A, float ke, const float* pv, float* dpv) {
+    int M = A.M;
+    dpv[0] = 2.0f * (ke - A.target) - pv[0] * pv[1] / A.Q[1];
+    for (int k = 1; k < M - 1; ++k)
+        dpv[k] = (pv[k - 1] * pv[k - 1] / A.Q[k - 1] - A.T) - pv[k + 1] * pv[k] / A.Q[k + 1];
+    dpv[M - 1] = pv[M - 2] * pv[M - 2] / A.Q[M - 2] - A.T;
+}
+
+// kinetic energy partials of the initial velocities: ke = 0.5 * sum(p^2/m), p = v*m (md.py:221-223)
+__global__ void __launch_bounds__(INT_THREADS) k_ke_init(IntArgs A, const float4* __restrict__ v4,
+                                                         double* __restrict__ ke_part) {
+    __shared__ double sm[INT_THREADS / 32];
+    double acc = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < A.n; s += gridDim.x * blockDim.x) {
+        float4 v = v4[s];
+        float m = v.w;
+        float px = v.x * m, py = v.y * m, pz = v.z * m;
+        acc += (double)(px * px / m) + (double)(py * py / m) + (double)(pz * pz / m);
+    }
+    double t = block_sum_double(acc, sm);
+    if (threadIdx.x == 0) ke_part[blockIdx.x] = 0.5 * t;
+}
+
+// step part A (sovlers.py:111-118): a0 from (v, f, pv); vh = 1/2 a0 dt; q += (v + vh) dt;
+// accumulates ke(v + vh) and checks the skin criterion against the positions of the last build.
+__global__ void __launch_bounds__(INT_THREADS) k_step_a(IntArgs A, float dt, int pv_sel, const Scalars* __restrict__ sc,
+                                                        const float4* __restrict__ v4, float4* __restrict__ vh4,
+                                                        float4* __restrict__ q4, const float4* __restrict__ f4,
+                                                        const float4* __restrict__ qref, int check_skin,
+                                                        double* __restrict__ ke_half_part, int* __restrict__ flags) {
+    __shared__ double sm[INT_THREADS / 32];
+    float pv0 = 0.f, Q0 = 1.f;
+    if (A.integrator == MDG_INT_NHC) { pv0 = sc->pv[pv_sel][0]; Q0 = A.Q[0]; }
+    double acc = 0;
+    bool viol = false;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < A.n; s += gridDim.x * blockDim.x) {
+        float4 v = v4[s];
+        float4 f = f4[s];
+        float4 q = q4[s];
+        float m = v.w;
+        float ax, ay, az;
+        if (A.integrator == MDG_INT_NHC) {
+            float px = v.x * m, py = v.y * m, pz = v.z * m;
+            ax = (f.x - pv0 * px / Q0) / m;
+            ay = (f.y - pv0 * py / Q0) / m;
+            az = (f.z - pv0 * pz / Q0) / m;
+        } else {
+            ax = f.x; ay = f.y; az = f.z;          // NVE: dv/dt = f, no mass division (md.py:146)
+        }
+        float hx = 0.5f * ax * dt, hy = 0.5f * ay * dt, hz = 0.5f * az * dt;
+        float ux = v.x + hx, uy = v.y + hy, uz = v.z + hz;
+        q.x = q.x + ux * dt;
+        q.y = q.y + uy * dt;
+        q.z = q.z + uz * dt;
+        vh4[s] = make_float4(hx, hy, hz, 0.f);
+        q4[s] = q;
+        if (A.integrator == MDG_INT_NHC) {
+            float px = ux * m, py = uy * m, pz = uz * m;
+            acc += (double)(px * px / m) + (double)(py * py / m) + (double)(pz * pz / m);
+        }
+        if (check_skin) {
+            float4 r = qref[s];
+            float dx = q.x - r.x, dy = q.y - r.y, dz = q.z - r.z;
+            viol |= (dx * dx + dy * dy + dz * dz) > A.half_skin2;
+        }
+    }
+    if (viol) flags[5] = 1;
+    if (A.integrator == MDG_INT_NHC) {
+        double t = block_sum_double(acc, sm);
+        if (threadIdx.x == 0) ke_half_part[blockIdx.x] = 0.5 * t;
+    }
+}
+
+// step part B (sovlers.py:120-127 + tinydiffeq.py:69): a1 from (v + vh, f_new, pv + ph);
+// v += vh + 1/2 a1 dt; pv += ph + 1/2 dpv1 dt; writes the trajectory frame (original order) and
+// accumulates ke(v_new) for the next step.
+__global__ void __launch_bounds__(INT_THREADS) k_step_b(IntArgs A, float dt, int pv_sel, Scalars* __restrict__ sc,
+                                                        float4* __restrict__ v4, const float4* __restrict__ vh4,
+                                                        const float4* __restrict__ q4, const float4* __restrict__ f4,
+                                                        const double* __restrict__ ke_part, const double* __restrict__ ke_half_part,
+                                                        int n_part, double* __restrict__ ke_next_part,
+                                                        float* __restrict__ traj_v, float* __restrict__ traj_q,
+                                                        float* __restrict__ traj_pv_row) {
+    __shared__ double sm[INT_THREADS / 32];
+    __shared__ float bc[2];
+    __shared__ float s_pvh0;
+    float pvh0 = 0.f, Q0 = 1.f;
+    if (A.integrator == MDG_INT_NHC) {
+        float ke0 = sum_partials(ke_part, n_part, sm, &bc[0]);
+        float ke1 = sum_partials(ke_half_part, n_part, sm, &bc[1]);
+        if (threadIdx.x == 0) {
+            float pv[MDG_MAX_CHAINS], ph[MDG_MAX_CHAINS], pvh[MDG_MAX_CHAINS], d0[MDG_MAX_CHAINS], d1[MDG_MAX_CHAINS];
+            for (int k = 0; k < A.M; ++k) pv[k] = sc->pv[pv_sel][k];
+            nhc_dpv(A, ke0, pv, d0);
+            for (int k = 0; k < A.M; ++k) { ph[k] = 0.5f * d0[k] * dt; pvh[k] = pv[k] + ph[k]; }
+            nhc_dpv(A, ke1, pvh, d1);
+            s_pvh0 = pvh[0];
+            if (blockIdx.x == 0) {
+                for (int k = 0; k < A.M; ++k) {
+                    float pn = pv[k] + (ph[k] + 0.5f * d1[k] * dt);
+                    sc->pv[pv_sel ^ 1][k] = pn;
+                    if (traj_pv_row) traj_pv_row[k] = pn;
+                }
+            }
+        }
+        __syncthreads();
+        pvh0 = s_pvh0;
+        Q0 = A.Q[0];
+    }
+    double acc = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < A.n; s += gridDim.x * blockDim.x) {
+        float4 v = v4[s];
+        float4 h = vh4[s];
+        float4 f = f4[s];
+        float m = v.w;
+        float ax, ay, az;
+        if (A.integrator == MDG_INT_NHC) {
+            float px = (v.x + h.x) * m, py = (v.y + h.y) * m, pz = (v.z + h.z) * m;
+            ax = (f.x - pvh0 * px / Q0) / m;
+            ay = (f.y - pvh0 * py / Q0) / m;
+            az = (f.z - pvh0 * pz / Q0) / m;
+        } else {
+            ax = f.x; ay = f.y; az = f.z;
+        }
+        v.x = v.x + (h.x + 0.5f * ax * dt);
+        v.y = v.y + (h.y + 0.5f * ay * dt);
+        v.z = v.z + (h.z + 0.5f * az * dt);
+        v4[s] = v;
+        if (A.integrator == MDG_INT_NHC) {
+            float px = v.x * m, py = v.y * m, pz = v.z * m;
+            acc += (double)(px * px / m) + (double)(py * py / m) + (double)(pz * pz / m);
+        }
+        if (traj_v) {
+            float4 q = q4[s];
+            int id = __float_as_int(q.w);
+            traj_v[3 * (size_t)id] = v.x; traj_v[3 * (size_t)id + 1] = v.y; traj_v[3 * (size_t)id + 2] = v.z;
+            traj_q[3 * (size_t)id] = q.x; traj_q[3 * (size_t)id + 1] = q.y; traj_q[3 * (size_t)id + 2] = q.z;
+        }
+    }
+    if (A.integrator == MDG_INT_NHC) {
+        double t = block_sum_double(acc, sm);
+        if (threadIdx.x == 0) ke_next_part[blockIdx.x] = 0.5 * t;
+    }
+}
+
+// state (re)ordering ---------------------------------------------------------------------------
+__global__ void k_init_v(int n, const int* __restrict__ perm, const float* __restrict__ v0,
+                         const float* __restrict__ mass, float4* __restrict__ v4) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = perm[s];
+    v4[s] = make_float4(v0[3 * i], v0[3 * i + 1], v0[3 * i + 2], mass[i]);
+}
+
+__global__ void k_permute2(int n, const int* __restrict__ perm, const float4* __restrict__ a_in, float4* __restrict__ a_out,
+                           const float4* __restrict__ b_in, float4* __restrict__ b_out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = perm[s];
+    a_out[s] = a_in[i];
+    b_out[s] = b_in[i];
+}
+
+__global__ void __launch_bounds__(256) k_energy_sum(int n, const float4* __restrict__ fs, double* __restrict__ part) {
+    __shared__ double sm[8];
+    double v = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) v += (double)fs[s].w;
+    double t = block_sum_double(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// epoch driver
+// ---------------------------------------------------------------------------------------------
+static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_mass, const float* d_v0,
+                    const float* d_q0, const float* h_pv0, const float* h_tgrid, int n_grid, float* d_traj_v,
+                    float* d_traj_q, float* h_traj_pv, float* h_last_energy, int rebuild_every, cudaStream_t st) {
+    const int nhc = p->integrator == MDG_INT_NHC;
+    const int M = nhc ? p->n_chains : 0;
+    const int stride = p->traj_stride < 1 ? 1 : p->traj_stride;
+    const double rlist = p->cutoff + (double)p->skin;
+    const bool retest = p->skin > 0.f;
+    IntArgs A;
+    memset(&A, 0, sizeof(A));
+    A.n = n;
+    A.integrator = p->integrator;
+    A.M = M;
+    for (int k = 0; k < M; ++k) A.Q[k] = p->Q[k];
+    A.T = (float)p->T;
+    A.target = (float)(p->T * (double)p->ndof * 0.5);
+    A.half_skin2 = 0.25f * p->skin * p->skin;
+    PotParams P = mdg_make_pot(p->pot_kind, p->pot_params, MDG_MAX_POT_PARAMS);
+
+    const int T = 256;
+    const int nb = (n + T - 1) / T;
+    int ib = nb < INT_MAX_BLOCKS ? nb : INT_MAX_BLOCKS;
+    if (ib < 1) ib = 1;
+    const int n_frames = (n_grid - 1) / stride + 1;
+
+    MDG_TRY(c->v4.reserve(2 * sizeof(float4) * (size_t)n));
+    MDG_TRY(c->vh4.reserve(2 * sizeof(float4) * (size_t)n));
+    MDG_TRY(c->qref.reserve(sizeof(float4) * (size_t)n));
+    MDG_TRY(c->fs.reserve(sizeof(float4) * (size_t)n));
+    MDG_TRY(c->pvbuf.reserve(sizeof(Scalars) + sizeof(float) * (size_t)n_frames * MDG_MAX_CHAINS));
+    MDG_TRY(c->kebuf.reserve(sizeof(double) * 4 * INT_MAX_BLOCKS));
+    float4* vbuf[2] = {c->v4.as<float4>(), c->v4.as<float4>() + n};
+    float4* hbuf[2] = {c->vh4.as<float4>(), c->vh4.as<float4>() + n};
+    int vsel = 0;
+    Scalars* sc = c->pvbuf.as<Scalars>();
+    float* d_traj_pv = (float*)(sc + 1);
+    double* ke_part[3] = {c->kebuf.as<double>(), c->kebuf.as<double>() + INT_MAX_BLOCKS,
+                          c->kebuf.as<double>() + 2 * INT_MAX_BLOCKS};
+    double* e_part = c->kebuf.as<double>() + 3 * INT_MAX_BLOCKS;
+
+    // scalars + flags
+    Scalars hs;
+    memset(&hs, 0, sizeof(hs));
+    for (int k = 0; k < M; ++k) hs.pv[0][k] = h_pv0 ? h_pv0[k] : 0.f;
+    MDG_CUDA(cudaMemcpyAsync(sc, &hs, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    MDG_TRY(c->flags.reserve(sizeof(int) * 8));
+    MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 8, st));
+
+    // initial sort + list at q0, state into sorted order
+    c->sel_a = c->sel_b = nullptr; c->ex_keys = nullptr; c->n_ex = 0;
+    MDG_TRY(mdg_i_build_list(c, d_q0, nullptr, n, p->cell, rlist, p->cutoff, st));
+    float4* q = c->qs_ptr;
+    k_init_v<<<nb, T, 0, st>>>(n, c->perm.as<int>(), d_v0, d_mass, vbuf[vsel]);
+    MDG_CUDA(cudaMemcpyAsync(c->qref.p, q, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    c->stat_launches += 1;
+    MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
+    if (nhc) { k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, vbuf[vsel], ke_part[0]); c->stat_launches++; }
+    // frame 0 = the initial state, verbatim
+    MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    MDG_CUDA(cudaMemcpyAsync(d_traj_q, d_q0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (M) MDG_CUDA(cudaMemcpyAsync(d_traj_pv, sc->pv[0], sizeof(float) * M, cudaMemcpyDeviceToDevice, st));
+
+    int pv_sel = 0, ke_cur = 0;
+    for (int g = 0; g + 1 < n_grid; ++g) {
+        float dt = h_tgrid[g + 1] - h_tgrid[g];          // fp32 subtraction, like t1 - t0 in tinydiffeq.py:67-68
+        bool do_rebuild = ((g + 1) % rebuild_every) == 0;
+        int ke_half = (ke_cur + 1) % 3, ke_next = (ke_cur + 2) % 3;
+        k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
+                                             c->qref.as<float4>(), (retest && !do_rebuild) ? 1 : 0, ke_part[ke_half],
+                                             c->flags.as<int>());
+        c->stat_launches++;
+        if (do_rebuild) {
+            MDG_TRY(mdg_i_build_list(c, nullptr, q, n, p->cell, rlist, p->cutoff, st));
+            q = c->qs_ptr;
+            if (c->path == 0) {
+                k_permute2<<<nb, T, 0, st>>>(n, c->perm.as<int>(), vbuf[vsel], vbuf[vsel ^ 1], hbuf[vsel], hbuf[vsel ^ 1]);
+                c->stat_launches++;
+                vsel ^= 1;
+            }
+            if (retest) MDG_CUDA(cudaMemcpyAsync(c->qref.p, q, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        }
+        MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
+        int gp = g + 1;
+        bool keep = (gp % stride) == 0;
+        size_t fr = (size_t)(gp / stride);
+        k_step_b<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
+                                             ke_part[ke_cur], ke_part[ke_half], ib, ke_part[ke_next],
+                                             keep ? d_traj_v + fr * 3 * (size_t)n : nullptr,
+                                             keep ? d_traj_q + fr * 3 * (size_t)n : nullptr,
+                                             (keep && M) ? d_traj_pv + fr * M : nullptr);
+        c->stat_launches++;
+        pv_sel ^= 1;
+        ke_cur = ke_next;
+    }
+    if (h_last_energy) {
+        k_energy_sum<<<ib, 256, 0, st>>>(n, c->fs.as<float4>(), e_part);
+        c->stat_launches++;
+    }
+    MDG_KERNEL_CHECK();
+    // read-backs (SYNC)
+    static thread_local double h_e[INT_MAX_BLOCKS];
+    if (h_last_energy) MDG_CUDA(cudaMemcpyAsync(h_e, e_part, sizeof(double) * ib, cudaMemcpyDeviceToHost, st));
+    if (M && h_traj_pv)
+        MDG_CUDA(cudaMemcpyAsync(h_traj_pv, d_traj_pv, sizeof(float) * (size_t)n_frames * M, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA(cudaMemcpyAsync(c->h_pinned, c->flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA(cudaStreamSynchronize(st));
+    if (h_last_energy) {
+        double e = 0;
+        for (int i = 0; i < ib; ++i) e += h_e[i];
+        *h_last_energy = (float)e;
+    }
+    if (c->h_pinned[0]) return MDG_E_CAPACITY;
+    if (c->h_pinned[5]) return MDG_E_SKIN;
+    return MDG_OK;
+}
+
+extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_mass, const float* d_v0,
+                          const float* d_q0, const float* h_pv0, const float* h_tgrid, int n_grid, float* d_traj_v,
+                          float* d_traj_q, float* h_traj_pv, float* h_last_energy, void* stream) {
+    if (!c || !p) { mdg_set_error("null ctx/params"); return MDG_E_BADARG; }
+    if (n <= 0 || n_grid < 1) { mdg_set_error("mdg_md_run: n=%d n_grid=%d", n, n_grid); return MDG_E_BADARG; }
+    if (p->integrator == MDG_INT_NHC && (p->n_chains < 2 || p->n_chains > MDG_MAX_CHAINS)) {
+        mdg_set_error("NHC needs 2 <= n_chains <= %d (got %d)", MDG_MAX_CHAINS, p->n_chains);
+        return MDG_E_BADARG;
+    }
+    if (p->integrator != MDG_INT_NHC && p->integrator != MDG_INT_NVE) { mdg_set_error("bad integrator"); return MDG_E_BADARG; }
+    MDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int K = p->rebuild_every < 1 ? 1 : p->rebuild_every;
+    if (!(p->skin > 0.f)) K = 1;
+    c->stat_launches = 0;
+    c->stat_rebuilds = 0;
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        int s = run_once(c, p, n, d_mass, d_v0, d_q0, h_pv0, h_tgrid, n_grid, d_traj_v, d_traj_q, h_traj_pv,
+                         h_last_energy, K, st);
+        if (s == MDG_E_CAPACITY) {
+            int need = c->h_pinned[2];
+            int cap = ((need + need / 8 + 31) / 32) * 32;
+            if (cap <= c->cap) cap = c->cap + 32;
+            c->cap = cap;
+            continue;
+        }
+        if (s == MDG_E_SKIN) {
+            if (K == 1) { mdg_set_error("skin violated with rebuild_every=1"); return MDG_E_SKIN; }
+            K = K / 2 < 1 ? 1 : K / 2;
+            continue;
+        }
+        c->stat_maxrow = K;   // report the rebuild interval that was finally used
+        return s;
+    }
+    mdg_set_error("mdg_md_run: could not satisfy capacity/skin constraints");
+    return MDG_E_CAPACITY;
+}

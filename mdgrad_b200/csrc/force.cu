@@ -1,0 +1,288 @@
+// force.cu - listed-pair energy/force kernels (K2+K3 in SURVEY.md 2c).
+// Replaces PairPotentials.forward (reference torchmd/interface.py:284-300: compute_dis
+// topology.py:5-12 -> u(r).sum()) and the autograd force F = -dE/dxyz (torchmd/md.py:227-228).
+#include "common.cuh"
+
+PotParams mdg_make_pot(int kind, const float* h_params, int n_params) {
+    PotParams P;
+    P.kind = kind;
+    for (int k = 0; k < MDG_MAX_POT_PARAMS; ++k) P.p[k] = (k < n_params) ? h_params[k] : 0.f;
+    P.aux = 0.f;
+    if (kind == MDG_POT_MORSE) {
+        // A = 0 if phi >= 0 else exp(2a/phi) - 2 exp(a/phi)  (potentials.py:82-85, numpy double)
+        double a = P.p[0], phi = P.p[1];
+        P.aux = (phi >= 0) ? 0.f : (float)(exp(2 * a / phi) - 2 * exp(a / phi));
+    }
+    return P;
+}
+
+// ---------------------------------------------------------------------------------------------
+// v1 list-streaming force kernel: GROUP lanes cooperate on one row (one atom); entries are
+// streamed with coalesced 4-byte loads, neighbor positions gathered from the sorted float4
+// array (L1/L2 resident), forces reduced with warp shuffles, one float4 store per atom.
+// RETEST: re-apply the reference membership test d2 < rc2 (exact arithmetic) to a skin list.
+// ---------------------------------------------------------------------------------------------
+template <int KIND, bool RETEST, bool WITH_DP, int GROUP>
+__global__ void __launch_bounds__(256) k_force_rows(int n, const float4* __restrict__ qs,
+                                                    const uint32_t* __restrict__ rows, const int* __restrict__ row_len,
+                                                    int cap, Box bx, float rc2, PotParams P, float4* __restrict__ fs,
+                                                    double* __restrict__ dp_partials) {
+    const int lane_in_group = threadIdx.x % GROUP;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+    float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
+    float dpa[MDG_MAX_POT_PARAMS] = {0.f, 0.f, 0.f, 0.f};
+    if (s < n) {
+        const float4 qi = qs[s];
+        const uint32_t* row = rows + (size_t)s * cap;
+        const int m = row_len[s];
+        for (int k = lane_in_group; k < m; k += GROUP) {
+            uint32_t e = __ldg(row + k);
+            int t = e & MDG_IDX_MASK;
+            uint32_t code = e >> MDG_IDX_BITS;
+            float4 qj = qs[t];
+            float dx, dy, dz, d2;
+            if (RETEST) {
+                dx = __fadd_rn(__fsub_rn(qj.x, qi.x), mdg_code_shift(code & 3u, bx.L[0]));
+                dy = __fadd_rn(__fsub_rn(qj.y, qi.y), mdg_code_shift((code >> 2) & 3u, bx.L[1]));
+                dz = __fadd_rn(__fsub_rn(qj.z, qi.z), mdg_code_shift((code >> 4) & 3u, bx.L[2]));
+                d2 = mdg_d2_exact(dx, dy, dz);
+                if (!(d2 < rc2) || d2 == 0.0f) continue;
+            } else {
+                dx = (qj.x - qi.x) + mdg_code_shift(code & 3u, bx.L[0]);
+                dy = (qj.y - qi.y) + mdg_code_shift((code >> 2) & 3u, bx.L[1]);
+                dz = (qj.z - qi.z) + mdg_code_shift((code >> 4) & 3u, bx.L[2]);
+                d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 == 0.0f) continue;
+            }
+            float e_p, g, dp[MDG_MAX_POT_PARAMS];
+            pair_eval<KIND, WITH_DP>(P, d2, e_p, g, dp);
+            fx -= g * dx;
+            fy -= g * dy;
+            fz -= g * dz;
+            en += 0.5f * e_p;
+            if (WITH_DP) {
+#pragma unroll
+                for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] += 0.5f * dp[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        en += __shfl_xor_sync(0xffffffffu, en, o);
+    }
+    if (s < n && lane_in_group == 0) fs[s] = make_float4(fx, fy, fz, en);
+    if (WITH_DP) {
+        // block-level reduction of the parameter gradients (double), one partial row per block
+        __shared__ double sm[8][MDG_MAX_POT_PARAMS];
+        double v[MDG_MAX_POT_PARAMS];
+#pragma unroll
+        for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) {
+            v[q] = (double)dpa[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        }
+        int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0)
+            for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) sm[w][q] = v[q];
+        __syncthreads();
+        if (threadIdx.x < MDG_MAX_POT_PARAMS) {
+            double t = 0;
+            for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) t += sm[ww][threadIdx.x];
+            dp_partials[(size_t)blockIdx.x * MDG_MAX_POT_PARAMS + threadIdx.x] = t;
+        }
+    }
+}
+
+template <bool RETEST, bool WITH_DP>
+static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
+    const int GROUP = 8, T = 256;
+    int n = c->n;
+    int nb = (int)(((int64_t)n * GROUP + T - 1) / T);
+#define LF(K)                                                                                                  \
+    k_force_rows<K, RETEST, WITH_DP, GROUP><<<nb, T, 0, st>>>(n, qs, c->rows.as<uint32_t>(), c->row_len.as<int>(), \
+                                                              c->cap, c->box, c->rc2, P, fs, dpp)
+    switch (P.kind) {
+        case MDG_POT_LJ: LF(MDG_POT_LJ); break;
+        case MDG_POT_LJFAM: LF(MDG_POT_LJFAM); break;
+        case MDG_POT_LJ69: LF(MDG_POT_LJ69); break;
+        case MDG_POT_EXV: LF(MDG_POT_EXV); break;
+        case MDG_POT_BUCK: LF(MDG_POT_BUCK); break;
+        case MDG_POT_MORSE: LF(MDG_POT_MORSE); break;
+        default: mdg_set_error("unknown potential kind %d", P.kind); return MDG_E_BADARG;
+    }
+#undef LF
+    c->stat_launches++;
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)c->n * 8 + 255) / 256); }
+
+int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, bool with_dp,
+                       double* d_dp_partials, cudaStream_t st) {
+    if (c->n == 0) return MDG_OK;
+    if (retest) {
+        if (with_dp) return launch_force<true, true>(c, P, d_qs, d_fs, d_dp_partials, st);
+        return launch_force<true, false>(c, P, d_qs, d_fs, d_dp_partials, st);
+    }
+    if (with_dp) return launch_force<false, true>(c, P, d_qs, d_fs, d_dp_partials, st);
+    return launch_force<false, false>(c, P, d_qs, d_fs, d_dp_partials, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// op-level plumbing: gather current positions into sorted order, scatter forces back, reduce E
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gather_sorted(int n, const float* __restrict__ xyz, const int* __restrict__ perm,
+                                float4* __restrict__ qs) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = perm[s];
+    qs[s] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
+}
+
+__global__ void k_scatter_force(int n, const float4* __restrict__ fs, const int* __restrict__ perm,
+                                float* __restrict__ force) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = perm[s];
+    float4 f = fs[s];
+    force[3 * i] = f.x;
+    force[3 * i + 1] = f.y;
+    force[3 * i + 2] = f.z;
+}
+
+__global__ void __launch_bounds__(256) k_energy_partials(int n, const float4* __restrict__ fs, double* __restrict__ part) {
+    __shared__ double sm[8];
+    double v = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) v += (double)fs[s].w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += sm[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+// single block: energy = sum(part[0..npart)), dparams[q] = sum over blocks of dp_part[b*4+q]
+__global__ void __launch_bounds__(256) k_finalize(int npart, const double* __restrict__ part, int ndp_blocks,
+                                                  const double* __restrict__ dp_part, float* __restrict__ energy,
+                                                  float* __restrict__ dparams) {
+    __shared__ double sm[8];
+    for (int what = 0; what < 1 + MDG_MAX_POT_PARAMS; ++what) {
+        if (what == 0 && !energy) continue;
+        if (what > 0 && !dparams) continue;
+        double v = 0;
+        if (what == 0)
+            for (int i = threadIdx.x; i < npart; i += blockDim.x) v += part[i];
+        else
+            for (int i = threadIdx.x; i < ndp_blocks; i += blockDim.x) v += dp_part[(size_t)i * MDG_MAX_POT_PARAMS + what - 1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0;
+            for (int w = 0; w < 8; ++w) t += sm[w];
+            if (what == 0) *energy = (float)t; else dparams[what - 1] = (float)t;
+        }
+    }
+}
+
+int mdg_i_pair_force_op(mdg_ctx* c, const PotParams& P, const float* d_xyz, int n, float* d_energy, float* d_force,
+                        float* d_dparams, cudaStream_t st) {
+    if (!c->built || n != c->n) { mdg_set_error("mdg_pair_force: no list built for n=%d", n); return MDG_E_STATE; }
+    if (n == 0) {
+        if (d_energy) MDG_CUDA(cudaMemsetAsync(d_energy, 0, sizeof(float), st));
+        if (d_dparams) MDG_CUDA(cudaMemsetAsync(d_dparams, 0, sizeof(float) * MDG_MAX_POT_PARAMS, st));
+        return MDG_OK;
+    }
+    const int T = 256;
+    int nb = (n + T - 1) / T;
+    MDG_TRY(c->fs.reserve(sizeof(float4) * (size_t)n));
+    int fblocks = mdg_i_force_blocks(c);
+    const int EPART = 296;
+    MDG_TRY(c->partials.reserve(sizeof(double) * ((size_t)EPART + (size_t)fblocks * MDG_MAX_POT_PARAMS)));
+    double* epart = c->partials.as<double>();
+    double* dpp = epart + EPART;
+    float4* qs = c->qs_ptr;
+    k_gather_sorted<<<nb, T, 0, st>>>(n, d_xyz, c->perm.as<int>(), qs);
+    c->stat_launches++;
+    MDG_TRY(mdg_i_force_sorted(c, P, qs, c->fs.as<float4>(), false, d_dparams != nullptr, dpp, st));
+    if (d_force) { k_scatter_force<<<nb, T, 0, st>>>(n, c->fs.as<float4>(), c->perm.as<int>(), d_force); c->stat_launches++; }
+    if (d_energy || d_dparams) {
+        int npart = nb < EPART ? nb : EPART;
+        if (d_energy) { k_energy_partials<<<npart, T, 0, st>>>(n, c->fs.as<float4>(), epart); c->stat_launches++; }
+        k_finalize<<<1, 256, 0, st>>>(npart, epart, fblocks, dpp, d_energy, d_dparams);
+        c->stat_launches++;
+    }
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic listed-pair distance op (compute_dis, reference torchmd/topology.py:5-12) fwd/bwd
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pair_dis_fwd(const float* __restrict__ xyz, const int64_t* __restrict__ nbr,
+                               const float* __restrict__ off, int64_t P, Box bx, float* __restrict__ dis) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    int64_t i = nbr[2 * p], j = nbr[2 * p + 1];
+    float dx = (xyz[3 * i] - xyz[3 * j]) - off[3 * p] * bx.L[0];
+    float dy = (xyz[3 * i + 1] - xyz[3 * j + 1]) - off[3 * p + 1] * bx.L[1];
+    float dz = (xyz[3 * i + 2] - xyz[3 * j + 2]) - off[3 * p + 2] * bx.L[2];
+    dis[p] = sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+__global__ void k_pair_dis_bwd(const float* __restrict__ xyz, const int64_t* __restrict__ nbr,
+                               const float* __restrict__ off, int64_t P, Box bx, const float* __restrict__ dis,
+                               const float* __restrict__ gdis, float* __restrict__ gxyz) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    int64_t i = nbr[2 * p], j = nbr[2 * p + 1];
+    float dx = (xyz[3 * i] - xyz[3 * j]) - off[3 * p] * bx.L[0];
+    float dy = (xyz[3 * i + 1] - xyz[3 * j + 1]) - off[3 * p + 1] * bx.L[1];
+    float dz = (xyz[3 * i + 2] - xyz[3 * j + 2]) - off[3 * p + 2] * bx.L[2];
+    float r = dis ? dis[p] : sqrtf(dx * dx + dy * dy + dz * dz);
+    float w = r > 0.f ? gdis[p] / r : 0.f;
+    atomicAdd(&gxyz[3 * i], w * dx);
+    atomicAdd(&gxyz[3 * i + 1], w * dy);
+    atomicAdd(&gxyz[3 * i + 2], w * dz);
+    atomicAdd(&gxyz[3 * j], -w * dx);
+    atomicAdd(&gxyz[3 * j + 1], -w * dy);
+    atomicAdd(&gxyz[3 * j + 2], -w * dz);
+}
+
+static Box make_box(const float* h_cell3) {
+    Box b;
+    for (int k = 0; k < 3; ++k) { b.L[k] = h_cell3[k]; b.invL[k] = 1.0f / h_cell3[k]; }
+    return b;
+}
+
+extern "C" int mdg_pair_dis_fwd(const float* d_xyz, int n, const int64_t* d_nbr, const float* d_offsets,
+                                int64_t n_pairs, const float* h_cell3, float* d_dis, void* stream) {
+    (void)n;
+    if (n_pairs <= 0) return MDG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_pair_dis_fwd<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(d_xyz, d_nbr, d_offsets, n_pairs, make_box(h_cell3), d_dis);
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+extern "C" int mdg_pair_dis_bwd(const float* d_xyz, int n, const int64_t* d_nbr, const float* d_offsets,
+                                int64_t n_pairs, const float* h_cell3, const float* d_dis, const float* d_grad_dis,
+                                float* d_grad_xyz, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MDG_CUDA(cudaMemsetAsync(d_grad_xyz, 0, sizeof(float) * 3 * (size_t)n, st));
+    if (n_pairs <= 0) return MDG_OK;
+    k_pair_dis_bwd<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(d_xyz, d_nbr, d_offsets, n_pairs, make_box(h_cell3),
+                                                                     d_dis, d_grad_dis, d_grad_xyz);
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}

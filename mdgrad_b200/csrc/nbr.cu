@@ -1,0 +1,641 @@
+// nbr.cu - cell-list build (device-wide counting sort) + neighbor-list construction and the
+// export in the reference's layout/order.  Replaces generate_nbr_list, reference
+// torchmd/topology.py:30-73 (K1 in SURVEY.md 2c).
+#include "common.cuh"
+
+#define ALLPAIRS_MAX_ATOMS 3072   // below this (or with < 3 cells on an axis) use the all-pairs search
+
+// ---------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_xyz(const float* __restrict__ xyz, float4* __restrict__ q, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
+}
+
+__global__ void k_iota(int* __restrict__ p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// exclusive scan, 3 phases -------------------------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* smem, int& total) {
+    // smem: SCAN_THREADS/32 ints
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) smem[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < (blockDim.x >> 5) ? smem[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        smem[lane] = s;  // inclusive warp totals (32 slots)
+    }
+    __syncthreads();
+    int wbase = w ? smem[w - 1] : 0;
+    total = smem[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return wbase + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int* __restrict__ in, int* __restrict__ out,
+                                                            int* __restrict__ tile_tot, int n) {
+    __shared__ int sm[32];
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int tot;
+    int ex = block_exclusive_scan(s, sm, tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_totals(int* __restrict__ tile_tot, int ntiles, int* __restrict__ grand) {
+    // single block; sequential over chunks of 1024
+    __shared__ int sm[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < ntiles; c0 += 1024) {
+        int i = c0 + threadIdx.x;
+        int v = i < ntiles ? tile_tot[i] : 0;
+        int tot;
+        int ex = block_exclusive_scan(v, sm, tot);
+        int carry = carry_s;
+        if (i < ntiles) tile_tot[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && grand) *grand = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int* __restrict__ out, const int* __restrict__ tile_tot, int n) {
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int add = tile_tot[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+// exclusive scan of d_in[0..n) into d_out[0..n); *d_total (device, optional) = sum
+int mdg_i_scan_exclusive(mdg_ctx* c, const int* d_in, int* d_out, int n, int* d_total, cudaStream_t st) {
+    if (n <= 0) {
+        if (d_total) MDG_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int), st));
+        return MDG_OK;
+    }
+    int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    MDG_TRY(c->scan_tmp.reserve(sizeof(int) * (size_t)(ntiles + 1)));
+    int* tt = c->scan_tmp.as<int>();
+    k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(d_in, d_out, tt, n);
+    k_scan_totals<<<1, 1024, 0, st>>>(tt, ntiles, d_total);
+    if (ntiles > 1) k_scan_add<<<ntiles, SCAN_THREADS, 0, st>>>(d_out, tt, n);
+    c->stat_launches += 2 + (ntiles > 1);
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell binning + counting sort
+// ---------------------------------------------------------------------------------------------
+struct Grid {
+    int   nc[3];
+    float L[3], invL[3];
+};
+
+__device__ __forceinline__ int cell_coord(float x, float L, float invL, int nc) {
+    // bin by the wrapped fractional coordinate; atoms need not be inside the box
+    float f = x * invL;
+    f -= floorf(f);               // [0,1]
+    int c = (int)(f * (float)nc);
+    return min(max(c, 0), nc - 1);
+}
+
+__global__ void k_bin(const float4* __restrict__ q, int n, Grid g, int* __restrict__ cell_of,
+                      int* __restrict__ slot_of, int* __restrict__ cell_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = q[i];
+    int cx = cell_coord(p.x, g.L[0], g.invL[0], g.nc[0]);
+    int cy = cell_coord(p.y, g.L[1], g.invL[1], g.nc[1]);
+    int cz = cell_coord(p.z, g.L[2], g.invL[2], g.nc[2]);
+    int c = (cz * g.nc[1] + cy) * g.nc[0] + cx;
+    cell_of[i] = c;
+    slot_of[i] = atomicAdd(&cell_count[c], 1);
+}
+
+__global__ void k_scatter(int n, const int* __restrict__ cell_of, const int* __restrict__ slot_of,
+                          const int* __restrict__ cell_start, int* __restrict__ perm_tmp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    perm_tmp[cell_start[cell_of[i]] + slot_of[i]] = i;
+}
+
+// one thread per cell: order the cell's atoms by ORIGINAL id (deterministic, history-free),
+// then emit the sorted positions and the permutation (index into the input array)
+__global__ void k_cellsort_gather(int ncell, const int* __restrict__ cell_start, const int* __restrict__ cell_count,
+                                  int* __restrict__ perm_tmp, const float4* __restrict__ qin,
+                                  float4* __restrict__ qs, int* __restrict__ perm) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    int b = cell_start[c], m = cell_count[c];
+    for (int a = 1; a < m; ++a) {
+        int pa = perm_tmp[b + a];
+        int ka = __float_as_int(qin[pa].w);
+        int k = a - 1;
+        while (k >= 0) {
+            int pk = perm_tmp[b + k];
+            if (__float_as_int(qin[pk].w) <= ka) break;
+            perm_tmp[b + k + 1] = pk;
+            --k;
+        }
+        perm_tmp[b + k + 1] = pa;
+    }
+    for (int a = 0; a < m; ++a) {
+        int pa = perm_tmp[b + a];
+        qs[b + a] = qin[pa];
+        perm[b + a] = pa;
+    }
+}
+
+// 27-cell stencil per cell, ascending linear id (so that row entries come out ascending)
+__global__ void k_stencil(Grid g, int* __restrict__ stencil) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int ncell = g.nc[0] * g.nc[1] * g.nc[2];
+    if (c >= ncell) return;
+    int cx = c % g.nc[0], cy = (c / g.nc[0]) % g.nc[1], cz = c / (g.nc[0] * g.nc[1]);
+    int s[27];
+    int m = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                int x = (cx + dx + g.nc[0]) % g.nc[0];
+                int y = (cy + dy + g.nc[1]) % g.nc[1];
+                int z = (cz + dz + g.nc[2]) % g.nc[2];
+                int v = (z * g.nc[1] + y) * g.nc[0] + x;
+                int k = m - 1;
+                while (k >= 0 && s[k] > v) { s[k + 1] = s[k]; --k; }
+                s[k + 1] = v;
+                ++m;
+            }
+    for (int k = 0; k < 27; ++k) stencil[c * 27 + k] = s[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair filters (species selection / exclusions), reference topology.py:15-27,37-53
+// ---------------------------------------------------------------------------------------------
+struct PairFilter {
+    const uint8_t* sel_a;
+    const uint8_t* sel_b;
+    const int64_t* ex_keys;
+    int n_ex;
+    int n;
+};
+
+__device__ __forceinline__ bool pair_allowed(const PairFilter& F, int ida, int idb) {
+    if (F.sel_a) {
+        bool ok = (F.sel_a[ida] && F.sel_b[idb]) || (F.sel_b[ida] && F.sel_a[idb]);
+        if (!ok) return false;
+    }
+    if (F.n_ex > 0) {
+        int lo = min(ida, idb), hi = max(ida, idb);
+        int64_t key = (int64_t)lo * F.n + hi;
+        int a = 0, b = F.n_ex - 1;
+        while (a <= b) {
+            int mid = (a + b) >> 1;
+            int64_t v = F.ex_keys[mid];
+            if (v == key) return false;
+            if (v < key) a = mid + 1; else b = mid - 1;
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// list construction.  One thread per (sorted) atom; row entries in ascending neighbor index.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool test_pair(const float4& qi, const float4& qj, const Box& bx, float r2max,
+                                          uint32_t& entry_code) {
+    int cx, cy, cz;
+    float dx = mdg_min_image_axis(qi.x, qj.x, bx.L[0], bx.invL[0], cx);
+    float dy = mdg_min_image_axis(qi.y, qj.y, bx.L[1], bx.invL[1], cy);
+    float dz = mdg_min_image_axis(qi.z, qj.z, bx.L[2], bx.invL[2], cz);
+    float d2 = mdg_d2_exact(dx, dy, dz);
+    entry_code = (uint32_t)(cx | (cy << 2) | (cz << 4)) << MDG_IDX_BITS;
+    return (d2 < r2max) && (d2 != 0.0f);
+}
+
+__global__ void __launch_bounds__(128) k_build_cells(int n, const float4* __restrict__ qs, const int* __restrict__ cell_sorted,
+                                                     const int* __restrict__ cell_start, const int* __restrict__ stencil,
+                                                     Box bx, float r2max, int cap, PairFilter F,
+                                                     uint32_t* __restrict__ rows, int* __restrict__ row_len,
+                                                     int* __restrict__ flags) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float4 qi = qs[s];
+    int idi = __float_as_int(qi.w);
+    int c = cell_sorted[s];
+    uint32_t* row = rows + (size_t)s * cap;
+    int cnt = 0;
+    bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
+    for (int k = 0; k < 27; ++k) {
+        int cc = stencil[c * 27 + k];
+        int t0 = cell_start[cc], t1 = cell_start[cc + 1];
+        for (int t = t0; t < t1; ++t) {
+            if (t == s) continue;
+            float4 qj = qs[t];
+            uint32_t code;
+            if (!test_pair(qi, qj, bx, r2max, code)) continue;
+            if (filt && !pair_allowed(F, idi, __float_as_int(qj.w))) continue;
+            if (cnt < cap) row[cnt] = (uint32_t)t | code;
+            ++cnt;
+        }
+    }
+    if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
+    row_len[s] = cnt;
+}
+
+// written per sorted atom: its cell id (needed by k_build_cells)
+__global__ void k_cell_sorted(int ncell, const int* __restrict__ cell_start, int* __restrict__ cell_sorted) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    for (int t = cell_start[c]; t < cell_start[c + 1]; ++t) cell_sorted[t] = c;
+}
+
+#define AP_TILE 128
+__global__ void __launch_bounds__(AP_TILE) k_build_allpairs(int n, const float4* __restrict__ qs, Box bx, float r2max,
+                                                            int cap, PairFilter F, uint32_t* __restrict__ rows,
+                                                            int* __restrict__ row_len, int* __restrict__ flags) {
+    __shared__ float4 tile[AP_TILE];
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 qi = s < n ? qs[s] : make_float4(0, 0, 0, 0);
+    int idi = __float_as_int(qi.w);
+    uint32_t* row = rows + (size_t)min(s, n - 1) * cap;
+    int cnt = 0;
+    bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
+    for (int t0 = 0; t0 < n; t0 += AP_TILE) {
+        __syncthreads();
+        if (t0 + threadIdx.x < n) tile[threadIdx.x] = qs[t0 + threadIdx.x];
+        __syncthreads();
+        if (s < n) {
+            int m = min(AP_TILE, n - t0);
+            for (int k = 0; k < m; ++k) {
+                int t = t0 + k;
+                if (t == s) continue;
+                float4 qj = tile[k];
+                uint32_t code;
+                if (!test_pair(qi, qj, bx, r2max, code)) continue;
+                if (filt && !pair_allowed(F, idi, __float_as_int(qj.w))) continue;
+                if (cnt < cap) row[cnt] = (uint32_t)t | code;
+                ++cnt;
+            }
+        }
+    }
+    if (s < n) {
+        if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
+        row_len[s] = cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: build
+// ---------------------------------------------------------------------------------------------
+static inline int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+// d_xyz (n x 3, original order) XOR d_q4_in (float4 with ids in .w, any order).
+int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int n, const float* h_cell3,
+                     double rlist, double cutoff, cudaStream_t st) {
+    if (n < 0 || n >= MDG_MAX_ATOMS) { mdg_set_error("n=%d out of range", n); return MDG_E_BADARG; }
+    for (int k = 0; k < 3; ++k)
+        if (!(h_cell3[k] > 0.f)) { mdg_set_error("cell length %d must be > 0", k); return MDG_E_BADARG; }
+    c->n = n;
+    c->built = false;
+    Grid g;
+    for (int k = 0; k < 3; ++k) {
+        c->box.L[k] = h_cell3[k];
+        c->box.invL[k] = 1.0f / h_cell3[k];  // correctly rounded fp32 reciprocal
+        g.L[k] = c->box.L[k];
+        g.invL[k] = c->box.invL[k];
+        int nck = (int)((double)h_cell3[k] / (rlist * 1.0001));
+        g.nc[k] = nck < 1 ? 1 : nck;
+    }
+    c->rlist2 = (float)(rlist * rlist);
+    c->rc2 = (float)(cutoff * cutoff);
+    bool cells_ok = g.nc[0] >= 3 && g.nc[1] >= 3 && g.nc[2] >= 3;
+    int path = (cells_ok && n > ALLPAIRS_MAX_ATOMS) ? 0 : 1;
+    // limit cell count relative to atoms (very dilute boxes): keep >= ~2 atoms per cell on average
+    if (path == 0) {
+        while ((int64_t)g.nc[0] * g.nc[1] * g.nc[2] > (int64_t)n && g.nc[0] > 3 && g.nc[1] > 3 && g.nc[2] > 3) {
+            for (int k = 0; k < 3; ++k) g.nc[k] = g.nc[k] > 3 ? g.nc[k] - 1 : 3;
+        }
+    }
+    bool grid_changed = (path != c->path) || g.nc[0] != c->nc[0] || g.nc[1] != c->nc[1] || g.nc[2] != c->nc[2] || c->ncell == 0;
+    c->path = path;
+    for (int k = 0; k < 3; ++k) c->nc[k] = g.nc[k];
+    int ncell = g.nc[0] * g.nc[1] * g.nc[2];
+    c->ncell = ncell;
+    if (n == 0) { c->built = true; c->npairs = 0; c->stat_entries = 0; return MDG_OK; }
+
+    // capacity estimate from the mean density (grown by the caller on overflow)
+    if (c->cap == 0) {
+        double vol = (double)h_cell3[0] * h_cell3[1] * h_cell3[2];
+        double avg = (double)n / vol * 4.18879 * rlist * rlist * rlist;
+        int want = roundup((int)(avg * 1.5) + 24, 32);
+        if (want > roundup(n, 32)) want = roundup(n, 32);
+        if (want < 32) want = 32;
+        c->cap = want;
+    }
+    MDG_TRY(c->qs_buf[0].reserve(sizeof(float4) * (size_t)n));
+    MDG_TRY(c->qs_buf[1].reserve(sizeof(float4) * (size_t)n));
+    MDG_TRY(c->perm.reserve(sizeof(int) * (size_t)n));
+    if (c->rows_wanted) {
+        MDG_TRY(c->rows.reserve(sizeof(uint32_t) * (size_t)n * c->cap));
+        MDG_TRY(c->row_len.reserve(sizeof(int) * (size_t)n));
+    }
+    MDG_TRY(c->flags.reserve(sizeof(int) * 8));
+    MDG_TRY(c->cell_of.reserve(sizeof(int) * (size_t)n));   // reused as cell_sorted after the scatter
+    const int T = 256;
+    int nb = (n + T - 1) / T;
+
+    // input as float4 + id
+    const float4* qin = d_q4_in;
+    if (!qin) {
+        MDG_TRY(c->q4b.reserve(sizeof(float4) * (size_t)n));
+        k_pack_xyz<<<nb, T, 0, st>>>(d_xyz, c->q4b.as<float4>(), n);
+        c->stat_launches++;
+        qin = c->q4b.as<float4>();
+    }
+    PairFilter F{c->sel_a, c->sel_b, c->ex_keys, c->n_ex, n};
+    float4* qs = (qin == c->qs_buf[0].as<float4>()) ? c->qs_buf[1].as<float4>() : c->qs_buf[0].as<float4>();
+    c->qs_ptr = qs;
+    MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 3, st));   // [0] overflow, [2] max row count
+    if (path == 0) {
+        MDG_TRY(c->slot_of.reserve(sizeof(int) * (size_t)n));
+        MDG_TRY(c->perm_tmp.reserve(sizeof(int) * (size_t)n));
+        MDG_TRY(c->cell_count.reserve(sizeof(int) * (size_t)(ncell + 1)));
+        MDG_TRY(c->cell_start.reserve(sizeof(int) * (size_t)(ncell + 2)));
+        MDG_TRY(c->stencil.reserve(sizeof(int) * (size_t)ncell * 27));
+        int ncb = (ncell + T - 1) / T;
+        if (grid_changed) { k_stencil<<<ncb, T, 0, st>>>(g, c->stencil.as<int>()); c->stat_launches++; }
+        MDG_CUDA(cudaMemsetAsync(c->cell_count.p, 0, sizeof(int) * (size_t)(ncell + 1), st));
+        k_bin<<<nb, T, 0, st>>>(qin, n, g, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_count.as<int>());
+        MDG_TRY(mdg_i_scan_exclusive(c, c->cell_count.as<int>(), c->cell_start.as<int>(), ncell + 1, nullptr, st));
+        k_scatter<<<nb, T, 0, st>>>(n, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_start.as<int>(), c->perm_tmp.as<int>());
+        k_cellsort_gather<<<ncb, T, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
+                                             qin, qs, c->perm.as<int>());
+        k_cell_sorted<<<ncb, T, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_of.as<int>());
+        if (c->rows_wanted)
+            k_build_cells<<<(n + 127) / 128, 128, 0, st>>>(n, qs, c->cell_of.as<int>(), c->cell_start.as<int>(), c->stencil.as<int>(),
+                                                          c->box, c->rlist2, c->cap, F, c->rows.as<uint32_t>(),
+                                                          c->row_len.as<int>(), c->flags.as<int>());
+        c->stat_launches += 4 + (c->rows_wanted ? 1 : 0);
+    } else {
+        MDG_CUDA(cudaMemcpyAsync(qs, qin, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        k_iota<<<nb, T, 0, st>>>(c->perm.as<int>(), n);
+        if (c->rows_wanted)
+            k_build_allpairs<<<(n + AP_TILE - 1) / AP_TILE, AP_TILE, 0, st>>>(n, qs, c->box, c->rlist2, c->cap, F,
+                                                                            c->rows.as<uint32_t>(), c->row_len.as<int>(),
+                                                                            c->flags.as<int>());
+        c->stat_launches += 1 + (c->rows_wanted ? 1 : 0);
+    }
+    MDG_KERNEL_CHECK();
+    c->built = c->rows_wanted;
+    c->stat_rebuilds++;
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// export in the reference layout and order (topology.py:66-73): rows i<j by ORIGINAL ids,
+// sorted (i, then j)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_export_count(int n, const float4* __restrict__ qs, const uint32_t* __restrict__ rows,
+                               const int* __restrict__ row_len, int cap, int* __restrict__ up_cnt) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int idi = __float_as_int(qs[s].w);
+    const uint32_t* row = rows + (size_t)s * cap;
+    int m = row_len[s], cnt = 0;
+    for (int k = 0; k < m; ++k) {
+        int t = row[k] & MDG_IDX_MASK;
+        cnt += (__float_as_int(qs[t].w) > idi);
+    }
+    up_cnt[idi] = cnt;
+}
+
+__global__ void k_export_fill(int n, const float4* __restrict__ qs, const uint32_t* __restrict__ rows,
+                              const int* __restrict__ row_len, int cap, const int* __restrict__ up_off, Box bx,
+                              int64_t* __restrict__ nbr, float* __restrict__ offsets, float* __restrict__ dis) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float4 qi = qs[s];
+    int idi = __float_as_int(qi.w);
+    const uint32_t* row = rows + (size_t)s * cap;
+    int m = row_len[s];
+    int64_t base = up_off[idi];
+    for (int k = 0; k < m; ++k) {
+        uint32_t e = row[k];
+        int t = e & MDG_IDX_MASK;
+        float4 qj = qs[t];
+        int idj = __float_as_int(qj.w);
+        if (idj <= idi) continue;
+        int rank = 0;
+        for (int k2 = 0; k2 < m; ++k2) {
+            int id2 = __float_as_int(qs[row[k2] & MDG_IDX_MASK].w);
+            rank += (id2 > idi && id2 < idj);
+        }
+        int64_t p = base + rank;
+        nbr[2 * p] = idi;
+        nbr[2 * p + 1] = idj;
+        uint32_t code = e >> MDG_IDX_BITS;
+        float ox = (float)((int)(code & 3u) - 1), oy = (float)((int)((code >> 2) & 3u) - 1),
+              oz = (float)((int)((code >> 4) & 3u) - 1);
+        offsets[3 * p] = ox;
+        offsets[3 * p + 1] = oy;
+        offsets[3 * p + 2] = oz;
+        if (dis) {
+            float dx = __fadd_rn(__fsub_rn(qj.x, qi.x), __fmul_rn(ox, bx.L[0]));
+            float dy = __fadd_rn(__fsub_rn(qj.y, qi.y), __fmul_rn(oy, bx.L[1]));
+            float dz = __fadd_rn(__fsub_rn(qj.z, qi.z), __fmul_rn(oz, bx.L[2]));
+            dis[p] = __fsqrt_rn(mdg_d2_exact(dx, dy, dz));
+        }
+    }
+}
+
+int mdg_i_export_count(mdg_ctx* c, cudaStream_t st, int64_t* h_npairs) {
+    int n = c->n;
+    if (n == 0) { *h_npairs = 0; c->npairs = 0; return MDG_OK; }
+    MDG_TRY(c->up_cnt.reserve(sizeof(int) * (size_t)(n + 1)));
+    MDG_TRY(c->up_off.reserve(sizeof(int) * (size_t)(n + 2)));
+    const int T = 256;
+    int nb = (n + T - 1) / T;
+    k_export_count<<<nb, T, 0, st>>>(n, c->qs_ptr, c->rows.as<uint32_t>(), c->row_len.as<int>(), c->cap,
+                                     c->up_cnt.as<int>());
+    c->stat_launches++;
+    int* d_total = c->flags.as<int>() + 4;
+    MDG_TRY(mdg_i_scan_exclusive(c, c->up_cnt.as<int>(), c->up_off.as<int>(), n, d_total, st));
+    MDG_CUDA(cudaMemcpyAsync(c->h_pinned, c->flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA(cudaStreamSynchronize(st));
+    if (c->h_pinned[0]) return MDG_E_CAPACITY;
+    c->npairs = c->h_pinned[4];
+    *h_npairs = c->npairs;
+    return MDG_OK;
+}
+
+int mdg_i_export_fill(mdg_ctx* c, int64_t* d_nbr, float* d_offsets, float* d_dis, cudaStream_t st) {
+    int n = c->n;
+    if (n == 0 || c->npairs == 0) return MDG_OK;
+    const int T = 128;
+    k_export_fill<<<(n + T - 1) / T, T, 0, st>>>(n, c->qs_ptr, c->rows.as<uint32_t>(), c->row_len.as<int>(),
+                                                 c->cap, c->up_off.as<int>(), c->box, d_nbr, d_offsets, d_dis);
+    c->stat_launches++;
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6  RDF: Gaussian-smeared pair-distance histogram (reference torchmd/observable.py:62-76,
+// nff/nn/layers.py:14-31).  Traverses the cell structure directly (no stored rows); every
+// undirected pair (id_j > id_i) with d < end + 0.5 contributes exp(-0.5/w^2 (d - mu_k)^2) to
+// bin k.  Terms beyond +-RDF_NSIG widths (< 3e-10 of a unit term) are skipped.
+// ---------------------------------------------------------------------------------------------
+#define RDF_NSIG 6.6f
+#define RDF_MAX_BINS 2048
+
+struct RdfArgs {
+    float start, dmu, inv_dmu, coeff, win;  // mu_k = start + k*dmu ; coeff = -0.5/w^2 ; win = NSIG*w
+    int   nbins;
+};
+
+__device__ __forceinline__ void rdf_add(const RdfArgs& R, float d, float* sh) {
+    int k0 = (int)ceilf((d - R.win - R.start) * R.inv_dmu);
+    int k1 = (int)floorf((d + R.win - R.start) * R.inv_dmu);
+    k0 = max(k0, 0);
+    k1 = min(k1, R.nbins - 1);
+    for (int k = k0; k <= k1; ++k) {
+        float x = d - (R.start + (float)k * R.dmu);
+        atomicAdd(&sh[k], expf(R.coeff * x * x));
+    }
+}
+
+template <bool CELLS>
+__global__ void __launch_bounds__(128) k_rdf(int n, const float4* __restrict__ qs, const int* __restrict__ cell_sorted,
+                                             const int* __restrict__ cell_start, const int* __restrict__ stencil, Box bx,
+                                             float r2max, PairFilter F, RdfArgs R, float* __restrict__ block_hist) {
+    extern __shared__ float sh[];
+    for (int k = threadIdx.x; k < R.nbins; k += blockDim.x) sh[k] = 0.f;
+    __syncthreads();
+    bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        float4 qi = qs[s];
+        int idi = __float_as_int(qi.w);
+        if (CELLS) {
+            int c = cell_sorted[s];
+            for (int k = 0; k < 27; ++k) {
+                int cc = stencil[c * 27 + k];
+                for (int t = cell_start[cc]; t < cell_start[cc + 1]; ++t) {
+                    float4 qj = qs[t];
+                    int idj = __float_as_int(qj.w);
+                    if (idj <= idi) continue;
+                    int cx, cy, cz;
+                    float dx = mdg_min_image_axis(qi.x, qj.x, bx.L[0], bx.invL[0], cx);
+                    float dy = mdg_min_image_axis(qi.y, qj.y, bx.L[1], bx.invL[1], cy);
+                    float dz = mdg_min_image_axis(qi.z, qj.z, bx.L[2], bx.invL[2], cz);
+                    float d2 = mdg_d2_exact(dx, dy, dz);
+                    if (!(d2 < r2max) || d2 == 0.f) continue;
+                    if (filt && !pair_allowed(F, idi, idj)) continue;
+                    rdf_add(R, __fsqrt_rn(d2), sh);
+                }
+            }
+        } else {
+            for (int t = 0; t < n; ++t) {
+                float4 qj = qs[t];
+                int idj = __float_as_int(qj.w);
+                if (idj <= idi) continue;
+                int cx, cy, cz;
+                float dx = mdg_min_image_axis(qi.x, qj.x, bx.L[0], bx.invL[0], cx);
+                float dy = mdg_min_image_axis(qi.y, qj.y, bx.L[1], bx.invL[1], cy);
+                float dz = mdg_min_image_axis(qi.z, qj.z, bx.L[2], bx.invL[2], cz);
+                float d2 = mdg_d2_exact(dx, dy, dz);
+                if (!(d2 < r2max) || d2 == 0.f) continue;
+                if (filt && !pair_allowed(F, idi, idj)) continue;
+                rdf_add(R, __fsqrt_rn(d2), sh);
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < R.nbins; k += blockDim.x) block_hist[(size_t)blockIdx.x * R.nbins + k] = sh[k];
+}
+
+__global__ void k_rdf_reduce(int nblocks, int nbins, const float* __restrict__ block_hist, float* __restrict__ count) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbins) return;
+    double t = 0;
+    for (int b = 0; b < nblocks; ++b) t += (double)block_hist[(size_t)b * nbins + k];
+    count[k] += (float)t;
+}
+
+extern "C" int mdg_rdf_accumulate(mdg_ctx* c, const float* d_xyz, int n, const float* h_cell3, double start, double end,
+                                  int nbins, double width, const uint8_t* d_sel_a, const uint8_t* d_sel_b,
+                                  float* d_count, void* stream) {
+    if (!c || !h_cell3 || !d_count || (n > 0 && !d_xyz)) { mdg_set_error("mdg_rdf_accumulate: null argument"); return MDG_E_BADARG; }
+    if (nbins < 2 || nbins > RDF_MAX_BINS) { mdg_set_error("mdg_rdf_accumulate: nbins=%d not in [2,%d]", nbins, RDF_MAX_BINS); return MDG_E_BADARG; }
+    if ((d_sel_a == nullptr) != (d_sel_b == nullptr)) { mdg_set_error("give both sel_a and sel_b or neither"); return MDG_E_BADARG; }
+    MDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return MDG_OK;
+    double rcut = end + 0.5;                 // observable.py:59
+    c->sel_a = d_sel_a; c->sel_b = d_sel_b; c->ex_keys = nullptr; c->n_ex = 0;
+    c->rows_wanted = false;
+    int s = mdg_i_build_list(c, d_xyz, nullptr, n, h_cell3, rcut, rcut, st);
+    c->rows_wanted = true;
+    MDG_TRY(s);
+    // mu = torch.linspace(start, end, nbins) in fp32; width default mu[1]-mu[0] (layers.py:55-59)
+    RdfArgs R;
+    float fstart = (float)start, fend = (float)end;
+    float step = (fend - fstart) / (float)(nbins - 1);
+    R.start = fstart;
+    R.dmu = step;
+    R.inv_dmu = 1.0f / step;
+    float w = width > 0 ? (float)width : step;
+    R.coeff = -0.5f / (w * w);
+    R.win = RDF_NSIG * w;
+    R.nbins = nbins;
+    int nblocks = c->sm_count * 4;
+    int maxb = (n + 127) / 128;
+    if (nblocks > maxb) nblocks = maxb;
+    MDG_TRY(c->partials.reserve(sizeof(float) * (size_t)nblocks * nbins + 64));
+    float* bh = c->partials.as<float>();
+    PairFilter F{d_sel_a, d_sel_b, nullptr, 0, n};
+    size_t shb = sizeof(float) * nbins;
+    if (c->path == 0)
+        k_rdf<true><<<nblocks, 128, shb, st>>>(n, c->qs_ptr, c->cell_of.as<int>(), c->cell_start.as<int>(),
+                                               c->stencil.as<int>(), c->box, c->rc2, F, R, bh);
+    else
+        k_rdf<false><<<nblocks, 128, shb, st>>>(n, c->qs_ptr, nullptr, nullptr, nullptr, c->box, c->rc2, F, R, bh);
+    k_rdf_reduce<<<(nbins + 127) / 128, 128, 0, st>>>(nblocks, nbins, bh, d_count);
+    c->stat_launches += 2;
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
