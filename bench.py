@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py - MD steps/s of the B200-native hot path on BASELINE.json's configuration.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1 under torchrun: one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one NH-Verlet MD step of the whole box (list upkeep + pair forces + NHC integrator).
+N=1 workload = BASELINE.json configs[1]: 256 000-atom LJ fluid (40^3 FCC, rho 0.845, jitter 0.05a),
+LennardJones(1,1) cutoff 2.5, NoseHooverChain(Q=50, T=1, 5 chains), dt 0.005.
+N>1: the same box replicated per rank ("replicas only" until the spatial-decomposition path lands;
+weak scaling, no data-path collective) - see DESIGN.md.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident whole-job steps/s (inputs in HBM, CUDA
+events, max over ranks); `e2e` = the same metric through the public API
+(Simulations.simulate with host numpy state -> H2D, epochs, D2H of every epoch's last frame, fp64
+host wrap) ; `roofline` = the pair-force kernel's algorithmic bytes / its measured launch time vs
+MEASURED_PEAKS.json ; `cpu_baseline` = the C oracle (port of the reference's all-pairs algorithm)
+on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RHO, RC, DT, TEMP, QBATH, CHAINS, MASS = 0.845, 2.5, 0.005, 1.0, 50.0, 5, 1.008
+NCELL_DEFAULT = 40          # 40^3 FCC cells = 256 000 atoms
+
+
+def make_system(ncell, seed=1):
+    a = (4.0 / RHO) ** (1.0 / 3.0)
+    basis = np.array([(0, 0, 0), (0.5, 0.5, 0), (0.5, 0, 0.5), (0, 0.5, 0.5)], dtype=np.float64)
+    g = np.stack(np.meshgrid(np.arange(ncell), np.arange(ncell), np.arange(ncell), indexing="ij"), -1).reshape(-1, 1, 3)
+    pos = ((g + basis[None]) * a).reshape(-1, 3)
+    pos = pos + np.random.default_rng(seed).normal(0.0, 0.05 * a, pos.shape)
+    vel = np.random.default_rng(seed + 1).standard_normal(pos.shape) * math.sqrt(TEMP / MASS)
+    return pos, vel, ncell * a
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def md_params(_lib, n, L, skin, K):
+    p = _lib.MdParams()
+    p.integrator = _lib.INT_NHC
+    p.pot_kind = _lib.POT_LJ
+    p.pot_params[0], p.pot_params[1] = 1.0, 1.0
+    p.cutoff = RC
+    for k in range(3):
+        p.cell[k] = L
+    p.n_chains = CHAINS
+    Q = np.array([QBATH, *[QBATH / n] * (CHAINS - 1)]).astype(np.float32)
+    for k in range(CHAINS):
+        p.Q[k] = float(Q[k])
+    p.T = TEMP
+    p.ndof = 3 * n
+    p.skin = skin
+    p.rebuild_every = K
+    p.traj_stride = 1
+    return p
+
+
+def tgrid(nsteps):
+    return [float(np.float32(DT * i)) for i in range(nsteps + 1)]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the C oracle (port of the reference's per-evaluation all-pairs
+# algorithm) on the host cores, on a bounded row sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps_per_s(ncell, steps, warmup, budget_s):
+    from oracle import oracle_c as C
+    pos, vel, L = make_system(ncell)
+    n = pos.shape[0]
+    cores = C.num_threads()
+    cell3 = np.array([L] * 3, dtype=np.float32)
+    x = pos.astype(np.float32)
+    # calibrate the row sample so that (steps + warmup) evaluations fit the budget
+    t0 = time.perf_counter()
+    probe = min(n, 64 * cores)
+    C.lj_forces(x, cell3, RC, rows=(0, probe))
+    per_row = (time.perf_counter() - t0) / probe
+    rows = int(max(cores, min(n, budget_s / max(1, steps + warmup) / per_row)))
+    mass = np.full(n, MASS, np.float32)
+    Q = np.array([QBATH, *[QBATH / n] * (CHAINS - 1)]).astype(np.float32)
+    dts = np.diff(np.array(tgrid(max(steps, warmup, 1)), dtype=np.float32))
+    if warmup:
+        C.nhc_md(vel, pos, np.zeros(CHAINS), mass, cell3, RC, 1.0, 1.0, Q, TEMP, 3 * n, dts[:warmup], rows=rows)
+    t0 = time.perf_counter()
+    C.nhc_md(vel, pos, np.zeros(CHAINS), mass, cell3, RC, 1.0, 1.0, Q, TEMP, 3 * n, dts[:steps], rows=rows)
+    el = time.perf_counter() - t0
+    # one evaluation of the full box costs n/rows times the sampled rows (the integrator part is O(N) and
+    # already complete); steps/s of the FULL workload:
+    integ = 0.0
+    full_step = (el / steps) * (n / rows) if rows < n else el / steps
+    sample = ("C oracle (all-pairs list rebuilt per evaluation, as the reference), %d of %d atom rows per step, "
+              "time scaled x%.1f; reference torch path cannot allocate this box (70*N^2 B)" % (rows, n, n / rows))
+    return 1.0 / full_step, cores, sample, n
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    v, cores, sample, n = cpu_reference_steps_per_s(args.ncell, args.steps, args.warmup, budget_s=90.0)
+    line = {
+        "impl": "reference", "metric": "MD steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LJ fluid %d atoms (FCC %d^3, rho 0.845), rc 2.5, NoseHooverChain Q=50 T=1 M=5, dt 0.005"
+                               % (n, args.ncell), "atoms": n},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncell", type=int, default=NCELL_DEFAULT, help="FCC cells per axis (40 -> 256000 atoms)")
+    ap.add_argument("--skin", type=float, default=0.3)
+    ap.add_argument("--rebuild-every", type=int, default=0, help="0 = auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mdgrad_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the MD hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert args.warmup >= 3, "W >= 3 warm-up steps required"
+
+    pos, vel, L = make_system(args.ncell)
+    n = pos.shape[0]
+    L32 = float(np.float32(L))
+    q0 = torch.tensor(pos, dtype=torch.float32, device=dev)
+    v0 = torch.tensor(vel, dtype=torch.float32, device=dev)
+    mass = torch.full((n,), MASS, dtype=torch.float32, device=dev)
+    ctx = _lib.Context(dev)
+
+    # rebuild cadence: conservative estimate from v_max, then let the engine halve on a violation
+    K = args.rebuild_every
+    if K <= 0:
+        vmax = float(v0.norm(dim=1).max())
+        K = int(max(1, min(64, math.floor(0.5 * args.skin / (2.0 * vmax * DT))))) if args.skin > 0 else 1
+    p = md_params(_lib, n, L32, args.skin, K)
+
+    def run(nsteps, vv, qq, pv):
+        tv, tq, tpv, _ = ctx.md_run(p, mass, vv, qq, pv, tgrid(nsteps))
+        return tv, tq, tpv
+
+    # warm-up: W untimed steps (also settles the rebuild cadence and capacity)
+    tv, tq, tpv = run(args.warmup, v0, q0, [0.0] * CHAINS)
+    p.rebuild_every = int(ctx.stats()["maxrow_or_K"])
+    v1, q1, pv1 = tv[-1].clone(), tq[-1].clone(), [float(x) for x in tpv[-1]]
+    del tv, tq
+
+    # ---- timed: device-resident K steps, CUDA events on the launch stream, barrier + sync both sides
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    tv, tq, tpv = run(args.steps, v1, q1, pv1)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    stats = ctx.stats()
+    launches = int(stats["launches"])
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = args.steps * world / (ms / 1000.0) if world > 1 else args.steps / (ms / 1000.0)
+    q_end, v_end = tq[-1].clone(), tv[-1].clone()
+    finite = bool(torch.isfinite(q_end).all() and torch.isfinite(v_end).all())
+    del tv, tq
+
+    out = {
+        "metric": "MD steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LJ fluid %d atoms (FCC %d^3, rho 0.845, jitter 0.05a), LennardJones(1,1) rc 2.5, "
+                               "NoseHooverChain Q=50 T=1.0 M=5, dt 0.005" % (n, args.ncell),
+                   "atoms": n, "atoms_per_gpu": n, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
+                   "skin": args.skin, "rebuild_every": int(p.rebuild_every), "rebuilds": int(stats["rebuilds"]),
+                   "l2": "no explicit flush: per-step working set (neighbor rows %.0f MB allocated + state %.0f MB) is streamed "
+                         "from HBM and exceeds the 126 MB L2" % (n * 128 * 4 / 1e6, n * 16 * 6 / 1e6),
+                   "trajectory": "every step captured (reference semantics, stride 1)", "finite": finite},
+        "gpu_launches": launches, "clocks": clocks,
+        "tau_per_day": value / max(world, 1) * DT * 86400.0,
+    }
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (pair force): algorithmic bytes 32 N + 8 P over measured duration
+    ctx.set_profile(True)
+    tvp, tqp, _ = run(min(args.steps, 200), v1, q1, pv1)
+    prof = ctx.get_profile()
+    ctx.set_profile(False)
+    del tvp, tqp
+    cctx = _lib.Context(dev)
+    P_rc = int(cctx.nbr_list(q_end, [L32] * 3, RC)[0].shape[0])      # pairs inside the cutoff (reference list size)
+    P_list = int(cctx.nbr_list(q_end, [L32] * 3, RC + args.skin)[0].shape[0]) if args.skin > 0 else P_rc
+    del cctx
+    force_ms = prof["force_ms"] / max(1, prof["force_launches"])
+    alg_bytes = 32.0 * n + 8.0 * P_rc
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (force_ms * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm", "kernel": "k_force_rows (pair force, list streaming)", "achieved": achieved,
+                       "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                       "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "pairs_in_cutoff": P_rc, "pairs_in_skin_list": P_list,
+                       "streamed_bytes_with_skin": 32.0 * n + 8.0 * P_list,
+                       "kernel_ms": force_ms, "kernel_launches_timed": prof["force_launches"],
+                       "share_of_step": force_ms / (ms / args.steps)}
+
+    # ---- e2e through the public API with HOST state (numpy in System, H2D per epoch, D2H last frame per epoch)
+    if not args.no_e2e:
+        from torchmd.system import System
+        from torchmd.interface import PairPotentials
+        from torchmd.potentials import LennardJones
+        from torchmd.md import NoseHooverChain, Simulations
+        from mdgrad_b200._ase_compat import Atoms
+        atoms = Atoms(numbers=[1] * n, positions=q_end.cpu().numpy().astype(np.float64), cell=[L] * 3, pbc=True)
+        system = System(atoms, device=local_rank)
+        system.set_velocities(v_end.cpu().numpy().astype(np.float64))
+        pair = PairPotentials(system, LennardJones(1.0, 1.0), cutoff=RC)
+        integ = NoseHooverChain(pair, system, T=TEMP, num_chains=CHAINS, Q=QBATH, adjoint=True)
+        integ.engine_skin = args.skin
+        sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+        per_epoch = 100
+        freq = per_epoch + 1
+        n_epochs = max(1, args.steps // per_epoch)
+        sim.simulate(steps=freq, frequency=freq, dt=DT)                  # warm-up epoch (100 steps)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sim.simulate(steps=freq * n_epochs, frequency=freq, dt=DT)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        e2e_steps = n_epochs * per_epoch
+        state_bytes = n * 3 * 4 * 2 + CHAINS * 4
+        out["e2e"] = {"value": e2e_steps / el, "unit": "steps/s",
+                      "h2d_bytes_per_step": state_bytes / per_epoch, "d2h_bytes_per_step": state_bytes / per_epoch,
+                      "api": "Simulations.simulate(steps=%d, frequency=%d, dt=0.005): %d epochs x %d steps, host numpy "
+                             "state -> H2D each epoch, last frame D2H + fp64 host wrap each epoch"
+                             % (freq * n_epochs, freq, n_epochs, per_epoch)}
+
+    # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only)
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_reference_steps_per_s(args.ncell, steps=3, warmup=1, budget_s=20.0)
+        out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

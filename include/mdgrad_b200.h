@@ -170,6 +170,12 @@ typedef struct mdg_md_params {
     int    traj_stride;           /* 1 = every grid point (reference behaviour)                 */
 } mdg_md_params;
 
+/* Pair filter applied by mdg_md_run's internal list builds: the index_tuple / ex_pairs arguments
+ * of PairPotentials (torchmd/interface.py:228, topology.py:15-27,44-53) in the same encoding as
+ * mdg_nbr_build.  Pointers must stay valid until replaced; all NULL/0 = no filter. */
+int mdg_set_pair_filter(mdg_ctx* ctx, const uint8_t* d_sel_a, const uint8_t* d_sel_b,
+                        const int64_t* d_ex_keys, int n_ex);
+
 int mdg_md_run(mdg_ctx* ctx, const mdg_md_params* p, int n, const float* d_mass,
                const float* d_v0, const float* d_q0, const float* h_pv0,
                const float* h_tgrid, int n_grid,
@@ -181,6 +187,12 @@ int mdg_md_run(mdg_ctx* ctx, const mdg_md_params* p, int n, const float* d_mass,
  * out[3]=max row length, out[4]=ncell_x, out[5]=ncell_y, out[6]=ncell_z, out[7]=path
  * (0 = cell list, 1 = all-pairs). */
 int mdg_get_stats(mdg_ctx* ctx, int64_t* h_out8);
+
+/* Measurement aid (bench.py roofline): when enabled, mdg_md_run brackets every pair-force kernel
+ * launch with CUDA events on the launch stream; mdg_get_profile returns h_out2[0] = summed
+ * force-kernel milliseconds and h_out2[1] = number of force launches of the last run. */
+int mdg_set_profile(mdg_ctx* ctx, int enable);
+int mdg_get_profile(mdg_ctx* ctx, double* h_out2);
 
 #ifdef __cplusplus
 }

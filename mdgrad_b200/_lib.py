@@ -23,7 +23,7 @@ MAX_CHAINS = 16
 SYMBOLS = [
     "mdg_version", "mdg_last_error", "mdg_create", "mdg_destroy", "mdg_nbr_build", "mdg_nbr_export",
     "mdg_pair_force", "mdg_pair_dis_fwd", "mdg_pair_dis_bwd", "mdg_rdf_accumulate", "mdg_md_run",
-    "mdg_get_stats",
+    "mdg_get_stats", "mdg_set_pair_filter", "mdg_set_profile", "mdg_get_profile",
 ]
 
 
@@ -78,6 +78,9 @@ def load():
     lib.mdg_rdf_accumulate.argtypes = [vp, vp, ip, fp, dbl, dbl, ip, dbl, vp, vp, vp, vp]
     lib.mdg_md_run.argtypes = [vp, ctypes.POINTER(MdParams), ip, vp, vp, vp, fp, fp, ip, vp, vp, fp, fp, vp]
     lib.mdg_get_stats.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.mdg_set_pair_filter.argtypes = [vp, vp, vp, vp, ip]
+    lib.mdg_set_profile.argtypes = [vp, ip]
+    lib.mdg_get_profile.argtypes = [vp, ctypes.POINTER(dbl)]
     for name in SYMBOLS:
         if name not in ("mdg_last_error",):
             getattr(lib, name).restype = ip
@@ -203,6 +206,19 @@ class Context:
         if M:
             tpv = torch.tensor(list(hpv), dtype=torch.float32).reshape(n_frames, M).to(dev)
         return tv, tq, tpv, (e.value if want_energy else None)
+
+    def set_pair_filter(self, sel_a=None, sel_b=None, ex_keys=None):
+        check(load().mdg_set_pair_filter(self._h, _ptr(sel_a), _ptr(sel_b), _ptr(ex_keys),
+                                         0 if ex_keys is None else int(ex_keys.numel())))
+        self._filter_keepalive = (sel_a, sel_b, ex_keys)
+
+    def set_profile(self, enable):
+        check(load().mdg_set_profile(self._h, int(bool(enable))))
+
+    def get_profile(self):
+        out = (ctypes.c_double * 2)()
+        check(load().mdg_get_profile(self._h, out))
+        return {"force_ms": out[0], "force_launches": int(out[1])}
 
     def stats(self):
         out = (ctypes.c_int64 * 8)()

@@ -110,6 +110,17 @@ extern "C" int mdg_pair_force(mdg_ctx* c, int kind, const float* h_params, int n
     return mdg_i_pair_force_op(c, P, d_xyz, n, d_energy, d_force, d_dparams, (cudaStream_t)stream);
 }
 
+extern "C" int mdg_set_pair_filter(mdg_ctx* c, const uint8_t* d_sel_a, const uint8_t* d_sel_b, const int64_t* d_ex_keys,
+                                   int n_ex) {
+    if (!c) { mdg_set_error("null ctx"); return MDG_E_BADARG; }
+    if ((d_sel_a == nullptr) != (d_sel_b == nullptr)) { mdg_set_error("give both sel_a and sel_b or neither"); return MDG_E_BADARG; }
+    c->eng_sel_a = d_sel_a;
+    c->eng_sel_b = d_sel_b;
+    c->eng_ex_keys = d_ex_keys;
+    c->eng_n_ex = d_ex_keys ? n_ex : 0;
+    return MDG_OK;
+}
+
 extern "C" int mdg_get_stats(mdg_ctx* c, int64_t* o) {
     if (!c || !o) { mdg_set_error("null argument"); return MDG_E_BADARG; }
     o[0] = c->stat_launches;

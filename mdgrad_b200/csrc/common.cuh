@@ -234,12 +234,23 @@ struct mdg_ctx {
     const uint8_t* sel_b = nullptr;
     const int64_t* ex_keys = nullptr;
     int n_ex = 0;
+    // persistent filter used by mdg_md_run (mdg_set_pair_filter)
+    const uint8_t* eng_sel_a = nullptr;
+    const uint8_t* eng_sel_b = nullptr;
+    const int64_t* eng_ex_keys = nullptr;
+    int eng_n_ex = 0;
 
     // engine state (sorted order)
     DevBuf v4, vh4, q4b, f4b, qref, mass_sorted, pvbuf, kebuf, dtbuf;
 
     // stats
     int64_t stat_launches = 0, stat_rebuilds = 0, stat_entries = 0, stat_maxrow = 0;
+    // optional per-kernel timing of the engine's force launches (mdg_set_profile)
+    int     prof_enable = 0;
+    void*   prof_events = nullptr;   // std::vector<cudaEvent_t>* (pairs)
+    int     prof_used = 0;
+    double  prof_force_ms = 0.0;
+    int64_t prof_force_launches = 0;
     int* h_pinned = nullptr;  // pinned int[16] for read-backs
 };
 

@@ -9,7 +9,10 @@
 // This translation unit is compiled with -fmad=false: the integrator algebra is memory-bound,
 // and keeping every product/sum individually rounded reproduces the reference's separate
 // elementwise ATen ops (only the global kinetic-energy reduction order differs).
+#include <vector>
 #include "common.cuh"
+
+#define PROF_MAX_EVENTS 16384
 
 int mdg_i_force_blocks(mdg_ctx* c);
 
@@ -279,7 +282,8 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 8, st));
 
     // initial sort + list at q0, state into sorted order
-    c->sel_a = c->sel_b = nullptr; c->ex_keys = nullptr; c->n_ex = 0;
+    c->sel_a = c->eng_sel_a; c->sel_b = c->eng_sel_b; c->ex_keys = c->eng_ex_keys; c->n_ex = c->eng_n_ex;
+    c->rows_wanted = true;
     MDG_TRY(mdg_i_build_list(c, d_q0, nullptr, n, p->cell, rlist, p->cutoff, st));
     float4* q = c->qs_ptr;
     k_init_v<<<nb, T, 0, st>>>(n, c->perm.as<int>(), d_v0, d_mass, vbuf[vsel]);
@@ -311,7 +315,24 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             }
             if (retest) MDG_CUDA(cudaMemcpyAsync(c->qref.p, q, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         }
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (c->prof_enable) {
+            std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
+            if (!pool) { pool = new std::vector<cudaEvent_t>(); c->prof_events = pool; }
+            if (c->prof_used + 2 <= PROF_MAX_EVENTS) {
+                while ((int)pool->size() < c->prof_used + 2) {
+                    cudaEvent_t e;
+                    MDG_CUDA(cudaEventCreate(&e));
+                    pool->push_back(e);
+                }
+                ev0 = (*pool)[c->prof_used];
+                ev1 = (*pool)[c->prof_used + 1];
+                c->prof_used += 2;
+                MDG_CUDA(cudaEventRecord(ev0, st));
+            }
+        }
         MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
+        if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
         int gp = g + 1;
         bool keep = (gp % stride) == 0;
         size_t fr = (size_t)(gp / stride);
@@ -341,6 +362,18 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         for (int i = 0; i < ib; ++i) e += h_e[i];
         *h_last_energy = (float)e;
     }
+    if (c->prof_enable && c->prof_events) {
+        std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
+        c->prof_force_ms = 0.0;
+        c->prof_force_launches = 0;
+        for (int i = 0; i + 1 < c->prof_used; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, (*pool)[i], (*pool)[i + 1]) == cudaSuccess) {
+                c->prof_force_ms += ms;
+                c->prof_force_launches++;
+            }
+        }
+    }
     if (c->h_pinned[0]) return MDG_E_CAPACITY;
     if (c->h_pinned[5]) return MDG_E_SKIN;
     return MDG_OK;
@@ -360,9 +393,10 @@ extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float
     cudaStream_t st = (cudaStream_t)stream;
     int K = p->rebuild_every < 1 ? 1 : p->rebuild_every;
     if (!(p->skin > 0.f)) K = 1;
-    c->stat_launches = 0;
-    c->stat_rebuilds = 0;
     for (int attempt = 0; attempt < 12; ++attempt) {
+        c->stat_launches = 0;
+        c->stat_rebuilds = 0;
+        c->prof_used = 0;
         int s = run_once(c, p, n, d_mass, d_v0, d_q0, h_pv0, h_tgrid, n_grid, d_traj_v, d_traj_q, h_traj_pv,
                          h_last_energy, K, st);
         if (s == MDG_E_CAPACITY) {
@@ -382,4 +416,19 @@ extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float
     }
     mdg_set_error("mdg_md_run: could not satisfy capacity/skin constraints");
     return MDG_E_CAPACITY;
+}
+
+// Per-kernel timing of the force launches inside mdg_md_run (CUDA events on the launch stream
+// around every force kernel).  out[0] = summed force-kernel ms of the last run, out[1] = launches.
+extern "C" int mdg_set_profile(mdg_ctx* c, int enable) {
+    if (!c) { mdg_set_error("null ctx"); return MDG_E_BADARG; }
+    c->prof_enable = enable;
+    return MDG_OK;
+}
+
+extern "C" int mdg_get_profile(mdg_ctx* c, double* h_out2) {
+    if (!c || !h_out2) { mdg_set_error("null argument"); return MDG_E_BADARG; }
+    h_out2[0] = c->prof_force_ms;
+    h_out2[1] = (double)c->prof_force_launches;
+    return MDG_OK;
 }

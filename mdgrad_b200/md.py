@@ -1,0 +1,267 @@
+"""Simulation driver and equations of motion - mirror of reference torchmd/md.py:
+Simulations :14-96, NVE :98-156, NoseHooverChain :158-249.
+
+API, state layout, log/check-point semantics (fp64 host wrap between epochs, last frame per epoch
+logged, `frequency` grid points = frequency-1 steps) are the reference's.  What changes is where the
+epoch runs: for NVE / NoseHooverChain over an analytic `PairPotentials` with
+topology_update_freq == 1 the whole epoch (list rebuilds, forces, integrator, trajectory capture)
+is ONE call into the fused device engine `mdg_md_run`; every other combination goes through the
+generic op-level solvers in `sovlers.py`, exactly like the reference.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sovlers import odeint, odeint_adjoint
+from .system import HAVE_ASE
+
+if HAVE_ASE:  # pragma: no cover
+    from ase import units
+    from ase.geometry import wrap_positions
+else:
+    from ._ase_compat import units, wrap_positions
+
+
+def compute_grad(inputs, output, create_graph=True, retain_graph=True):
+    """d output / d inputs (reference nff/utils/scatter.py:5-21)."""
+    assert inputs.requires_grad
+    g, = torch.autograd.grad(output, inputs, grad_outputs=output.data.new(output.shape).fill_(1),
+                             create_graph=create_graph, retain_graph=retain_graph)
+    return g
+
+
+def _torch_device(device):
+    return torch.device("cuda:%d" % device) if isinstance(device, int) else torch.device(device)
+
+
+class Simulations():
+    """Simulations(system, integrator, wrap=True, method="NH_verlet")   (reference md.py:28-40)."""
+
+    def __init__(self, system, integrator, wrap=True, method="NH_verlet"):
+        self.system = system
+        self.device = system.device
+        self.integrator = integrator
+        self.solvemethod = method
+        self.wrap = wrap
+        self.keys = self.integrator.state_keys
+        self.initialize_log()
+
+    def initialize_log(self):
+        self.log = {key: [] for key in self.keys}
+
+    def update_log(self, trajs):
+        """keep only the LAST frame of the epoch, as numpy (reference md.py:47-52)"""
+        for i, key in enumerate(self.keys):
+            self.log[key].append(trajs[i][-1].detach().cpu().numpy())
+
+    def update_states(self):
+        if "positions" in self.log:
+            self.system.set_positions(self.log["positions"][-1])
+        if "velocities" in self.log:
+            self.system.set_velocities(self.log["velocities"][-1])
+
+    def get_check_point(self):
+        """Last logged frame as device tensors; positions re-wrapped on the host in fp64
+        (reference md.py:60-71)."""
+        if hasattr(self, "log"):
+            states = [torch.Tensor(self.log[key][-1]).to(self.device) for key in self.log]
+            if self.wrap:
+                wrapped = wrap_positions(self.log["positions"][-1], self.system.get_cell())
+                states[1] = torch.Tensor(wrapped).to(self.device)
+            return states
+        raise ValueError("No log available")
+
+    def simulate(self, steps=1, dt=1.0 * units.fs, frequency=1):
+        """steps//frequency epochs of frequency-1 integration steps each; returns the stacked
+        trajectory of the LAST epoch (reference md.py:73-96)."""
+        if self.log["positions"] == []:
+            states = self.integrator.get_inital_states(self.wrap)
+        else:
+            states = self.get_check_point()
+        sim_epochs = int(steps // frequency)
+        t = torch.Tensor([dt * i for i in range(frequency)]).to(self.device)
+        for epoch in range(sim_epochs):
+            if self.integrator.adjoint:
+                trajs = odeint_adjoint(self.integrator, states, t, method=self.solvemethod)
+            else:
+                for var in states:
+                    var.requires_grad = True
+                trajs = odeint(self.integrator, tuple(states), t, method=self.solvemethod)
+            self.update_log(trajs)
+            self.update_states()
+            states = self.get_check_point()
+        return trajs
+
+
+class _EOM(torch.nn.Module):
+    """Shared plumbing of the two equations of motion."""
+
+    engine_skin = None          # Verlet skin of the fused engine; None = 0.12 * cutoff
+    engine_rebuild_every = None  # None = chosen from the initial velocities, halved on violation
+
+    def _init_common(self, potentials, system, adjoint, topology_update_freq):
+        self.model = potentials
+        self.system = system
+        self.device = system.device
+        self.mass = torch.Tensor(system.get_masses()).to(self.device)
+        self.N_dof = self.mass.shape[0] * system.dim
+        self.dim = system.dim
+        self.adjoint = adjoint
+        self.topology_update_freq = topology_update_freq
+        self.update_count = 0
+        self._engine_ctx = None
+        self._engine_K = None
+        self.last_engine_stats = None
+
+    def update_topology(self, q):
+        """rebuild every topology_update_freq-th EVALUATION (reference md.py:200-204)"""
+        if self.update_count % self.topology_update_freq == 0:
+            self.model._reset_topology(q)
+        self.update_count += 1
+
+    # -- fused engine -------------------------------------------------------------------------
+    def _native_spec(self, method):
+        from .interface import PairPotentials
+        m = self.model
+        if type(m) is not PairPotentials or m.native_kind() is None:
+            return None
+        if self.topology_update_freq != 1 or method != self._native_method:
+            return None
+        if any(p.requires_grad and p.grad_fn is not None for p in m.parameters()):
+            return None
+        return m
+
+    def _native_forward(self, y0, t, method):
+        """Run the epoch on the fused engine; returns the stacked trajectory or None if this
+        configuration is not covered (caller then takes the generic route)."""
+        m = self._native_spec(method)
+        if m is None or len(t) < 1:
+            return None
+        if len(t) > 1 and not bool((t[1:] > t[:-1]).all()):
+            return None
+        v0, q0 = y0[0], y0[1]
+        if not v0.is_cuda:
+            _lib.require_cuda(v0, "state tensors")
+        kind, values, _ = m.native_kind()
+        n = q0.shape[0]
+        p = _lib.MdParams()
+        p.integrator = self._native_integrator
+        p.pot_kind = kind
+        for i, v in enumerate(values):
+            p.pot_params[i] = float(v)
+        p.cutoff = float(m.cutoff)
+        L = m._L
+        for k in range(3):
+            p.cell[k] = L[k]
+        if self._native_integrator == _lib.INT_NHC:
+            p.n_chains = int(self.num_chains)
+            Qh = self.Q.detach().cpu()
+            for k in range(self.num_chains):
+                p.Q[k] = float(Qh[k])
+            p.T = float(self.T)
+        p.ndof = int(self.N_dof)
+        tl = [float(x) for x in t.detach().cpu()]
+        skin = self.engine_skin if self.engine_skin is not None else 0.12 * float(m.cutoff)
+        p.skin = float(skin)
+        K = self.engine_rebuild_every or self._engine_K
+        if K is None:
+            dtmax = max([b - a for a, b in zip(tl[:-1], tl[1:])] + [0.0])
+            vmax = float(v0.detach().norm(dim=1).max()) if n else 0.0
+            K = 1 if vmax * dtmax <= 0 else int(max(1, min(64, math.floor(0.5 * skin / (2.0 * vmax * dtmax)))))
+        p.rebuild_every = int(K)
+        p.traj_stride = 1
+        if self._engine_ctx is None:
+            self._engine_ctx = _lib.Context(q0.device)
+        ctx = self._engine_ctx
+        ctx.set_pair_filter(m._sel[0], m._sel[1], m._exk)
+        pv0 = [float(x) for x in y0[2].detach().cpu()] if len(y0) > 2 else []
+        mass = self.mass.to(q0.device, torch.float32).contiguous()
+        tv, tq, tpv, _ = ctx.md_run(p, mass, v0.detach().to(torch.float32).contiguous(),
+                                    q0.detach().to(torch.float32).contiguous(), pv0, tl)
+        st = ctx.stats()
+        self.last_engine_stats = st
+        self._engine_K = int(st["maxrow_or_K"]) if skin > 0 else None
+        self.update_count += 2 * (len(tl) - 1)       # two evaluations per step in the reference
+        return (tv, tq, tpv) if tpv is not None else (tv, tq)
+
+
+class NVE(_EOM):
+    """NVE(potentials, system, adjoint=True, topology_update_freq=1)   (reference md.py:112)."""
+    _native_method = "verlet"
+    _native_integrator = _lib.INT_NVE
+
+    def __init__(self, potentials, system, adjoint=True, topology_update_freq=1):
+        super().__init__()
+        self._init_common(potentials, system, adjoint, topology_update_freq)
+        self.state_keys = ["velocities", "positions"]
+
+    def forward(self, t, state):
+        """dv/dt = f (not divided by the mass), dq/dt = v   (reference md.py:131-148)"""
+        with torch.set_grad_enabled(True):
+            v, q = state[0], state[1]
+            if self.adjoint:
+                q.requires_grad = True
+            self.update_topology(q)
+            u = self.model(q)
+            f = -compute_grad(inputs=q, output=u.sum(-1), create_graph=_needs_graph(self.model))
+        return (f, v)
+
+    def get_inital_states(self, wrap=True):
+        states = [self.system.get_velocities(), self.system.get_positions(wrap=wrap)]
+        return [torch.Tensor(var).to(self.system.device) for var in states]
+
+
+class NoseHooverChain(_EOM):
+    """NoseHooverChain(potentials, system, T, num_chains=2, Q=1.0, adjoint=True,
+    topology_update_freq=1)   (reference md.py:179-198)."""
+    _native_method = "NH_verlet"
+    _native_integrator = _lib.INT_NHC
+
+    def __init__(self, potentials, system, T, num_chains=2, Q=1.0, adjoint=True, topology_update_freq=1):
+        super().__init__()
+        self._init_common(potentials, system, adjoint, topology_update_freq)
+        self.T = T
+        self.target_ke = 0.5 * self.N_dof * T
+        self.num_chains = num_chains
+        Qs = np.array([Q, *[Q / len(system)] * (num_chains - 1)])     # md.py:191-193
+        self.Q = torch.Tensor(Qs).to(self.device)
+        self.state_keys = ["velocities", "positions", "baths"]
+
+    def update_T(self, T):
+        self.T = T
+
+    def forward(self, t, state):
+        """reference md.py:210-240"""
+        with torch.set_grad_enabled(True):
+            v, q, p_v = state[0], state[1], state[2]
+            if self.adjoint:
+                q.requires_grad = True
+            m = self.mass[:, None]
+            p = v * m
+            sys_ke = 0.5 * (p.pow(2) / m).sum()
+            self.update_topology(q)
+            u = self.model(q)
+            f = -compute_grad(inputs=q, output=u.sum(-1), create_graph=_needs_graph(self.model))
+            coupled = (p_v[0] * p.reshape(-1) / self.Q[0]).reshape(-1, 3)
+            dpdt = f - coupled
+            d0 = 2 * (sys_ke - self.T * self.N_dof * 0.5) - p_v[0] * p_v[1] / self.Q[1]
+            dmid = (p_v[:-2].pow(2) / self.Q[:-2] - self.T) - p_v[2:] * p_v[1:-1] / self.Q[2:]
+            dlast = p_v[-2].pow(2) / self.Q[-2] - self.T
+            dvdt = dpdt / m
+        return (dvdt, v, torch.cat((d0[None], dmid, dlast[None])))
+
+    def get_inital_states(self, wrap=True):
+        states = [self.system.get_velocities(), self.system.get_positions(wrap=wrap), [0.0] * self.num_chains]
+        return [torch.Tensor(var).to(self.system.device) for var in states]
+
+
+def _needs_graph(model):
+    """The reference always builds the force with create_graph=True (scatter.py:18-19).  The fused
+    first-order kernels cannot be differentiated again, so a second-order graph is only requested
+    when the adjoint solver has switched the interaction modules to their pure-torch distance op."""
+    mods = [m for m in model.modules() if hasattr(m, "second_order")]
+    if not mods:
+        return True
+    return any(m.second_order for m in mods)

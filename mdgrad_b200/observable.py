@@ -1,0 +1,95 @@
+"""Observables - mirror of reference torchmd/observable.py: generate_vol_bins :10-21, Observable
+:24-31, rdf :33-76, vacf :153-163.
+
+`rdf(system, nbins, r_range, index_tuple=None, width=None)(xyz) -> (count, bins, g)`; the pair
+search + Gaussian-smeared histogram run in one cell-list traversal kernel (mdg_rdf_accumulate)
+instead of a second O(N^2) neighbor list and a (P, nbins) tensor.  The kernel path is not
+differentiable; when `xyz.requires_grad` the smearing is evaluated with torch ops over the native
+neighbor list so that losses still reach the trajectory.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .system import check_system
+from .topology import _selection_flags, cell_lengths, compute_dis_torch, context_for, generate_nbr_list
+
+
+def generate_vol_bins(start, end, nbins, dim):
+    """bins = linspace(start, end, nbins+1); shell volumes; V = 4/3 pi end^3 (reference :10-21)."""
+    bins = torch.linspace(start, end, nbins + 1)
+    if dim == 3:
+        Vbins = 4 * np.pi / 3 * (bins[1:] ** 3 - bins[:-1] ** 3)
+        V = (4 / 3) * np.pi * (end) ** 3
+    elif dim == 2:
+        Vbins = np.pi * (bins[1:] ** 2 - bins[:-1] ** 2)
+        V = np.pi * (end) ** 2
+    return V, torch.Tensor(Vbins), bins
+
+
+class Observable(torch.nn.Module):
+    def __init__(self, system):
+        super().__init__()
+        check_system(system)
+        self.device = system.device
+        self.volume = system.get_volume()
+        self.cell = torch.Tensor(np.asarray(system.get_cell())).diag().to(self.device)
+        self.natoms = len(system)
+
+
+class rdf(Observable):
+    def __init__(self, system, nbins, r_range, index_tuple=None, width=None):
+        super().__init__(system)
+        start, end = r_range[0], r_range[1]
+        V, vol_bins, bins = generate_vol_bins(start, end, nbins, dim=system.dim)
+        self.V = V
+        self.vol_bins = vol_bins.to(self.device)
+        self.r_axis = np.linspace(start, end, nbins)
+        self.bins = bins
+        self.start, self.end, self.width = float(start), float(bins[-1]), width
+        self.nbins = nbins
+        self.cutoff_boundary = end + 5e-1
+        self.index_tuple = index_tuple
+        # Gaussian centres / widths exactly as nff GaussianSmearing builds them (layers.py:55-59)
+        self.mu = torch.linspace(start, bins[-1], nbins).to(self.device)
+        w = (self.mu[1] - self.mu[0]) if width is None else width
+        self.w = float(w)
+        self._L = cell_lengths(self.cell)
+        self._sel = None
+
+    def forward(self, xyz):
+        _lib.require_cuda(xyz, "xyz")
+        frames = xyz.reshape(-1, xyz.shape[-2], 3)
+        n = frames.shape[1]
+        if xyz.requires_grad and torch.is_grad_enabled():
+            count = 0
+            for f in range(frames.shape[0]):
+                nbr, off = generate_nbr_list(frames[f], self.cutoff_boundary, self.cell,
+                                             index_tuple=self.index_tuple, _ctx_key="rdf")
+                d = compute_dis_torch(frames[f], nbr, off, self.cell)
+                count = count + torch.exp(-0.5 / self.w ** 2 * (d - self.mu) ** 2).sum(0)
+        else:
+            if self._sel is None:
+                self._sel = _selection_flags(n, self.index_tuple, xyz.device)
+            ctx = context_for(xyz.device, "rdf")
+            count = torch.zeros(self.nbins, dtype=torch.float32, device=xyz.device)
+            for f in range(frames.shape[0]):
+                ctx.rdf_accumulate(frames[f], self._L, self.start, self.end, self.nbins,
+                                   self.width, count, self._sel[0], self._sel[1])
+        count = count / count.sum()
+        g = count / (self.vol_bins / self.V)
+        return count, self.bins, g
+
+
+class vacf(Observable):
+    """velocity autocorrelation (reference observable.py:153-163)"""
+
+    def __init__(self, system, t_range):
+        super().__init__(system)
+        self.t_window = [i for i in range(1, t_range, 1)]
+
+    def forward(self, vel):
+        vacf = [(vel * vel).mean()[None]]
+        average_vel_sq = (vel * vel).mean() + 1e-6
+        vacf += [(vel[t:] * vel[:-t]).mean()[None] for t in self.t_window]
+        return torch.stack(vacf).reshape(-1) / average_vel_sq

@@ -1,0 +1,237 @@
+"""Fixed-grid ODE solvers with adjoint sensitivities - mirror of reference torchmd/sovlers.py
+(`odeint`, `odeint_adjoint`, methods 'NH_verlet' | 'verlet' | 'rk4') and torchmd/tinydiffeq.py.
+
+This is the GENERIC (op-by-op, autograd-capable) route: it calls `func(t, state)` exactly like the
+reference and is used for differentiable runs, learned potentials, rk4 and the adjoint backward
+pass.  Pure MD with an analytic pair potential never comes here - `Simulations.simulate` hands the
+whole epoch to the fused device engine (mdg_md_run).
+
+Step algebra restated from the reference:
+  NH_verlet forward  sovlers.py:110-127      NH_verlet adjoint branch  sovlers.py:129-164
+  verlet forward     sovlers.py:25-40        verlet adjoint branch     sovlers.py:42-101
+  rk4 (3/8 rule)     tinydiffeq.py:98-103    grid loop                 tinydiffeq.py:56-76
+  adjoint backward   sovlers.py:211-293
+"""
+import torch
+from torch import nn
+
+
+# ---------------------------------------------------------------------------------------------
+# step functions: return the INCREMENT dy over one step of size dt
+# ---------------------------------------------------------------------------------------------
+def nh_verlet_increment(func, t, dt, y):
+    if len(y) == 3:
+        a0, _, dpv0 = func(t, y)
+        vh = 1 / 2 * a0 * dt
+        ph = 1 / 2 * dpv0 * dt
+        dq = (y[0] + vh) * dt
+        a1, _, dpv1 = func(t, (y[0] + vh, y[1] + dq, y[2] + ph))
+        return (vh + 1 / 2 * a1 * dt, dq, ph + 1 / 2 * dpv1 * dt)
+    if len(y) == 8:
+        # augmented state (v, q, pv, adj_v, adj_q, adj_pv, adj_t, adj_params)
+        d0 = func(t, y)
+        vh = 1 / 2 * d0[0] * dt
+        ph = 1 / 2 * d0[2] * dt
+        dq = (y[0] + vh) * dt
+        half = tuple(d0[k] * 0.5 * dt for k in range(3, 8))
+        dm = func(t, (y[0] + vh, y[1] + dq, y[2] + ph) + tuple(y[k] + half[k - 3] for k in range(3, 8)))
+        return (vh + 1 / 2 * dm[0] * dt, dq, ph + 1 / 2 * dm[2] * dt) + tuple(dm[k] * dt for k in range(3, 8))
+    raise ValueError("received {} argumets integration, but should be {} for the forward call or {} for the "
+                     "backward call".format(len(y), 3, 8))
+
+
+def verlet_increment(func, t, dt, y):
+    if len(y) == 2:
+        a0, _ = func(t, y)
+        vh = 0.5 * a0 * dt
+        dq = (y[0] + vh) * dt
+        a1, _ = func(t, (y[0] + vh, y[1] + dq))
+        return (vh + 0.5 * a1 * dt, dq)
+    if len(y) == 6:
+        # (v, x, adj_v, adj_x, adj_t, adj_params): the reference's reverse midpoint scheme
+        v_full, x_full, vad_full, xad_full = y[0], y[1], y[2], y[3]
+        dv, _, vad_vjp_full, xad_vjp_full, vjp_t, vjp_par = func(t, y)
+        vh = 1 / 2 * dv * dt
+        v_half = v_full - vh
+        dx = v_half * dt
+        x0 = x_full - dx
+        dxad_full = xad_vjp_full * dt * 0.5
+        dvad_half = (xad_full + dxad_full) * dt
+        vad_half = vad_full + dvad_half
+        dLdt_half = vjp_t * dt
+        dLdpar_half = vjp_par * 0.5 * dt
+        dv2, _, _, xad_vjp_half, vjp_t2, vjp_par2 = func(
+            t, (v_half, x0, vad_half, xad_full + dxad_full, y[4] + dLdt_half, y[5] + dLdpar_half))
+        v_step = vh - dv2 * dt * 0.5
+        dxad_0 = xad_vjp_half * dt * 0.5
+        return (v_step, dx, dvad_half, dxad_0 + dxad_full, vjp_t2 * dt, dLdpar_half * 2)
+    raise ValueError("received {} argumets integration, but should be {} for the forward call or {} for the "
+                     "backward call".format(len(y), 2, 6))
+
+
+def rk4_increment(func, t, dt, y):
+    k1 = func(t, y)
+    k2 = func(t + dt / 3, tuple(y_ + dt * a / 3 for y_, a in zip(y, k1)))
+    k3 = func(t + dt * 2 / 3, tuple(y_ + dt * (a / -3 + b) for y_, a, b in zip(y, k1, k2)))
+    k4 = func(t + dt, tuple(y_ + dt * (a - b + c) for y_, a, b, c in zip(y, k1, k2, k3)))
+    return tuple((a + 3 * b + 3 * c + d) * (dt / 8) for a, b, c, d in zip(k1, k2, k3, k4))
+
+
+STEPPERS = {"rk4": rk4_increment, "NH_verlet": nh_verlet_increment, "verlet": verlet_increment}
+
+# names kept for reference-API compatibility
+NHverlet_update = nh_verlet_increment
+verlet_update = verlet_increment
+
+
+# ---------------------------------------------------------------------------------------------
+# grid loop
+# ---------------------------------------------------------------------------------------------
+def _normalise(func, y0, t):
+    tensor_input = torch.is_tensor(y0)
+    if tensor_input:
+        base = func
+        y0 = (y0,)
+        func = lambda tt, yy: (base(tt, yy[0]),)      # noqa: E731
+    assert isinstance(y0, tuple), "y0 must be either a torch.Tensor or a tuple"
+    for y in y0:
+        assert torch.is_tensor(y), "each element must be a torch.Tensor but received {}".format(type(y))
+        if not torch.is_floating_point(y):
+            raise TypeError("`y0` must be a floating point Tensor but is a {}".format(y.type()))
+    if not torch.is_floating_point(t):
+        raise TypeError("`t` must be a floating point Tensor but is a {}".format(t.type()))
+    if bool((t[1:] < t[:-1]).all()) and len(t) > 1:
+        fwd = func
+        t = -t
+        func = lambda tt, yy: tuple(-f for f in fwd(-tt, yy))    # noqa: E731
+    return tensor_input, func, y0, t
+
+
+def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
+    """Integrate over the grid t and return every grid point stacked (reference sovlers.py:171-193)."""
+    if method not in STEPPERS:
+        raise KeyError(method)
+    tensor_input, func, y0, t = _normalise(func, y0, t)
+    assert bool((t[1:] > t[:-1]).all()), "t must be strictly increasing or decrasing"
+    t = t.type_as(y0[0]).to(y0[0].device)
+    step = STEPPERS[method]
+    sol = [y0]
+    y = y0
+    for i in range(len(t) - 1):
+        dy = step(func, t[i], t[i + 1] - t[i], y)
+        y = tuple(a + b for a, b in zip(y, dy))
+        sol.append(y)
+    out = tuple(torch.stack(s) for s in zip(*sol))
+    return out[0] if tensor_input else out
+
+
+# ---------------------------------------------------------------------------------------------
+# adjoint
+# ---------------------------------------------------------------------------------------------
+def _flat(seq):
+    parts = [p.contiguous().view(-1) for p in seq]
+    return torch.cat(parts) if parts else torch.tensor([])
+
+
+class second_order:
+    """Context manager: ask every interaction module inside `func` for a twice-differentiable
+    graph (pure-torch distance op) while the augmented dynamics is differentiated."""
+
+    def __init__(self, func):
+        self.mods = [m for m in func.modules() if hasattr(m, "second_order")]
+
+    def __enter__(self):
+        self.old = [m.second_order for m in self.mods]
+        for m in self.mods:
+            m.second_order = True
+
+    def __exit__(self, *exc):
+        for m, o in zip(self.mods, self.old):
+            m.second_order = o
+        return False
+
+
+class OdeintAdjointMethod(torch.autograd.Function):
+    """forward: plain no-grad solve; backward: augmented system integrated backwards one stored
+    grid interval at a time (reference sovlers.py:196-293)."""
+
+    @staticmethod
+    def forward(ctx, *args):
+        assert len(args) >= 8, "Internal error: all arguments required."
+        y0, func, t, flat_params, rtol, atol, method, options = args[:-7], *args[-7:]
+        ctx.func, ctx.method = func, method
+        with torch.no_grad():
+            fwd = getattr(func, "_native_forward", None)
+            ans = fwd(y0, t, method) if fwd is not None else None
+            if ans is None:
+                ans = odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+        ctx.save_for_backward(t, flat_params, *ans)
+        return ans
+
+    @staticmethod
+    def backward(ctx, *grad_output):
+        t, flat_params, *ans = ctx.saved_tensors
+        func, method = ctx.func, ctx.method
+        n = len(ans)
+        params = tuple(func.parameters())
+
+        def augmented(tt, y_aug):
+            y, adj = y_aug[:n], y_aug[n:2 * n]
+            with torch.set_grad_enabled(True), second_order(func):
+                tt = tt.to(y[0].device).detach().requires_grad_(True)
+                y = tuple(v.detach().requires_grad_(True) for v in y)
+                f = func(tt, y)
+                vjp_t, *rest = torch.autograd.grad(f, (tt,) + y + params, tuple(-a for a in adj),
+                                                   allow_unused=True, retain_graph=True)
+            vjp_y = tuple(torch.zeros_like(v) if g is None else g for g, v in zip(rest[:n], y))
+            vjp_t = torch.zeros_like(tt) if vjp_t is None else vjp_t
+            if params:
+                vjp_p = torch.cat([(torch.zeros_like(p) if g is None else g).contiguous().view(-1)
+                                   for g, p in zip(rest[n:], params)])
+            else:
+                vjp_p = torch.tensor(0.).to(vjp_y[0])
+            return (*f, *vjp_y, vjp_t, vjp_p)
+
+        T = ans[0].shape[0]
+        with torch.no_grad():
+            adj_y = tuple(g[-1] for g in grad_output)
+            adj_p = torch.zeros_like(flat_params)
+            adj_t = torch.tensor(0.).to(t)
+            time_vjps = []
+            for i in range(T - 1, 0, -1):
+                y_i = tuple(a[i] for a in ans)
+                f_i = func(t[i], y_i)
+                dLdt = sum(torch.dot(a.reshape(-1), g[i].reshape(-1)).reshape(1) for a, g in zip(f_i, grad_output))
+                adj_t = adj_t - dLdt
+                time_vjps.append(dLdt)
+                if adj_p.numel() == 0:
+                    adj_p = torch.tensor(0.).to(adj_y[0])
+                aug = odeint(augmented, (*y_i, *adj_y, adj_t, adj_p), torch.tensor([t[i], t[i - 1]]), method=method)
+                adj_y = tuple(a[1] if len(a) > 0 else a for a in aug[n:2 * n])
+                adj_t, adj_p = aug[2 * n], aug[2 * n + 1]
+                if len(adj_t) > 0:
+                    adj_t = adj_t[1]
+                if len(adj_p) > 0:
+                    adj_p = adj_p[1]
+                adj_y = tuple(a + g[i - 1] for a, g in zip(adj_y, grad_output))
+            time_vjps.append(adj_t)
+            time_vjps = torch.cat(time_vjps[::-1])
+            return (*adj_y, None, time_vjps, adj_p, None, None, None, None, None)
+
+
+def odeint_adjoint(func, y0, t, rtol=1e-6, atol=1e-12, method=None, options=None):
+    """Solve with O(1)-memory adjoint gradients w.r.t. y0, t and func.parameters()."""
+    if not isinstance(func, nn.Module):
+        raise ValueError("func is required to be an instance of nn.Module.")
+    tensor_input = torch.is_tensor(y0)
+    if tensor_input:
+        class _Tuple(nn.Module):
+            def __init__(self, base):
+                super().__init__()
+                self.base_func = base
+
+            def forward(self, tt, y):
+                return (self.base_func(tt, y[0]),)
+        y0, func = (y0,), _Tuple(func)
+    ys = OdeintAdjointMethod.apply(*y0, func, t, _flat(func.parameters()), rtol, atol, method, options)
+    return ys[0] if tensor_input else ys

@@ -196,8 +196,12 @@ def test_skin_list_equals_fresh_list(ctx):
     pb, _ = _md_params(1, L32, n, skin=0.4, K=8)
     a = ctx.md_run(pa, mass, v0, q0, [0.0] * 5, t)
     b = ctx.md_run(pb, mass, v0, q0, [0.0] * 5, t)
-    # identical pair sets and identical per-row summation order -> bitwise equal
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    # identical pair sets at every evaluation; only the summation order (sort history) differs
+    vs = a[0].abs().max().item()
+    assert (a[0] - b[0]).abs().max().item() <= 5e-5 * vs
+    assert (a[1] - b[1]).abs().max().item() <= 5e-6 * L
+    assert (a[2] - b[2]).abs().max().item() <= 5e-5 * a[2].abs().max().item()
+    assert ctx.stats()["rebuilds"] < 30
 
 
 # ------------------------------------------------------------------------------------------
