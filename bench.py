@@ -31,7 +31,30 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-RHO, RC, DT, TEMP, QBATH, CHAINS, MASS = 0.845, 2.5, 0.005, 1.0, 50.0, 5, 1.008
+import faulthandler
+
+faulthandler.enable()
+if os.environ.get("BENCH_WATCHDOG"):      # dump all python stacks and exit if the run takes longer than this
+    faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
+_T0 = time.time()
+
+
+def log(msg):
+    if os.environ.get("BENCH_VERBOSE", "1") != "0" and int(os.environ.get("RANK", "0")) == 0:
+        print("[bench %7.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
+RHO, RC, DT, TEMP, QBATH_256, CHAINS, MASS = 0.845, 2.5, 0.005, 1.0, 50.0, 5, 1.008
+
+
+def qbath(n):
+    """Heat-bath mass.  The reference scripts use Q=50 for their 256-atom boxes with bath masses
+    [Q, Q/N, ...] (torchmd/md.py:191-193).  Taken literally at N=256000 that chain diverges within ~20
+    steps - in the reference formulation itself (reproduced with the CPU oracle at N=6912) - because the
+    chain starts at pv=0 and the anti-friction rate of the second link grows like N/Q.  Keeping the
+    reference's equations and Q_k = Q/N rule, Q is scaled with N so the thermostat frequency equals the
+    reference's own 256-atom runs: Q = 50 * N / 256.  (Same kernels, same bytes per step.)"""
+    return QBATH_256 * max(n, 256) / 256.0
 NCELL_DEFAULT = 40          # 40^3 FCC cells = 256 000 atoms
 
 
@@ -112,7 +135,7 @@ def md_params(_lib, n, L, skin, K):
     for k in range(3):
         p.cell[k] = L
     p.n_chains = CHAINS
-    Q = np.array([QBATH, *[QBATH / n] * (CHAINS - 1)]).astype(np.float32)
+    Q = np.array([qbath(n), *[qbath(n) / n] * (CHAINS - 1)]).astype(np.float32)
     for k in range(CHAINS):
         p.Q[k] = float(Q[k])
     p.T = TEMP
@@ -123,8 +146,27 @@ def md_params(_lib, n, L, skin, K):
     return p
 
 
-def tgrid(nsteps):
-    return [float(np.float32(DT * i)) for i in range(nsteps + 1)]
+def tgrid(nsteps, dt=DT):
+    return [float(np.float32(dt * i)) for i in range(nsteps + 1)]
+
+
+def equilibrate(ctx, _lib, torch, n, L, mass, v, q, skin, log):
+    """UNTIMED set-up: melt / thermalise the jittered FCC start with NVE epochs + velocity rescaling
+    (through the same fused engine), because the reference's Nose-Hoover chain - bath masses
+    Q/N (torchmd/md.py:191-193) - is stiff for 256k atoms and diverges (also in the CPU oracle) when
+    started far from equilibrium.  Returns (v, q) at T ~= TEMP."""
+    p = md_params(_lib, n, L, skin, 4)
+    p.integrator = _lib.INT_NVE
+    schedule = [(0.001, 50)] * 4 + [(0.0025, 50)] * 6 + [(DT, 50)] * 30
+    for i, (dt, nst) in enumerate(schedule):
+        tv, tq, _, _ = ctx.md_run(p, mass, v, q, [], tgrid(nst, dt))
+        v, q = tv[-1].clone(), tq[-1].clone()
+        t_inst = float((mass[:, None] * v * v).sum() / (3 * n))
+        v = v * math.sqrt(TEMP / t_inst)
+        del tv, tq
+        if i % 8 == 0 or i == len(schedule) - 1:
+            log("  equilibration epoch %d: dt=%.4f T_inst=%.4f K=%d" % (i, dt, t_inst, ctx.stats()["maxrow_or_K"]))
+    return v, q
 
 
 # ------------------------------------------------------------------------------------------------
@@ -145,7 +187,7 @@ def cpu_reference_steps_per_s(ncell, steps, warmup, budget_s):
     per_row = (time.perf_counter() - t0) / probe
     rows = int(max(cores, min(n, budget_s / max(1, steps + warmup) / per_row)))
     mass = np.full(n, MASS, np.float32)
-    Q = np.array([QBATH, *[QBATH / n] * (CHAINS - 1)]).astype(np.float32)
+    Q = np.array([qbath(n), *[qbath(n) / n] * (CHAINS - 1)]).astype(np.float32)
     dts = np.diff(np.array(tgrid(max(steps, warmup, 1)), dtype=np.float32))
     if warmup:
         C.nhc_md(vel, pos, np.zeros(CHAINS), mass, cell3, RC, 1.0, 1.0, Q, TEMP, 3 * n, dts[:warmup], rows=rows)
@@ -169,7 +211,7 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "MD steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LJ fluid %d atoms (FCC %d^3, rho 0.845), rc 2.5, NoseHooverChain Q=50 T=1 M=5, dt 0.005"
+        "config": {"workload": "LJ fluid %d atoms (FCC %d^3, rho 0.845), rc 2.5, NoseHooverChain Q=50*N/256 T=1 M=5, dt 0.005"
                                % (n, args.ncell), "atoms": n},
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -229,8 +271,17 @@ def main():
         tv, tq, tpv, _ = ctx.md_run(p, mass, vv, qq, pv, tgrid(nsteps))
         return tv, tq, tpv
 
+    log("set-up: equilibrating %d atoms (NVE + rescale, untimed)" % n)
+    v0, q0 = equilibrate(ctx, _lib, torch, n, L32, mass, v0, q0, args.skin, log)
+    vmax = float(v0.norm(dim=1).max())
+    if args.rebuild_every <= 0 and args.skin > 0:
+        K = int(max(1, min(64, math.floor(0.5 * args.skin / (2.0 * vmax * DT)))))
+        p.rebuild_every = K
+
     # warm-up: W untimed steps (also settles the rebuild cadence and capacity)
+    log("system ready: n=%d L=%.3f K=%d skin=%.2f; warm-up %d steps" % (n, L, K, args.skin, args.warmup))
     tv, tq, tpv = run(args.warmup, v0, q0, [0.0] * CHAINS)
+    log("warm-up done: %s" % ctx.stats())
     p.rebuild_every = int(ctx.stats()["maxrow_or_K"])
     v1, q1, pv1 = tv[-1].clone(), tq[-1].clone(), [float(x) for x in tpv[-1]]
     del tv, tq
@@ -249,8 +300,10 @@ def main():
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    log("timed region done: %.3f ms for %d steps" % (ms, args.steps))
     clocks = sampler.stop()
     stats = ctx.stats()
+    log("clocks %s stats %s" % (clocks, stats))
     launches = int(stats["launches"])
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -266,7 +319,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "LJ fluid %d atoms (FCC %d^3, rho 0.845, jitter 0.05a), LennardJones(1,1) rc 2.5, "
-                               "NoseHooverChain Q=50 T=1.0 M=5, dt 0.005" % (n, args.ncell),
+                               "NoseHooverChain Q=50*N/256 T=1.0 M=5, dt 0.005; start equilibrated by untimed NVE+rescale set-up" % (n, args.ncell),
                    "atoms": n, "atoms_per_gpu": n, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
                    "skin": args.skin, "rebuild_every": int(p.rebuild_every), "rebuilds": int(stats["rebuilds"]),
                    "l2": "no explicit flush: per-step working set (neighbor rows %.0f MB allocated + state %.0f MB) is streamed "
@@ -284,6 +337,7 @@ def main():
     prof = ctx.get_profile()
     ctx.set_profile(False)
     del tvp, tqp
+    log("force-kernel profile pass done: %s" % prof)
     cctx = _lib.Context(dev)
     P_rc = int(cctx.nbr_list(q_end, [L32] * 3, RC)[0].shape[0])      # pairs inside the cutoff (reference list size)
     P_list = int(cctx.nbr_list(q_end, [L32] * 3, RC + args.skin)[0].shape[0]) if args.skin > 0 else P_rc
@@ -292,6 +346,7 @@ def main():
     alg_bytes = 32.0 * n + 8.0 * P_rc
     peak, peak_src = peaks()
     achieved = alg_bytes / (force_ms * 1e-3) / 1e9
+    log("pair counts done: P_rc=%d P_list=%d force %.4f ms" % (P_rc, P_list, force_ms))
     out["roofline"] = {"bound": "hbm", "kernel": "k_force_rows (pair force, list streaming)", "achieved": achieved,
                        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                        "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "pairs_in_cutoff": P_rc, "pairs_in_skin_list": P_list,
@@ -310,14 +365,16 @@ def main():
         system = System(atoms, device=local_rank)
         system.set_velocities(v_end.cpu().numpy().astype(np.float64))
         pair = PairPotentials(system, LennardJones(1.0, 1.0), cutoff=RC)
-        integ = NoseHooverChain(pair, system, T=TEMP, num_chains=CHAINS, Q=QBATH, adjoint=True)
+        integ = NoseHooverChain(pair, system, T=TEMP, num_chains=CHAINS, Q=qbath(n), adjoint=True)
         integ.engine_skin = args.skin
         sim = Simulations(system, integ, wrap=True, method="NH_verlet")
         per_epoch = 100
         freq = per_epoch + 1
         n_epochs = max(1, args.steps // per_epoch)
+        log("e2e: API objects built, warm-up epoch")
         sim.simulate(steps=freq, frequency=freq, dt=DT)                  # warm-up epoch (100 steps)
         torch.cuda.synchronize()
+        log("e2e: timed epochs")
         t0 = time.perf_counter()
         sim.simulate(steps=freq * n_epochs, frequency=freq, dt=DT)
         torch.cuda.synchronize()
@@ -332,7 +389,9 @@ def main():
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only)
     if world == 1 and not args.no_cpu_baseline:
+        log("cpu baseline (C oracle, bounded sample)")
         v, cores, sample, _ = cpu_reference_steps_per_s(args.ncell, steps=3, warmup=1, budget_s=20.0)
+        log("cpu baseline done")
         out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(out))
     if world > 1:

@@ -40,6 +40,7 @@ extern "C" {
 #define MDG_E_STATE      -4   /* call order violated (e.g. export before build) */
 #define MDG_E_SKIN       -5   /* an atom moved more than skin/2 between list rebuilds */
 #define MDG_E_NCCL       -6
+#define MDG_E_NUMERIC    -7   /* non-finite coordinates (diverged dynamics) or a collapsed cell */
 
 /* pair potential kinds: reference torchmd/potentials.py */
 #define MDG_POT_LJ        0   /* LennardJones   :317-327  params (sigma, epsilon)            */

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmdgrad_b200.so")
 
 MDG_OK, MDG_E_BADARG, MDG_E_CUDA, MDG_E_CAPACITY, MDG_E_STATE, MDG_E_SKIN, MDG_E_NCCL = 0, -1, -2, -3, -4, -5, -6
+MDG_E_NUMERIC = -7
 POT_LJ, POT_LJFAM, POT_LJ69, POT_EXV, POT_BUCK, POT_MORSE = range(6)
 INT_NVE, INT_NHC = 0, 1
 MAX_POT_PARAMS = 4

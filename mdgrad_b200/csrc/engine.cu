@@ -374,6 +374,11 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             }
         }
     }
+    if (c->h_pinned[6] || c->h_pinned[7]) {
+        mdg_set_error("mdg_md_run: non-finite coordinates or collapsed cell (occupancy %d) - the dynamics diverged",
+                      c->h_pinned[7]);
+        return MDG_E_NUMERIC;
+    }
     if (c->h_pinned[0]) return MDG_E_CAPACITY;
     if (c->h_pinned[5]) return MDG_E_SKIN;
     return MDG_OK;

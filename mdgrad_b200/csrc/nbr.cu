@@ -134,10 +134,11 @@ __device__ __forceinline__ int cell_coord(float x, float L, float invL, int nc) 
 }
 
 __global__ void k_bin(const float4* __restrict__ q, int n, Grid g, int* __restrict__ cell_of,
-                      int* __restrict__ slot_of, int* __restrict__ cell_count) {
+                      int* __restrict__ slot_of, int* __restrict__ cell_count, int* __restrict__ flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = q[i];
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) flags[6] = 1;   // diverged dynamics: reported, never binned blindly
     int cx = cell_coord(p.x, g.L[0], g.invL[0], g.nc[0]);
     int cy = cell_coord(p.y, g.L[1], g.invL[1], g.nc[1]);
     int cz = cell_coord(p.z, g.L[2], g.invL[2], g.nc[2]);
@@ -155,12 +156,14 @@ __global__ void k_scatter(int n, const int* __restrict__ cell_of, const int* __r
 
 // one thread per cell: order the cell's atoms by ORIGINAL id (deterministic, history-free),
 // then emit the sorted positions and the permutation (index into the input array)
+#define MAX_CELL_SORT 4096
 __global__ void k_cellsort_gather(int ncell, const int* __restrict__ cell_start, const int* __restrict__ cell_count,
                                   int* __restrict__ perm_tmp, const float4* __restrict__ qin,
-                                  float4* __restrict__ qs, int* __restrict__ perm) {
+                                  float4* __restrict__ qs, int* __restrict__ perm, int* __restrict__ flags) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
     int b = cell_start[c], m = cell_count[c];
+    if (m > MAX_CELL_SORT) { flags[7] = m; m = 0; }   // absurd occupancy (collapsed / diverged system): flag, do not spin
     for (int a = 1; a < m; ++a) {
         int pa = perm_tmp[b + a];
         int ka = __float_as_int(qin[pa].w);
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(128) k_build_cells(int n, const float4* __rest
                                                      int* __restrict__ flags) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
+    if (flags[6] | flags[7]) { row_len[s] = 0; return; }   // non-finite / collapsed input: empty list, error reported by the host
     float4 qi = qs[s];
     int idi = __float_as_int(qi.w);
     int c = cell_sorted[s];
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(AP_TILE) k_build_allpairs(int n, const float4*
     __shared__ float4 tile[AP_TILE];
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     float4 qi = s < n ? qs[s] : make_float4(0, 0, 0, 0);
+    if (!(isfinite(qi.x) && isfinite(qi.y) && isfinite(qi.z))) flags[6] = 1;
     int idi = __float_as_int(qi.w);
     uint32_t* row = rows + (size_t)min(s, n - 1) * cap;
     int cnt = 0;
@@ -391,6 +396,7 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
     float4* qs = (qin == c->qs_buf[0].as<float4>()) ? c->qs_buf[1].as<float4>() : c->qs_buf[0].as<float4>();
     c->qs_ptr = qs;
     MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 3, st));   // [0] overflow, [2] max row count
+    MDG_CUDA(cudaMemsetAsync(c->flags.as<int>() + 6, 0, sizeof(int) * 2, st));   // [6] non-finite, [7] cell overflow
     if (path == 0) {
         MDG_TRY(c->slot_of.reserve(sizeof(int) * (size_t)n));
         MDG_TRY(c->perm_tmp.reserve(sizeof(int) * (size_t)n));
@@ -400,11 +406,11 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         int ncb = (ncell + T - 1) / T;
         if (grid_changed) { k_stencil<<<ncb, T, 0, st>>>(g, c->stencil.as<int>()); c->stat_launches++; }
         MDG_CUDA(cudaMemsetAsync(c->cell_count.p, 0, sizeof(int) * (size_t)(ncell + 1), st));
-        k_bin<<<nb, T, 0, st>>>(qin, n, g, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_count.as<int>());
+        k_bin<<<nb, T, 0, st>>>(qin, n, g, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_count.as<int>(), c->flags.as<int>());
         MDG_TRY(mdg_i_scan_exclusive(c, c->cell_count.as<int>(), c->cell_start.as<int>(), ncell + 1, nullptr, st));
         k_scatter<<<nb, T, 0, st>>>(n, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_start.as<int>(), c->perm_tmp.as<int>());
         k_cellsort_gather<<<ncb, T, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
-                                             qin, qs, c->perm.as<int>());
+                                             qin, qs, c->perm.as<int>(), c->flags.as<int>());
         k_cell_sorted<<<ncb, T, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_of.as<int>());
         if (c->rows_wanted)
             k_build_cells<<<(n + 127) / 128, 128, 0, st>>>(n, qs, c->cell_of.as<int>(), c->cell_start.as<int>(), c->stencil.as<int>(),
@@ -497,6 +503,10 @@ int mdg_i_export_count(mdg_ctx* c, cudaStream_t st, int64_t* h_npairs) {
     MDG_TRY(mdg_i_scan_exclusive(c, c->up_cnt.as<int>(), c->up_off.as<int>(), n, d_total, st));
     MDG_CUDA(cudaMemcpyAsync(c->h_pinned, c->flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
     MDG_CUDA(cudaStreamSynchronize(st));
+    if (c->h_pinned[6] || c->h_pinned[7]) {
+        mdg_set_error("neighbor list: non-finite coordinates or collapsed cell (occupancy %d)", c->h_pinned[7]);
+        return MDG_E_NUMERIC;
+    }
     if (c->h_pinned[0]) return MDG_E_CAPACITY;
     c->npairs = c->h_pinned[4];
     *h_npairs = c->npairs;
