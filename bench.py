@@ -264,7 +264,7 @@ def main():
     K = args.rebuild_every
     if K <= 0:
         vmax = float(v0.norm(dim=1).max())
-        K = int(max(1, min(64, math.floor(0.5 * args.skin / (2.0 * vmax * DT))))) if args.skin > 0 else 1
+        K = int(max(1, min(64, math.floor(0.5 * args.skin / (1.1 * vmax * DT))))) if args.skin > 0 else 1
     p = md_params(_lib, n, L32, args.skin, K)
 
     def run(nsteps, vv, qq, pv):
@@ -275,7 +275,7 @@ def main():
     v0, q0 = equilibrate(ctx, _lib, torch, n, L32, mass, v0, q0, args.skin, log)
     vmax = float(v0.norm(dim=1).max())
     if args.rebuild_every <= 0 and args.skin > 0:
-        K = int(max(1, min(64, math.floor(0.5 * args.skin / (2.0 * vmax * DT)))))
+        K = int(max(1, min(64, math.floor(0.5 * args.skin / (1.1 * vmax * DT)))))
         p.rebuild_every = K
 
     # warm-up: W untimed steps (also settles the rebuild cadence and capacity)

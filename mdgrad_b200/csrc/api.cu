@@ -74,6 +74,7 @@ extern "C" int mdg_nbr_build(mdg_ctx* c, const float* d_xyz, int n, const float*
     c->ex_keys = d_ex_keys;
     c->n_ex = d_ex_keys ? n_ex : 0;
     c->rows_wanted = true;
+    c->fast_build = false;       // the exported list must be bit-exact
     c->stat_launches = 0;
     for (int attempt = 0; attempt < 10; ++attempt) {
         MDG_TRY(mdg_i_build_list(c, d_xyz, nullptr, n, h_cell3, cutoff, cutoff, st));

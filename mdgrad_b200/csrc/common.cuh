@@ -108,7 +108,9 @@ __device__ __forceinline__ float mdg_code_shift(uint32_t code2, float L) {
 struct PotParams {
     int   kind;
     float p[MDG_MAX_POT_PARAMS];
-    float aux;  // Morse: A0
+    float aux;  // Morse: A0 ; LJ: sigma^2
+    float se, sg;                       // post-loop scales of the per-atom energy / force sums
+    float sdp[MDG_MAX_POT_PARAMS];      // post-loop scales of the parameter-gradient sums
 };
 
 __device__ __forceinline__ float mdg_ipow(float x, int n) {
@@ -122,19 +124,28 @@ __device__ __forceinline__ float mdg_ipow(float x, int n) {
     return r;
 }
 
+// 1-ulp reciprocal on the SFU (MUFU.RCP); energies/forces are tolerance-parity (1e-5), membership is not affected
+__device__ __forceinline__ float mdg_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Per-pair values are returned UNSCALED for the hot kinds; the per-atom sums are multiplied once by
+// (se, sg, sdp[]) after the neighbor loop (mdg_pot_scales).  LJ: e_raw = s6 (s6 - 1), g_raw = s6 (2 s6 - 1) / r^2
+// with s6 = (sigma^2 / r^2)^3, so u = 4 eps e_raw and -u'/r = 24 eps g_raw.
 template <int KIND, bool WITH_DP>
 __device__ __forceinline__ void pair_eval(const PotParams& P, float d2, float& e, float& g, float* dp) {
     if (KIND == MDG_POT_LJ) {
-        float sigma = P.p[0], eps = P.p[1];
-        float r2i = 1.0f / d2;
-        float s2 = sigma * sigma * r2i;
+        float r2i = mdg_rcp(d2);
+        float s2 = P.aux * r2i;               // aux = sigma^2
         float s6 = s2 * s2 * s2;
-        float s12 = s6 * s6;
-        e = 4.0f * eps * (s12 - s6);
-        g = 24.0f * eps * (2.0f * s12 - s6) * r2i;
+        float w = s6 * (2.0f * s6 - 1.0f);
+        e = s6 * (s6 - 1.0f);
+        g = w * r2i;
         if (WITH_DP) {
-            dp[0] = 24.0f * eps * (2.0f * s12 - s6) / sigma;
-            dp[1] = 4.0f * (s12 - s6);
+            dp[0] = w;                        // * 24 eps / sigma
+            dp[1] = e;                        // * 4
         }
     } else if (KIND == MDG_POT_LJFAM || KIND == MDG_POT_LJ69) {
         float sigma = P.p[0], eps = P.p[1];
@@ -214,7 +225,8 @@ struct mdg_ctx {
     int    cap = 0;           // row capacity (entries), multiple of 32
     bool   built = false;
     bool   has_sel = false;
-    bool   rows_wanted = true; // false: sort into cells only (RDF traversal needs no stored rows)
+    bool   fast_build = false; // engine skin lists: approximate (FMA) membership at the list radius is allowed
+    bool   rows_wanted = true;// false: sort into cells only (RDF traversal needs no stored rows)
 
     // cell / sort tables
     DevBuf cell_of, slot_of, cell_count, cell_start, perm, perm_tmp, stencil;

@@ -284,6 +284,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     // initial sort + list at q0, state into sorted order
     c->sel_a = c->eng_sel_a; c->sel_b = c->eng_sel_b; c->ex_keys = c->eng_ex_keys; c->n_ex = c->eng_n_ex;
     c->rows_wanted = true;
+    c->fast_build = retest;      // skin list: every entry is re-tested exactly by the force kernel
     MDG_TRY(mdg_i_build_list(c, d_q0, nullptr, n, p->cell, rlist, p->cutoff, st));
     float4* q = c->qs_ptr;
     k_init_v<<<nb, T, 0, st>>>(n, c->perm.as<int>(), d_v0, d_mass, vbuf[vsel]);

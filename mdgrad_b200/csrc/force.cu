@@ -8,6 +8,16 @@ PotParams mdg_make_pot(int kind, const float* h_params, int n_params) {
     P.kind = kind;
     for (int k = 0; k < MDG_MAX_POT_PARAMS; ++k) P.p[k] = (k < n_params) ? h_params[k] : 0.f;
     P.aux = 0.f;
+    P.se = P.sg = 1.f;
+    for (int k = 0; k < MDG_MAX_POT_PARAMS; ++k) P.sdp[k] = 1.f;
+    if (kind == MDG_POT_LJ) {
+        float sigma = P.p[0], eps = P.p[1];
+        P.aux = sigma * sigma;
+        P.se = 4.0f * eps;
+        P.sg = 24.0f * eps;
+        P.sdp[0] = 24.0f * eps / sigma;
+        P.sdp[1] = 4.0f;
+    }
     if (kind == MDG_POT_MORSE) {
         // A = 0 if phi >= 0 else exp(2a/phi) - 2 exp(a/phi)  (potentials.py:82-85, numpy double)
         double a = P.p[0], phi = P.p[1];
@@ -35,22 +45,23 @@ __global__ void __launch_bounds__(256) k_force_rows(int n, const float4* __restr
         const float4 qi = qs[s];
         const uint32_t* row = rows + (size_t)s * cap;
         const int m = row_len[s];
+        const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;   // no image shift on any axis
         for (int k = lane_in_group; k < m; k += GROUP) {
             uint32_t e = __ldg(row + k);
-            int t = e & MDG_IDX_MASK;
-            uint32_t code = e >> MDG_IDX_BITS;
-            float4 qj = qs[t];
-            float dx, dy, dz, d2;
+            float4 qj = qs[e & MDG_IDX_MASK];
+            // x_j - x_i: fp32 subtraction is exact-rounded either way; adding a zero shift is a no-op bit-wise
+            float dx = __fsub_rn(qj.x, qi.x), dy = __fsub_rn(qj.y, qi.y), dz = __fsub_rn(qj.z, qi.z);
+            if ((e & ~MDG_IDX_MASK) != ZERO_CODE) {         // rare: pair crosses the periodic boundary
+                uint32_t code = e >> MDG_IDX_BITS;
+                dx = __fadd_rn(dx, mdg_code_shift(code & 3u, bx.L[0]));
+                dy = __fadd_rn(dy, mdg_code_shift((code >> 2) & 3u, bx.L[1]));
+                dz = __fadd_rn(dz, mdg_code_shift((code >> 4) & 3u, bx.L[2]));
+            }
+            float d2;
             if (RETEST) {
-                dx = __fadd_rn(__fsub_rn(qj.x, qi.x), mdg_code_shift(code & 3u, bx.L[0]));
-                dy = __fadd_rn(__fsub_rn(qj.y, qi.y), mdg_code_shift((code >> 2) & 3u, bx.L[1]));
-                dz = __fadd_rn(__fsub_rn(qj.z, qi.z), mdg_code_shift((code >> 4) & 3u, bx.L[2]));
-                d2 = mdg_d2_exact(dx, dy, dz);
+                d2 = mdg_d2_exact(dx, dy, dz);              // reference arithmetic: membership must be bit-exact
                 if (!(d2 < rc2) || d2 == 0.0f) continue;
             } else {
-                dx = (qj.x - qi.x) + mdg_code_shift(code & 3u, bx.L[0]);
-                dy = (qj.y - qi.y) + mdg_code_shift((code >> 2) & 3u, bx.L[1]);
-                dz = (qj.z - qi.z) + mdg_code_shift((code >> 4) & 3u, bx.L[2]);
                 d2 = dx * dx + dy * dy + dz * dz;
                 if (d2 == 0.0f) continue;
             }
@@ -59,11 +70,17 @@ __global__ void __launch_bounds__(256) k_force_rows(int n, const float4* __restr
             fx -= g * dx;
             fy -= g * dy;
             fz -= g * dz;
-            en += 0.5f * e_p;
+            en += e_p;
             if (WITH_DP) {
 #pragma unroll
-                for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] += 0.5f * dp[q];
+                for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] += dp[q];
             }
+        }
+        fx *= P.sg; fy *= P.sg; fz *= P.sg;
+        en *= 0.5f * P.se;
+        if (WITH_DP) {
+#pragma unroll
+            for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] *= 0.5f * P.sdp[q];
         }
     }
 #pragma unroll

@@ -183,6 +183,55 @@ __global__ void k_cellsort_gather(int ncell, const int* __restrict__ cell_start,
     }
 }
 
+// Warp-per-cell variant: each lane holds one atom of the cell, its rank = number of atoms in the cell
+// with a smaller original id (ids are unique), computed with shuffles; writes the sorted positions,
+// the permutation and the per-atom cell id in one pass.  Cells with more than 32 atoms fall back to
+// the serial insertion sort on lane 0 (rare: > 1.5x the mean occupancy at liquid density).
+__global__ void __launch_bounds__(256) k_cellsort_warp(int ncell, const int* __restrict__ cell_start, const int* __restrict__ cell_count,
+                                                       int* __restrict__ perm_tmp, const float4* __restrict__ qin,
+                                                       float4* __restrict__ qs, int* __restrict__ perm,
+                                                       int* __restrict__ cell_sorted, int* __restrict__ flags) {
+    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (c >= ncell) return;
+    int b = cell_start[c], m = cell_count[c];
+    if (m <= 32) {
+        int pa = lane < m ? perm_tmp[b + lane] : 0;
+        float4 q = lane < m ? qin[pa] : make_float4(0, 0, 0, 0);
+        int key = lane < m ? __float_as_int(q.w) : 0x7fffffff;
+        int rank = 0;
+        for (int o = 0; o < m; ++o) rank += (__shfl_sync(0xffffffffu, key, o) < key);
+        if (lane < m) {
+            qs[b + rank] = q;
+            perm[b + rank] = pa;
+            cell_sorted[b + rank] = c;
+        }
+        return;
+    }
+    if (m > MAX_CELL_SORT) { if (lane == 0) flags[7] = m; m = 0; }
+    if (lane == 0) {
+        for (int a = 1; a < m; ++a) {
+            int pa = perm_tmp[b + a];
+            int ka = __float_as_int(qin[pa].w);
+            int k = a - 1;
+            while (k >= 0) {
+                int pk = perm_tmp[b + k];
+                if (__float_as_int(qin[pk].w) <= ka) break;
+                perm_tmp[b + k + 1] = pk;
+                --k;
+            }
+            perm_tmp[b + k + 1] = pa;
+        }
+    }
+    __syncwarp();
+    for (int a = lane; a < m; a += 32) {
+        int pa = perm_tmp[b + a];
+        qs[b + a] = qin[pa];
+        perm[b + a] = pa;
+        cell_sorted[b + a] = c;
+    }
+}
+
 // 27-cell stencil per cell, ascending linear id (so that row entries come out ascending)
 __global__ void k_stencil(Grid g, int* __restrict__ stencil) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -279,6 +328,124 @@ __global__ void __launch_bounds__(128) k_build_cells(int n, const float4* __rest
     }
     if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
     row_len[s] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast builder for the engine's Verlet-SKIN list.  Membership at the list radius does not have to
+// be bit-exact (the force kernel re-tests every entry against rc^2 with the reference arithmetic),
+// so candidates are screened with a 7-instruction FMA distance test on cell-local coordinates that
+// are staged once per cell in shared memory.  One warp per cell, one lane per atom of the cell; all
+// lanes scan the same staged candidate stream (broadcast LDS.128, no bank conflicts), rows come
+// out in ascending neighbor index.  The image code of an accepted pair is the integer image
+// difference of the two atoms (x = (frac + n) L): off = -(I_j - I_i), identical to the reference's
+// -(red > 0.5) + (red < -0.5) for every pair that can be within the cutoff; |m| >= 2 pairs are the
+// ones the reference's single +-1 correction loses (SURVEY 7 "unwrapped positions") and are dropped.
+// ---------------------------------------------------------------------------------------------
+#define FB_STAGE_CAP 768
+
+__device__ __forceinline__ void local_coord(float x, float L, float invL, float origin, float& l, int& I) {
+    float f = x * invL;
+    float nf = floorf(f);
+    float u = (f - nf) - origin;        // fractional position relative to the cell origin
+    float r = rintf(u);                 // nearest periodic image of the cell frame
+    l = (u - r) * L;
+    I = (int)nf + (int)r;
+}
+
+template <bool SMALLBOX>
+__global__ void __launch_bounds__(32) k_build_fast(int ncell, const float4* __restrict__ qs, const int* __restrict__ cell_start,
+                                                   const int* __restrict__ stencil, Box bx, int ncx, int ncy, int ncz,
+                                                   float r2list, int cap, PairFilter F, uint32_t* __restrict__ rows,
+                                                   int* __restrict__ row_len, int* __restrict__ flags) {
+    __shared__ float4 s_loc[FB_STAGE_CAP];      // local x,y,z ; w = sorted index t (int bits)
+    __shared__ uint32_t s_img[FB_STAGE_CAP];    // packed image integers (I + 512) per axis, 10 bits each
+    const int c = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int a0 = cell_start[c], na = cell_start[c + 1] - a0;
+    if (na == 0) return;
+    if (flags[6] | flags[7]) {
+        for (int a = lane; a < na; a += 32) row_len[a0 + a] = 0;
+        return;
+    }
+    const int cx = c % ncx, cy = (c / ncx) % ncy, cz = c / (ncx * ncy);
+    const float ox = (float)cx / (float)ncx, oy = (float)cy / (float)ncy, oz = (float)cz / (float)ncz;
+    const bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
+    for (int pass = 0; pass < na; pass += 32) {
+        const int s = a0 + pass + lane;
+        const bool act = (pass + lane) < na;
+        float lix = 0.f, liy = 0.f, liz = 0.f;
+        int Iix = 0, Iiy = 0, Iiz = 0, idi = 0;
+        if (act) {
+            float4 qi = qs[s];
+            idi = __float_as_int(qi.w);
+            local_coord(qi.x, bx.L[0], bx.invL[0], ox, lix, Iix);
+            local_coord(qi.y, bx.L[1], bx.invL[1], oy, liy, Iiy);
+            local_coord(qi.z, bx.L[2], bx.invL[2], oz, liz, Iiz);
+        }
+        uint32_t* row = rows + (size_t)(act ? s : a0) * cap;
+        int cnt = 0;
+        int k = 0;                       // next stencil cell to stage
+        int koff = 0;                    // atoms of cell k already staged (cells larger than the stage)
+        while (k < 27) {
+            // ---- stage as many stencil cells as fit -------------------------------------------
+            __syncwarp();
+            int ns = 0;
+            while (k < 27) {
+                int cc = stencil[c * 27 + k];
+                int t0 = cell_start[cc] + koff, t1 = cell_start[cc + 1];
+                int m = t1 - t0;
+                int room = FB_STAGE_CAP - ns;
+                int take = m < room ? m : room;
+                for (int a = lane; a < take; a += 32) {
+                    float4 qj = qs[t0 + a];
+                    float lx, ly, lz;
+                    int Ix, Iy, Iz;
+                    local_coord(qj.x, bx.L[0], bx.invL[0], ox, lx, Ix);
+                    local_coord(qj.y, bx.L[1], bx.invL[1], oy, ly, Iy);
+                    local_coord(qj.z, bx.L[2], bx.invL[2], oz, lz, Iz);
+                    s_loc[ns + a] = make_float4(lx, ly, lz, __int_as_float(t0 + a));
+                    s_img[ns + a] = (uint32_t)((Ix + 512) & 1023) | ((uint32_t)((Iy + 512) & 1023) << 10) |
+                                    ((uint32_t)((Iz + 512) & 1023) << 20);
+                }
+                ns += take;
+                if (take < m) { koff += take; break; }   // stage full: scan, then continue with this cell
+                koff = 0;
+                ++k;
+            }
+            __syncwarp();
+            // ---- scan the staged candidates (every lane: its own atom vs the broadcast stream) ----
+            if (act) {
+#pragma unroll 4
+                for (int a = 0; a < ns; ++a) {
+                    float4 lj = s_loc[a];
+                    float dx = lj.x - lix, dy = lj.y - liy, dz = lj.z - liz;
+                    int kx = 0, ky = 0, kz = 0;
+                    if (SMALLBOX) {
+                        float fx = rintf(dx * bx.invL[0]), fy = rintf(dy * bx.invL[1]), fz = rintf(dz * bx.invL[2]);
+                        dx -= fx * bx.L[0]; dy -= fy * bx.L[1]; dz -= fz * bx.L[2];
+                        kx = (int)fx; ky = (int)fy; kz = (int)fz;
+                    }
+                    float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (d2 < r2list) {
+                        int t = __float_as_int(lj.w);
+                        if (t == s) continue;
+                        uint32_t im = s_img[a];
+                        int mx = (int)(im & 1023u) - 512 - Iix + kx;
+                        int my = (int)((im >> 10) & 1023u) - 512 - Iiy + ky;
+                        int mz = (int)((im >> 20) & 1023u) - 512 - Iiz + kz;
+                        if ((unsigned)(mx + 1) > 2u || (unsigned)(my + 1) > 2u || (unsigned)(mz + 1) > 2u) continue;
+                        if (filt && !pair_allowed(F, idi, __float_as_int(qs[t].w))) continue;
+                        if (cnt < cap) row[cnt] = (uint32_t)t | ((uint32_t)((1 - mx) | ((1 - my) << 2) | ((1 - mz) << 4)) << MDG_IDX_BITS);
+                        ++cnt;
+                    }
+                }
+            }
+        }
+        if (act) {
+            if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
+            row_len[s] = cnt;
+        }
+    }
 }
 
 // written per sorted atom: its cell id (needed by k_build_cells)
@@ -409,14 +576,26 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         k_bin<<<nb, T, 0, st>>>(qin, n, g, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_count.as<int>(), c->flags.as<int>());
         MDG_TRY(mdg_i_scan_exclusive(c, c->cell_count.as<int>(), c->cell_start.as<int>(), ncell + 1, nullptr, st));
         k_scatter<<<nb, T, 0, st>>>(n, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_start.as<int>(), c->perm_tmp.as<int>());
-        k_cellsort_gather<<<ncb, T, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
-                                             qin, qs, c->perm.as<int>(), c->flags.as<int>());
-        k_cell_sorted<<<ncb, T, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_of.as<int>());
-        if (c->rows_wanted)
-            k_build_cells<<<(n + 127) / 128, 128, 0, st>>>(n, qs, c->cell_of.as<int>(), c->cell_start.as<int>(), c->stencil.as<int>(),
-                                                          c->box, c->rlist2, c->cap, F, c->rows.as<uint32_t>(),
-                                                          c->row_len.as<int>(), c->flags.as<int>());
-        c->stat_launches += 4 + (c->rows_wanted ? 1 : 0);
+        k_cellsort_warp<<<(ncell + 7) / 8, 256, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
+                                                         qin, qs, c->perm.as<int>(), c->cell_of.as<int>(), c->flags.as<int>());
+        if (c->rows_wanted) {
+            if (c->fast_build && rlist > cutoff) {
+                bool small = g.nc[0] < 5 || g.nc[1] < 5 || g.nc[2] < 5;
+                if (small)
+                    k_build_fast<true><<<ncell, 32, 0, st>>>(ncell, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box,
+                                                             g.nc[0], g.nc[1], g.nc[2], c->rlist2, c->cap, F,
+                                                             c->rows.as<uint32_t>(), c->row_len.as<int>(), c->flags.as<int>());
+                else
+                    k_build_fast<false><<<ncell, 32, 0, st>>>(ncell, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box,
+                                                              g.nc[0], g.nc[1], g.nc[2], c->rlist2, c->cap, F,
+                                                              c->rows.as<uint32_t>(), c->row_len.as<int>(), c->flags.as<int>());
+            } else {
+                k_build_cells<<<(n + 127) / 128, 128, 0, st>>>(n, qs, c->cell_of.as<int>(), c->cell_start.as<int>(), c->stencil.as<int>(),
+                                                              c->box, c->rlist2, c->cap, F, c->rows.as<uint32_t>(),
+                                                              c->row_len.as<int>(), c->flags.as<int>());
+            }
+        }
+        c->stat_launches += 3 + (c->rows_wanted ? 1 : 0);
     } else {
         MDG_CUDA(cudaMemcpyAsync(qs, qin, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         k_iota<<<nb, T, 0, st>>>(c->perm.as<int>(), n);

@@ -169,7 +169,7 @@ class _EOM(torch.nn.Module):
         if K is None:
             dtmax = max([b - a for a, b in zip(tl[:-1], tl[1:])] + [0.0])
             vmax = float(v0.detach().norm(dim=1).max()) if n else 0.0
-            K = 1 if vmax * dtmax <= 0 else int(max(1, min(64, math.floor(0.5 * skin / (2.0 * vmax * dtmax)))))
+            K = 1 if vmax * dtmax <= 0 else int(max(1, min(64, math.floor(0.5 * skin / (1.1 * vmax * dtmax)))))
         p.rebuild_every = int(K)
         p.traj_stride = 1
         if self._engine_ctx is None:
