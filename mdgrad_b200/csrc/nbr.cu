@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(128) k_build_cells(int n, const float4* __rest
 // -(red > 0.5) + (red < -0.5) for every pair that can be within the cutoff; |m| >= 2 pairs are the
 // ones the reference's single +-1 correction loses (SURVEY 7 "unwrapped positions") and are dropped.
 // ---------------------------------------------------------------------------------------------
+#include "build_fast.cuh"
+#if 0   // first attempt (lane = atom, broadcast candidates): the accept branch diverges on ~97% of candidates; kept for the record
 #define FB_STAGE_CAP 768
 
 __device__ __forceinline__ void local_coord(float x, float L, float invL, float origin, float& l, int& I) {
@@ -447,6 +449,8 @@ __global__ void __launch_bounds__(32) k_build_fast(int ncell, const float4* __re
         }
     }
 }
+
+#endif
 
 // written per sorted atom: its cell id (needed by k_build_cells)
 __global__ void k_cell_sorted(int ncell, const int* __restrict__ cell_start, int* __restrict__ cell_sorted) {
@@ -579,16 +583,11 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         k_cellsort_warp<<<(ncell + 7) / 8, 256, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
                                                          qin, qs, c->perm.as<int>(), c->cell_of.as<int>(), c->flags.as<int>());
         if (c->rows_wanted) {
-            if (c->fast_build && rlist > cutoff) {
-                bool small = g.nc[0] < 5 || g.nc[1] < 5 || g.nc[2] < 5;
-                if (small)
-                    k_build_fast<true><<<ncell, 32, 0, st>>>(ncell, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box,
-                                                             g.nc[0], g.nc[1], g.nc[2], c->rlist2, c->cap, F,
-                                                             c->rows.as<uint32_t>(), c->row_len.as<int>(), c->flags.as<int>());
-                else
-                    k_build_fast<false><<<ncell, 32, 0, st>>>(ncell, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box,
-                                                              g.nc[0], g.nc[1], g.nc[2], c->rlist2, c->cap, F,
-                                                              c->rows.as<uint32_t>(), c->row_len.as<int>(), c->flags.as<int>());
+            bool roomy = g.nc[0] >= 5 && g.nc[1] >= 5 && g.nc[2] >= 5;   // stencil extent < half a box
+            if (c->fast_build && rlist > cutoff && roomy) {
+                k_build_fast<<<(ncell + FB_WARPS - 1) / FB_WARPS, FB_WARPS * 32, 0, st>>>(
+                    ncell, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box, g.nc[0], g.nc[1], g.nc[2], c->rlist2,
+                    c->cap, F, c->rows.as<uint32_t>(), c->row_len.as<int>(), c->flags.as<int>());
             } else {
                 k_build_cells<<<(n + 127) / 128, 128, 0, st>>>(n, qs, c->cell_of.as<int>(), c->cell_start.as<int>(), c->stencil.as<int>(),
                                                               c->box, c->rlist2, c->cap, F, c->rows.as<uint32_t>(),

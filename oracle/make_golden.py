@@ -1,0 +1,106 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference
+through oracle/ref_import.py) on seeded inputs.  Run in the authoring container only; the fixtures
+are committed so that the GPU box (no /root/reference) can check the CUDA path and the oracle
+against genuine reference outputs.
+
+    python oracle/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_import  # noqa: E402
+from mdgrad_b200._ase_compat import FaceCenteredCubic  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    with ref_import.active() as ref:
+        # ---- G1: neighbor lists (reference torchmd/topology.py:30-73) on random boxes -------------
+        for tag, (n, L, rc, seed) in {"a": (400, 7.3, 2.5, 0), "b": (900, 11.1, 3.1, 1), "c": (1500, 21.84, 4.9, 2)}.items():
+            rng = np.random.default_rng(seed)
+            cell = np.array([L, L * 1.1, L * 0.9], dtype=np.float32)
+            xyz = rng.uniform(-0.3 * cell, 1.3 * cell, (n, 3)).astype(np.float32)
+            xyz[5] = xyz[17]
+            nbr, dis, off = ref.topology.generate_nbr_list(torch.tensor(xyz), rc, torch.tensor(cell), get_dis=True)
+            A, B = list(range(0, n, 3)), list(range(1, n, 2))
+            ex = rng.integers(0, n, (50, 2))
+            nbr_m, off_m = ref.topology.generate_nbr_list(torch.tensor(xyz), rc, torch.diag(torch.tensor(cell)),
+                                                          index_tuple=(A, B), ex_pairs=torch.tensor(ex))
+            np.savez_compressed(os.path.join(OUT, "nbr_%s.npz" % tag), xyz=xyz, cell=cell, rc=rc,
+                                nbr=nbr.numpy().astype(np.int32), off=off.numpy().astype(np.int8), dis=dis.numpy(),
+                                sel_a=np.array(A, np.int32), sel_b=np.array(B, np.int32), ex=ex.astype(np.int32),
+                                nbr_m=nbr_m.numpy().astype(np.int32), off_m=off_m.numpy().astype(np.int8))
+        # ---- G2: FCC known answers + pair energies/forces for every analytic potential ---------------
+        atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+        system = ref.system.System(atoms, device="cpu")
+        rng = np.random.default_rng(7)
+        xyz = torch.tensor(system.get_positions() + rng.normal(0, 0.05, (108, 3)), dtype=torch.float32)
+        pots = {
+            "lj": ref.potentials.LennardJones(1.0, 1.0),
+            "ljfam": ref.potentials.LJFamily(1.0, 0.8, attr_pow=5, rep_pow=10),
+            "lj69": ref.potentials.LennardJones69(1.1, 0.7),
+            "exv": ref.potentials.ExcludedVolume(1.0, 0.5, 12),
+            "buck": ref.potentials.Buck(1000.0, 3.5, 2.0),
+            "morse": ref.potentials.ModifiedMorse(6.0, 2.0),
+        }
+        out = {"xyz": xyz.numpy(), "cell": np.diag(system.get_cell()).astype(np.float32)}
+        for name, pot in pots.items():
+            pair = ref.interface.PairPotentials(system, pot, cutoff=2.5)
+            pair._reset_topology(xyz)
+            q = xyz.clone().requires_grad_(True)
+            e = pair(q)
+            params = [p for p in pot.parameters()]
+            grads = torch.autograd.grad(e, [q] + params, allow_unused=True)
+            out["e_" + name] = e.detach().numpy()
+            out["f_" + name] = (-grads[0]).numpy()
+            out["dp_" + name] = np.array([g.item() for g in grads[1:]], dtype=np.float64)
+        pair = ref.interface.PairPotentials(system, pots["lj"], cutoff=2.5)
+        out["fcc_pairs"] = np.array(pair.nbr_list.shape[0])
+        out["fcc_energy"] = pair(torch.Tensor(system.get_positions())).detach().numpy()
+        np.savez_compressed(os.path.join(OUT, "pair_fcc108.npz"), **out)
+        # ---- G3: C1 trajectory: simulate(steps=50, frequency=50, dt=0.01) (BASELINE configs[0]) ------
+        atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+        system = ref.system.System(atoms, device="cpu")
+        np.random.seed(0)
+        system.set_temperature(1.0)
+        v0 = system.get_velocities().copy()
+        q0 = system.get_positions(wrap=True).copy()
+        lj = ref.potentials.LennardJones(1.0, 1.0)
+        pair = ref.interface.PairPotentials(system, lj, cutoff=2.5)
+        integ = ref.md.NoseHooverChain(pair, system, T=1.0, num_chains=5, Q=50.0, adjoint=True, topology_update_freq=1)
+        sim = ref.md.Simulations(system, integ, wrap=True, method="NH_verlet")
+        v, q, pv = sim.simulate(steps=50, frequency=50, dt=0.01)
+        # adjoint gradients of a scalar loss w.r.t. sigma / epsilon (reference sovlers.py:211-293)
+        loss = (q[-1] ** 2).sum() + (v[20] * v[30]).sum() + pv[-1].sum()
+        loss.backward()
+        obs = ref.observable.rdf(system, 100, (0.75, 2.0))
+        count, bins, g = obs(q[-1].detach())
+        np.savez_compressed(os.path.join(OUT, "c1_traj.npz"), v0=v0, q0=q0, v=v.detach().numpy(), q=q.detach().numpy(),
+                            pv=pv.detach().numpy(), dsigma=lj.sigma.grad.numpy(), depsilon=lj.epsilon.grad.numpy(),
+                            rdf_count=count.numpy(), rdf_bins=bins.numpy(), rdf_g=g.numpy(),
+                            log_q_last=sim.log["positions"][-1], update_count=np.array(integ.update_count))
+        # NVE / verlet
+        atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+        system = ref.system.System(atoms, device="cpu")
+        np.random.seed(1)
+        system.set_temperature(0.5)
+        v0 = system.get_velocities().copy()
+        q0 = system.get_positions(wrap=True).copy()
+        pair = ref.interface.PairPotentials(system, ref.potentials.LennardJones(1.0, 1.0), cutoff=2.5)
+        integ = ref.md.NVE(pair, system, adjoint=True)
+        sim = ref.md.Simulations(system, integ, wrap=True, method="verlet")
+        v, q = sim.simulate(steps=20, frequency=20, dt=0.005)
+        np.savez_compressed(os.path.join(OUT, "c1_nve.npz"), v0=v0, q0=q0, v=v.detach().numpy(), q=q.detach().numpy())
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()

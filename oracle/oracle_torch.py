@@ -166,7 +166,8 @@ def pair_energy_forces(xyz, nbr, offsets, cell, kind, params, need_param_grads=F
         pp = tuple(ps)
     r = pair_distance(q, nbr, offsets, cell)
     e = u_pair(r, kind, pp).sum()
-    wrt = [q] + ([x for x in ps if x.requires_grad] if need_param_grads else [])
+    n_tensor_params = {"lj": 2, "ljfam": 2, "lj69": 2, "exv": 2, "buck": 3, "morse": 0}[kind]
+    wrt = [q] + (ps[:n_tensor_params] if need_param_grads else [])
     grads = torch.autograd.grad(e, wrt, allow_unused=True)
     out = (e.detach(), -grads[0])
     if need_param_grads:

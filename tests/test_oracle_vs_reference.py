@@ -1,0 +1,44 @@
+"""CPU, authoring container only: live diff of the oracle restatement and of the generic solvers
+against the UNMODIFIED reference imported from /root/reference (skipped where it is absent)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_torch as O
+from oracle import ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+
+
+def test_neighbor_list_live():
+    ref = ref_import.load()
+    rng = np.random.default_rng(5)
+    for n, L, rc in [(300, 6.5, 2.5), (700, 14.0, 4.9)]:
+        xyz = torch.tensor(rng.uniform(-0.4 * L, 1.4 * L, (n, 3)), dtype=torch.float32)
+        cell = torch.tensor([L, 1.2 * L, 0.8 * L], dtype=torch.float32)
+        a = ref.topology.generate_nbr_list(xyz, rc, cell, get_dis=True)
+        b = O.neighbor_list(xyz, rc, cell, get_dis=True, block=128)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_adjoint_solver_live():
+    """My odeint_adjoint driving the REFERENCE's own NoseHooverChain module reproduces the reference's
+    odeint_adjoint bit for bit (trajectory and d loss / d sigma, epsilon)."""
+    from mdgrad_b200 import sovlers as S
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    with ref_import.active() as ref:
+        res = []
+        for impl in (ref.sovlers.odeint_adjoint, S.odeint_adjoint):
+            atoms = FaceCenteredCubic(symbol="H", size=(2, 2, 2), latticeconstant=1.679 * 1.5, pbc=True)
+            system = ref.system.System(atoms, device="cpu")
+            np.random.seed(0)
+            system.set_temperature(1.0)
+            lj = ref.potentials.LennardJones(1.0, 1.0)
+            integ = ref.md.NoseHooverChain(ref.interface.PairPotentials(system, lj, cutoff=2.5), system, T=1.0,
+                                           num_chains=5, Q=50.0, adjoint=True)
+            t = torch.Tensor([0.01 * i for i in range(8)])
+            v, q, pv = impl(integ, tuple(integ.get_inital_states(True)), t, method="NH_verlet")
+            ((q[-1] ** 2).sum() + (v[3] * v[5]).sum() + pv[-1].sum()).backward()
+            res.append((v.detach(), q.detach(), pv.detach(), lj.sigma.grad.clone(), lj.epsilon.grad.clone()))
+        for a, b in zip(*res):
+            assert torch.equal(a, b)
