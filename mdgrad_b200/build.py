@@ -29,7 +29,8 @@ def _sources():
 
 def _stamp(path, flags):
     h = hashlib.sha1()
-    for p in [path, os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "mdgrad_b200.h")]:
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    for p in [path] + headers + [os.path.join(ROOT, "include", "mdgrad_b200.h")]:
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(flags).encode())
