@@ -183,8 +183,9 @@ class Context:
         self._keepalive = (xyz, sel_a, sel_b)
 
     # -- K4 + driver ------------------------------------------------------------------------
-    def md_run(self, params, mass, v0, q0, pv0, tgrid, want_energy=False):
-        """Runs one epoch; returns (traj_v, traj_q, traj_pv or None, last_energy or None)."""
+    def md_run(self, params, mass, v0, q0, pv0, tgrid, want_energy=False, out=None):
+        """Runs one epoch; returns (traj_v, traj_q, traj_pv or None, last_energy or None).
+        `out=(traj_v, traj_q)` reuses caller-allocated (n_frames, N, 3) fp32 CUDA buffers."""
         for t, nm in ((mass, "mass"), (v0, "v0"), (q0, "q0")):
             require_cuda(t, nm)
         dev = q0.device
@@ -192,8 +193,12 @@ class Context:
         n_grid = len(tgrid)
         stride = max(1, params.traj_stride)
         n_frames = (n_grid - 1) // stride + 1
-        tv = torch.empty((n_frames, n, 3), dtype=torch.float32, device=dev)
-        tq = torch.empty((n_frames, n, 3), dtype=torch.float32, device=dev)
+        if out is not None:
+            tv, tq = out
+            assert tv.shape == (n_frames, n, 3) and tq.shape == (n_frames, n, 3) and tv.is_contiguous() and tq.is_contiguous()
+        else:
+            tv = torch.empty((n_frames, n, 3), dtype=torch.float32, device=dev)
+            tq = torch.empty((n_frames, n, 3), dtype=torch.float32, device=dev)
         M = params.n_chains if params.integrator == INT_NHC else 0
         hpv = (ctypes.c_float * max(1, n_frames * M))()
         hpv0 = _farr(pv0 if M else [0.0], max(1, M))

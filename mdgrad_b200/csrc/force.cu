@@ -46,34 +46,47 @@ __global__ void __launch_bounds__(256) k_force_rows(int n, const float4* __restr
         const uint32_t* row = rows + (size_t)s * cap;
         const int m = row_len[s];
         const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;   // no image shift on any axis
-        for (int k = lane_in_group; k < m; k += GROUP) {
-            uint32_t e = __ldg(row + k);
-            float4 qj = qs[e & MDG_IDX_MASK];
-            // x_j - x_i: fp32 subtraction is exact-rounded either way; adding a zero shift is a no-op bit-wise
-            float dx = __fsub_rn(qj.x, qi.x), dy = __fsub_rn(qj.y, qi.y), dz = __fsub_rn(qj.z, qi.z);
-            if ((e & ~MDG_IDX_MASK) != ZERO_CODE) {         // rare: pair crosses the periodic boundary
-                uint32_t code = e >> MDG_IDX_BITS;
-                dx = __fadd_rn(dx, mdg_code_shift(code & 3u, bx.L[0]));
-                dy = __fadd_rn(dy, mdg_code_shift((code >> 2) & 3u, bx.L[1]));
-                dz = __fadd_rn(dz, mdg_code_shift((code >> 4) & 3u, bx.L[2]));
-            }
-            float d2;
-            if (RETEST) {
-                d2 = mdg_d2_exact(dx, dy, dz);              // reference arithmetic: membership must be bit-exact
-                if (!(d2 < rc2) || d2 == 0.0f) continue;
-            } else {
-                d2 = dx * dx + dy * dy + dz * dz;
-                if (d2 == 0.0f) continue;
-            }
-            float e_p, g, dp[MDG_MAX_POT_PARAMS];
-            pair_eval<KIND, WITH_DP>(P, d2, e_p, g, dp);
-            fx -= g * dx;
-            fy -= g * dy;
-            fz -= g * dz;
-            en += e_p;
-            if (WITH_DP) {
+        // each lane streams 4 consecutive entries per iteration with one 16-byte load (rows are 128-byte
+        // aligned, cap is a multiple of 32) and issues the 4 position gathers back to back
+        for (int k0 = lane_in_group * 4; k0 < m; k0 += GROUP * 4) {
+            const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(row + k0));
+            const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
+            float4 qj[4];
 #pragma unroll
-                for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] += dp[q];
+            for (int u = 0; u < 4; ++u) qj[u] = (k0 + u < m) ? qs[es[u] & MDG_IDX_MASK] : qi;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k0 + u >= m) break;
+                const uint32_t e = es[u];
+                // x_j - x_i: adding a zero image shift is a bit-wise no-op, so the common case skips it
+                float dx = __fsub_rn(qj[u].x, qi.x), dy = __fsub_rn(qj[u].y, qi.y), dz = __fsub_rn(qj[u].z, qi.z);
+                if ((e & ~MDG_IDX_MASK) != ZERO_CODE) {         // rare: pair crosses the periodic boundary
+                    uint32_t code = e >> MDG_IDX_BITS;
+                    dx = __fadd_rn(dx, mdg_code_shift(code & 3u, bx.L[0]));
+                    dy = __fadd_rn(dy, mdg_code_shift((code >> 2) & 3u, bx.L[1]));
+                    dz = __fadd_rn(dz, mdg_code_shift((code >> 4) & 3u, bx.L[2]));
+                }
+                float d2;
+                bool in;
+                if (RETEST) {
+                    d2 = mdg_d2_exact(dx, dy, dz);              // reference arithmetic: membership must be bit-exact
+                    in = (d2 < rc2) && (d2 != 0.0f);
+                } else {
+                    d2 = dx * dx + dy * dy + dz * dz;
+                    in = d2 != 0.0f;
+                }
+                if (in) {
+                    float e_p, g, dp[MDG_MAX_POT_PARAMS];
+                    pair_eval<KIND, WITH_DP>(P, d2, e_p, g, dp);
+                    fx -= g * dx;
+                    fy -= g * dy;
+                    fz -= g * dz;
+                    en += e_p;
+                    if (WITH_DP) {
+#pragma unroll
+                        for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] += dp[q];
+                    }
+                }
             }
         }
         fx *= P.sg; fy *= P.sg; fz *= P.sg;

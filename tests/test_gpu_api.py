@@ -109,6 +109,8 @@ def test_c1_simulate_vs_reference_fixture():
     integ = NoseHooverChain(pair, system, T=1.0, num_chains=5, Q=50.0, adjoint=True, topology_update_freq=1)
     sim = Simulations(system, integ, wrap=True, method="NH_verlet")
     v, q, pv = sim.simulate(steps=50, frequency=50, dt=0.01)
+    assert v.requires_grad                      # adjoint=True: outputs are attached to the adjoint solve
+    v, q, pv = v.detach(), q.detach(), pv.detach()
     assert integ.last_engine_stats is not None and integ.update_count == 98
     assert v.shape == (50, 108, 3) and q.shape == (50, 108, 3) and pv.shape == (50, 5)
     assert np.array_equal(v[0].cpu().numpy(), g["v"][0]) and np.array_equal(q[0].cpu().numpy(), g["q"][0])
@@ -138,6 +140,7 @@ def test_nve_simulate_vs_reference_fixture():
     integ = NVE(PairPotentials(system, LennardJones(1.0, 1.0), cutoff=2.5), system, adjoint=True)
     sim = Simulations(system, integ, wrap=True, method="verlet")
     v, q = sim.simulate(steps=20, frequency=20, dt=0.005)
+    v, q = v.detach(), q.detach()
     assert np.abs(q[-1].cpu().numpy() - g["q"][-1]).max() < 2e-5
     assert np.abs(v[-1].cpu().numpy() - g["v"][-1]).max() < 2e-4
 
