@@ -7,8 +7,8 @@
 A "step" is one NH-Verlet MD step of the whole box (list upkeep + pair forces + NHC integrator).
 N=1 workload = BASELINE.json configs[1]: 256 000-atom LJ fluid (40^3 FCC, rho 0.845, jitter 0.05a),
 LennardJones(1,1) cutoff 2.5, NoseHooverChain(Q=50, T=1, 5 chains), dt 0.005.
-N>1: the same box replicated per rank ("replicas only" until the spatial-decomposition path lands;
-weak scaling, no data-path collective) - see DESIGN.md.
+N>1: weak scaling - the box grows along z with the GPU count (256 000 atoms per GPU); one spatial slab of
+whole cell layers per rank, NCCL ghost-layer halo exchange + one 2-double all-reduce per step (dist.cu).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident whole-job steps/s (inputs in HBM, CUDA
 events, max over ranks); `e2e` = the same metric through the public API
@@ -58,10 +58,12 @@ def qbath(n):
 NCELL_DEFAULT = 40          # 40^3 FCC cells = 256 000 atoms
 
 
-def make_system(ncell, seed=1):
+def make_system(ncell, seed=1, zmult=1):
+    """FCC ncell x ncell x (ncell*zmult) box at rho 0.845, jitter 0.05a, Maxwell velocities at T=1.
+    Returns positions, velocities (fp64) and the box edge L of the cubic unit (Lz = L * zmult)."""
     a = (4.0 / RHO) ** (1.0 / 3.0)
     basis = np.array([(0, 0, 0), (0.5, 0.5, 0), (0.5, 0, 0.5), (0, 0.5, 0.5)], dtype=np.float64)
-    g = np.stack(np.meshgrid(np.arange(ncell), np.arange(ncell), np.arange(ncell), indexing="ij"), -1).reshape(-1, 1, 3)
+    g = np.stack(np.meshgrid(np.arange(ncell), np.arange(ncell), np.arange(ncell * zmult), indexing="ij"), -1).reshape(-1, 1, 3)
     pos = ((g + basis[None]) * a).reshape(-1, 3)
     pos = pos + np.random.default_rng(seed).normal(0.0, 0.05 * a, pos.shape)
     vel = np.random.default_rng(seed + 1).standard_normal(pos.shape) * math.sqrt(TEMP / MASS)
@@ -126,7 +128,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def md_params(_lib, n, L, skin, K):
+def md_params(_lib, n, L, skin, K, zmult=1):
     p = _lib.MdParams()
     p.integrator = _lib.INT_NHC
     p.pot_kind = _lib.POT_LJ
@@ -134,6 +136,7 @@ def md_params(_lib, n, L, skin, K):
     p.cutoff = RC
     for k in range(3):
         p.cell[k] = L
+    p.cell[2] = float(np.float32(L * zmult))
     p.n_chains = CHAINS
     Q = np.array([qbath(n), *[qbath(n) / n] * (CHAINS - 1)]).astype(np.float32)
     for k in range(CHAINS):
@@ -150,17 +153,27 @@ def tgrid(nsteps, dt=DT):
     return [float(np.float32(dt * i)) for i in range(nsteps + 1)]
 
 
-def equilibrate(ctx, _lib, torch, n, L, mass, v, q, skin, log):
+def assemble(torch, frame, world):
+    """multi-GPU: frames hold the owned atoms only (zero elsewhere) -> sum over ranks."""
+    if world > 1:
+        import torch.distributed as dist
+        frame = frame.clone()
+        dist.all_reduce(frame)
+    return frame
+
+
+def equilibrate(ctx, _lib, torch, n, L, mass, v, q, skin, log, zmult=1, world=1):
     """UNTIMED set-up: melt / thermalise the jittered FCC start with NVE epochs + velocity rescaling
     (through the same fused engine), because the reference's Nose-Hoover chain - bath masses
     Q/N (torchmd/md.py:191-193) - is stiff for 256k atoms and diverges (also in the CPU oracle) when
     started far from equilibrium.  Returns (v, q) at T ~= TEMP."""
-    p = md_params(_lib, n, L, skin, 4)
+    p = md_params(_lib, n, L, skin, 4, zmult)
     p.integrator = _lib.INT_NVE
     schedule = [(0.001, 50)] * 4 + [(0.0025, 50)] * 6 + [(DT, 50)] * 30
     for i, (dt, nst) in enumerate(schedule):
+        p.traj_stride = nst
         tv, tq, _, _ = ctx.md_run(p, mass, v, q, [], tgrid(nst, dt))
-        v, q = tv[-1].clone(), tq[-1].clone()
+        v, q = assemble(torch, tv[-1], world), assemble(torch, tq[-1], world)
         t_inst = float((mass[:, None] * v * v).sum() / (3 * n))
         v = v * math.sqrt(TEMP / t_inst)
         del tv, tq
@@ -173,12 +186,12 @@ def equilibrate(ctx, _lib, torch, n, L, mass, v, q, skin, log):
 # CPU baseline / reference arm: the C oracle (port of the reference's per-evaluation all-pairs
 # algorithm) on the host cores, on a bounded row sample of the same workload
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps_per_s(ncell, steps, warmup, budget_s):
+def cpu_reference_steps_per_s(ncell, steps, warmup, budget_s, zmult=1):
     from oracle import oracle_c as C
-    pos, vel, L = make_system(ncell)
+    pos, vel, L = make_system(ncell, zmult=zmult)
     n = pos.shape[0]
     cores = C.num_threads()
-    cell3 = np.array([L] * 3, dtype=np.float32)
+    cell3 = np.array([L, L, L * zmult], dtype=np.float32)
     x = pos.astype(np.float32)
     # calibrate the row sample so that (steps + warmup) evaluations fit the budget
     t0 = time.perf_counter()
@@ -200,13 +213,13 @@ def cpu_reference_steps_per_s(ncell, steps, warmup, budget_s):
     full_step = (el / steps) * (n / rows) if rows < n else el / steps
     sample = ("C oracle (all-pairs list rebuilt per evaluation, as the reference), %d of %d atom rows per step, "
               "time scaled x%.1f; reference torch path cannot allocate this box (70*N^2 B)" % (rows, n, n / rows))
-    return 1.0 / full_step, cores, sample, n
+    return zmult / full_step, cores, sample, n     # 256k-atom-box equivalents per second (see value_definition)
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    v, cores, sample, n = cpu_reference_steps_per_s(args.ncell, args.steps, args.warmup, budget_s=90.0)
+    v, cores, sample, n = cpu_reference_steps_per_s(args.ncell, args.steps, args.warmup, budget_s=90.0, zmult=max(1, args.gpus))
     line = {
         "impl": "reference", "metric": "MD steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
@@ -226,8 +239,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ncell", type=int, default=NCELL_DEFAULT, help="FCC cells per axis (40 -> 256000 atoms)")
-    ap.add_argument("--skin", type=float, default=0.3)
+    ap.add_argument("--ncell", type=int, default=NCELL_DEFAULT, help="FCC cells per axis (40 -> 256000 atoms per GPU)")
+    ap.add_argument("--skin", type=float, default=0.45)
     ap.add_argument("--rebuild-every", type=int, default=0, help="0 = auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -252,46 +265,46 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert args.warmup >= 3, "W >= 3 warm-up steps required"
 
-    pos, vel, L = make_system(args.ncell)
+    # N = 1: BASELINE configs[1] (256 000 atoms).  N > 1: weak scaling - the box grows along z with the GPU count
+    # (256 000 atoms per GPU, one spatial slab per rank, NCCL ghost-layer halo + 2-double KE all-reduce per step).
+    pos, vel, L = make_system(args.ncell, zmult=world)
     n = pos.shape[0]
     L32 = float(np.float32(L))
     q0 = torch.tensor(pos, dtype=torch.float32, device=dev)
     v0 = torch.tensor(vel, dtype=torch.float32, device=dev)
     mass = torch.full((n,), MASS, dtype=torch.float32, device=dev)
     ctx = _lib.Context(dev)
+    if world > 1:
+        ctx.dist_init()
 
-    # rebuild cadence: conservative estimate from v_max, then let the engine halve on a violation
+    p = md_params(_lib, n, L32, args.skin, 4, world)
+    log("set-up: equilibrating %d atoms (NVE + rescale, untimed)" % n)
+    v0, q0 = equilibrate(ctx, _lib, torch, n, L32, mass, v0, q0, args.skin, log, world, world)
     K = args.rebuild_every
-    if K <= 0:
+    if K <= 0:   # rebuild cadence from v_max; the engine halves it (and redoes the epoch) on a skin violation
         vmax = float(v0.norm(dim=1).max())
         K = int(max(1, min(64, math.floor(0.5 * args.skin / (1.1 * vmax * DT))))) if args.skin > 0 else 1
-    p = md_params(_lib, n, L32, args.skin, K)
+    p.rebuild_every = K
+    # single GPU: every step captured (reference semantics).  multi GPU: first + last frame only (a 1000-frame
+    # trajectory of the whole multi-million-atom box would not fit beside the state).
+    full_traj = world == 1
 
     def run(nsteps, vv, qq, pv, out=None):
+        p.traj_stride = 1 if full_traj else nsteps
         tv, tq, tpv, _ = ctx.md_run(p, mass, vv, qq, pv, tgrid(nsteps), out=out)
         return tv, tq, tpv
 
-    log("set-up: equilibrating %d atoms (NVE + rescale, untimed)" % n)
-    v0, q0 = equilibrate(ctx, _lib, torch, n, L32, mass, v0, q0, args.skin, log)
-    vmax = float(v0.norm(dim=1).max())
-    if args.rebuild_every <= 0 and args.skin > 0:
-        K = int(max(1, min(64, math.floor(0.5 * args.skin / (1.1 * vmax * DT)))))
-        p.rebuild_every = K
-
-    # warm-up: W untimed steps (also settles the rebuild cadence and capacity)
-    log("system ready: n=%d L=%.3f K=%d skin=%.2f; warm-up %d steps" % (n, L, K, args.skin, args.warmup))
+    log("system ready: n=%d L=%.3f K=%d skin=%.2f world=%d; warm-up %d steps" % (n, L, K, args.skin, world, args.warmup))
     tv, tq, tpv = run(args.warmup, v0, q0, [0.0] * CHAINS)
     log("warm-up done: %s" % ctx.stats())
     p.rebuild_every = int(ctx.stats()["maxrow_or_K"])
-    v1, q1, pv1 = tv[-1].clone(), tq[-1].clone(), [float(x) for x in tpv[-1]]
+    v1, q1, pv1 = assemble(torch, tv[-1], world), assemble(torch, tq[-1], world), [float(x) for x in tpv[-1]]
     del tv, tq
 
     # ---- timed: device-resident K steps, CUDA events on the launch stream, barrier + sync both sides
     sampler = ClockSampler(local_rank)
-    # trajectory buffers (every step is captured, reference semantics) allocated and touched BEFORE timing:
-    # cudaMalloc of GBs is not part of an MD step
-    out = (torch.zeros((args.steps + 1, n, 3), dtype=torch.float32, device=dev),
-           torch.zeros((args.steps + 1, n, 3), dtype=torch.float32, device=dev))
+    nfr = args.steps + 1 if full_traj else 2
+    out = (torch.zeros((nfr, n, 3), dtype=torch.float32, device=dev), torch.zeros((nfr, n, 3), dtype=torch.float32, device=dev))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -313,28 +326,41 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = args.steps * world / (ms / 1000.0) if world > 1 else args.steps / (ms / 1000.0)
-    q_end, v_end = tq[-1].clone(), tv[-1].clone()
+    box_steps_per_s = args.steps / (ms / 1000.0)
+    value = box_steps_per_s * world          # 256k-atom-box equivalents per second (= atom-steps/s / 256000)
+    q_end, v_end = assemble(torch, tq[-1], world), assemble(torch, tv[-1], world)
     finite = bool(torch.isfinite(q_end).all() and torch.isfinite(v_end).all())
     del tv, tq
     out = None
     torch.cuda.empty_cache()
 
-    out = {
+    res = {
         "metric": "MD steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LJ fluid %d atoms (FCC %d^3, rho 0.845, jitter 0.05a), LennardJones(1,1) rc 2.5, "
-                               "NoseHooverChain Q=50*N/256 T=1.0 M=5, dt 0.005; start equilibrated by untimed NVE+rescale set-up" % (n, args.ncell),
-                   "atoms": n, "atoms_per_gpu": n, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
+        "config": {"workload": "LJ fluid, %d atoms per GPU (FCC %dx%dx%d, rho 0.845, jitter 0.05a), LennardJones(1,1) rc 2.5, "
+                               "NoseHooverChain Q=50*N/256 T=1.0 M=5, dt 0.005; start equilibrated by untimed NVE+rescale set-up"
+                               % (n // world, args.ncell, args.ncell, args.ncell * world),
+                   "atoms": n, "atoms_per_gpu": n // world,
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   "spatial slabs x%d along z in the global cell-sorted index space; per step: NCCL ghost-layer "
+                                   "halo (2 send + 2 recv) + one 2-double all-reduce; per rebuild: state all-gather" % world),
+                   "value_definition": "steps/s of the whole box x n_gpus (the box grows with the GPU count: 256000 atoms per GPU), "
+                                       "i.e. atom-steps/s / 256000; box_steps_per_s is the raw rate of the %d-atom box" % n,
+                   "box_steps_per_s": box_steps_per_s,
                    "skin": args.skin, "rebuild_every": int(p.rebuild_every), "rebuilds": int(stats["rebuilds"]),
-                   "l2": "no explicit flush: per-step working set (neighbor rows %.0f MB allocated + state %.0f MB) is streamed "
-                         "from HBM and exceeds the 126 MB L2" % (n * 128 * 4 / 1e6, n * 16 * 6 / 1e6),
-                   "trajectory": "every step captured (reference semantics, stride 1)", "finite": finite},
+                   "l2": "no explicit flush: per-step working set (neighbor rows ~%.0f MB + state %.0f MB per GPU) is streamed "
+                         "from HBM and exceeds the 126 MB L2" % (n / world * 96 * 4 / 1e6, n * 16 * 6 / 1e6),
+                   "trajectory": "every step captured (reference semantics, stride 1)" if full_traj else "first and last frame only",
+                   "finite": finite},
         "gpu_launches": launches, "clocks": clocks,
-        "tau_per_day": value / max(world, 1) * DT * 86400.0,
+        "tau_per_day": box_steps_per_s * DT * 86400.0,
     }
-    if rank != 0:
+    if world > 1:
+        if rank == 0:
+            print(json.dumps(res))
+        ctx.dist_finalize()
+        dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (pair force): algorithmic bytes 32 N + 8 P over measured duration
@@ -353,10 +379,12 @@ def main():
     peak, peak_src = peaks()
     achieved = alg_bytes / (force_ms * 1e-3) / 1e9
     log("pair counts done: P_rc=%d P_list=%d force %.4f ms" % (P_rc, P_list, force_ms))
-    out["roofline"] = {"bound": "hbm", "kernel": "k_force_rows (pair force, list streaming)", "achieved": achieved,
-                       "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                       "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "pairs_in_cutoff": P_rc, "pairs_in_skin_list": P_list,
-                       "streamed_bytes_with_skin": 32.0 * n + 8.0 * P_list,
+    res["roofline"] = {"bound": "hbm", "kernel": "k_force_rows (pair force, list streaming)", "achieved": achieved,
+                       "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 104.2e6 + 4.8e6,
+                       "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                         "(profiles/r01_ncu_summary.md, skin 0.45)",
+                       "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "pairs_in_cutoff": P_rc,
+                       "pairs_in_skin_list": P_list, "streamed_bytes_with_skin": 32.0 * n + 8.0 * P_list,
                        "kernel_ms": force_ms, "kernel_launches_timed": prof["force_launches"],
                        "share_of_step": force_ms / (ms / args.steps)}
 
@@ -387,21 +415,19 @@ def main():
         el = time.perf_counter() - t0
         e2e_steps = n_epochs * per_epoch
         state_bytes = n * 3 * 4 * 2 + CHAINS * 4
-        out["e2e"] = {"value": e2e_steps / el, "unit": "steps/s",
+        res["e2e"] = {"value": e2e_steps / el, "unit": "steps/s",
                       "h2d_bytes_per_step": state_bytes / per_epoch, "d2h_bytes_per_step": state_bytes / per_epoch,
                       "api": "Simulations.simulate(steps=%d, frequency=%d, dt=0.005): %d epochs x %d steps, host numpy "
                              "state -> H2D each epoch, last frame D2H + fp64 host wrap each epoch"
                              % (freq * n_epochs, freq, n_epochs, per_epoch)}
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only)
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         log("cpu baseline (C oracle, bounded sample)")
         v, cores, sample, _ = cpu_reference_steps_per_s(args.ncell, steps=3, warmup=1, budget_s=20.0)
         log("cpu baseline done")
-        out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+        res["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(res))
 
 
 if __name__ == "__main__":

@@ -189,6 +189,24 @@ int mdg_md_run(mdg_ctx* ctx, const mdg_md_params* p, int n, const float* d_mass,
  * (0 = cell list, 1 = all-pairs). */
 int mdg_get_stats(mdg_ctx* ctx, int64_t* h_out8);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  The reference has no distributed code; this is the
+ * spatial decomposition of SURVEY 8e: slabs of whole z-layers of cells in the global cell-sorted
+ * index space, per-step ghost-position halo (ncclSend/ncclRecv of two contiguous ranges), one
+ * 2-double KE all-reduce per step, state all-gather + identical re-sort at every list rebuild.
+ *   mdg_slab_plan      : host-only; layers [out4[0], out4[1]) and the lower/upper neighbour ranks.
+ *   mdg_dist_unique_id : rank 0 creates the NCCL unique id (128 bytes); broadcast it out of band
+ *                        (e.g. torch.distributed) and call mdg_dist_init on every rank.
+ *   nccl_lib_path      : the libnccl.so.2 the process already uses (torch's), NULL = default search.
+ * After mdg_dist_init(world > 1) mdg_md_run integrates only the context's own slab: every rank
+ * passes the same full (N) inputs; trajectory frames hold the owned atoms only (zero elsewhere;
+ * sum across ranks to assemble) ; bath trajectory and energy are replicated.
+ * ------------------------------------------------------------------------------------------ */
+int mdg_slab_plan(int ncz, int world, int rank, int* h_out4);
+int mdg_dist_unique_id(const char* nccl_lib_path, char* h_out128);
+int mdg_dist_init(mdg_ctx* ctx, const char* nccl_lib_path, const char* h_id128, int rank, int world);
+int mdg_dist_finalize(mdg_ctx* ctx);
+
 /* Measurement aid (bench.py roofline): when enabled, mdg_md_run brackets every pair-force kernel
  * launch with CUDA events on the launch stream; mdg_get_profile returns h_out2[0] = summed
  * force-kernel milliseconds and h_out2[1] = number of force launches of the last run. */

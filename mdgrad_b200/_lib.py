@@ -25,6 +25,7 @@ SYMBOLS = [
     "mdg_version", "mdg_last_error", "mdg_create", "mdg_destroy", "mdg_nbr_build", "mdg_nbr_export",
     "mdg_pair_force", "mdg_pair_dis_fwd", "mdg_pair_dis_bwd", "mdg_rdf_accumulate", "mdg_md_run",
     "mdg_get_stats", "mdg_set_pair_filter", "mdg_set_profile", "mdg_get_profile",
+    "mdg_slab_plan", "mdg_dist_unique_id", "mdg_dist_init", "mdg_dist_finalize",
 ]
 
 
@@ -81,6 +82,10 @@ def load():
     lib.mdg_get_stats.argtypes = [vp, ctypes.POINTER(i64)]
     lib.mdg_set_pair_filter.argtypes = [vp, vp, vp, vp, ip]
     lib.mdg_set_profile.argtypes = [vp, ip]
+    lib.mdg_slab_plan.argtypes = [ip, ip, ip, ctypes.POINTER(ip)]
+    lib.mdg_dist_unique_id.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    lib.mdg_dist_init.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ip, ip]
+    lib.mdg_dist_finalize.argtypes = [vp]
     lib.mdg_get_profile.argtypes = [vp, ctypes.POINTER(dbl)]
     for name in SYMBOLS:
         if name not in ("mdg_last_error",):
@@ -218,6 +223,29 @@ class Context:
                                          0 if ex_keys is None else int(ex_keys.numel())))
         self._filter_keepalive = (sel_a, sel_b, ex_keys)
 
+    # -- multi-GPU ----------------------------------------------------------------------------
+    def dist_init(self, group=None):
+        """Join this context to an NCCL communicator spanning torch.distributed's (default) group: rank 0
+        creates the NCCL unique id, it is broadcast through torch.distributed, every rank calls
+        mdg_dist_init.  After this, md_run integrates only this rank's slab (see include/mdgrad_b200.h)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        path = nccl_library_path().encode()
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            check(load().mdg_dist_unique_id(path, buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, src=0, group=group)
+        ident = bytes(t.cpu().tolist())
+        with torch.cuda.device(self.device):
+            check(load().mdg_dist_init(self._h, path, ident, rank, world))
+        self.rank, self.world = rank, world
+
+    def dist_finalize(self):
+        check(load().mdg_dist_finalize(self._h))
+
     def set_profile(self, enable):
         check(load().mdg_set_profile(self._h, int(bool(enable))))
 
@@ -231,6 +259,20 @@ class Context:
         check(load().mdg_get_stats(self._h, out))
         keys = ["launches", "rebuilds", "entries", "maxrow_or_K", "ncx", "ncy", "ncz", "path"]
         return dict(zip(keys, list(out)))
+
+
+def nccl_library_path():
+    """The libnccl.so.2 that torch itself uses (one NCCL runtime per process - SURVEY A9)."""
+    sp = os.path.dirname(os.path.dirname(torch.__file__))
+    cand = os.path.join(sp, "nvidia", "nccl", "lib", "libnccl.so.2")
+    return cand if os.path.exists(cand) else "libnccl.so.2"
+
+
+def slab_plan(ncz, world, rank):
+    """(zlo, zhi, rank_below, rank_above): host-only logic of the slab decomposition."""
+    out = (ctypes.c_int * 4)()
+    check(load().mdg_slab_plan(int(ncz), int(world), int(rank), out))
+    return tuple(out)
 
 
 def pair_dis_fwd(xyz, nbr, offsets, cell3):

@@ -35,7 +35,7 @@ __device__ __forceinline__ uint32_t pack_img(int Ix, int Iy, int Iz) {
     return (uint32_t)((Ix + 512) & 1023) | ((uint32_t)((Iy + 512) & 1023) << 10) | ((uint32_t)((Iz + 512) & 1023) << 20);
 }
 
-__global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int ncell, const float4* __restrict__ qs,
+__global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int ncell, const float4* __restrict__ qs,
                                                              const int* __restrict__ cell_start, const int* __restrict__ stencil,
                                                              Box bx, int ncx, int ncy, int ncz, float r2list, int cap,
                                                              PairFilter F, uint32_t* __restrict__ rows,
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int ncell, const f
     __shared__ int s_pre[FB_WARPS][28];                        // candidate-index prefix over the 27 stencil cells
     __shared__ int s_cs[FB_WARPS][27];                         // cell_start of the stencil cells
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * FB_WARPS + w;
+    const int c = cell0 + blockIdx.x * FB_WARPS + w;          // cells [cell0, ncell) (ncell = end of this rank's range)
     if (c >= ncell) return;
     const int a0 = cell_start[c], na = cell_start[c + 1] - a0;
     if (na == 0) return;

@@ -225,6 +225,17 @@ struct mdg_ctx {
     int    cap = 0;           // row capacity (entries), multiple of 32
     bool   built = false;
     bool   has_sel = false;
+    // atom / cell range this context computes (whole box unless a multi-GPU slab plan is active)
+    int    own_s0 = 0, own_s1 = 0;   // sorted-atom range [own_s0, own_s1) of rows / forces / integration
+    int    own_c0 = 0, own_c1 = 0;   // cell range whose rows are built
+    int    rows_s0 = 0;              // first row held in `rows` (rows are allocated for the own range only)
+    bool   slab = false;             // true: own_* are set by the distributed engine after the sort
+    int    slab_zlo = 0, slab_zhi = 0;
+    // distributed state (dist.cu): one NCCL communicator per context
+    int    dist_rank = 0, dist_world = 1;
+    void*  dist_comm = nullptr;
+    int*   h_layers = nullptr;       // pinned: atom offset of every z-layer of cells (ncz + 1 entries)
+    int    n_layers = 0;
     bool   fast_build = false; // engine skin lists: approximate (FMA) membership at the list radius is allowed
     bool   rows_wanted = true;// false: sort into cells only (RDF traversal needs no stored rows)
 

@@ -1,5 +1,5 @@
 // engine.cu - fused Velocity-Verlet / Nose-Hoover-chain integrator kernels (K4 in SURVEY.md 2c)
-// and the device-resident MD epoch driver.
+// and the device-resident MD epoch driver (single GPU, or one slab of a multi-GPU run - dist.cu).
 //
 // Replaces the hot loop of Simulations.simulate (reference torchmd/md.py:73-96) ->
 // FixedGridODESolver.integrate (torchmd/tinydiffeq.py:56-76) -> NHverlet_update / verlet_update
@@ -11,6 +11,7 @@
 // elementwise ATen ops (only the global kinetic-energy reduction order differs).
 #include <vector>
 #include "common.cuh"
+#include "dist.cuh"
 
 #define PROF_MAX_EVENTS 16384
 
@@ -20,7 +21,7 @@ int mdg_i_force_blocks(mdg_ctx* c);
 #define INT_MAX_BLOCKS 592   // 148 SMs x 4 resident CTAs; grid-stride beyond that
 
 struct IntArgs {
-    int    n;
+    int    s0, s1;                 // sorted-atom range integrated by this context
     int    integrator;
     int    M;                      // chains
     float  Q[MDG_MAX_CHAINS];
@@ -29,8 +30,7 @@ struct IntArgs {
     float  half_skin2;             // (skin/2)^2
 };
 
-// scalar state on device ----------------------------------------------------------------------
-//   pv[2][MDG_MAX_CHAINS] ping-pong bath momenta, ph[MDG_MAX_CHAINS] half-step increments
+// scalar state on device: ping-pong bath momenta
 struct Scalars {
     float pv[2][MDG_MAX_CHAINS];
     float ph[MDG_MAX_CHAINS];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_ke_init(IntArgs A, const float4
                                                          double* __restrict__ ke_part) {
     __shared__ double sm[INT_THREADS / 32];
     double acc = 0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < A.n; s += gridDim.x * blockDim.x) {
+    for (int s = A.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < A.s1; s += gridDim.x * blockDim.x) {
         float4 v = v4[s];
         float m = v.w;
         float px = v.x * m, py = v.y * m, pz = v.z * m;
@@ -80,6 +80,18 @@ __global__ void __launch_bounds__(INT_THREADS) k_ke_init(IntArgs A, const float4
     }
     double t = block_sum_double(acc, sm);
     if (threadIdx.x == 0) ke_part[blockIdx.x] = 0.5 * t;
+}
+
+// multi-GPU: collapse two local partial arrays into dke[0..1] (then one 2-double all-reduce)
+__global__ void __launch_bounds__(INT_THREADS) k_ke_pack(const double* __restrict__ a, int na, const double* __restrict__ b, int nb,
+                                                         double* __restrict__ dke) {
+    __shared__ double sm[INT_THREADS / 32];
+    double va = 0, vb = 0;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) va += a[i];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) vb += b[i];
+    double ta = block_sum_double(va, sm);
+    double tb = block_sum_double(vb, sm);
+    if (threadIdx.x == 0) { dke[0] = ta; dke[1] = tb; }
 }
 
 // step part A (sovlers.py:111-118): a0 from (v, f, pv); vh = 1/2 a0 dt; q += (v + vh) dt;
@@ -94,7 +106,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_a(IntArgs A, float dt, int
     if (A.integrator == MDG_INT_NHC) { pv0 = sc->pv[pv_sel][0]; Q0 = A.Q[0]; }
     double acc = 0;
     bool viol = false;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < A.n; s += gridDim.x * blockDim.x) {
+    for (int s = A.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < A.s1; s += gridDim.x * blockDim.x) {
         float4 v = v4[s];
         float4 f = f4[s];
         float4 q = q4[s];
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_b(IntArgs A, float dt, int
         Q0 = A.Q[0];
     }
     double acc = 0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < A.n; s += gridDim.x * blockDim.x) {
+    for (int s = A.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < A.s1; s += gridDim.x * blockDim.x) {
         float4 v = v4[s];
         float4 h = vh4[s];
         float4 f = f4[s];
@@ -222,12 +234,73 @@ __global__ void k_permute2(int n, const int* __restrict__ perm, const float4* __
     b_out[s] = b_in[i];
 }
 
-__global__ void __launch_bounds__(256) k_energy_sum(int n, const float4* __restrict__ fs, double* __restrict__ part) {
+// multi-GPU frame 0: each rank writes the atoms it owns (frames are summed across ranks by the caller)
+__global__ void k_frame_own(int s0, int s1, const float4* __restrict__ v4, const float4* __restrict__ q4,
+                            float* __restrict__ traj_v, float* __restrict__ traj_q) {
+    int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s1) return;
+    float4 q = q4[s], v = v4[s];
+    int id = __float_as_int(q.w);
+    traj_v[3 * (size_t)id] = v.x; traj_v[3 * (size_t)id + 1] = v.y; traj_v[3 * (size_t)id + 2] = v.z;
+    traj_q[3 * (size_t)id] = q.x; traj_q[3 * (size_t)id + 1] = q.y; traj_q[3 * (size_t)id + 2] = q.z;
+}
+
+__global__ void __launch_bounds__(256) k_energy_sum(int s0, int s1, const float4* __restrict__ fs, double* __restrict__ part) {
     __shared__ double sm[8];
     double v = 0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) v += (double)fs[s].w;
+    for (int s = s0 + blockIdx.x * blockDim.x + threadIdx.x; s < s1; s += gridDim.x * blockDim.x) v += (double)fs[s].w;
     double t = block_sum_double(v, sm);
     if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU communication steps (NCCL on the engine's stream)
+// ---------------------------------------------------------------------------------------------
+static int owner_of_layer(int z, int ncz, int world) {
+    int plan[4];
+    for (int r = 0; r < world; ++r) {
+        mdg_slab_plan(ncz, world, r, plan);
+        if (z >= plan[0] && z < plan[1]) return r;
+    }
+    return 0;
+}
+
+// ghost positions: my bottom layer -> rank below, my top layer -> rank above; receive their counterparts
+static int halo_exchange(mdg_ctx* c, float4* q, cudaStream_t st) {
+    NcclApi* N = mdg_nccl();
+    const int ncz = c->n_layers - 1, R = c->dist_world;
+    const int zlo = c->slab_zlo, zhi = c->slab_zhi;
+    const int zl = (zlo - 1 + ncz) % ncz, zu = zhi % ncz;             // ghost layers
+    const int below = owner_of_layer(zl, ncz, R), above = owner_of_layer(zu, ncz, R);
+    const int* L = c->h_layers;
+    MDG_TRY(mdg_nccl_check(N->GroupStart(), "GroupStart"));
+    // sends (own boundary layers)
+    MDG_TRY(mdg_nccl_check(N->Send(q + L[zlo], (size_t)(L[zlo + 1] - L[zlo]) * 4, MDG_NCCL_FLOAT32, below, c->dist_comm, st), "Send"));
+    MDG_TRY(mdg_nccl_check(N->Send(q + L[zhi - 1], (size_t)(L[zhi] - L[zhi - 1]) * 4, MDG_NCCL_FLOAT32, above, c->dist_comm, st), "Send"));
+    // receives (ghost layers); message order per peer: the peer's "up" send matches my "below" recv
+    MDG_TRY(mdg_nccl_check(N->Recv(q + L[zu], (size_t)(L[zu + 1] - L[zu]) * 4, MDG_NCCL_FLOAT32, above, c->dist_comm, st), "Recv"));
+    MDG_TRY(mdg_nccl_check(N->Recv(q + L[zl], (size_t)(L[zl + 1] - L[zl]) * 4, MDG_NCCL_FLOAT32, below, c->dist_comm, st), "Recv"));
+    MDG_TRY(mdg_nccl_check(N->GroupEnd(), "GroupEnd"));
+    return MDG_OK;
+}
+
+// every rank contributes its own range of q, v, vh (old slab plan) -> everyone holds the full state
+static int state_allgather(mdg_ctx* c, float4* q, float4* v, float4* vh, cudaStream_t st) {
+    NcclApi* N = mdg_nccl();
+    const int ncz = c->n_layers - 1, R = c->dist_world;
+    MDG_TRY(mdg_nccl_check(N->GroupStart(), "GroupStart"));
+    for (int r = 0; r < R; ++r) {
+        int plan[4];
+        mdg_slab_plan(ncz, R, r, plan);
+        int a0 = c->h_layers[plan[0]], a1 = c->h_layers[plan[1]];
+        size_t cnt = (size_t)(a1 - a0) * 4;
+        if (cnt == 0) continue;
+        MDG_TRY(mdg_nccl_check(N->Broadcast(q + a0, q + a0, cnt, MDG_NCCL_FLOAT32, r, c->dist_comm, st), "Broadcast"));
+        MDG_TRY(mdg_nccl_check(N->Broadcast(v + a0, v + a0, cnt, MDG_NCCL_FLOAT32, r, c->dist_comm, st), "Broadcast"));
+        MDG_TRY(mdg_nccl_check(N->Broadcast(vh + a0, vh + a0, cnt, MDG_NCCL_FLOAT32, r, c->dist_comm, st), "Broadcast"));
+    }
+    MDG_TRY(mdg_nccl_check(N->GroupEnd(), "GroupEnd"));
+    return MDG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -241,9 +314,11 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     const int stride = p->traj_stride < 1 ? 1 : p->traj_stride;
     const double rlist = p->cutoff + (double)p->skin;
     const bool retest = p->skin > 0.f;
+    const bool dist = c->dist_world > 1;
+    NcclApi* N = mdg_nccl();
+    if (dist && !retest) { mdg_set_error("multi-GPU runs need a Verlet skin (skin > 0)"); return MDG_E_BADARG; }
     IntArgs A;
     memset(&A, 0, sizeof(A));
-    A.n = n;
     A.integrator = p->integrator;
     A.M = M;
     for (int k = 0; k < M; ++k) A.Q[k] = p->Q[k];
@@ -254,8 +329,6 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
 
     const int T = 256;
     const int nb = (n + T - 1) / T;
-    int ib = nb < INT_MAX_BLOCKS ? nb : INT_MAX_BLOCKS;
-    if (ib < 1) ib = 1;
     const int n_frames = (n_grid - 1) / stride + 1;
 
     MDG_TRY(c->v4.reserve(2 * sizeof(float4) * (size_t)n));
@@ -263,7 +336,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     MDG_TRY(c->qref.reserve(sizeof(float4) * (size_t)n));
     MDG_TRY(c->fs.reserve(sizeof(float4) * (size_t)n));
     MDG_TRY(c->pvbuf.reserve(sizeof(Scalars) + sizeof(float) * (size_t)n_frames * MDG_MAX_CHAINS));
-    MDG_TRY(c->kebuf.reserve(sizeof(double) * 4 * INT_MAX_BLOCKS));
+    MDG_TRY(c->kebuf.reserve(sizeof(double) * (4 * INT_MAX_BLOCKS + 8)));
     float4* vbuf[2] = {c->v4.as<float4>(), c->v4.as<float4>() + n};
     float4* hbuf[2] = {c->vh4.as<float4>(), c->vh4.as<float4>() + n};
     int vsel = 0;
@@ -272,6 +345,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     double* ke_part[3] = {c->kebuf.as<double>(), c->kebuf.as<double>() + INT_MAX_BLOCKS,
                           c->kebuf.as<double>() + 2 * INT_MAX_BLOCKS};
     double* e_part = c->kebuf.as<double>() + 3 * INT_MAX_BLOCKS;
+    double* dke = c->kebuf.as<double>() + 4 * INT_MAX_BLOCKS;          // [0]=ke(v), [1]=ke(v+vh), global (multi-GPU)
 
     // scalars + flags
     Scalars hs;
@@ -281,32 +355,46 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     MDG_TRY(c->flags.reserve(sizeof(int) * 8));
     MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 8, st));
 
-    // initial sort + list at q0, state into sorted order
+    // initial sort + list at q0, state into sorted order (every rank holds the full inputs)
     c->sel_a = c->eng_sel_a; c->sel_b = c->eng_sel_b; c->ex_keys = c->eng_ex_keys; c->n_ex = c->eng_n_ex;
     c->rows_wanted = true;
     c->fast_build = retest;      // skin list: every entry is re-tested exactly by the force kernel
+    c->slab = dist;
     MDG_TRY(mdg_i_build_list(c, d_q0, nullptr, n, p->cell, rlist, p->cutoff, st));
     float4* q = c->qs_ptr;
     k_init_v<<<nb, T, 0, st>>>(n, c->perm.as<int>(), d_v0, d_mass, vbuf[vsel]);
     MDG_CUDA(cudaMemcpyAsync(c->qref.p, q, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    MDG_CUDA(cudaMemsetAsync(hbuf[vsel], 0, sizeof(float4) * (size_t)n, st));
     c->stat_launches += 1;
+    A.s0 = c->own_s0; A.s1 = c->own_s1;
+    int nown = A.s1 - A.s0;
+    int ib = (nown + T - 1) / T;
+    ib = ib < 1 ? 1 : (ib > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : ib);
     MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
     if (nhc) { k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, vbuf[vsel], ke_part[0]); c->stat_launches++; }
-    // frame 0 = the initial state, verbatim
-    MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
-    MDG_CUDA(cudaMemcpyAsync(d_traj_q, d_q0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (!dist) {   // frame 0 = the initial state, verbatim
+        MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        MDG_CUDA(cudaMemcpyAsync(d_traj_q, d_q0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    } else {       // owned atoms only; frames are assembled by summing over ranks
+        MDG_CUDA(cudaMemsetAsync(d_traj_v, 0, sizeof(float) * 3 * (size_t)n * n_frames, st));
+        MDG_CUDA(cudaMemsetAsync(d_traj_q, 0, sizeof(float) * 3 * (size_t)n * n_frames, st));
+        if (nown > 0) k_frame_own<<<(nown + T - 1) / T, T, 0, st>>>(A.s0, A.s1, vbuf[vsel], q, d_traj_v, d_traj_q);
+    }
     if (M) MDG_CUDA(cudaMemcpyAsync(d_traj_pv, sc->pv[0], sizeof(float) * M, cudaMemcpyDeviceToDevice, st));
 
-    int pv_sel = 0, ke_cur = 0;
+    int pv_sel = 0, ke_cur = 0, ib_cur = ib;    // ib_cur: number of partials in ke_part[ke_cur]
     for (int g = 0; g + 1 < n_grid; ++g) {
         float dt = h_tgrid[g + 1] - h_tgrid[g];          // fp32 subtraction, like t1 - t0 in tinydiffeq.py:67-68
         bool do_rebuild = ((g + 1) % rebuild_every) == 0;
         int ke_half = (ke_cur + 1) % 3, ke_next = (ke_cur + 2) % 3;
+        // partial arrays must have matching lengths within one step: zero-pad when the block count changes
         k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
                                              c->qref.as<float4>(), (retest && !do_rebuild) ? 1 : 0, ke_part[ke_half],
                                              c->flags.as<int>());
         c->stat_launches++;
+        int ib_half = ib;
         if (do_rebuild) {
+            if (dist) MDG_TRY(state_allgather(c, q, vbuf[vsel], hbuf[vsel], st));
             MDG_TRY(mdg_i_build_list(c, nullptr, q, n, p->cell, rlist, p->cutoff, st));
             q = c->qs_ptr;
             if (c->path == 0) {
@@ -314,7 +402,23 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                 c->stat_launches++;
                 vsel ^= 1;
             }
+            A.s0 = c->own_s0; A.s1 = c->own_s1;
+            nown = A.s1 - A.s0;
+            ib = (nown + T - 1) / T;
+            ib = ib < 1 ? 1 : (ib > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : ib);
             if (retest) MDG_CUDA(cudaMemcpyAsync(c->qref.p, q, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        } else if (dist) {
+            MDG_TRY(halo_exchange(c, q, st));
+        }
+        const double* ke_a = ke_part[ke_cur];
+        const double* ke_b = ke_part[ke_half];
+        int n_part_a = ib_cur, n_part_b = ib_half;
+        if (dist && nhc) {   // global kinetic energies: one all-reduce of 2 doubles (the NHC bath couples all atoms)
+            k_ke_pack<<<1, INT_THREADS, 0, st>>>(ke_part[ke_cur], ib_cur, ke_part[ke_half], ib_half, dke);
+            MDG_TRY(mdg_nccl_check(N->AllReduce(dke, dke, 2, MDG_NCCL_FLOAT64, MDG_NCCL_SUM, c->dist_comm, st), "AllReduce"));
+            ke_a = dke; ke_b = dke + 1;
+            n_part_a = n_part_b = 1;
+            c->stat_launches++;
         }
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (c->prof_enable) {
@@ -337,32 +441,37 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         int gp = g + 1;
         bool keep = (gp % stride) == 0;
         size_t fr = (size_t)(gp / stride);
+        // k_step_b sums `n_part` partials of BOTH arrays: they have equal length except across a slab change,
+        // where the shorter one was written by fewer blocks - pass the common count and rely on the zero tail
+        int n_part = n_part_a;     // == n_part_b: single GPU keeps a constant block count, multi-GPU passes scalars
+        (void)n_part_b;
         k_step_b<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
-                                             ke_part[ke_cur], ke_part[ke_half], ib, ke_part[ke_next],
+                                             ke_a, ke_b, n_part, ke_part[ke_next],
                                              keep ? d_traj_v + fr * 3 * (size_t)n : nullptr,
                                              keep ? d_traj_q + fr * 3 * (size_t)n : nullptr,
                                              (keep && M) ? d_traj_pv + fr * M : nullptr);
         c->stat_launches++;
         pv_sel ^= 1;
         ke_cur = ke_next;
+        ib_cur = ib;
     }
     if (h_last_energy) {
-        k_energy_sum<<<ib, 256, 0, st>>>(n, c->fs.as<float4>(), e_part);
-        c->stat_launches++;
+        k_energy_sum<<<ib, 256, 0, st>>>(A.s0, A.s1, c->fs.as<float4>(), e_part);
+        k_ke_pack<<<1, INT_THREADS, 0, st>>>(e_part, ib, e_part, 0, dke + 6);
+        if (dist) MDG_TRY(mdg_nccl_check(N->AllReduce(dke + 6, dke + 6, 1, MDG_NCCL_FLOAT64, MDG_NCCL_SUM, c->dist_comm, st), "AllReduce"));
+        c->stat_launches += 2;
     }
+    if (dist)   // all ranks must take the same retry decision
+        MDG_TRY(mdg_nccl_check(N->AllReduce(c->flags.p, c->flags.p, 8, MDG_NCCL_INT32, MDG_NCCL_MAX, c->dist_comm, st), "AllReduce"));
     MDG_KERNEL_CHECK();
     // read-backs (SYNC)
-    static thread_local double h_e[INT_MAX_BLOCKS];
-    if (h_last_energy) MDG_CUDA(cudaMemcpyAsync(h_e, e_part, sizeof(double) * ib, cudaMemcpyDeviceToHost, st));
+    double h_e = 0;
+    if (h_last_energy) MDG_CUDA(cudaMemcpyAsync(&h_e, dke + 6, sizeof(double), cudaMemcpyDeviceToHost, st));
     if (M && h_traj_pv)
         MDG_CUDA(cudaMemcpyAsync(h_traj_pv, d_traj_pv, sizeof(float) * (size_t)n_frames * M, cudaMemcpyDeviceToHost, st));
     MDG_CUDA(cudaMemcpyAsync(c->h_pinned, c->flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
     MDG_CUDA(cudaStreamSynchronize(st));
-    if (h_last_energy) {
-        double e = 0;
-        for (int i = 0; i < ib; ++i) e += h_e[i];
-        *h_last_energy = (float)e;
-    }
+    if (h_last_energy) *h_last_energy = (float)h_e;
     if (c->prof_enable && c->prof_events) {
         std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
         c->prof_force_ms = 0.0;
@@ -399,6 +508,7 @@ extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float
     cudaStream_t st = (cudaStream_t)stream;
     int K = p->rebuild_every < 1 ? 1 : p->rebuild_every;
     if (!(p->skin > 0.f)) K = 1;
+    int status = MDG_E_CAPACITY;
     for (int attempt = 0; attempt < 12; ++attempt) {
         c->stat_launches = 0;
         c->stat_rebuilds = 0;
@@ -413,15 +523,17 @@ extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float
             continue;
         }
         if (s == MDG_E_SKIN) {
-            if (K == 1) { mdg_set_error("skin violated with rebuild_every=1"); return MDG_E_SKIN; }
+            if (K == 1) { mdg_set_error("skin violated with rebuild_every=1"); status = MDG_E_SKIN; break; }
             K = K / 2 < 1 ? 1 : K / 2;
             continue;
         }
         c->stat_maxrow = K;   // report the rebuild interval that was finally used
-        return s;
+        status = s;
+        break;
     }
-    mdg_set_error("mdg_md_run: could not satisfy capacity/skin constraints");
-    return MDG_E_CAPACITY;
+    c->slab = false;
+    if (status == MDG_E_CAPACITY) mdg_set_error("mdg_md_run: could not satisfy capacity/skin constraints");
+    return status;
 }
 
 // Per-kernel timing of the force launches inside mdg_md_run (CUDA events on the launch stream

@@ -33,12 +33,12 @@ PotParams mdg_make_pot(int kind, const float* h_params, int n_params) {
 // RETEST: re-apply the reference membership test d2 < rc2 (exact arithmetic) to a skin list.
 // ---------------------------------------------------------------------------------------------
 template <int KIND, bool RETEST, bool WITH_DP, int GROUP>
-__global__ void __launch_bounds__(256) k_force_rows(int n, const float4* __restrict__ qs,
+__global__ void __launch_bounds__(256) k_force_rows(int s0, int n, const float4* __restrict__ qs,
                                                     const uint32_t* __restrict__ rows, const int* __restrict__ row_len,
                                                     int cap, Box bx, float rc2, PotParams P, float4* __restrict__ fs,
                                                     double* __restrict__ dp_partials) {
     const int lane_in_group = threadIdx.x % GROUP;
-    const int s = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+    const int s = s0 + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;      // rows [s0, n) (n = end of this rank's range)
     float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
     float dpa[MDG_MAX_POT_PARAMS] = {0.f, 0.f, 0.f, 0.f};
     if (s < n) {
@@ -129,10 +129,13 @@ __global__ void __launch_bounds__(256) k_force_rows(int n, const float4* __restr
 template <bool RETEST, bool WITH_DP>
 static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
     const int GROUP = 8, T = 256;
-    int n = c->n;
-    int nb = (int)(((int64_t)n * GROUP + T - 1) / T);
+    int s0 = c->own_s0, n = c->own_s1;
+    int nb = (int)(((int64_t)(n - s0) * GROUP + T - 1) / T);
+    if (nb <= 0) return MDG_OK;
+    // rows are allocated for the own range only: address them by the global sorted index
+    const uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
 #define LF(K)                                                                                                  \
-    k_force_rows<K, RETEST, WITH_DP, GROUP><<<nb, T, 0, st>>>(n, qs, c->rows.as<uint32_t>(), c->row_len.as<int>(), \
+    k_force_rows<K, RETEST, WITH_DP, GROUP><<<nb, T, 0, st>>>(s0, n, qs, rows_base, c->row_len.as<int>(),      \
                                                               c->cap, c->box, c->rc2, P, fs, dpp)
     switch (P.kind) {
         case MDG_POT_LJ: LF(MDG_POT_LJ); break;
@@ -149,7 +152,7 @@ static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4
     return MDG_OK;
 }
 
-int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)c->n * 8 + 255) / 256); }
+int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)(c->own_s1 - c->own_s0) * 8 + 255) / 256); }
 
 int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, bool with_dp,
                        double* d_dp_partials, cudaStream_t st) {

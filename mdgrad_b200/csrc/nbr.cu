@@ -3,6 +3,8 @@
 // torchmd/topology.py:30-73 (K1 in SURVEY.md 2c).
 #include "common.cuh"
 
+extern "C" int mdg_slab_plan(int ncz, int world, int rank, int* out4);
+
 #define ALLPAIRS_MAX_ATOMS 3072   // below this (or with < 3 cells on an axis) use the all-pairs search
 
 // ---------------------------------------------------------------------------------------------
@@ -299,12 +301,12 @@ __device__ __forceinline__ bool test_pair(const float4& qi, const float4& qj, co
     return (d2 < r2max) && (d2 != 0.0f);
 }
 
-__global__ void __launch_bounds__(128) k_build_cells(int n, const float4* __restrict__ qs, const int* __restrict__ cell_sorted,
+__global__ void __launch_bounds__(128) k_build_cells(int s0, int n, const float4* __restrict__ qs, const int* __restrict__ cell_sorted,
                                                      const int* __restrict__ cell_start, const int* __restrict__ stencil,
                                                      Box bx, float r2max, int cap, PairFilter F,
                                                      uint32_t* __restrict__ rows, int* __restrict__ row_len,
                                                      int* __restrict__ flags) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;      // rows [s0, n)
     if (s >= n) return;
     if (flags[6] | flags[7]) { row_len[s] = 0; return; }   // non-finite / collapsed input: empty list, error reported by the host
     float4 qi = qs[s];
@@ -546,9 +548,10 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
     MDG_TRY(c->qs_buf[0].reserve(sizeof(float4) * (size_t)n));
     MDG_TRY(c->qs_buf[1].reserve(sizeof(float4) * (size_t)n));
     MDG_TRY(c->perm.reserve(sizeof(int) * (size_t)n));
-    if (c->rows_wanted) {
-        MDG_TRY(c->rows.reserve(sizeof(uint32_t) * (size_t)n * c->cap));
-        MDG_TRY(c->row_len.reserve(sizeof(int) * (size_t)n));
+    if (c->rows_wanted) MDG_TRY(c->row_len.reserve(sizeof(int) * (size_t)n));
+    if (c->slab && (path != 0 || g.nc[2] < 2)) {
+        mdg_set_error("distributed slab decomposition needs the cell-list path (N > %d, >= 3 cells per axis)", ALLPAIRS_MAX_ATOMS);
+        return MDG_E_BADARG;
     }
     MDG_TRY(c->flags.reserve(sizeof(int) * 8));
     MDG_TRY(c->cell_of.reserve(sizeof(int) * (size_t)n));   // reused as cell_sorted after the scatter
@@ -582,22 +585,50 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         k_scatter<<<nb, T, 0, st>>>(n, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_start.as<int>(), c->perm_tmp.as<int>());
         k_cellsort_warp<<<(ncell + 7) / 8, 256, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
                                                          qin, qs, c->perm.as<int>(), c->cell_of.as<int>(), c->flags.as<int>());
+        // ---- range of rows this context owns: everything, or (distributed) whole z-layers of cells -------
+        c->own_s0 = 0; c->own_s1 = n; c->own_c0 = 0; c->own_c1 = ncell; c->rows_s0 = 0;
+        if (c->slab) {
+            // atom offset of every z-layer of cells -> host (SYNC, once per rebuild): sizes the halo / all-gather messages
+            int nxy = g.nc[0] * g.nc[1], ncz = g.nc[2];
+            int plan[4];
+            MDG_TRY(mdg_slab_plan(ncz, c->dist_world, c->dist_rank, plan));
+            c->slab_zlo = plan[0]; c->slab_zhi = plan[1];
+            if (!c->h_layers || c->n_layers < ncz + 1) {
+                if (c->h_layers) cudaFreeHost(c->h_layers);
+                MDG_CUDA(cudaMallocHost((void**)&c->h_layers, sizeof(int) * (size_t)(ncz + 1)));
+            }
+            c->n_layers = ncz + 1;
+            MDG_CUDA(cudaMemcpy2DAsync(c->h_layers, sizeof(int), c->cell_start.as<int>(), sizeof(int) * (size_t)nxy, sizeof(int),
+                                       (size_t)(ncz + 1), cudaMemcpyDeviceToHost, st));
+            MDG_CUDA(cudaStreamSynchronize(st));
+            c->own_c0 = c->slab_zlo * nxy; c->own_c1 = c->slab_zhi * nxy;
+            c->own_s0 = c->h_layers[c->slab_zlo]; c->own_s1 = c->h_layers[c->slab_zhi];
+            c->rows_s0 = c->own_s0;
+        }
         if (c->rows_wanted) {
+            MDG_TRY(c->rows.reserve(sizeof(uint32_t) * (size_t)(c->own_s1 - c->own_s0 + 1) * c->cap));
+            uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
             bool roomy = g.nc[0] >= 5 && g.nc[1] >= 5 && g.nc[2] >= 5;   // stencil extent < half a box
             if (c->fast_build && rlist > cutoff && roomy) {
-                k_build_fast<<<(ncell + FB_WARPS - 1) / FB_WARPS, FB_WARPS * 32, 0, st>>>(
-                    ncell, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box, g.nc[0], g.nc[1], g.nc[2], c->rlist2,
-                    c->cap, F, c->rows.as<uint32_t>(), c->row_len.as<int>(), c->flags.as<int>());
+                int ncl = c->own_c1 - c->own_c0;
+                if (ncl > 0)
+                    k_build_fast<<<(ncl + FB_WARPS - 1) / FB_WARPS, FB_WARPS * 32, 0, st>>>(
+                        c->own_c0, c->own_c1, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box, g.nc[0], g.nc[1], g.nc[2],
+                        c->rlist2, c->cap, F, rows_base, c->row_len.as<int>(), c->flags.as<int>());
             } else {
-                k_build_cells<<<(n + 127) / 128, 128, 0, st>>>(n, qs, c->cell_of.as<int>(), c->cell_start.as<int>(), c->stencil.as<int>(),
-                                                              c->box, c->rlist2, c->cap, F, c->rows.as<uint32_t>(),
-                                                              c->row_len.as<int>(), c->flags.as<int>());
+                int nl = c->own_s1 - c->own_s0;
+                if (nl > 0)
+                    k_build_cells<<<(nl + 127) / 128, 128, 0, st>>>(c->own_s0, c->own_s1, qs, c->cell_of.as<int>(), c->cell_start.as<int>(),
+                                                                  c->stencil.as<int>(), c->box, c->rlist2, c->cap, F, rows_base,
+                                                                  c->row_len.as<int>(), c->flags.as<int>());
             }
         }
         c->stat_launches += 3 + (c->rows_wanted ? 1 : 0);
     } else {
         MDG_CUDA(cudaMemcpyAsync(qs, qin, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         k_iota<<<nb, T, 0, st>>>(c->perm.as<int>(), n);
+        c->own_s0 = 0; c->own_s1 = n; c->own_c0 = 0; c->own_c1 = ncell; c->rows_s0 = 0;
+        if (c->rows_wanted) MDG_TRY(c->rows.reserve(sizeof(uint32_t) * (size_t)n * c->cap));
         if (c->rows_wanted)
             k_build_allpairs<<<(n + AP_TILE - 1) / AP_TILE, AP_TILE, 0, st>>>(n, qs, c->box, c->rlist2, c->cap, F,
                                                                             c->rows.as<uint32_t>(), c->row_len.as<int>(),
