@@ -33,6 +33,9 @@ sys.path.insert(0, ROOT)
 
 import faulthandler
 
+# keep stdout = ONE JSON line: NCCL prints its version banner to stdout unless its log is redirected
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_%h_%p.log")
+
 faulthandler.enable()
 if os.environ.get("BENCH_WATCHDOG"):      # dump all python stacks and exit if the run takes longer than this
     faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)

@@ -217,17 +217,17 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_b(IntArgs A, float dt, int
 }
 
 // state (re)ordering ---------------------------------------------------------------------------
-__global__ void k_init_v(int n, const int* __restrict__ perm, const float* __restrict__ v0,
+__global__ void k_init_v(int s0, int n, const int* __restrict__ perm, const float* __restrict__ v0,
                          const float* __restrict__ mass, float4* __restrict__ v4) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;       // own range [s0, n): perm is only defined there in slab mode
     if (s >= n) return;
     int i = perm[s];
     v4[s] = make_float4(v0[3 * i], v0[3 * i + 1], v0[3 * i + 2], mass[i]);
 }
 
-__global__ void k_permute2(int n, const int* __restrict__ perm, const float4* __restrict__ a_in, float4* __restrict__ a_out,
+__global__ void k_permute2(int s0, int n, const int* __restrict__ perm, const float4* __restrict__ a_in, float4* __restrict__ a_out,
                            const float4* __restrict__ b_in, float4* __restrict__ b_out) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;      // new sorted range [s0, n)
     if (s >= n) return;
     int i = perm[s];
     a_out[s] = a_in[i];
@@ -266,26 +266,35 @@ static int owner_of_layer(int z, int ncz, int world) {
 }
 
 // ghost positions: my bottom layer -> rank below, my top layer -> rank above; receive their counterparts
-static int halo_exchange(mdg_ctx* c, float4* q, cudaStream_t st) {
+static int halo_exchange_nogroup(mdg_ctx* c, float4* q, cudaStream_t st) {
     NcclApi* N = mdg_nccl();
     const int ncz = c->n_layers - 1, R = c->dist_world;
     const int zlo = c->slab_zlo, zhi = c->slab_zhi;
     const int zl = (zlo - 1 + ncz) % ncz, zu = zhi % ncz;             // ghost layers
     const int below = owner_of_layer(zl, ncz, R), above = owner_of_layer(zu, ncz, R);
     const int* L = c->h_layers;
-    MDG_TRY(mdg_nccl_check(N->GroupStart(), "GroupStart"));
     // sends (own boundary layers)
     MDG_TRY(mdg_nccl_check(N->Send(q + L[zlo], (size_t)(L[zlo + 1] - L[zlo]) * 4, MDG_NCCL_FLOAT32, below, c->dist_comm, st), "Send"));
     MDG_TRY(mdg_nccl_check(N->Send(q + L[zhi - 1], (size_t)(L[zhi] - L[zhi - 1]) * 4, MDG_NCCL_FLOAT32, above, c->dist_comm, st), "Send"));
     // receives (ghost layers); message order per peer: the peer's "up" send matches my "below" recv
     MDG_TRY(mdg_nccl_check(N->Recv(q + L[zu], (size_t)(L[zu + 1] - L[zu]) * 4, MDG_NCCL_FLOAT32, above, c->dist_comm, st), "Recv"));
     MDG_TRY(mdg_nccl_check(N->Recv(q + L[zl], (size_t)(L[zl + 1] - L[zl]) * 4, MDG_NCCL_FLOAT32, below, c->dist_comm, st), "Recv"));
+    return MDG_OK;
+}
+
+static int halo_exchange(mdg_ctx* c, float4* q, cudaStream_t st) {
+    NcclApi* N = mdg_nccl();
+    MDG_TRY(mdg_nccl_check(N->GroupStart(), "GroupStart"));
+    MDG_TRY(halo_exchange_nogroup(c, q, st));
     MDG_TRY(mdg_nccl_check(N->GroupEnd(), "GroupEnd"));
     return MDG_OK;
 }
 
-// every rank contributes its own range of q, v, vh (old slab plan) -> everyone holds the full state
-static int state_allgather(mdg_ctx* c, float4* q, float4* v, float4* vh, cudaStream_t st) {
+// Rebuild exchange (old slab plan): positions of ALL atoms are all-gathered (every rank repeats the global
+// binning so that the sorted index space stays identical everywhere); velocities / half-kicks are only
+// needed for atoms a rank may own next, i.e. its old slab plus the adjacent layer on each side (an atom
+// moves less than skin/2 << one cell layer between rebuilds) -> the same two-range halo pattern.
+static int state_exchange(mdg_ctx* c, float4* q, float4* v, float4* vh, cudaStream_t st) {
     NcclApi* N = mdg_nccl();
     const int ncz = c->n_layers - 1, R = c->dist_world;
     MDG_TRY(mdg_nccl_check(N->GroupStart(), "GroupStart"));
@@ -296,9 +305,9 @@ static int state_allgather(mdg_ctx* c, float4* q, float4* v, float4* vh, cudaStr
         size_t cnt = (size_t)(a1 - a0) * 4;
         if (cnt == 0) continue;
         MDG_TRY(mdg_nccl_check(N->Broadcast(q + a0, q + a0, cnt, MDG_NCCL_FLOAT32, r, c->dist_comm, st), "Broadcast"));
-        MDG_TRY(mdg_nccl_check(N->Broadcast(v + a0, v + a0, cnt, MDG_NCCL_FLOAT32, r, c->dist_comm, st), "Broadcast"));
-        MDG_TRY(mdg_nccl_check(N->Broadcast(vh + a0, vh + a0, cnt, MDG_NCCL_FLOAT32, r, c->dist_comm, st), "Broadcast"));
     }
+    MDG_TRY(halo_exchange_nogroup(c, v, st));
+    MDG_TRY(halo_exchange_nogroup(c, vh, st));
     MDG_TRY(mdg_nccl_check(N->GroupEnd(), "GroupEnd"));
     return MDG_OK;
 }
@@ -362,7 +371,8 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     c->slab = dist;
     MDG_TRY(mdg_i_build_list(c, d_q0, nullptr, n, p->cell, rlist, p->cutoff, st));
     float4* q = c->qs_ptr;
-    k_init_v<<<nb, T, 0, st>>>(n, c->perm.as<int>(), d_v0, d_mass, vbuf[vsel]);
+    if (c->own_s1 > c->own_s0)
+        k_init_v<<<(c->own_s1 - c->own_s0 + T - 1) / T, T, 0, st>>>(c->own_s0, c->own_s1, c->perm.as<int>(), d_v0, d_mass, vbuf[vsel]);
     MDG_CUDA(cudaMemcpyAsync(c->qref.p, q, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     MDG_CUDA(cudaMemsetAsync(hbuf[vsel], 0, sizeof(float4) * (size_t)n, st));
     c->stat_launches += 1;
@@ -394,19 +404,22 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         c->stat_launches++;
         int ib_half = ib;
         if (do_rebuild) {
-            if (dist) MDG_TRY(state_allgather(c, q, vbuf[vsel], hbuf[vsel], st));
+            if (dist) MDG_TRY(state_exchange(c, q, vbuf[vsel], hbuf[vsel], st));
             MDG_TRY(mdg_i_build_list(c, nullptr, q, n, p->cell, rlist, p->cutoff, st));
             q = c->qs_ptr;
-            if (c->path == 0) {
-                k_permute2<<<nb, T, 0, st>>>(n, c->perm.as<int>(), vbuf[vsel], vbuf[vsel ^ 1], hbuf[vsel], hbuf[vsel ^ 1]);
+            A.s0 = c->own_s0; A.s1 = c->own_s1;
+            nown = A.s1 - A.s0;
+            if (c->path == 0) {    // v, vh follow their atoms into the new order (own range only: ghosts carry positions only)
+                if (nown > 0)
+                    k_permute2<<<(nown + T - 1) / T, T, 0, st>>>(A.s0, A.s1, c->perm.as<int>(), vbuf[vsel], vbuf[vsel ^ 1],
+                                                               hbuf[vsel], hbuf[vsel ^ 1]);
                 c->stat_launches++;
                 vsel ^= 1;
             }
-            A.s0 = c->own_s0; A.s1 = c->own_s1;
-            nown = A.s1 - A.s0;
             ib = (nown + T - 1) / T;
             ib = ib < 1 ? 1 : (ib > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : ib);
-            if (retest) MDG_CUDA(cudaMemcpyAsync(c->qref.p, q, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            if (retest && nown > 0)
+                MDG_CUDA(cudaMemcpyAsync(c->qref.as<float4>() + A.s0, q + A.s0, sizeof(float4) * (size_t)nown, cudaMemcpyDeviceToDevice, st));
         } else if (dist) {
             MDG_TRY(halo_exchange(c, q, st));
         }

@@ -189,11 +189,11 @@ __global__ void k_cellsort_gather(int ncell, const int* __restrict__ cell_start,
 // with a smaller original id (ids are unique), computed with shuffles; writes the sorted positions,
 // the permutation and the per-atom cell id in one pass.  Cells with more than 32 atoms fall back to
 // the serial insertion sort on lane 0 (rare: > 1.5x the mean occupancy at liquid density).
-__global__ void __launch_bounds__(256) k_cellsort_warp(int ncell, const int* __restrict__ cell_start, const int* __restrict__ cell_count,
+__global__ void __launch_bounds__(256) k_cellsort_warp(int cell0, int ncell, const int* __restrict__ cell_start, const int* __restrict__ cell_count,
                                                        int* __restrict__ perm_tmp, const float4* __restrict__ qin,
                                                        float4* __restrict__ qs, int* __restrict__ perm,
                                                        int* __restrict__ cell_sorted, int* __restrict__ flags) {
-    int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int c = cell0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // cells [cell0, ncell)
     int lane = threadIdx.x & 31;
     if (c >= ncell) return;
     int b = cell_start[c], m = cell_count[c];
@@ -583,8 +583,26 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         k_bin<<<nb, T, 0, st>>>(qin, n, g, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_count.as<int>(), c->flags.as<int>());
         MDG_TRY(mdg_i_scan_exclusive(c, c->cell_count.as<int>(), c->cell_start.as<int>(), ncell + 1, nullptr, st));
         k_scatter<<<nb, T, 0, st>>>(n, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_start.as<int>(), c->perm_tmp.as<int>());
-        k_cellsort_warp<<<(ncell + 7) / 8, 256, 0, st>>>(ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
-                                                         qin, qs, c->perm.as<int>(), c->cell_of.as<int>(), c->flags.as<int>());
+        if (!c->slab) {
+            k_cellsort_warp<<<(ncell + 7) / 8, 256, 0, st>>>(0, ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
+                                                             qin, qs, c->perm.as<int>(), c->cell_of.as<int>(), c->flags.as<int>());
+        } else {
+            // distributed: only the cells of this rank's slab and of its two ghost layers are ever read -> sort just those
+            // (the binning / scan above stay global so that every rank keeps the same sorted index space)
+            int nxy = g.nc[0] * g.nc[1], ncz = g.nc[2];
+            int plan[4];
+            MDG_TRY(mdg_slab_plan(ncz, c->dist_world, c->dist_rank, plan));
+            int zl = (plan[0] - 1 + ncz) % ncz, zu = plan[1] % ncz;
+            int ranges[3][2] = {{plan[0] * nxy, plan[1] * nxy}, {zl * nxy, (zl + 1) * nxy}, {zu * nxy, (zu + 1) * nxy}};
+            for (int k = 0; k < 3; ++k) {
+                if (k == 2 && zu == zl) break;                       // single ghost layer shared by both sides
+                int nc_k = ranges[k][1] - ranges[k][0];
+                if (nc_k <= 0) continue;
+                k_cellsort_warp<<<(nc_k + 7) / 8, 256, 0, st>>>(ranges[k][0], ranges[k][1], c->cell_start.as<int>(), c->cell_count.as<int>(),
+                                                                c->perm_tmp.as<int>(), qin, qs, c->perm.as<int>(), c->cell_of.as<int>(),
+                                                                c->flags.as<int>());
+            }
+        }
         // ---- range of rows this context owns: everything, or (distributed) whole z-layers of cells -------
         c->own_s0 = 0; c->own_s1 = n; c->own_c0 = 0; c->own_c1 = ncell; c->rows_s0 = 0;
         if (c->slab) {
