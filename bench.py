@@ -33,8 +33,16 @@ sys.path.insert(0, ROOT)
 
 import faulthandler
 
-# keep stdout = ONE JSON line: NCCL prints its version banner to stdout unless its log is redirected
-os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_%h_%p.log")
+# keep stdout = ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1 behind python's back, so
+# fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of the real stdout
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
 
 faulthandler.enable()
 if os.environ.get("BENCH_WATCHDOG"):      # dump all python stacks and exit if the run takes longer than this
@@ -232,7 +240,7 @@ def run_reference_arm(args, rank, world):
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -361,7 +369,7 @@ def main():
     }
     if world > 1:
         if rank == 0:
-            print(json.dumps(res))
+            emit(res)
         ctx.dist_finalize()
         dist.destroy_process_group()
         return
@@ -430,7 +438,7 @@ def main():
         v, cores, sample, _ = cpu_reference_steps_per_s(args.ncell, steps=3, warmup=1, budget_s=20.0)
         log("cpu baseline done")
         res["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(res))
+    emit(res)
 
 
 if __name__ == "__main__":

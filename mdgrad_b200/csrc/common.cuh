@@ -228,12 +228,15 @@ struct mdg_ctx {
     // atom / cell range this context computes (whole box unless a multi-GPU slab plan is active)
     int    own_s0 = 0, own_s1 = 0;   // sorted-atom range [own_s0, own_s1) of rows / forces / integration
     int    own_c0 = 0, own_c1 = 0;   // cell range whose rows are built
+    int    force_s0 = -1, force_s1 = 0;   // >= 0: explicit row sub-range for the next force launch
     int    rows_s0 = 0;              // first row held in `rows` (rows are allocated for the own range only)
     bool   slab = false;             // true: own_* are set by the distributed engine after the sort
     int    slab_zlo = 0, slab_zhi = 0;
     // distributed state (dist.cu): one NCCL communicator per context
     int    dist_rank = 0, dist_world = 1;
     void*  dist_comm = nullptr;
+    cudaStream_t comm_stream = nullptr;            // NCCL side stream: halo + KE all-reduce overlap the interior forces
+    cudaEvent_t  ev_a = nullptr, ev_halo = nullptr, ev_ke = nullptr;
     int*   h_layers = nullptr;       // pinned: atom offset of every z-layer of cells (ncz + 1 entries)
     int    n_layers = 0;
     bool   fast_build = false; // engine skin lists: approximate (FMA) membership at the list radius is allowed
@@ -283,5 +286,7 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_sorted_i
 int mdg_i_scan_exclusive(mdg_ctx* c, const int* d_in, int* d_out, int n, int* d_total, cudaStream_t st);
 int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest,
                        bool with_dp, double* d_dp_partials, cudaStream_t st);
+int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, int s0, int s1,
+                      cudaStream_t st);
 PotParams mdg_make_pot(int kind, const float* h_params, int n_params);
 int mdg_i_check_flags(mdg_ctx* c, cudaStream_t st, bool sync);

@@ -326,6 +326,12 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     const bool dist = c->dist_world > 1;
     NcclApi* N = mdg_nccl();
     if (dist && !retest) { mdg_set_error("multi-GPU runs need a Verlet skin (skin > 0)"); return MDG_E_BADARG; }
+    if (dist && !c->comm_stream) {
+        MDG_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        MDG_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+        MDG_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+        MDG_CUDA(cudaEventCreateWithFlags(&c->ev_ke, cudaEventDisableTiming));
+    }
     IntArgs A;
     memset(&A, 0, sizeof(A));
     A.integrator = p->integrator;
@@ -420,19 +426,16 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             ib = ib < 1 ? 1 : (ib > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : ib);
             if (retest && nown > 0)
                 MDG_CUDA(cudaMemcpyAsync(c->qref.as<float4>() + A.s0, q + A.s0, sizeof(float4) * (size_t)nown, cudaMemcpyDeviceToDevice, st));
-        } else if (dist) {
-            MDG_TRY(halo_exchange(c, q, st));
         }
+        // ---- communication + forces ------------------------------------------------------------------------
+        //  single GPU            : force on all rows.
+        //  multi GPU, rebuild    : state_exchange above already refreshed everything -> KE all-reduce, force on all rows.
+        //  multi GPU, plain step : side stream = ghost-layer halo, then the 2-double KE all-reduce; main stream =
+        //                          forces of the INTERIOR layers (no ghost needed) meanwhile, then the two boundary
+        //                          layers once the ghosts arrived, then k_step_b once the kinetic energies arrived.
         const double* ke_a = ke_part[ke_cur];
         const double* ke_b = ke_part[ke_half];
         int n_part_a = ib_cur, n_part_b = ib_half;
-        if (dist && nhc) {   // global kinetic energies: one all-reduce of 2 doubles (the NHC bath couples all atoms)
-            k_ke_pack<<<1, INT_THREADS, 0, st>>>(ke_part[ke_cur], ib_cur, ke_part[ke_half], ib_half, dke);
-            MDG_TRY(mdg_nccl_check(N->AllReduce(dke, dke, 2, MDG_NCCL_FLOAT64, MDG_NCCL_SUM, c->dist_comm, st), "AllReduce"));
-            ke_a = dke; ke_b = dke + 1;
-            n_part_a = n_part_b = 1;
-            c->stat_launches++;
-        }
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (c->prof_enable) {
             std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
@@ -446,11 +449,44 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                 ev0 = (*pool)[c->prof_used];
                 ev1 = (*pool)[c->prof_used + 1];
                 c->prof_used += 2;
-                MDG_CUDA(cudaEventRecord(ev0, st));
             }
         }
-        MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
-        if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
+        if (!dist) {
+            if (ev0) MDG_CUDA(cudaEventRecord(ev0, st));
+            MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
+            if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
+        } else {
+            cudaStream_t cs = c->comm_stream;
+            MDG_CUDA(cudaEventRecord(c->ev_a, st));                    // positions + KE partials of this step are ready
+            MDG_CUDA(cudaStreamWaitEvent(cs, c->ev_a, 0));
+            const int* Ly = c->h_layers;
+            const int zlo = c->slab_zlo, zhi = c->slab_zhi;
+            bool split = !do_rebuild && (zhi - zlo) >= 3;
+            if (!do_rebuild) {
+                MDG_TRY(halo_exchange(c, q, cs));
+                MDG_CUDA(cudaEventRecord(c->ev_halo, cs));
+            }
+            if (nhc) {
+                k_ke_pack<<<1, INT_THREADS, 0, cs>>>(ke_part[ke_cur], ib_cur, ke_part[ke_half], ib_half, dke);
+                MDG_TRY(mdg_nccl_check(N->AllReduce(dke, dke, 2, MDG_NCCL_FLOAT64, MDG_NCCL_SUM, c->dist_comm, cs), "AllReduce"));
+                MDG_CUDA(cudaEventRecord(c->ev_ke, cs));
+                ke_a = dke; ke_b = dke + 1;
+                n_part_a = n_part_b = 1;
+                c->stat_launches++;
+            }
+            if (ev0) MDG_CUDA(cudaEventRecord(ev0, st));
+            if (split) {
+                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], st));     // interior
+                MDG_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
+                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], st));         // bottom layer
+                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], st));         // top layer
+            } else {
+                if (!do_rebuild) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
+                MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
+            }
+            if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
+            if (nhc) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_ke, 0));
+        }
         int gp = g + 1;
         bool keep = (gp % stride) == 0;
         size_t fr = (size_t)(gp / stride);

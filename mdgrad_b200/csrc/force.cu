@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_force_rows(int s0, int n, const float4*
 template <bool RETEST, bool WITH_DP>
 static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
     const int GROUP = 8, T = 256;
-    int s0 = c->own_s0, n = c->own_s1;
+    int s0 = c->force_s0 >= 0 ? c->force_s0 : c->own_s0, n = c->force_s0 >= 0 ? c->force_s1 : c->own_s1;
     int nb = (int)(((int64_t)(n - s0) * GROUP + T - 1) / T);
     if (nb <= 0) return MDG_OK;
     // rows are allocated for the own range only: address them by the global sorted index
@@ -153,6 +153,17 @@ static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4
 }
 
 int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)(c->own_s1 - c->own_s0) * 8 + 255) / 256); }
+
+// explicit sub-range of the own rows (multi-GPU: interior layers first, boundary layers after the halo arrived)
+int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, int s0, int s1,
+                      cudaStream_t st) {
+    if (s1 <= s0) return MDG_OK;
+    c->force_s0 = s0;
+    c->force_s1 = s1;
+    int r = mdg_i_force_sorted(c, P, d_qs, d_fs, retest, false, nullptr, st);
+    c->force_s0 = -1;
+    return r;
+}
 
 int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, bool with_dp,
                        double* d_dp_partials, cudaStream_t st) {
