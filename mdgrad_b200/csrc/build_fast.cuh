@@ -18,8 +18,8 @@
 // Requires >= 5 cells per axis (stencil extent < half a box), else the exact builder is used.
 #pragma once
 
-#define FB_WARPS 3
-#define FB_BATCH 1024            // candidates per batch (32 chunks of 32)
+#define FB_WARPS 4
+#define FB_BATCH 736             // candidates per batch (23 chunks of 32; a 27-cell stencil holds ~650 at liquid density)
 #define FB_CHUNKS (FB_BATCH / 32)
 
 __device__ __forceinline__ void local_coord(float x, float L, float invL, float origin, float& l, int& I) {
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         const int s = a0 + pass + lane;                        // this lane's atom (phase 2)
         const bool act = lane < np;
         int Iix = 0, Iiy = 0, Iiz = 0, idi = 0;
+        uint32_t imc = 0;
         if (act) {
             float4 qi = qs[s];
             float lx, ly, lz;
@@ -88,7 +89,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
             local_coord(qi.y, bx.L[1], bx.invL[1], oy, ly, Iiy);
             local_coord(qi.z, bx.L[2], bx.invL[2], oz, lz, Iiz);
             s_ctr[w][lane] = make_float4(lx, ly, lz, 0.f);
+            imc = pack_img(Iix, Iiy, Iiz);
         }
+        // image of the pass: if every atom of the cell and every candidate share it, all codes are "no shift"
+        const uint32_t im0 = __shfl_sync(0xffffffffu, imc, 0);
+        const bool ctr_uniform = __all_sync(0xffffffffu, !act || imc == im0);
         uint32_t* row = rows + (size_t)(act ? s : a0) * cap;
         int cnt = 0;
         for (int B = 0; B < total; B += FB_BATCH) {
@@ -97,6 +102,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
             __syncwarp();
             // ---------------- phase 1: lane = candidate -------------------------------------------
             int kk = 0;
+            bool cand_uniform = true;
             for (int ch = 0; ch < nch; ++ch) {
                 const int a = B + (ch << 5) + lane;
                 const bool valid = a < B + nb;
@@ -110,20 +116,21 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     local_coord(qj.x, bx.L[0], bx.invL[0], ox, lx, Ix);
                     local_coord(qj.y, bx.L[1], bx.invL[1], oy, ly, Iy);
                     local_coord(qj.z, bx.L[2], bx.invL[2], oz, lz, Iz);
-                    s_img[w][a - B] = pack_img(Ix, Iy, Iz);
+                    uint32_t imj = pack_img(Ix, Iy, Iz);
+                    s_img[w][a - B] = imj;
                     s_t[w][a - B] = t;
+                    cand_uniform = cand_uniform && (imj == im0);
                 }
-                const int tself0 = a0 + pass;
 #pragma unroll 4
-                for (int i = 0; i < np; ++i) {
+                for (int i = 0; i < np; ++i) {          // (the self pair passes here and is dropped in phase 2)
                     float4 ci = s_ctr[w][i];
                     float dx = lx - ci.x, dy = ly - ci.y, dz = lz - ci.z;
                     float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    bool acc = (d2 < r2list) && (t != tself0 + i);
-                    uint32_t m = __ballot_sync(0xffffffffu, acc);
+                    uint32_t m = __ballot_sync(0xffffffffu, d2 < r2list);
                     if (lane == 0) s_mask[w][i][ch] = m;
                 }
             }
+            const bool uniform = ctr_uniform && __all_sync(0xffffffffu, cand_uniform) && !filt;
             __syncwarp();
             // ---------------- phase 2: lane = atom ------------------------------------------------
             // One flattened loop per lane over ALL its set bits of the batch: lanes drift apart across
@@ -142,6 +149,12 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     m &= m - 1;
                     int al = (ch << 5) + b;                    // index within the batch
                     int t = s_t[w][al];
+                    if (t == s) continue;                      // self
+                    if (uniform) {                             // interior cells: no pair crosses a periodic boundary
+                        if (cnt < cap) row[cnt] = (uint32_t)t | ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
+                        ++cnt;
+                        continue;
+                    }
                     uint32_t im = s_img[w][al];
                     int mx = (int)(im & 1023u) - 512 - Iix;
                     int my = (int)((im >> 10) & 1023u) - 512 - Iiy;
