@@ -420,10 +420,19 @@ def main():
         sim.simulate(steps=freq, frequency=freq, dt=DT)                  # warm-up epoch (100 steps)
         torch.cuda.synchronize()
         log("e2e: timed epochs")
+        prof = None
+        if os.environ.get("BENCH_PROFILE_E2E"):
+            import cProfile
+            prof = cProfile.Profile()
+            prof.enable()
         t0 = time.perf_counter()
         sim.simulate(steps=freq * n_epochs, frequency=freq, dt=DT)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
+        if prof is not None:
+            import pstats
+            prof.disable()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(22)
         e2e_steps = n_epochs * per_epoch
         state_bytes = n * 3 * 4 * 2 + CHAINS * 4
         res["e2e"] = {"value": e2e_steps / el, "unit": "steps/s",

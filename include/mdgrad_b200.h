@@ -190,6 +190,22 @@ int mdg_md_run(mdg_ctx* ctx, const mdg_md_params* p, int n, const float* d_mass,
 int mdg_get_stats(mdg_ctx* ctx, int64_t* h_out8);
 
 /* ------------------------------------------------------------------------------------------
+ * K5  SchNet continuous-filter convolution, aggregation part - replaces the gather-multiply-
+ *     scatter of the reference message passing: SchNetConv.message nff/nn/modules.py:568-572
+ *     (h[a0]*W, h[a1]*W) + MessagePassingModule.forward/aggregate nff/nn/graphconv.py:43-53
+ *     (two scatter_add, nff/utils/scatter.py:24-45):
+ *         out[k] = sum over edges e incident to node k of h[other(e,k)] * W[e]     (N x F)
+ * mdg_graph_build  : node -> incident-edge CSR from the reference-layout list d_nbr (E x 2 int64,
+ *                    must stay valid until the next build); deterministic order, no atomics in
+ *                    the reduction.
+ * mdg_cfconv_agg   : the forward above; ALSO the gradient w.r.t. h (apply it to the upstream grad).
+ * mdg_cfconv_edge_grad : gW[e] = h[a0]*g[a1] + h[a1]*g[a0]                        (E x F)
+ * ------------------------------------------------------------------------------------------ */
+int mdg_graph_build(mdg_ctx* ctx, const int64_t* d_nbr, int64_t n_edges, int n, void* stream);
+int mdg_cfconv_agg(mdg_ctx* ctx, const float* d_h, const float* d_W, int n, int n_filters, float* d_out, void* stream);
+int mdg_cfconv_edge_grad(mdg_ctx* ctx, const float* d_h, const float* d_g, int n, int n_filters, float* d_gW, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The reference has no distributed code; this is the
  * spatial decomposition of SURVEY 8e: slabs of whole z-layers of cells in the global cell-sorted
  * index space, per-step ghost-position halo (ncclSend/ncclRecv of two contiguous ranges), one

@@ -26,6 +26,7 @@ SYMBOLS = [
     "mdg_pair_force", "mdg_pair_dis_fwd", "mdg_pair_dis_bwd", "mdg_rdf_accumulate", "mdg_md_run",
     "mdg_get_stats", "mdg_set_pair_filter", "mdg_set_profile", "mdg_get_profile",
     "mdg_slab_plan", "mdg_dist_unique_id", "mdg_dist_init", "mdg_dist_finalize",
+    "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad",
 ]
 
 
@@ -86,6 +87,9 @@ def load():
     lib.mdg_dist_unique_id.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
     lib.mdg_dist_init.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ip, ip]
     lib.mdg_dist_finalize.argtypes = [vp]
+    lib.mdg_graph_build.argtypes = [vp, vp, i64, ip, vp]
+    lib.mdg_cfconv_agg.argtypes = [vp, vp, vp, ip, ip, vp, vp]
+    lib.mdg_cfconv_edge_grad.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     lib.mdg_get_profile.argtypes = [vp, ctypes.POINTER(dbl)]
     for name in SYMBOLS:
         if name not in ("mdg_last_error",):
@@ -222,6 +226,30 @@ class Context:
         check(load().mdg_set_pair_filter(self._h, _ptr(sel_a), _ptr(sel_b), _ptr(ex_keys),
                                          0 if ex_keys is None else int(ex_keys.numel())))
         self._filter_keepalive = (sel_a, sel_b, ex_keys)
+
+    # -- K5: SchNet cfconv aggregation ---------------------------------------------------------
+    def graph_build(self, nbr, n):
+        require_cuda(nbr, "nbr_list")
+        nbr = nbr.to(torch.int64).contiguous()
+        with torch.cuda.device(nbr.device):
+            check(load().mdg_graph_build(self._h, _ptr(nbr), nbr.shape[0], int(n), _stream(nbr.device)))
+        self._graph_keepalive = nbr
+        self._graph_n = int(n)
+
+    def cfconv_agg(self, h, W):
+        require_cuda(h, "h")
+        h, W = h.contiguous(), W.contiguous()
+        out = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            check(load().mdg_cfconv_agg(self._h, _ptr(h), _ptr(W), h.shape[0], h.shape[1], _ptr(out), _stream(h.device)))
+        return out
+
+    def cfconv_edge_grad(self, h, g, n_edges):
+        h, g = h.contiguous(), g.contiguous()
+        gW = torch.empty((n_edges, h.shape[1]), dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            check(load().mdg_cfconv_edge_grad(self._h, _ptr(h), _ptr(g), h.shape[0], h.shape[1], _ptr(gW), _stream(h.device)))
+        return gW
 
     # -- multi-GPU ----------------------------------------------------------------------------
     def dist_init(self, group=None):

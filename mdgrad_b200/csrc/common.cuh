@@ -266,6 +266,12 @@ struct mdg_ctx {
     const int64_t* eng_ex_keys = nullptr;
     int eng_n_ex = 0;
 
+    // SchNet graph (graph.cu): node -> incident-edge CSR of the last mdg_graph_build
+    DevBuf g_off, g_cnt, g_edge, g_other;
+    int     g_n = -1;
+    int64_t g_edges = 0;
+    const int64_t* g_nbr = nullptr;
+
     // engine state (sorted order)
     DevBuf v4, vh4, q4b, f4b, qref, mass_sorted, pvbuf, kebuf, dtbuf;
 

@@ -1,0 +1,135 @@
+// graph.cu - SchNet continuous-filter convolution, aggregation part (K5 in SURVEY.md 2c).
+//
+// Replaces the gather-multiply-scatter of the reference message passing:
+//   message  = (h[a0] * W, h[a1] * W)                     nff/nn/modules.py:568-572 (SchNetConv.message)
+//   agg      = scatter_add(m0 -> a1) + scatter_add(m1 -> a0)   nff/nn/graphconv.py:43-53, nff/utils/scatter.py:24-45
+// i.e. agg[k] = sum over edges e incident to node k of h[other(e,k)] * W[e]   (features elementwise),
+// with an atomics-free, deterministic segment reduction over a node->incident-edge CSR that is built
+// once per topology from the reference-layout (E,2) int64 neighbor list.
+// Backward: d/dh is the SAME operator applied to the upstream gradient (the incidence structure is
+// symmetric); d/dW[e] = h[a0]*g[a1] + h[a1]*g[a0].
+// The dense layers around it (filter MLP, node / update GEMMs) go through cuBLAS this round; the
+// tcgen05 path is the planned replacement.
+#include "common.cuh"
+
+__global__ void k_inc_count(const int64_t* __restrict__ nbr, int64_t E, int n, int* __restrict__ cnt) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int a0 = (int)nbr[2 * e], a1 = (int)nbr[2 * e + 1];
+    if ((unsigned)a0 < (unsigned)n) atomicAdd(&cnt[a0], 1);
+    if ((unsigned)a1 < (unsigned)n) atomicAdd(&cnt[a1], 1);
+}
+
+__global__ void k_inc_fill(const int64_t* __restrict__ nbr, int64_t E, int n, const int* __restrict__ off,
+                           int* __restrict__ cursor, int* __restrict__ inc_edge, int* __restrict__ inc_other) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int a0 = (int)nbr[2 * e], a1 = (int)nbr[2 * e + 1];
+    if ((unsigned)a0 < (unsigned)n) { int p = off[a0] + atomicAdd(&cursor[a0], 1); inc_edge[p] = (int)e; inc_other[p] = a1; }
+    if ((unsigned)a1 < (unsigned)n) { int p = off[a1] + atomicAdd(&cursor[a1], 1); inc_edge[p] = (int)e; inc_other[p] = a0; }
+}
+
+// deterministic order: each node's incident entries sorted by edge id (thread per node, short lists)
+__global__ void k_inc_sort(int n, const int* __restrict__ off, int* __restrict__ inc_edge, int* __restrict__ inc_other) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int b = off[k], m = off[k + 1] - b;
+    for (int a = 1; a < m; ++a) {
+        int e = inc_edge[b + a], o = inc_other[b + a];
+        int j = a - 1;
+        while (j >= 0 && inc_edge[b + j] > e) { inc_edge[b + j + 1] = inc_edge[b + j]; inc_other[b + j + 1] = inc_other[b + j]; --j; }
+        inc_edge[b + j + 1] = e;
+        inc_other[b + j + 1] = o;
+    }
+}
+
+// one warp per node; lanes stride the feature dimension in float4 (F % 4 == 0) or scalar
+template <bool VEC4>
+__global__ void __launch_bounds__(256) k_cfconv_agg(int n, int F, const int* __restrict__ off, const int* __restrict__ inc_edge,
+                                                    const int* __restrict__ inc_other, const float* __restrict__ h,
+                                                    const float* __restrict__ W, float* __restrict__ out) {
+    int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (k >= n) return;
+    int b = off[k], e1 = off[k + 1];
+    if (VEC4) {
+        int F4 = F >> 2;
+        for (int f = lane; f < F4; f += 32) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = b; p < e1; ++p) {
+                int e = inc_edge[p], o = inc_other[p];
+                float4 w = reinterpret_cast<const float4*>(W + (size_t)e * F)[f];
+                float4 x = reinterpret_cast<const float4*>(h + (size_t)o * F)[f];
+                acc.x += x.x * w.x; acc.y += x.y * w.y; acc.z += x.z * w.z; acc.w += x.w * w.w;
+            }
+            reinterpret_cast<float4*>(out + (size_t)k * F)[f] = acc;
+        }
+    } else {
+        for (int f = lane; f < F; f += 32) {
+            float acc = 0.f;
+            for (int p = b; p < e1; ++p) acc += h[(size_t)inc_other[p] * F + f] * W[(size_t)inc_edge[p] * F + f];
+            out[(size_t)k * F + f] = acc;
+        }
+    }
+}
+
+__global__ void k_cfconv_edge_grad(int64_t E, int F, const int64_t* __restrict__ nbr, const float* __restrict__ h,
+                                   const float* __restrict__ g, float* __restrict__ gW) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= E * F) return;
+    int64_t e = idx / F;
+    int f = (int)(idx - e * F);
+    int64_t a0 = nbr[2 * e], a1 = nbr[2 * e + 1];
+    gW[idx] = h[a0 * F + f] * g[a1 * F + f] + h[a1 * F + f] * g[a0 * F + f];
+}
+
+extern "C" int mdg_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, void* stream) {
+    if (!c || (n_edges > 0 && !d_nbr) || n < 0 || n_edges < 0 || 2 * n_edges > 0x7fffffffLL) { mdg_set_error("mdg_graph_build: bad arguments"); return MDG_E_BADARG; }
+    MDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->g_n = n;
+    c->g_edges = n_edges;
+    c->g_nbr = d_nbr;
+    MDG_TRY(c->g_off.reserve(sizeof(int) * (size_t)(n + 2)));
+    MDG_TRY(c->g_cnt.reserve(sizeof(int) * (size_t)(n + 2)));
+    MDG_TRY(c->g_edge.reserve(sizeof(int) * (size_t)(2 * n_edges + 1)));
+    MDG_TRY(c->g_other.reserve(sizeof(int) * (size_t)(2 * n_edges + 1)));
+    MDG_CUDA(cudaMemsetAsync(c->g_cnt.p, 0, sizeof(int) * (size_t)(n + 1), st));
+    if (n_edges > 0) k_inc_count<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(d_nbr, n_edges, n, c->g_cnt.as<int>());
+    MDG_TRY(mdg_i_scan_exclusive(c, c->g_cnt.as<int>(), c->g_off.as<int>(), n + 1, nullptr, st));
+    MDG_CUDA(cudaMemsetAsync(c->g_cnt.p, 0, sizeof(int) * (size_t)(n + 1), st));
+    if (n_edges > 0) {
+        k_inc_fill<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(d_nbr, n_edges, n, c->g_off.as<int>(), c->g_cnt.as<int>(),
+                                                                   c->g_edge.as<int>(), c->g_other.as<int>());
+        k_inc_sort<<<(n + 127) / 128, 128, 0, st>>>(n, c->g_off.as<int>(), c->g_edge.as<int>(), c->g_other.as<int>());
+    }
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+extern "C" int mdg_cfconv_agg(mdg_ctx* c, const float* d_h, const float* d_W, int n, int F, float* d_out, void* stream) {
+    if (!c || !d_h || !d_out || F <= 0) { mdg_set_error("mdg_cfconv_agg: bad arguments"); return MDG_E_BADARG; }
+    if (n != c->g_n) { mdg_set_error("mdg_cfconv_agg: graph was built for %d nodes, got %d", c->g_n, n); return MDG_E_STATE; }
+    MDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return MDG_OK;
+    int nb = (int)(((int64_t)n * 32 + 255) / 256);
+    if ((F & 3) == 0 && (((uintptr_t)d_h | (uintptr_t)d_W | (uintptr_t)d_out) & 15) == 0)
+        k_cfconv_agg<true><<<nb, 256, 0, st>>>(n, F, c->g_off.as<int>(), c->g_edge.as<int>(), c->g_other.as<int>(), d_h, d_W, d_out);
+    else
+        k_cfconv_agg<false><<<nb, 256, 0, st>>>(n, F, c->g_off.as<int>(), c->g_edge.as<int>(), c->g_other.as<int>(), d_h, d_W, d_out);
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+extern "C" int mdg_cfconv_edge_grad(mdg_ctx* c, const float* d_h, const float* d_g, int n, int F, float* d_gW, void* stream) {
+    if (!c || !d_h || !d_g || F <= 0) { mdg_set_error("mdg_cfconv_edge_grad: bad arguments"); return MDG_E_BADARG; }
+    if (n != c->g_n) { mdg_set_error("mdg_cfconv_edge_grad: graph was built for %d nodes, got %d", c->g_n, n); return MDG_E_STATE; }
+    MDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t tot = c->g_edges * (int64_t)F;
+    if (tot == 0) return MDG_OK;
+    k_cfconv_edge_grad<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(c->g_edges, F, c->g_nbr, d_h, d_g, d_gW);
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}

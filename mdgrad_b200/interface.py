@@ -137,3 +137,10 @@ class Stack(torch.nn.Module):
             term = self.models[key](x).sum().reshape(-1)
             result = term if result is None else result + term
         return result
+
+
+def __getattr__(name):
+    if name == "GNNPotentials":          # lives in gnn.py (imports this module)
+        from .gnn import GNNPotentials
+        return GNNPotentials
+    raise AttributeError(name)

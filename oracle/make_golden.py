@@ -102,5 +102,48 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--schnet" not in sys.argv:
     main()
+
+
+def schnet_golden():
+    """G4: SchNet energies/forces through the reference GNNPotentials (incl. its raw-offset quirk) on a 64-water
+    box (reference data/water_init_64.xyz, rc 5.85 > box/2 -> single-image semantics) and a 512-atom diamond Si box."""
+    import re
+    torch.manual_seed(0)
+    from mdgrad_b200._ase_compat import Atoms, Diamond
+    with ref_import.active() as ref:
+        # ---- water ----
+        lines = open(os.path.join(ref_import.REF_ROOT, "data", "water_init_64.xyz")).read().splitlines()
+        nat = int(lines[0])
+        Lbox = float(re.search(r'Lattice="([0-9.eE+-]+)', lines[1]).group(1))
+        sym, pos = [], []
+        for ln in lines[2:2 + nat]:
+            f = ln.split()
+            sym.append(f[0]); pos.append([float(x) for x in f[1:4]])
+        atoms = Atoms(symbols=sym, positions=np.array(pos), cell=[Lbox] * 3, pbc=True)
+        for tag, atoms, params in [
+            ("water", atoms, {"n_atom_basis": 64, "n_filters": 64, "n_gaussians": 29, "n_convolutions": 2,
+                              "cutoff": 5.847718540914188, "trainable_gauss": False}),
+            ("si", Diamond("Si", (4, 4, 4), 5.45933), {"n_atom_basis": 48, "n_filters": 40, "n_gaussians": 33,
+                                                      "n_convolutions": 3, "cutoff": 4.9, "trainable_gauss": False}),
+        ]:
+            rng = np.random.default_rng(11)
+            atoms.set_positions(atoms.get_positions() + rng.normal(0, 0.05, (len(atoms), 3)))
+            system = ref.system.System(atoms, device="cpu")
+            torch.manual_seed(1)
+            model = ref.schnet.SchNet(params)
+            gnn = ref.interface.GNNPotentials(system, model, cutoff=params["cutoff"])
+            xyz = torch.Tensor(system.get_positions()).requires_grad_(True)
+            e = gnn(xyz)
+            f = -torch.autograd.grad(e.sum(), xyz)[0]
+            sd = {("w_" + k): v.numpy() for k, v in model.state_dict().items()}
+            np.savez_compressed(os.path.join(OUT, "schnet_%s.npz" % tag), numbers=system.get_atomic_numbers(),
+                                positions=system.get_positions(), cell=np.diag(system.get_cell()),
+                                energy=e.detach().numpy(), forces=f.numpy(), n_edges=np.array(gnn.inputs["nbr_list"].shape[0]),
+                                **{k: np.array(v) for k, v in params.items() if k != "trainable_gauss"}, **sd)
+            print(tag, "E", e.item(), "edges", gnn.inputs["nbr_list"].shape[0], "|F|max", f.abs().max().item())
+
+
+if __name__ == "__main__" and "--schnet" in sys.argv:
+    schnet_golden()
