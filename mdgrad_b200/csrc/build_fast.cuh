@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                                                              const int* __restrict__ cell_start, const int* __restrict__ stencil,
                                                              Box bx, int ncx, int ncy, int ncz, float r2list, int cap,
                                                              PairFilter F, uint32_t* __restrict__ rows,
-                                                             int* __restrict__ row_len, int* __restrict__ flags) {
+                                                             int* __restrict__ row_len, int* __restrict__ flags,
+                                                             unsigned char* __restrict__ cell_local) {
     __shared__ uint32_t s_mask[FB_WARPS][32][FB_CHUNKS + 1];   // [atom][chunk], padded: conflict-free for lane = atom
     __shared__ uint32_t s_img[FB_WARPS][FB_BATCH];
     __shared__ int s_t[FB_WARPS][FB_BATCH];                     // sorted index of each staged candidate
@@ -71,6 +72,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
     }
     __syncwarp();
     const int total = s_pre[w][27];
+    // Row entries reference the cell's STENCIL STREAM (the 27 stencil cells concatenated in table order) when it
+    // fits the force kernel's shared-memory stage; the force kernel stages the same stream and gathers from smem.
+    const bool local_idx = (cell_local != nullptr) && (total <= MDG_STREAM_CAP);
+    if (cell_local && lane == 0) cell_local[c] = local_idx ? 1 : 0;
     const int cx = c % ncx, cy = (c / ncx) % ncy, cz = c / (ncx * ncy);
     const float ox = (float)cx / (float)ncx, oy = (float)cy / (float)ncy, oz = (float)cz / (float)ncz;
     const bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
@@ -150,8 +155,9 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     int al = (ch << 5) + b;                    // index within the batch
                     int t = s_t[w][al];
                     if (t == s) continue;                      // self
+                    const uint32_t ref = local_idx ? (uint32_t)(B + al) : (uint32_t)t;   // stencil-stream index, or global index
                     if (uniform) {                             // interior cells: no pair crosses a periodic boundary
-                        if (cnt < cap) row[cnt] = (uint32_t)t | ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
+                        if (cnt < cap) row[cnt] = ref | ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
                         ++cnt;
                         continue;
                     }
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     if ((unsigned)(mx + 1) > 2u || (unsigned)(my + 1) > 2u || (unsigned)(mz + 1) > 2u) continue;
                     if (filt && !pair_allowed(F, idi, __float_as_int(qs[t].w))) continue;
                     if (cnt < cap)
-                        row[cnt] = (uint32_t)t | ((uint32_t)((1 - mx) | ((1 - my) << 2) | ((1 - mz) << 4)) << MDG_IDX_BITS);
+                        row[cnt] = ref | ((uint32_t)((1 - mx) | ((1 - my) << 2) | ((1 - mz) << 4)) << MDG_IDX_BITS);
                     ++cnt;
                 }
             }

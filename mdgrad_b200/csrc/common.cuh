@@ -62,6 +62,7 @@ struct DevBuf {
 // 2 bits per axis holding off_k + 1 in {0,1,2} (off = reference `offsets` row-relative:
 // computed from d = x_j - x_i of the row atom i, topology.py:35,59-62)
 // ---------------------------------------------------------------------------------------------
+#define MDG_STREAM_CAP 1024   // max atoms of a 27-cell stencil stream staged in shared memory by k_force_cells
 #define MDG_IDX_BITS 26
 #define MDG_IDX_MASK ((1u << MDG_IDX_BITS) - 1u)
 #define MDG_MAX_ATOMS (1 << MDG_IDX_BITS)
@@ -228,6 +229,7 @@ struct mdg_ctx {
     // atom / cell range this context computes (whole box unless a multi-GPU slab plan is active)
     int    own_s0 = 0, own_s1 = 0;   // sorted-atom range [own_s0, own_s1) of rows / forces / integration
     int    own_c0 = 0, own_c1 = 0;   // cell range whose rows are built
+    int    force_c0 = 0, force_c1 = 0;    // matching cell sub-range (whole z-layers)
     int    force_s0 = -1, force_s1 = 0;   // >= 0: explicit row sub-range for the next force launch
     int    rows_s0 = 0;              // first row held in `rows` (rows are allocated for the own range only)
     bool   slab = false;             // true: own_* are set by the distributed engine after the sort
@@ -248,6 +250,8 @@ struct mdg_ctx {
     float4* qs_ptr = nullptr; //   the previous output), w = original index (int bits)
     // list
     DevBuf rows, row_len;     // uint32 [n*cap], int [n]
+    DevBuf cell_local;        // uchar [ncell]: 1 = the cell's rows hold stencil-stream indices (k_force_cells), 0 = global
+    bool   rows_local = false; // the current list was built by k_build_fast in stream-index form
     DevBuf flags;             // int[8]: 0 = capacity overflow, 1 = skin violation
     // export scratch
     DevBuf up_cnt, up_off, scan_tmp;
@@ -293,6 +297,6 @@ int mdg_i_scan_exclusive(mdg_ctx* c, const int* d_in, int* d_out, int n, int* d_
 int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest,
                        bool with_dp, double* d_dp_partials, cudaStream_t st);
 int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, int s0, int s1,
-                      cudaStream_t st);
+                      int c0, int c1, cudaStream_t st);
 PotParams mdg_make_pot(int kind, const float* h_params, int n_params);
 int mdg_i_check_flags(mdg_ctx* c, cudaStream_t st, bool sync);

@@ -476,10 +476,14 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             }
             if (ev0) MDG_CUDA(cudaEventRecord(ev0, st));
             if (split) {
-                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], st));     // interior
+                const int nxy = c->nc[0] * c->nc[1];
+                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
+                                          (zhi - 1) * nxy, st));                                                      // interior
                 MDG_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
-                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], st));         // bottom layer
-                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], st));         // top layer
+                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], zlo * nxy,
+                                          (zlo + 1) * nxy, st));                                                      // bottom layer
+                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
+                                          zhi * nxy, st));                                                            // top layer
             } else {
                 if (!do_rebuild) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
                 MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));

@@ -126,6 +126,133 @@ __global__ void __launch_bounds__(256) k_force_rows(int s0, int n, const float4*
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// v2 force kernel for lists built by k_build_fast in STREAM-INDEX form: one CTA per cell.  The CTA
+// stages the cell's stencil stream (the atoms of its 27 stencil cells, concatenated in table order -
+// exactly the order the builder enumerated) into shared memory with coalesced float4 loads, then
+// 8 lanes per row stream the row (16-byte loads) and gather neighbor positions FROM SHARED MEMORY:
+// the row entries are stream indices, so no translation is needed.  Removes the L1 gather wavefronts
+// (~20 distinct lines per 32-lane gather) and the L1/L2 latency from the inner loop.
+// Cells whose stream exceeds MDG_STREAM_CAP keep global indices (cell_local[c] == 0) and gather from qs.
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) k_force_cells(int cell0, int cell1, const float4* __restrict__ qs,
+                                                     const int* __restrict__ cell_start, const int* __restrict__ stencil,
+                                                     const unsigned char* __restrict__ cell_local,
+                                                     const uint32_t* __restrict__ rows, const int* __restrict__ row_len, int cap,
+                                                     Box bx, float rc2, PotParams P, float4* __restrict__ fs) {
+    __shared__ float4 s_q[MDG_STREAM_CAP];
+    __shared__ int s_pre[28];
+    __shared__ int s_cs[27];
+    const int c = cell0 + blockIdx.x;
+    if (c >= cell1) return;
+    const int a0 = cell_start[c], na = cell_start[c + 1] - a0;
+    if (na == 0) return;
+    const bool local = cell_local[c] != 0;
+    if (local) {
+        if (threadIdx.x < 32) {
+            int lane = threadIdx.x;
+            int cc = lane < 27 ? stencil[c * 27 + lane] : 0;
+            int cs = lane < 27 ? cell_start[cc] : 0;
+            int x = lane < 27 ? cell_start[cc + 1] - cs : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane < 27) { s_pre[lane + 1] = x; s_cs[lane] = cs; }
+            if (lane == 0) s_pre[0] = 0;
+        }
+        __syncthreads();
+        const int total = s_pre[27];
+        for (int a = threadIdx.x; a < total; a += blockDim.x) {
+            int lo = 0, hi = 26;                      // largest k with s_pre[k] <= a
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (s_pre[mid] <= a) lo = mid; else hi = mid - 1;
+            }
+            s_q[a] = qs[s_cs[lo] + (a - s_pre[lo])];
+        }
+        __syncthreads();
+    }
+    const int lane_in_group = threadIdx.x & 7;
+    const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
+    for (int r0 = 0; r0 < na; r0 += 32) {
+        const int r = r0 + (threadIdx.x >> 3);
+        float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
+        if (r < na) {
+            const int s = a0 + r;
+            const float4 qi = qs[s];
+            const uint32_t* row = rows + (size_t)s * cap;
+            const int m = row_len[s];
+            for (int k0 = lane_in_group * 4; k0 < m; k0 += 32) {
+                const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(row + k0));
+                const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
+                float4 qj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t idx = es[u] & MDG_IDX_MASK;
+                    qj[u] = (k0 + u < m) ? (local ? s_q[idx] : qs[idx]) : qi;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u >= m) break;
+                    const uint32_t e = es[u];
+                    float dx = __fsub_rn(qj[u].x, qi.x), dy = __fsub_rn(qj[u].y, qi.y), dz = __fsub_rn(qj[u].z, qi.z);
+                    if ((e & ~MDG_IDX_MASK) != ZERO_CODE) {
+                        uint32_t code = e >> MDG_IDX_BITS;
+                        dx = __fadd_rn(dx, mdg_code_shift(code & 3u, bx.L[0]));
+                        dy = __fadd_rn(dy, mdg_code_shift((code >> 2) & 3u, bx.L[1]));
+                        dz = __fadd_rn(dz, mdg_code_shift((code >> 4) & 3u, bx.L[2]));
+                    }
+                    float d2 = mdg_d2_exact(dx, dy, dz);       // reference arithmetic: membership must be bit-exact
+                    if ((d2 < rc2) && (d2 != 0.0f)) {
+                        float e_p, g, dp[MDG_MAX_POT_PARAMS];
+                        pair_eval<KIND, false>(P, d2, e_p, g, dp);
+                        fx -= g * dx;
+                        fy -= g * dy;
+                        fz -= g * dz;
+                        en += e_p;
+                    }
+                }
+            }
+            fx *= P.sg; fy *= P.sg; fz *= P.sg;
+            en *= 0.5f * P.se;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            en += __shfl_xor_sync(0xffffffffu, en, o);
+        }
+        if (r < na && lane_in_group == 0) fs[a0 + r] = make_float4(fx, fy, fz, en);
+    }
+}
+
+static int launch_force_cells(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, int c0, int c1, cudaStream_t st) {
+    if (c1 <= c0) return MDG_OK;
+    const uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
+#define LC(K)                                                                                                          \
+    k_force_cells<K><<<c1 - c0, 256, 0, st>>>(c0, c1, qs, c->cell_start.as<int>(), c->stencil.as<int>(),               \
+                                             c->cell_local.as<unsigned char>(), rows_base, c->row_len.as<int>(), c->cap, \
+                                             c->box, c->rc2, P, fs)
+    switch (P.kind) {
+        case MDG_POT_LJ: LC(MDG_POT_LJ); break;
+        case MDG_POT_LJFAM: LC(MDG_POT_LJFAM); break;
+        case MDG_POT_LJ69: LC(MDG_POT_LJ69); break;
+        case MDG_POT_EXV: LC(MDG_POT_EXV); break;
+        case MDG_POT_BUCK: LC(MDG_POT_BUCK); break;
+        case MDG_POT_MORSE: LC(MDG_POT_MORSE); break;
+        default: mdg_set_error("unknown potential kind %d", P.kind); return MDG_E_BADARG;
+    }
+#undef LC
+    c->stat_launches++;
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
 template <bool RETEST, bool WITH_DP>
 static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
     const int GROUP = 8, T = 256;
@@ -156,10 +283,12 @@ int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)(c->own_s1 - c->own_
 
 // explicit sub-range of the own rows (multi-GPU: interior layers first, boundary layers after the halo arrived)
 int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, int s0, int s1,
-                      cudaStream_t st) {
+                      int c0, int c1, cudaStream_t st) {
     if (s1 <= s0) return MDG_OK;
     c->force_s0 = s0;
     c->force_s1 = s1;
+    c->force_c0 = c0;
+    c->force_c1 = c1;
     int r = mdg_i_force_sorted(c, P, d_qs, d_fs, retest, false, nullptr, st);
     c->force_s0 = -1;
     return r;
@@ -168,6 +297,12 @@ int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4
 int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, bool with_dp,
                        double* d_dp_partials, cudaStream_t st) {
     if (c->n == 0) return MDG_OK;
+    if (c->rows_local) {
+        // stream-index rows (k_build_fast): only the cell-staged kernel can read them
+        if (!retest || with_dp) { mdg_set_error("stream-index lists support the re-testing engine path only"); return MDG_E_STATE; }
+        int c0 = c->force_s0 >= 0 ? c->force_c0 : c->own_c0, c1 = c->force_s0 >= 0 ? c->force_c1 : c->own_c1;
+        return launch_force_cells(c, P, d_qs, d_fs, c0, c1, st);
+    }
     if (retest) {
         if (with_dp) return launch_force<true, true>(c, P, d_qs, d_fs, d_dp_partials, st);
         return launch_force<true, false>(c, P, d_qs, d_fs, d_dp_partials, st);
