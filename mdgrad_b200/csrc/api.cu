@@ -1,5 +1,6 @@
 // api.cu - C-ABI entry points of libmdgrad_b200.so (context, neighbor list, pair force, stats).
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -44,6 +45,8 @@ extern "C" int mdg_create(int device, mdg_ctx** out) {
     int s = c->flags.reserve(sizeof(int) * 8);
     if (s != MDG_OK) { cudaFreeHost(c->h_pinned); delete c; return s; }
     cudaMemset(c->flags.p, 0, sizeof(int) * 8);
+    const char* fk = getenv("MDG_FORCE_KERNEL");
+    c->want_stream_rows = fk && strcmp(fk, "cells") == 0;
     *out = c;
     return MDG_OK;
 }
@@ -54,9 +57,15 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
     DevBuf* bufs[] = {&c->cell_of, &c->slot_of, &c->cell_count, &c->cell_start, &c->perm, &c->perm_tmp, &c->stencil,
                       &c->qs_buf[0], &c->qs_buf[1], &c->rows, &c->row_len, &c->flags, &c->up_cnt, &c->up_off,
                       &c->scan_tmp, &c->fs, &c->partials, &c->v4, &c->vh4, &c->q4b, &c->f4b, &c->qref,
-                      &c->mass_sorted, &c->pvbuf, &c->kebuf, &c->dtbuf};
+                      &c->mass_sorted, &c->pvbuf, &c->kebuf, &c->dtbuf, &c->cell_local, &c->g_off, &c->g_cnt, &c->g_edge,
+                      &c->g_other};
     for (DevBuf* b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_layers) cudaFreeHost(c->h_layers);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->ev_ke) cudaEventDestroy(c->ev_ke);
     delete c;
     return MDG_OK;
 }

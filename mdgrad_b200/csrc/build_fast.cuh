@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         for (int a = lane; a < na; a += 32) row_len[a0 + a] = 0;
         return;
     }
-    // stencil prefix (warp scan over 27 counts)
+    // stencil prefix (warp scan over 27 counts) and the stencil slot of the cell itself
+    int kself_slot = 0;
     {
         int cc = lane < 27 ? stencil[c * 27 + lane] : 0;
         int cs = lane < 27 ? cell_start[cc] : 0;
@@ -69,12 +70,13 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         }
         if (lane < 27) { s_pre[w][lane + 1] = x; s_cs[w][lane] = cs; }
         if (lane == 0) s_pre[w][0] = 0;
+        kself_slot = __ffs(__ballot_sync(0xffffffffu, lane < 27 && cc == c)) - 1;
     }
     __syncwarp();
     const int total = s_pre[w][27];
     // Row entries reference the cell's STENCIL STREAM (the 27 stencil cells concatenated in table order) when it
     // fits the force kernel's shared-memory stage; the force kernel stages the same stream and gathers from smem.
-    const bool local_idx = (cell_local != nullptr) && (total <= MDG_STREAM_CAP);
+    const bool local_idx = (cell_local != nullptr) && (total <= MDG_STREAM_CAP);   // only with MDG_FORCE_KERNEL=cells
     if (cell_local && lane == 0) cell_local[c] = local_idx ? 1 : 0;
     const int cx = c % ncx, cy = (c / ncx) % ncy, cz = c / (ncx * ncy);
     const float ox = (float)cx / (float)ncx, oy = (float)cy / (float)ncy, oz = (float)cz / (float)ncz;
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         if (act) {
             if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
             row_len[s] = cnt;
+            mdg_pad_row(row, cnt, cap, local_idx ? (uint32_t)(s_pre[w][kself_slot] + pass + lane) : (uint32_t)s);
         }
         __syncwarp();
     }

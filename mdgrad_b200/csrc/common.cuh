@@ -95,6 +95,16 @@ __device__ __forceinline__ uint32_t mdg_pack_entry(int j, int cx, int cy, int cz
     return (uint32_t)j | ((uint32_t)(cx | (cy << 2) | (cz << 4)) << MDG_IDX_BITS);
 }
 
+// Rows are padded to a multiple of 32 entries with SELF entries (index of the row atom, no image shift):
+// their d2 is exactly 0 and the reference's `d2 != 0` test drops them, so the force kernels can stream whole
+// 32-entry blocks without bounds guards.  (row_len keeps the true length for the export.)
+__device__ __forceinline__ void mdg_pad_row(uint32_t* row, int cnt, int cap, uint32_t self_ref) {
+    int end = (cnt + 31) & ~31;
+    if (end > cap) end = cap;
+    const uint32_t e = self_ref | ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
+    for (int k = cnt; k < end; ++k) row[k] = e;
+}
+
 // image shift (off*L) for a packed code, per axis
 __device__ __forceinline__ float mdg_code_shift(uint32_t code2, float L) {
     // code2 in {0,1,2} -> off in {-1,0,+1}
@@ -251,6 +261,7 @@ struct mdg_ctx {
     // list
     DevBuf rows, row_len;     // uint32 [n*cap], int [n]
     DevBuf cell_local;        // uchar [ncell]: 1 = the cell's rows hold stencil-stream indices (k_force_cells), 0 = global
+    bool   want_stream_rows = false;   // MDG_FORCE_KERNEL=cells: A/B switch for the shared-memory-staged force kernel
     bool   rows_local = false; // the current list was built by k_build_fast in stream-index form
     DevBuf flags;             // int[8]: 0 = capacity overflow, 1 = skin violation
     // export scratch

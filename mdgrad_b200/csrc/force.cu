@@ -32,6 +32,13 @@ PotParams mdg_make_pot(int kind, const float* h_params, int n_params) {
 // array (L1/L2 resident), forces reduced with warp shuffles, one float4 store per atom.
 // RETEST: re-apply the reference membership test d2 < rc2 (exact arithmetic) to a skin list.
 // ---------------------------------------------------------------------------------------------
+// float4 gather with a single mad.wide address computation
+__device__ __forceinline__ float4 mdg_gather4(const float4* __restrict__ base, uint32_t idx) {
+    const float4* p;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(p) : "r"(idx), "l"(base));
+    return __ldg(p);
+}
+
 template <int KIND, bool RETEST, bool WITH_DP, int GROUP>
 __global__ void __launch_bounds__(256) k_force_rows(int s0, int n, const float4* __restrict__ qs,
                                                     const uint32_t* __restrict__ rows, const int* __restrict__ row_len,
@@ -48,15 +55,15 @@ __global__ void __launch_bounds__(256) k_force_rows(int s0, int n, const float4*
         const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;   // no image shift on any axis
         // each lane streams 4 consecutive entries per iteration with one 16-byte load (rows are 128-byte
         // aligned, cap is a multiple of 32) and issues the 4 position gathers back to back
+        // rows are padded to 32-entry blocks with self entries (d2 == 0 -> dropped): no bounds guards in the loop
         for (int k0 = lane_in_group * 4; k0 < m; k0 += GROUP * 4) {
             const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(row + k0));
             const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
             float4 qj[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) qj[u] = (k0 + u < m) ? qs[es[u] & MDG_IDX_MASK] : qi;
+            for (int u = 0; u < 4; ++u) qj[u] = mdg_gather4(qs, es[u] & MDG_IDX_MASK);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (k0 + u >= m) break;
                 const uint32_t e = es[u];
                 // x_j - x_i: adding a zero image shift is a bit-wise no-op, so the common case skips it
                 float dx = __fsub_rn(qj[u].x, qi.x), dy = __fsub_rn(qj[u].y, qi.y), dz = __fsub_rn(qj[u].z, qi.z);

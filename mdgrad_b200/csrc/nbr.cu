@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(AP_TILE) k_build_allpairs(int n, const float4*
     if (s < n) {
         if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
         row_len[s] = cnt;
+        mdg_pad_row(row, cnt, cap, (uint32_t)s);
     }
 }
 
@@ -634,8 +635,9 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
                 if (ncl > 0)
                     k_build_fast<<<(ncl + FB_WARPS - 1) / FB_WARPS, FB_WARPS * 32, 0, st>>>(
                         c->own_c0, c->own_c1, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box, g.nc[0], g.nc[1], g.nc[2],
-                        c->rlist2, c->cap, F, rows_base, c->row_len.as<int>(), c->flags.as<int>(), c->cell_local.as<unsigned char>());
-                c->rows_local = true;
+                        c->rlist2, c->cap, F, rows_base, c->row_len.as<int>(), c->flags.as<int>(),
+                        c->want_stream_rows ? c->cell_local.as<unsigned char>() : nullptr);
+                c->rows_local = c->want_stream_rows;
             } else {
                 int nl = c->own_s1 - c->own_s0;
                 if (nl > 0)

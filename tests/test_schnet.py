@@ -119,7 +119,8 @@ def test_schnet_md_through_generic_route():
     model = SchNet(params)
     model.load_state_dict(sd)
     gnn = GNNPotentials(system, model.cuda(), cutoff=params["cutoff"])
-    prior = PairPotentials(system, ExcludedVolume(2.6, 0.015, 12).cuda(), cutoff=params["cutoff"])
+    oxy = [int(i) for i in np.nonzero(g["numbers"] == 8)[0]]            # O-O prior only (as the reference's water runs)
+    prior = PairPotentials(system, ExcludedVolume(2.6, 0.015, 12).cuda(), cutoff=params["cutoff"], index_tuple=(oxy, oxy))
     integ = NoseHooverChain(Stack({"gnn": gnn, "prior": prior}), system, T=298.0 * units.kB, num_chains=5, Q=50.0, adjoint=True)
     sim = Simulations(system, integ, wrap=True, method="NH_verlet")
     v, q, pv = sim.simulate(steps=6, frequency=6, dt=0.5 * units.fs)
