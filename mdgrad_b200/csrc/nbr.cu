@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(128) k_build_cells(int s0, int n, const float4
     }
     if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
     row_len[s] = cnt;
+    mdg_pad_row(row, cnt, cap, (uint32_t)s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -344,115 +345,6 @@ __global__ void __launch_bounds__(128) k_build_cells(int s0, int n, const float4
 // ones the reference's single +-1 correction loses (SURVEY 7 "unwrapped positions") and are dropped.
 // ---------------------------------------------------------------------------------------------
 #include "build_fast.cuh"
-#if 0   // first attempt (lane = atom, broadcast candidates): the accept branch diverges on ~97% of candidates; kept for the record
-#define FB_STAGE_CAP 768
-
-__device__ __forceinline__ void local_coord(float x, float L, float invL, float origin, float& l, int& I) {
-    float f = x * invL;
-    float nf = floorf(f);
-    float u = (f - nf) - origin;        // fractional position relative to the cell origin
-    float r = rintf(u);                 // nearest periodic image of the cell frame
-    l = (u - r) * L;
-    I = (int)nf + (int)r;
-}
-
-template <bool SMALLBOX>
-__global__ void __launch_bounds__(32) k_build_fast(int ncell, const float4* __restrict__ qs, const int* __restrict__ cell_start,
-                                                   const int* __restrict__ stencil, Box bx, int ncx, int ncy, int ncz,
-                                                   float r2list, int cap, PairFilter F, uint32_t* __restrict__ rows,
-                                                   int* __restrict__ row_len, int* __restrict__ flags) {
-    __shared__ float4 s_loc[FB_STAGE_CAP];      // local x,y,z ; w = sorted index t (int bits)
-    __shared__ uint32_t s_img[FB_STAGE_CAP];    // packed image integers (I + 512) per axis, 10 bits each
-    const int c = blockIdx.x;
-    const int lane = threadIdx.x;
-    const int a0 = cell_start[c], na = cell_start[c + 1] - a0;
-    if (na == 0) return;
-    if (flags[6] | flags[7]) {
-        for (int a = lane; a < na; a += 32) row_len[a0 + a] = 0;
-        return;
-    }
-    const int cx = c % ncx, cy = (c / ncx) % ncy, cz = c / (ncx * ncy);
-    const float ox = (float)cx / (float)ncx, oy = (float)cy / (float)ncy, oz = (float)cz / (float)ncz;
-    const bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
-    for (int pass = 0; pass < na; pass += 32) {
-        const int s = a0 + pass + lane;
-        const bool act = (pass + lane) < na;
-        float lix = 0.f, liy = 0.f, liz = 0.f;
-        int Iix = 0, Iiy = 0, Iiz = 0, idi = 0;
-        if (act) {
-            float4 qi = qs[s];
-            idi = __float_as_int(qi.w);
-            local_coord(qi.x, bx.L[0], bx.invL[0], ox, lix, Iix);
-            local_coord(qi.y, bx.L[1], bx.invL[1], oy, liy, Iiy);
-            local_coord(qi.z, bx.L[2], bx.invL[2], oz, liz, Iiz);
-        }
-        uint32_t* row = rows + (size_t)(act ? s : a0) * cap;
-        int cnt = 0;
-        int k = 0;                       // next stencil cell to stage
-        int koff = 0;                    // atoms of cell k already staged (cells larger than the stage)
-        while (k < 27) {
-            // ---- stage as many stencil cells as fit -------------------------------------------
-            __syncwarp();
-            int ns = 0;
-            while (k < 27) {
-                int cc = stencil[c * 27 + k];
-                int t0 = cell_start[cc] + koff, t1 = cell_start[cc + 1];
-                int m = t1 - t0;
-                int room = FB_STAGE_CAP - ns;
-                int take = m < room ? m : room;
-                for (int a = lane; a < take; a += 32) {
-                    float4 qj = qs[t0 + a];
-                    float lx, ly, lz;
-                    int Ix, Iy, Iz;
-                    local_coord(qj.x, bx.L[0], bx.invL[0], ox, lx, Ix);
-                    local_coord(qj.y, bx.L[1], bx.invL[1], oy, ly, Iy);
-                    local_coord(qj.z, bx.L[2], bx.invL[2], oz, lz, Iz);
-                    s_loc[ns + a] = make_float4(lx, ly, lz, __int_as_float(t0 + a));
-                    s_img[ns + a] = (uint32_t)((Ix + 512) & 1023) | ((uint32_t)((Iy + 512) & 1023) << 10) |
-                                    ((uint32_t)((Iz + 512) & 1023) << 20);
-                }
-                ns += take;
-                if (take < m) { koff += take; break; }   // stage full: scan, then continue with this cell
-                koff = 0;
-                ++k;
-            }
-            __syncwarp();
-            // ---- scan the staged candidates (every lane: its own atom vs the broadcast stream) ----
-            if (act) {
-#pragma unroll 4
-                for (int a = 0; a < ns; ++a) {
-                    float4 lj = s_loc[a];
-                    float dx = lj.x - lix, dy = lj.y - liy, dz = lj.z - liz;
-                    int kx = 0, ky = 0, kz = 0;
-                    if (SMALLBOX) {
-                        float fx = rintf(dx * bx.invL[0]), fy = rintf(dy * bx.invL[1]), fz = rintf(dz * bx.invL[2]);
-                        dx -= fx * bx.L[0]; dy -= fy * bx.L[1]; dz -= fz * bx.L[2];
-                        kx = (int)fx; ky = (int)fy; kz = (int)fz;
-                    }
-                    float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    if (d2 < r2list) {
-                        int t = __float_as_int(lj.w);
-                        if (t == s) continue;
-                        uint32_t im = s_img[a];
-                        int mx = (int)(im & 1023u) - 512 - Iix + kx;
-                        int my = (int)((im >> 10) & 1023u) - 512 - Iiy + ky;
-                        int mz = (int)((im >> 20) & 1023u) - 512 - Iiz + kz;
-                        if ((unsigned)(mx + 1) > 2u || (unsigned)(my + 1) > 2u || (unsigned)(mz + 1) > 2u) continue;
-                        if (filt && !pair_allowed(F, idi, __float_as_int(qs[t].w))) continue;
-                        if (cnt < cap) row[cnt] = (uint32_t)t | ((uint32_t)((1 - mx) | ((1 - my) << 2) | ((1 - mz) << 4)) << MDG_IDX_BITS);
-                        ++cnt;
-                    }
-                }
-            }
-        }
-        if (act) {
-            if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
-            row_len[s] = cnt;
-        }
-    }
-}
-
-#endif
 
 // written per sorted atom: its cell id (needed by k_build_cells)
 __global__ void k_cell_sorted(int ncell, const int* __restrict__ cell_start, int* __restrict__ cell_sorted) {
