@@ -243,6 +243,9 @@ struct mdg_ctx {
     int    force_s0 = -1, force_s1 = 0;   // >= 0: explicit row sub-range for the next force launch
     int    rows_s0 = 0;              // first row held in `rows` (rows are allocated for the own range only)
     bool   slab = false;             // true: own_* are set by the distributed engine after the sort
+    bool   slab_local = false;       // rebuild touches own +- 2 layers only (engine refreshed them by a 2-layer exchange)
+    bool   layers_fresh = false;     // h_layers already holds the offsets of the sort in progress
+    DevBuf lay_tot;                  // per-layer atom totals / offsets (distributed local rebuild)
     int    slab_zlo = 0, slab_zhi = 0;
     // distributed state (dist.cu): one NCCL communicator per context
     int    dist_rank = 0, dist_world = 1;

@@ -290,24 +290,26 @@ static int halo_exchange(mdg_ctx* c, float4* q, cudaStream_t st) {
     return MDG_OK;
 }
 
-// Rebuild exchange (old slab plan): positions of ALL atoms are all-gathered (every rank repeats the global
-// binning so that the sorted index space stays identical everywhere); velocities / half-kicks are only
-// needed for atoms a rank may own next, i.e. its old slab plus the adjacent layer on each side (an atom
-// moves less than skin/2 << one cell layer between rebuilds) -> the same two-range halo pattern.
+// Rebuild exchange (old slab plan): each rank sends its bottom / top TWO layers of (q, v, vh) to the rank below /
+// above and receives theirs in place (same global index ranges on both sides).  Afterwards a rank holds valid state
+// on the old layers [zlo-2, zhi+2) - a superset of everything that can be in its new slab + ghost layers.
 static int state_exchange(mdg_ctx* c, float4* q, float4* v, float4* vh, cudaStream_t st) {
     NcclApi* N = mdg_nccl();
     const int ncz = c->n_layers - 1, R = c->dist_world;
+    const int zlo = c->slab_zlo, zhi = c->slab_zhi;
+    if (zhi - zlo < 2) { mdg_set_error("distributed run: every rank needs >= 2 cell layers (ncz=%d, world=%d)", ncz, R); return MDG_E_BADARG; }
+    const int below = owner_of_layer((zlo - 1 + ncz) % ncz, ncz, R), above = owner_of_layer(zhi % ncz, ncz, R);
+    const int* L = c->h_layers;
+    const int rl0 = (zlo - 2 + ncz) % ncz, ru0 = zhi % ncz;      // first of the two layers received from below / above
+    float4* arr[3] = {q, v, vh};
     MDG_TRY(mdg_nccl_check(N->GroupStart(), "GroupStart"));
-    for (int r = 0; r < R; ++r) {
-        int plan[4];
-        mdg_slab_plan(ncz, R, r, plan);
-        int a0 = c->h_layers[plan[0]], a1 = c->h_layers[plan[1]];
-        size_t cnt = (size_t)(a1 - a0) * 4;
-        if (cnt == 0) continue;
-        MDG_TRY(mdg_nccl_check(N->Broadcast(q + a0, q + a0, cnt, MDG_NCCL_FLOAT32, r, c->dist_comm, st), "Broadcast"));
+    for (int a = 0; a < 3; ++a) {
+        float4* x = arr[a];
+        MDG_TRY(mdg_nccl_check(N->Send(x + L[zlo], (size_t)(L[zlo + 2] - L[zlo]) * 4, MDG_NCCL_FLOAT32, below, c->dist_comm, st), "Send"));
+        MDG_TRY(mdg_nccl_check(N->Send(x + L[zhi - 2], (size_t)(L[zhi] - L[zhi - 2]) * 4, MDG_NCCL_FLOAT32, above, c->dist_comm, st), "Send"));
+        MDG_TRY(mdg_nccl_check(N->Recv(x + L[ru0], (size_t)(L[ru0 + 2] - L[ru0]) * 4, MDG_NCCL_FLOAT32, above, c->dist_comm, st), "Recv"));
+        MDG_TRY(mdg_nccl_check(N->Recv(x + L[rl0], (size_t)(L[rl0 + 2] - L[rl0]) * 4, MDG_NCCL_FLOAT32, below, c->dist_comm, st), "Recv"));
     }
-    MDG_TRY(halo_exchange_nogroup(c, v, st));
-    MDG_TRY(halo_exchange_nogroup(c, vh, st));
     MDG_TRY(mdg_nccl_check(N->GroupEnd(), "GroupEnd"));
     return MDG_OK;
 }
@@ -411,7 +413,9 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         int ib_half = ib;
         if (do_rebuild) {
             if (dist) MDG_TRY(state_exchange(c, q, vbuf[vsel], hbuf[vsel], st));
+            c->slab_local = dist;
             MDG_TRY(mdg_i_build_list(c, nullptr, q, n, p->cell, rlist, p->cutoff, st));
+            c->slab_local = false;
             q = c->qs_ptr;
             A.s0 = c->own_s0; A.s1 = c->own_s1;
             nown = A.s1 - A.s0;

@@ -2,6 +2,7 @@
 // export in the reference's layout/order.  Replaces generate_nbr_list, reference
 // torchmd/topology.py:30-73 (K1 in SURVEY.md 2c).
 #include "common.cuh"
+#include "dist.cuh"
 
 extern "C" int mdg_slab_plan(int ncz, int world, int rank, int* out4);
 
@@ -135,9 +136,9 @@ __device__ __forceinline__ int cell_coord(float x, float L, float invL, int nc) 
     return min(max(c, 0), nc - 1);
 }
 
-__global__ void k_bin(const float4* __restrict__ q, int n, Grid g, int* __restrict__ cell_of,
+__global__ void k_bin(const float4* __restrict__ q, int i0, int n, Grid g, int* __restrict__ cell_of,
                       int* __restrict__ slot_of, int* __restrict__ cell_count, int* __restrict__ flags) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;          // atoms [i0, n)
     if (i >= n) return;
     float4 p = q[i];
     if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) flags[6] = 1;   // diverged dynamics: reported, never binned blindly
@@ -149,11 +150,62 @@ __global__ void k_bin(const float4* __restrict__ q, int n, Grid g, int* __restri
     slot_of[i] = atomicAdd(&cell_count[c], 1);
 }
 
-__global__ void k_scatter(int n, const int* __restrict__ cell_of, const int* __restrict__ slot_of,
-                          const int* __restrict__ cell_start, int* __restrict__ perm_tmp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// zwin0/zwin_n: only atoms whose new cell lies in the z-layer window [zwin0, zwin0 + zwin_n) (periodic) are placed
+// (distributed rebuild: a rank places the atoms of its slab + ghost layers only); zwin_n <= 0 = everything
+__global__ void k_scatter(int i0, int n, const int* __restrict__ cell_of, const int* __restrict__ slot_of,
+                          const int* __restrict__ cell_start, int* __restrict__ perm_tmp, int nxy, int ncz, int zwin0, int zwin_n) {
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    perm_tmp[cell_start[cell_of[i]] + slot_of[i]] = i;
+    int c = cell_of[i];
+    if (zwin_n > 0) {
+        int lz = (c / nxy - zwin0 + ncz) % ncz;
+        if (lz >= zwin_n) return;
+    }
+    perm_tmp[cell_start[c] + slot_of[i]] = i;
+}
+
+// ---- distributed local rebuild helpers -----------------------------------------------------------
+// totals of the layers this rank owns (complete after binning own +- 2 layers); zero elsewhere -> all-reduce
+__global__ void k_layer_totals(const int* __restrict__ cell_count, int nxy, int ncz, int zlo, int zhi, int* __restrict__ tot) {
+    __shared__ int sm[32];
+    int z = blockIdx.x;
+    int v = 0;
+    if (z >= zlo && z < zhi)
+        for (int k = threadIdx.x; k < nxy; k += blockDim.x) v += cell_count[z * nxy + k];
+    int dummy;
+    int ex = block_exclusive_scan(v, sm, dummy);
+    (void)ex;
+    if (threadIdx.x == 0) tot[z] = dummy;
+}
+
+__global__ void k_layer_offsets(const int* __restrict__ tot, int ncz, int* __restrict__ off) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int acc = 0;
+        for (int z = 0; z < ncz; ++z) { off[z] = acc; acc += tot[z]; }
+        off[ncz] = acc;
+    }
+}
+
+// cell_start of the cells of layer (zwin0 + blockIdx.x) % ncz = layer offset + exclusive scan of the cell counts
+__global__ void __launch_bounds__(SCAN_THREADS) k_cellstart_layer(const int* __restrict__ cell_count, const int* __restrict__ lay_off,
+                                                                 int nxy, int ncz, int zwin0, int* __restrict__ cell_start) {
+    __shared__ int sm[32];
+    __shared__ int carry_s;
+    int z = (zwin0 + blockIdx.x) % ncz;
+    if (threadIdx.x == 0) carry_s = lay_off[z];
+    __syncthreads();
+    for (int k0 = 0; k0 < nxy; k0 += blockDim.x) {
+        int k = k0 + threadIdx.x;
+        int v = k < nxy ? cell_count[z * nxy + k] : 0;
+        int tot;
+        int ex = block_exclusive_scan(v, sm, tot);
+        int carry = carry_s;
+        if (k < nxy) cell_start[z * nxy + k] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cell_start[(z + 1) * nxy] = lay_off[z + 1];    // end sentinel of the layer (same value from any block)
 }
 
 // one thread per cell: order the cell's atoms by ORIGINAL id (deterministic, history-free),
@@ -473,9 +525,64 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         int ncb = (ncell + T - 1) / T;
         if (grid_changed) { k_stencil<<<ncb, T, 0, st>>>(g, c->stencil.as<int>()); c->stat_launches++; }
         MDG_CUDA(cudaMemsetAsync(c->cell_count.p, 0, sizeof(int) * (size_t)(ncell + 1), st));
-        k_bin<<<nb, T, 0, st>>>(qin, n, g, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_count.as<int>(), c->flags.as<int>());
-        MDG_TRY(mdg_i_scan_exclusive(c, c->cell_count.as<int>(), c->cell_start.as<int>(), ncell + 1, nullptr, st));
-        k_scatter<<<nb, T, 0, st>>>(n, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_start.as<int>(), c->perm_tmp.as<int>());
+        const bool local_rebuild = c->slab && c->slab_local && qin == d_q4_in;
+        if (!local_rebuild) {
+            k_bin<<<nb, T, 0, st>>>(qin, 0, n, g, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_count.as<int>(), c->flags.as<int>());
+            MDG_TRY(mdg_i_scan_exclusive(c, c->cell_count.as<int>(), c->cell_start.as<int>(), ncell + 1, nullptr, st));
+            k_scatter<<<nb, T, 0, st>>>(0, n, c->cell_of.as<int>(), c->slot_of.as<int>(), c->cell_start.as<int>(), c->perm_tmp.as<int>(),
+                                        g.nc[0] * g.nc[1], g.nc[2], 0, 0);
+        } else {
+            // ---- distributed LOCAL rebuild: nothing here scales with the total atom count --------------------------
+            // The engine has just refreshed q (and v, vh) on the old layers [zlo-2, zhi+2) through a two-layer halo
+            // exchange.  An atom moves far less than a layer between rebuilds, so every atom of the new layers
+            // [zlo-1, zhi+1) is among them: bin those, all-reduce the per-layer totals (ncz ints) for the global layer
+            // offsets, scan the counts of the window's cells, place the window's atoms.
+            NcclApi* N = mdg_nccl();
+            const int nxy = g.nc[0] * g.nc[1], ncz = g.nc[2];
+            int plan[4];
+            MDG_TRY(mdg_slab_plan(ncz, c->dist_world, c->dist_rank, plan));
+            const int zlo = plan[0], zhi = plan[1];
+            if (zhi - zlo < 2 || (zhi - zlo) + 4 > ncz) {
+                mdg_set_error("distributed run: every rank needs >= 2 cell layers and the box >= own + 4 layers (ncz=%d, world=%d)", ncz, c->dist_world);
+                return MDG_E_BADARG;
+            }
+            if (ncz + 1 != c->n_layers) { mdg_set_error("cell grid changed during a distributed run"); return MDG_E_STATE; }
+            const int* Lold = c->h_layers;                        // offsets of the PREVIOUS sort
+            int pieces[3][2];
+            int np = 0;
+            {   // old layers zlo-2 .. zhi+1 (periodic) as contiguous index ranges
+                int za = zlo - 2, zb = zhi + 2;
+                if (za < 0) { pieces[np][0] = Lold[za + ncz]; pieces[np][1] = Lold[ncz]; ++np; za = 0; }
+                int zb_in = zb > ncz ? ncz : zb;
+                pieces[np][0] = Lold[za]; pieces[np][1] = Lold[zb_in]; ++np;
+                if (zb > ncz) { pieces[np][0] = Lold[0]; pieces[np][1] = Lold[zb - ncz]; ++np; }
+            }
+            for (int k = 0; k < np; ++k) {
+                int cnt = pieces[k][1] - pieces[k][0];
+                if (cnt > 0)
+                    k_bin<<<(cnt + T - 1) / T, T, 0, st>>>(qin, pieces[k][0], pieces[k][1], g, c->cell_of.as<int>(), c->slot_of.as<int>(),
+                                                           c->cell_count.as<int>(), c->flags.as<int>());
+            }
+            MDG_TRY(c->lay_tot.reserve(sizeof(int) * (size_t)(2 * ncz + 4)));
+            int* lay_tot = c->lay_tot.as<int>();
+            int* lay_off = lay_tot + ncz + 1;
+            k_layer_totals<<<ncz, SCAN_THREADS, 0, st>>>(c->cell_count.as<int>(), nxy, ncz, zlo, zhi, lay_tot);
+            MDG_TRY(mdg_nccl_check(N->AllReduce(lay_tot, lay_tot, (size_t)ncz, MDG_NCCL_INT32, MDG_NCCL_SUM, c->dist_comm, st), "AllReduce"));
+            k_layer_offsets<<<1, 32, 0, st>>>(lay_tot, ncz, lay_off);
+            const int zwin0 = (zlo - 1 + ncz) % ncz, zwin_n = zhi - zlo + 2;
+            k_cellstart_layer<<<zwin_n, SCAN_THREADS, 0, st>>>(c->cell_count.as<int>(), lay_off, nxy, ncz, zwin0, c->cell_start.as<int>());
+            for (int k = 0; k < np; ++k) {
+                int cnt = pieces[k][1] - pieces[k][0];
+                if (cnt > 0)
+                    k_scatter<<<(cnt + T - 1) / T, T, 0, st>>>(pieces[k][0], pieces[k][1], c->cell_of.as<int>(), c->slot_of.as<int>(),
+                                                               c->cell_start.as<int>(), c->perm_tmp.as<int>(), nxy, ncz, zwin0, zwin_n);
+            }
+            // new layer offsets -> host (SYNC): sizes the halo messages until the next rebuild
+            MDG_CUDA(cudaMemcpyAsync(c->h_layers, lay_off, sizeof(int) * (size_t)(ncz + 1), cudaMemcpyDeviceToHost, st));
+            MDG_CUDA(cudaStreamSynchronize(st));
+            c->layers_fresh = true;
+            c->stat_launches += 6;
+        }
         if (!c->slab) {
             k_cellsort_warp<<<(ncell + 7) / 8, 256, 0, st>>>(0, ncell, c->cell_start.as<int>(), c->cell_count.as<int>(), c->perm_tmp.as<int>(),
                                                              qin, qs, c->perm.as<int>(), c->cell_of.as<int>(), c->flags.as<int>());
@@ -509,9 +616,12 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
                 MDG_CUDA(cudaMallocHost((void**)&c->h_layers, sizeof(int) * (size_t)(ncz + 1)));
             }
             c->n_layers = ncz + 1;
-            MDG_CUDA(cudaMemcpy2DAsync(c->h_layers, sizeof(int), c->cell_start.as<int>(), sizeof(int) * (size_t)nxy, sizeof(int),
-                                       (size_t)(ncz + 1), cudaMemcpyDeviceToHost, st));
-            MDG_CUDA(cudaStreamSynchronize(st));
+            if (!c->layers_fresh) {
+                MDG_CUDA(cudaMemcpy2DAsync(c->h_layers, sizeof(int), c->cell_start.as<int>(), sizeof(int) * (size_t)nxy, sizeof(int),
+                                           (size_t)(ncz + 1), cudaMemcpyDeviceToHost, st));
+                MDG_CUDA(cudaStreamSynchronize(st));
+            }
+            c->layers_fresh = false;
             c->own_c0 = c->slab_zlo * nxy; c->own_c1 = c->slab_zhi * nxy;
             c->own_s0 = c->h_layers[c->slab_zlo]; c->own_s1 = c->h_layers[c->slab_zhi];
             c->rows_s0 = c->own_s0;
