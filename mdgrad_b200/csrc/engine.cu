@@ -329,7 +329,10 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     NcclApi* N = mdg_nccl();
     if (dist && !retest) { mdg_set_error("multi-GPU runs need a Verlet skin (skin > 0)"); return MDG_E_BADARG; }
     if (dist && !c->comm_stream) {
-        MDG_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        // highest priority: the NCCL kernels must get SM slots while the (long) interior force kernel is running
+        int prio_lo = 0, prio_hi = 0;
+        MDG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        MDG_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi));
         MDG_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
         MDG_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
         MDG_CUDA(cudaEventCreateWithFlags(&c->ev_ke, cudaEventDisableTiming));
