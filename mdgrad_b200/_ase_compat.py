@@ -199,7 +199,8 @@ def wrap_positions(positions, cell, pbc=True, center=(0.5, 0.5, 0.5), eps=1e-7):
     cell = np.asarray(cell, dtype=float)
     if cell.shape == (3,):
         cell = np.diag(cell)
-    # (ASE solves cell^T f^T = pos^T; the result is made contiguous here so the column updates below stream)
+    # (ASE solves cell^T f^T = pos^T; kept verbatim - a plain division differs in the last bits - and made contiguous
+    #  so that the column updates below stream)
     fractional = np.ascontiguousarray(np.linalg.solve(cell.T, np.asarray(positions, dtype=float).T).T) - shift
     for i, periodic in enumerate(pbc):
         if periodic:

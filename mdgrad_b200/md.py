@@ -121,6 +121,15 @@ class _EOM(torch.nn.Module):
             self.model._reset_topology(q)
         self.update_count += 1
 
+    def force(self, q):
+        """-dU/dq at q with the reference's side effects (requires_grad on q, topology update, md.py:216-228)."""
+        with torch.set_grad_enabled(True):
+            if self.adjoint:
+                q.requires_grad = True
+            self.update_topology(q)
+            u = self.model(q)
+            return -compute_grad(inputs=q, output=u.sum(-1), create_graph=_needs_graph(self.model))
+
     # -- fused engine -------------------------------------------------------------------------
     def _native_spec(self, method):
         from .interface import PairPotentials
@@ -199,14 +208,10 @@ class NVE(_EOM):
 
     def forward(self, t, state):
         """dv/dt = f (not divided by the mass), dq/dt = v   (reference md.py:131-148)"""
-        with torch.set_grad_enabled(True):
-            v, q = state[0], state[1]
-            if self.adjoint:
-                q.requires_grad = True
-            self.update_topology(q)
-            u = self.model(q)
-            f = -compute_grad(inputs=q, output=u.sum(-1), create_graph=_needs_graph(self.model))
-        return (f, v)
+        return self.derivative(t, state, self.force(state[1]))
+
+    def derivative(self, t, state, f):
+        return (f, state[0])
 
     def get_inital_states(self, wrap=True):
         states = [self.system.get_velocities(), self.system.get_positions(wrap=wrap)]
@@ -234,16 +239,15 @@ class NoseHooverChain(_EOM):
 
     def forward(self, t, state):
         """reference md.py:210-240"""
+        return self.derivative(t, state, self.force(state[1]))
+
+    def derivative(self, t, state, f):
+        """thermostat algebra of md.py:221-240 for a given force"""
         with torch.set_grad_enabled(True):
             v, q, p_v = state[0], state[1], state[2]
-            if self.adjoint:
-                q.requires_grad = True
             m = self.mass[:, None]
             p = v * m
             sys_ke = 0.5 * (p.pow(2) / m).sum()
-            self.update_topology(q)
-            u = self.model(q)
-            f = -compute_grad(inputs=q, output=u.sum(-1), create_graph=_needs_graph(self.model))
             coupled = (p_v[0] * p.reshape(-1) / self.Q[0]).reshape(-1, 3)
             dpdt = f - coupled
             d0 = 2 * (sys_ke - self.T * self.N_dof * 0.5) - p_v[0] * p_v[1] / self.Q[1]

@@ -92,8 +92,8 @@ class _CfconvAgg(torch.autograd.Function):
 class NativeGraph:
     """node -> incident-edge CSR of one (E,2) neighbor list, owned by a native context."""
 
-    def __init__(self, nbr, n):
-        self.ctx = _lib.Context(nbr.device)
+    def __init__(self, nbr, n, ctx=None):
+        self.ctx = ctx if ctx is not None else _lib.Context(nbr.device)    # contexts are reused across topology updates
         self.ctx.graph_build(nbr, n)
         self.nbr, self.n = nbr, n
 
@@ -231,8 +231,9 @@ class SchNet(nn.Module):
         a = batch["nbr_list"]
         g = batch.get("_native_graph")
         if g is None or g.nbr is not a:
-            g = NativeGraph(a, n)
+            g = NativeGraph(a, n, ctx=batch.get("_native_ctx"))
             batch["_native_graph"] = g
+            batch["_native_ctx"] = g.ctx
         return g
 
     def convolve(self, batch, xyz=None):

@@ -140,3 +140,44 @@ def test_potential_modules_match_reference_formulas():
     assert m(r).shape == (50, 1)
     from torchmd.interface import PairPotentials
     assert P.PairPotentials is PairPotentials          # exported from both modules (SURVEY naming trap)
+
+
+def test_force_reuse_loop_is_bitwise_the_two_evaluation_solver():
+    """odeint_reuse_force (one force evaluation per step) == odeint (two, like the reference), bit for bit,
+    for NoseHooverChain and NVE over a CPU-capable toy interaction; bookkeeping counts two per step."""
+    from torchmd.md import NVE, NoseHooverChain
+    from torchmd.sovlers import odeint, odeint_reuse_force
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.k = torch.nn.Parameter(torch.tensor([1.3]))
+            self.resets = 0
+
+        def _reset_topology(self, q):
+            self.resets += 1
+
+        def forward(self, q):
+            d = q[:, None, :] - q[None, :, :]
+            r2 = (d ** 2).sum(-1) + torch.eye(q.shape[0])
+            return (self.k * torch.exp(-r2)).sum() + 0.1 * (q ** 2).sum()
+
+    rng = np.random.default_rng(0)
+    s = System(Atoms(numbers=[1] * 12, positions=rng.uniform(0, 3, (12, 3)), cell=[3.0] * 3, pbc=True), device="cpu")
+    s.set_velocities(rng.normal(0, 1, (12, 3)))
+    t = torch.Tensor([0.01 * i for i in range(9)])
+    for cls, method, kw in ((NoseHooverChain, "NH_verlet", dict(T=1.0, num_chains=3, Q=5.0)), (NVE, "verlet", {})):
+        a_model, b_model = Toy(), Toy()
+        a, b = cls(a_model, s, **kw), cls(b_model, s, **kw)
+        ya = tuple(x.clone() for x in a.get_inital_states(True))
+        yb = tuple(x.clone() for x in b.get_inital_states(True))
+        with torch.no_grad():
+            ra = odeint(a, ya, t, method=method)
+            rb = odeint_reuse_force(b, yb, t, method)
+        assert rb is not None and all(torch.equal(x, y) for x, y in zip(ra, rb))
+        assert a.update_count == b.update_count == 16
+        assert a_model.resets == 16 and b_model.resets == 9          # half the neighbor-list rebuilds
+    c = NoseHooverChain(Toy(), s, T=1.0, num_chains=3, Q=5.0, topology_update_freq=3)
+    assert odeint_reuse_force(c, tuple(c.get_inital_states(True)), t, "NH_verlet") is None
