@@ -9,6 +9,7 @@
 // This translation unit is compiled with -fmad=false: the integrator algebra is memory-bound,
 // and keeping every product/sum individually rounded reproduces the reference's separate
 // elementwise ATen ops (only the global kinetic-energy reduction order differs).
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 #include "dist.cuh"
@@ -216,6 +217,108 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_b(IntArgs A, float dt, int
     }
 }
 
+// Fused B(n) + A(n+1): the second half-kick of step n and the first half-kick + drift of step n+1 read the same
+// force, velocities and positions, so one pass does both (saves one read of v, f, q and one launch per step).
+// Bath scalars of step n+1 come from the same redundant per-block computation as in k_step_b.
+__global__ void __launch_bounds__(INT_THREADS) k_step_ba(IntArgs A, float dt, float dt_next, int pv_sel, Scalars* __restrict__ sc,
+                                                         float4* __restrict__ v4, float4* __restrict__ vh4, float4* __restrict__ q4,
+                                                         const float4* __restrict__ f4, const double* __restrict__ ke_part,
+                                                         const double* __restrict__ ke_half_part, int n_part,
+                                                         double* __restrict__ ke_next_part, double* __restrict__ ke_half_next_part,
+                                                         float* __restrict__ traj_v, float* __restrict__ traj_q,
+                                                         float* __restrict__ traj_pv_row, const float4* __restrict__ qref,
+                                                         int check_skin_next, int* __restrict__ flags) {
+    __shared__ double sm[INT_THREADS / 32];
+    __shared__ float bc[2];
+    __shared__ float s_pvh0, s_pvn0;
+    float pvh0 = 0.f, pvn0 = 0.f, Q0 = 1.f;
+    if (A.integrator == MDG_INT_NHC) {
+        float ke0 = sum_partials(ke_part, n_part, sm, &bc[0]);
+        float ke1 = sum_partials(ke_half_part, n_part, sm, &bc[1]);
+        if (threadIdx.x == 0) {
+            float pv[MDG_MAX_CHAINS], ph[MDG_MAX_CHAINS], pvh[MDG_MAX_CHAINS], d0[MDG_MAX_CHAINS], d1[MDG_MAX_CHAINS];
+            for (int k = 0; k < A.M; ++k) pv[k] = sc->pv[pv_sel][k];
+            nhc_dpv(A, ke0, pv, d0);
+            for (int k = 0; k < A.M; ++k) { ph[k] = 0.5f * d0[k] * dt; pvh[k] = pv[k] + ph[k]; }
+            nhc_dpv(A, ke1, pvh, d1);
+            s_pvh0 = pvh[0];
+            s_pvn0 = pv[0] + (ph[0] + 0.5f * d1[0] * dt);
+            if (blockIdx.x == 0) {
+                for (int k = 0; k < A.M; ++k) {
+                    float pn = pv[k] + (ph[k] + 0.5f * d1[k] * dt);
+                    sc->pv[pv_sel ^ 1][k] = pn;
+                    if (traj_pv_row) traj_pv_row[k] = pn;
+                }
+            }
+        }
+        __syncthreads();
+        pvh0 = s_pvh0;
+        pvn0 = s_pvn0;
+        Q0 = A.Q[0];
+    }
+    double acc_v = 0, acc_h = 0;
+    bool viol = false;
+    for (int s = A.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < A.s1; s += gridDim.x * blockDim.x) {
+        float4 v = v4[s];
+        float4 h = vh4[s];
+        float4 f = f4[s];
+        float4 q = q4[s];
+        float m = v.w;
+        float ax, ay, az;
+        // ---- B(n) ----
+        if (A.integrator == MDG_INT_NHC) {
+            float px = (v.x + h.x) * m, py = (v.y + h.y) * m, pz = (v.z + h.z) * m;
+            ax = (f.x - pvh0 * px / Q0) / m;
+            ay = (f.y - pvh0 * py / Q0) / m;
+            az = (f.z - pvh0 * pz / Q0) / m;
+        } else {
+            ax = f.x; ay = f.y; az = f.z;
+        }
+        v.x = v.x + (h.x + 0.5f * ax * dt);
+        v.y = v.y + (h.y + 0.5f * ay * dt);
+        v.z = v.z + (h.z + 0.5f * az * dt);
+        v4[s] = v;
+        if (traj_v) {
+            int id = __float_as_int(q.w);
+            traj_v[3 * (size_t)id] = v.x; traj_v[3 * (size_t)id + 1] = v.y; traj_v[3 * (size_t)id + 2] = v.z;
+            traj_q[3 * (size_t)id] = q.x; traj_q[3 * (size_t)id + 1] = q.y; traj_q[3 * (size_t)id + 2] = q.z;
+        }
+        // ---- A(n+1) ----
+        float px = v.x * m, py = v.y * m, pz = v.z * m;
+        if (A.integrator == MDG_INT_NHC) {
+            acc_v += (double)(px * px / m) + (double)(py * py / m) + (double)(pz * pz / m);
+            ax = (f.x - pvn0 * px / Q0) / m;
+            ay = (f.y - pvn0 * py / Q0) / m;
+            az = (f.z - pvn0 * pz / Q0) / m;
+        } else {
+            ax = f.x; ay = f.y; az = f.z;
+        }
+        float hx = 0.5f * ax * dt_next, hy = 0.5f * ay * dt_next, hz = 0.5f * az * dt_next;
+        float ux = v.x + hx, uy = v.y + hy, uz = v.z + hz;
+        q.x = q.x + ux * dt_next;
+        q.y = q.y + uy * dt_next;
+        q.z = q.z + uz * dt_next;
+        vh4[s] = make_float4(hx, hy, hz, 0.f);
+        q4[s] = q;
+        if (A.integrator == MDG_INT_NHC) {
+            float qx = ux * m, qy = uy * m, qz = uz * m;
+            acc_h += (double)(qx * qx / m) + (double)(qy * qy / m) + (double)(qz * qz / m);
+        }
+        if (check_skin_next) {
+            float4 r = qref[s];
+            float dx = q.x - r.x, dy = q.y - r.y, dz = q.z - r.z;
+            viol |= (dx * dx + dy * dy + dz * dz) > A.half_skin2;
+        }
+    }
+    if (viol) flags[5] = 1;
+    if (A.integrator == MDG_INT_NHC) {
+        double t = block_sum_double(acc_v, sm);
+        if (threadIdx.x == 0) ke_next_part[blockIdx.x] = 0.5 * t;
+        double t2 = block_sum_double(acc_h, sm);
+        if (threadIdx.x == 0) ke_half_next_part[blockIdx.x] = 0.5 * t2;
+    }
+}
+
 // state (re)ordering ---------------------------------------------------------------------------
 __global__ void k_init_v(int s0, int n, const int* __restrict__ perm, const float* __restrict__ v0,
                          const float* __restrict__ mass, float4* __restrict__ v4) {
@@ -356,16 +459,19 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     MDG_TRY(c->qref.reserve(sizeof(float4) * (size_t)n));
     MDG_TRY(c->fs.reserve(sizeof(float4) * (size_t)n));
     MDG_TRY(c->pvbuf.reserve(sizeof(Scalars) + sizeof(float) * (size_t)n_frames * MDG_MAX_CHAINS));
-    MDG_TRY(c->kebuf.reserve(sizeof(double) * (4 * INT_MAX_BLOCKS + 8)));
+    MDG_TRY(c->kebuf.reserve(sizeof(double) * (5 * INT_MAX_BLOCKS + 8)));
     float4* vbuf[2] = {c->v4.as<float4>(), c->v4.as<float4>() + n};
     float4* hbuf[2] = {c->vh4.as<float4>(), c->vh4.as<float4>() + n};
     int vsel = 0;
     Scalars* sc = c->pvbuf.as<Scalars>();
     float* d_traj_pv = (float*)(sc + 1);
-    double* ke_part[3] = {c->kebuf.as<double>(), c->kebuf.as<double>() + INT_MAX_BLOCKS,
-                          c->kebuf.as<double>() + 2 * INT_MAX_BLOCKS};
-    double* e_part = c->kebuf.as<double>() + 3 * INT_MAX_BLOCKS;
-    double* dke = c->kebuf.as<double>() + 4 * INT_MAX_BLOCKS;          // [0]=ke(v), [1]=ke(v+vh), global (multi-GPU)
+    double* kb = c->kebuf.as<double>();
+    double* e_part = kb + 4 * INT_MAX_BLOCKS;
+    double* dke = kb + 5 * INT_MAX_BLOCKS;          // [0]=ke(v), [1]=ke(v+vh), global (multi-GPU)
+    // kinetic-energy partial arrays: [cur_v, cur_half] are read by B(n), [nxt_v, nxt_half] written by B(n) / A(n+1)
+    double* ke_v_cur = kb, *ke_h_cur = kb + INT_MAX_BLOCKS, *ke_v_nxt = kb + 2 * INT_MAX_BLOCKS, *ke_h_nxt = kb + 3 * INT_MAX_BLOCKS;
+    const char* fz = getenv("MDG_FUSED_STEP");
+    const bool fused = !(fz && fz[0] == '0');
 
     // scalars + flags
     Scalars hs;
@@ -392,7 +498,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     int ib = (nown + T - 1) / T;
     ib = ib < 1 ? 1 : (ib > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : ib);
     MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
-    if (nhc) { k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, vbuf[vsel], ke_part[0]); c->stat_launches++; }
+    if (nhc) { k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, vbuf[vsel], ke_v_cur); c->stat_launches++; }
     if (!dist) {   // frame 0 = the initial state, verbatim
         MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
         MDG_CUDA(cudaMemcpyAsync(d_traj_q, d_q0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -403,17 +509,21 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     }
     if (M) MDG_CUDA(cudaMemcpyAsync(d_traj_pv, sc->pv[0], sizeof(float) * M, cudaMemcpyDeviceToDevice, st));
 
-    int pv_sel = 0, ke_cur = 0, ib_cur = ib;    // ib_cur: number of partials in ke_part[ke_cur]
-    for (int g = 0; g + 1 < n_grid; ++g) {
+    // Loop structure.  Unfused: A(g) ; [rebuild | halo] ; force ; B(g).   Fused (default): A(0) once, then per step
+    // [rebuild | halo] ; force ; BA(g) = B(g) + A(g+1) in one pass (plain B for the last step).
+    int pv_sel = 0;
+    int ib_prev = ib;                       // block count of the launch(es) that wrote the *_cur partial arrays
+    const int nsteps = n_grid - 1;
+    bool a_done = false;                    // A(g) already executed by the previous fused kernel
+    for (int g = 0; g < nsteps; ++g) {
         float dt = h_tgrid[g + 1] - h_tgrid[g];          // fp32 subtraction, like t1 - t0 in tinydiffeq.py:67-68
         bool do_rebuild = ((g + 1) % rebuild_every) == 0;
-        int ke_half = (ke_cur + 1) % 3, ke_next = (ke_cur + 2) % 3;
-        // partial arrays must have matching lengths within one step: zero-pad when the block count changes
-        k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
-                                             c->qref.as<float4>(), (retest && !do_rebuild) ? 1 : 0, ke_part[ke_half],
-                                             c->flags.as<int>());
-        c->stat_launches++;
-        int ib_half = ib;
+        if (!a_done) {
+            k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
+                                                 c->qref.as<float4>(), (retest && !do_rebuild) ? 1 : 0, ke_h_cur,
+                                                 c->flags.as<int>());
+            c->stat_launches++;
+        }
         if (do_rebuild) {
             if (dist) MDG_TRY(state_exchange(c, q, vbuf[vsel], hbuf[vsel], st));
             c->slab_local = dist;
@@ -439,10 +549,10 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         //  multi GPU, rebuild    : state_exchange above already refreshed everything -> KE all-reduce, force on all rows.
         //  multi GPU, plain step : side stream = ghost-layer halo, then the 2-double KE all-reduce; main stream =
         //                          forces of the INTERIOR layers (no ghost needed) meanwhile, then the two boundary
-        //                          layers once the ghosts arrived, then k_step_b once the kinetic energies arrived.
-        const double* ke_a = ke_part[ke_cur];
-        const double* ke_b = ke_part[ke_half];
-        int n_part_a = ib_cur, n_part_b = ib_half;
+        //                          layers once the ghosts arrived, then B once the kinetic energies arrived.
+        const double* ke_a = ke_v_cur;
+        const double* ke_b = ke_h_cur;
+        int n_part = ib_prev;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (c->prof_enable) {
             std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
@@ -474,11 +584,11 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                 MDG_CUDA(cudaEventRecord(c->ev_halo, cs));
             }
             if (nhc) {
-                k_ke_pack<<<1, INT_THREADS, 0, cs>>>(ke_part[ke_cur], ib_cur, ke_part[ke_half], ib_half, dke);
+                k_ke_pack<<<1, INT_THREADS, 0, cs>>>(ke_v_cur, ib_prev, ke_h_cur, ib_prev, dke);
                 MDG_TRY(mdg_nccl_check(N->AllReduce(dke, dke, 2, MDG_NCCL_FLOAT64, MDG_NCCL_SUM, c->dist_comm, cs), "AllReduce"));
                 MDG_CUDA(cudaEventRecord(c->ev_ke, cs));
                 ke_a = dke; ke_b = dke + 1;
-                n_part_a = n_part_b = 1;
+                n_part = 1;
                 c->stat_launches++;
             }
             if (ev0) MDG_CUDA(cudaEventRecord(ev0, st));
@@ -501,19 +611,27 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         int gp = g + 1;
         bool keep = (gp % stride) == 0;
         size_t fr = (size_t)(gp / stride);
-        // k_step_b sums `n_part` partials of BOTH arrays: they have equal length except across a slab change,
-        // where the shorter one was written by fewer blocks - pass the common count and rely on the zero tail
-        int n_part = n_part_a;     // == n_part_b: single GPU keeps a constant block count, multi-GPU passes scalars
-        (void)n_part_b;
-        k_step_b<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
-                                             ke_a, ke_b, n_part, ke_part[ke_next],
-                                             keep ? d_traj_v + fr * 3 * (size_t)n : nullptr,
-                                             keep ? d_traj_q + fr * 3 * (size_t)n : nullptr,
-                                             (keep && M) ? d_traj_pv + fr * M : nullptr);
+        float* tv = keep ? d_traj_v + fr * 3 * (size_t)n : nullptr;
+        float* tq = keep ? d_traj_q + fr * 3 * (size_t)n : nullptr;
+        float* tp = (keep && M) ? d_traj_pv + fr * M : nullptr;
+        if (fused && g + 1 < nsteps) {
+            float dt_next = h_tgrid[g + 2] - h_tgrid[g + 1];
+            bool next_rebuild = ((g + 2) % rebuild_every) == 0;
+            k_step_ba<<<ib, INT_THREADS, 0, st>>>(A, dt, dt_next, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
+                                                  ke_a, ke_b, n_part, ke_v_nxt, ke_h_nxt, tv, tq, tp, c->qref.as<float4>(),
+                                                  (retest && !next_rebuild) ? 1 : 0, c->flags.as<int>());
+            a_done = true;
+            { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
+            { double* t2 = ke_h_cur; ke_h_cur = ke_h_nxt; ke_h_nxt = t2; }
+        } else {
+            k_step_b<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
+                                                 ke_a, ke_b, n_part, ke_v_nxt, tv, tq, tp);
+            a_done = false;
+            { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
+        }
         c->stat_launches++;
         pv_sel ^= 1;
-        ke_cur = ke_next;
-        ib_cur = ib;
+        ib_prev = ib;
     }
     if (h_last_energy) {
         k_energy_sum<<<ib, 256, 0, st>>>(A.s0, A.s1, c->fs.as<float4>(), e_part);
