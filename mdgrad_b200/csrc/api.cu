@@ -13,6 +13,7 @@ void mdg_set_error(const char* fmt, ...) {
 }
 
 int mdg_i_export_count(mdg_ctx* c, cudaStream_t st, int64_t* h_npairs);
+void mdg_i_release_profile(mdg_ctx* c);
 int mdg_i_export_fill(mdg_ctx* c, int64_t* d_nbr, float* d_offsets, float* d_dis, cudaStream_t st);
 int mdg_i_pair_force_op(mdg_ctx* c, const PotParams& P, const float* d_xyz, int n, float* d_energy, float* d_force,
                         float* d_dparams, cudaStream_t st);
@@ -62,6 +63,7 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_layers) cudaFreeHost(c->h_layers);
+    mdg_i_release_profile(c);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);

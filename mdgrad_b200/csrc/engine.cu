@@ -451,7 +451,6 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     PotParams P = mdg_make_pot(p->pot_kind, p->pot_params, MDG_MAX_POT_PARAMS);
 
     const int T = 256;
-    const int nb = (n + T - 1) / T;
     const int n_frames = (n_grid - 1) / stride + 1;
 
     MDG_TRY(c->v4.reserve(2 * sizeof(float4) * (size_t)n));
@@ -712,6 +711,14 @@ extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float
     c->slab = false;
     if (status == MDG_E_CAPACITY) mdg_set_error("mdg_md_run: could not satisfy capacity/skin constraints");
     return status;
+}
+
+void mdg_i_release_profile(mdg_ctx* c) {
+    std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
+    if (!pool) return;
+    for (cudaEvent_t e : *pool) cudaEventDestroy(e);
+    delete pool;
+    c->prof_events = nullptr;
 }
 
 // Per-kernel timing of the force launches inside mdg_md_run (CUDA events on the launch stream
