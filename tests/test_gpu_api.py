@@ -186,3 +186,20 @@ def test_stack_and_masks():
     e1 = O.pair_energy_forces(xyz.cpu(), n1, o1, cell, "lj", (1.0, 1.0))[0]
     e2 = O.pair_energy_forces(xyz.cpu(), n2, o2, cell, "exv", (0.9, 0.5, 12))[0]
     assert abs(e.item() - (e1 + e2).item()) <= 1e-5 * abs((e1 + e2).item())
+
+
+def test_simulate_frequency_one_integrates_zero_steps():
+    """frequency=1 (the default) integrates zero steps but still logs one frame per epoch."""
+    from torchmd.interface import PairPotentials
+    from torchmd.potentials import LennardJones
+    from torchmd.md import NoseHooverChain, Simulations
+    system = _fcc_system()
+    q_before = system.get_positions().copy()
+    integ = NoseHooverChain(PairPotentials(system, LennardJones(1.0, 1.0), cutoff=2.5), system, T=1.0, num_chains=5, Q=50.0)
+    sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+    v, q, pv = sim.simulate(steps=3, frequency=1, dt=0.01)
+    assert v.shape == (1, 108, 3) and q.shape == (1, 108, 3) and pv.shape == (1, 5)
+    assert len(sim.log["positions"]) == 3 and integ.update_count == 0
+    assert np.allclose(system.get_positions(), q_before, atol=1e-5)
+    with pytest.raises(UnboundLocalError):
+        sim.simulate(steps=2, frequency=5, dt=0.01)

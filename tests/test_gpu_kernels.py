@@ -218,3 +218,74 @@ def test_rdf_parity(ctx, ncell):
     ctx.rdf_accumulate(xyz.to(dev), [L] * 3, 0.75, end, 100, None, count)
     c = count / count.sum()
     torch.testing.assert_close(c.cpu(), co, rtol=1e-5, atol=1e-5 * co.max().item())
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases: empty / single-atom / no-pairs inputs, zero-step epochs, capacity growth
+# ------------------------------------------------------------------------------------------
+def test_edge_empty_and_single_atom(ctx):
+    dev = _dev()
+    for n in (0, 1):
+        xyz = torch.rand(n, 3, device=dev) * 4.0
+        nbr, off, dis = ctx.nbr_list(xyz, [5.0, 5.0, 5.0], 2.5, get_dis=True)
+        assert nbr.shape == (0, 2) and off.shape == (0, 3) and dis.shape == (0,)
+        if n:
+            e, f, _ = ctx.pair_force(0, [1.0, 1.0], xyz)
+            assert e.item() == 0.0 and float(f.abs().max()) == 0.0
+    # two atoms exactly at the cutoff distance are NOT neighbors (strict <), one ulp inside they are
+    rc = 2.5
+    a = torch.tensor([[1.0, 1.0, 1.0], [1.0 + rc, 1.0, 1.0]], device=dev)
+    assert ctx.nbr_list(a, [20.0] * 3, rc)[0].shape[0] == 0
+    b = a.clone()
+    b[1, 0] = torch.nextafter(b[1, 0], torch.tensor(0.0, device=dev))
+    nbr_o, _ = O.neighbor_list(b.cpu(), rc, torch.tensor([20.0] * 3))
+    assert ctx.nbr_list(b, [20.0] * 3, rc)[0].shape[0] == nbr_o.shape[0]
+
+
+def test_edge_no_pairs_in_range_and_dilute_cells(ctx):
+    # very dilute box on the cell path: most cells empty, few pairs
+    rng = np.random.default_rng(0)
+    n = 4000
+    xyz = torch.tensor(rng.uniform(0, 200.0, (n, 3)), dtype=torch.float32)
+    nbr_o, off_o = O.neighbor_list(xyz, 2.5, torch.tensor([200.0] * 3), block=512)
+    nbr, off = ctx.nbr_list(xyz.to(_dev()), [200.0] * 3, 2.5)
+    assert torch.equal(nbr.cpu(), nbr_o) and torch.equal(off.cpu(), off_o)
+    e, f, _ = ctx.pair_force(0, [1.0, 1.0], xyz.to(_dev()))
+    eo = O.pair_energy_forces(xyz, nbr_o, off_o, torch.tensor([200.0] * 3), "lj", (1.0, 1.0))[0] if nbr_o.shape[0] else torch.tensor(0.0)
+    assert abs(e.item() - eo.item()) <= 1e-5 * max(1.0, abs(eo.item()))
+
+
+def test_edge_dense_cluster_grows_row_capacity(ctx):
+    # a dense blob in a large box: the mean-density capacity estimate is far too small -> internal growth + retry
+    rng = np.random.default_rng(1)
+    blob = rng.normal(10.0, 0.9, (600, 3))
+    gas = rng.uniform(0, 60.0, (3400, 3))
+    xyz = torch.tensor(np.concatenate([blob, gas]), dtype=torch.float32)
+    nbr_o, off_o = O.neighbor_list(xyz, 2.5, torch.tensor([60.0] * 3), block=512)
+    nbr, off = ctx.nbr_list(xyz.to(_dev()), [60.0] * 3, 2.5)
+    assert torch.equal(nbr.cpu(), nbr_o) and torch.equal(off.cpu(), off_o)
+    assert ctx.stats()["maxrow_or_K"] > 100
+
+
+def test_edge_zero_step_epoch(ctx):
+    pos, vel, L = O.lj_system(3, jitter=0.02, seed=9, a=1.679)
+    n = pos.shape[0]
+    dev = _dev()
+    q0 = torch.tensor(pos, dtype=torch.float32, device=dev)
+    v0 = torch.tensor(vel, dtype=torch.float32, device=dev)
+    mass = torch.full((n,), 1.008, device=dev)
+    p, _ = _md_params(1, float(np.float32(L)), n)
+    tv, tq, tpv, e = ctx.md_run(p, mass, v0, q0, [0.1, 0.2, 0.3, 0.4, 0.5], [0.0], want_energy=True)
+    assert tv.shape == (1, n, 3) and torch.equal(tv[0], v0) and torch.equal(tq[0], q0)
+    assert tpv.shape == (1, 5) and abs(tpv[0, 2].item() - 0.3) < 1e-7
+    nbr_o, off_o = O.neighbor_list(q0.cpu(), 2.5, torch.tensor([float(np.float32(L))] * 3))
+    eo = O.pair_energy_forces(q0.cpu(), nbr_o, off_o, torch.tensor([float(np.float32(L))] * 3), "lj", (1.0, 1.0))[0]
+    assert abs(e - eo.item()) <= 2e-5 * abs(eo.item())
+
+
+def test_edge_atoms_outside_the_box_and_unwrapped(ctx):
+    # atoms several boxes away from the cell (unwrapped trajectories): same list as the oracle
+    xyz, cell = _rand_system(5000, 18.0, 21, spread=2.2)
+    nbr_o, off_o = O.neighbor_list(xyz, 2.5, cell, block=512)
+    nbr, off = ctx.nbr_list(xyz.to(_dev()), cell.tolist(), 2.5)
+    assert torch.equal(nbr.cpu(), nbr_o) and torch.equal(off.cpu(), off_o)
