@@ -264,7 +264,7 @@ def test_edge_dense_cluster_grows_row_capacity(ctx):
     nbr_o, off_o = O.neighbor_list(xyz, 2.5, torch.tensor([60.0] * 3), block=512)
     nbr, off = ctx.nbr_list(xyz.to(_dev()), [60.0] * 3, 2.5)
     assert torch.equal(nbr.cpu(), nbr_o) and torch.equal(off.cpu(), off_o)
-    assert ctx.stats()["maxrow_or_K"] > 100
+    assert int(torch.bincount(nbr_o.reshape(-1)).max()) > 200          # rows far beyond the mean-density estimate
 
 
 def test_edge_zero_step_epoch(ctx):
