@@ -48,6 +48,8 @@ extern "C" int mdg_create(int device, mdg_ctx** out) {
     cudaMemset(c->flags.p, 0, sizeof(int) * 8);
     const char* fk = getenv("MDG_FORCE_KERNEL");
     c->want_stream_rows = fk && strcmp(fk, "cells") == 0;
+    const char* fg = getenv("MDG_FORCE_GROUP");
+    c->force_group = (fg && atoi(fg) == 4) ? 4 : 8;
     *out = c;
     return MDG_OK;
 }

@@ -260,9 +260,9 @@ static int launch_force_cells(mdg_ctx* c, const PotParams& P, const float4* qs, 
     return MDG_OK;
 }
 
-template <bool RETEST, bool WITH_DP>
-static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
-    const int GROUP = 8, T = 256;
+template <bool RETEST, bool WITH_DP, int GROUP>
+static int launch_force_g(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
+    const int T = 256;
     int s0 = c->force_s0 >= 0 ? c->force_s0 : c->own_s0, n = c->force_s0 >= 0 ? c->force_s1 : c->own_s1;
     int nb = (int)(((int64_t)(n - s0) * GROUP + T - 1) / T);
     if (nb <= 0) return MDG_OK;
@@ -284,6 +284,13 @@ static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4
     c->stat_launches++;
     MDG_KERNEL_CHECK();
     return MDG_OK;
+}
+
+// lanes per row: 8 (default) or 4 (MDG_FORCE_GROUP=4; only the hot engine variant is instantiated for it)
+template <bool RETEST, bool WITH_DP>
+static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
+    if (RETEST && !WITH_DP && c->force_group == 4) return launch_force_g<RETEST, WITH_DP, 4>(c, P, qs, fs, dpp, st);
+    return launch_force_g<RETEST, WITH_DP, 8>(c, P, qs, fs, dpp, st);
 }
 
 int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)(c->own_s1 - c->own_s0) * 8 + 255) / 256); }

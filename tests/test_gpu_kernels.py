@@ -289,3 +289,12 @@ def test_edge_atoms_outside_the_box_and_unwrapped(ctx):
     nbr_o, off_o = O.neighbor_list(xyz, 2.5, cell, block=512)
     nbr, off = ctx.nbr_list(xyz.to(_dev()), cell.tolist(), 2.5)
     assert torch.equal(nbr.cpu(), nbr_o) and torch.equal(off.cpu(), off_o)
+
+
+def test_known_answers_fcc500(ctx):
+    a = (4 / 0.8442) ** (1 / 3)
+    xyz = torch.tensor(O.fcc_positions(5, a), dtype=torch.float32).to(_dev())
+    nbr, off = ctx.nbr_list(xyz, [5 * a] * 3, 2.5)
+    assert nbr.shape[0] == 13500
+    e, f, _ = ctx.pair_force(0, [1.0, 1.0], xyz)
+    assert abs(e.item() - (-3386.684)) < 1e-5 * 3386.7 + 1e-3

@@ -108,3 +108,16 @@ def test_c_oracle_forces_vs_torch_oracle():
     ec, fc = C.lj_forces(xyz.numpy(), cell.numpy(), 2.5)
     assert abs(ec - e.item()) < 1e-5 * abs(e.item())
     assert np.abs(fc - f.numpy()).max() < 1e-5 * np.abs(f.numpy()).max()
+
+
+def test_known_answers_fcc500():
+    # FCC 5x5x5 at rho 0.8442 -> 13 500 pairs (54 neighbours per atom), E = -3386.684 (fp32 / fp64)
+    a = (4 / 0.8442) ** (1 / 3)
+    xyz = torch.tensor(O.fcc_positions(5, a), dtype=torch.float32)
+    cell = torch.tensor([5 * a] * 3, dtype=torch.float32)
+    nbr, off = O.neighbor_list(xyz, 2.5, cell)
+    assert nbr.shape[0] == 13500 and int(torch.bincount(nbr.reshape(-1)).min()) == 54
+    e = O.pair_energy_forces(xyz, nbr, off, cell, "lj", (1.0, 1.0))[0]
+    assert abs(e.item() - (-3386.684)) < 2e-3
+    ec, _ = C.lj_forces(xyz.numpy(), cell.numpy(), 2.5)
+    assert abs(ec - (-3386.684)) < 2e-3
