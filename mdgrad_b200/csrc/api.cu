@@ -49,7 +49,7 @@ extern "C" int mdg_create(int device, mdg_ctx** out) {
     const char* fk = getenv("MDG_FORCE_KERNEL");
     c->want_stream_rows = fk && strcmp(fk, "cells") == 0;
     const char* fg = getenv("MDG_FORCE_GROUP");
-    c->force_group = (fg && atoi(fg) == 4) ? 4 : 8;
+    c->force_group = (fg && (atoi(fg) == 8 || atoi(fg) == 2)) ? atoi(fg) : 4;
     *out = c;
     return MDG_OK;
 }

@@ -264,7 +264,7 @@ struct mdg_ctx {
     // list
     DevBuf rows, row_len;     // uint32 [n*cap], int [n]
     DevBuf cell_local;        // uchar [ncell]: 1 = the cell's rows hold stencil-stream indices (k_force_cells), 0 = global
-    int    force_group = 8;            // lanes per row in k_force_rows (MDG_FORCE_GROUP=4|8)
+    int    force_group = 4;            // lanes per row in k_force_rows (MDG_FORCE_GROUP=2|4|8)
     bool   want_stream_rows = false;   // MDG_FORCE_KERNEL=cells: A/B switch for the shared-memory-staged force kernel
     bool   rows_local = false; // the current list was built by k_build_fast in stream-index form
     DevBuf flags;             // int[8]: 0 = capacity overflow, 1 = skin violation

@@ -286,14 +286,15 @@ static int launch_force_g(mdg_ctx* c, const PotParams& P, const float4* qs, floa
     return MDG_OK;
 }
 
-// lanes per row: 8 (default) or 4 (MDG_FORCE_GROUP=4; only the hot engine variant is instantiated for it)
+// lanes per row: 4 (default; measured 60.0 us vs 65.8 us with 8 on the 256k-atom box) - MDG_FORCE_GROUP=2|4|8
 template <bool RETEST, bool WITH_DP>
 static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
-    if (RETEST && !WITH_DP && c->force_group == 4) return launch_force_g<RETEST, WITH_DP, 4>(c, P, qs, fs, dpp, st);
-    return launch_force_g<RETEST, WITH_DP, 8>(c, P, qs, fs, dpp, st);
+    if (c->force_group == 8) return launch_force_g<RETEST, WITH_DP, 8>(c, P, qs, fs, dpp, st);
+    if (c->force_group == 2 && RETEST && !WITH_DP) return launch_force_g<RETEST, WITH_DP, 2>(c, P, qs, fs, dpp, st);
+    return launch_force_g<RETEST, WITH_DP, 4>(c, P, qs, fs, dpp, st);
 }
 
-int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)(c->own_s1 - c->own_s0) * 8 + 255) / 256); }
+int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)(c->own_s1 - c->own_s0) * c->force_group + 255) / 256); }
 
 // explicit sub-range of the own rows (multi-GPU: interior layers first, boundary layers after the halo arrived)
 int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, int s0, int s1,
