@@ -8,6 +8,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_sessionstart(session):
+    """Build the C-ABI library (nvcc, sm_100a - cross-compiles without a GPU) and the C oracle if they are missing,
+    so that a fresh checkout can run the suite directly."""
+    lib = os.path.join(ROOT, "mdgrad_b200", "libmdgrad_b200.so")
+    if not os.path.exists(lib):
+        from mdgrad_b200 import build as b
+        b.build()
+        b.build_oracle()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
     config.addinivalue_line("markers", "reference: needs the read-only reference tree at /root/reference")
