@@ -199,13 +199,30 @@ def wrap_positions(positions, cell, pbc=True, center=(0.5, 0.5, 0.5), eps=1e-7):
     cell = np.asarray(cell, dtype=float)
     if cell.shape == (3,):
         cell = np.diag(cell)
-    # (ASE solves cell^T f^T = pos^T; kept verbatim - a plain division differs in the last bits - and made contiguous
-    #  so that the column updates below stream)
-    fractional = np.ascontiguousarray(np.linalg.solve(cell.T, np.asarray(positions, dtype=float).T).T) - shift
-    for i, periodic in enumerate(pbc):
-        if periodic:
-            fractional[:, i] %= 1.0
-            fractional[:, i] += shift[i]
+    pos = np.asarray(positions, dtype=float)
+    off = cell - np.diag(np.diag(cell))
+    ortho = pos.ndim == 2 and not off.any() and np.all(np.diag(cell) != 0)
+    if ortho:
+        # Orthorhombic cell (the only kind the pair path supports): ASE's `solve(cell^T, pos^T)^T` is an LU solve
+        # whose back-substitution (OpenBLAS dtrsm) MULTIPLIES by the reciprocal of the diagonal - a plain division
+        # differs in the last bit, the reciprocal product is bit-identical (tests/test_cabi_and_host.py) - and it
+        # skips numpy's per-column gufunc marshalling, which costs ~60 ms for 256k atoms.
+        fractional = pos * (1.0 / np.diag(cell))
+        fractional -= shift
+    else:
+        fractional = np.ascontiguousarray(np.linalg.solve(cell.T, pos.T).T) - shift
+    # `x % 1.0` == `x - floor(x)` bit for bit (fmod is exact, both round a - floor(a) once); floor vectorises
+    if pbc.all():
+        fractional -= np.floor(fractional)
+        fractional += shift
+    else:
+        for i, periodic in enumerate(pbc):
+            if periodic:
+                fractional[:, i] -= np.floor(fractional[:, i])
+                fractional[:, i] += shift[i]
+    if ortho:       # dot with a diagonal matrix = f_i * c_ii + 0 + 0: the same bits without a threaded BLAS call
+        fractional *= np.diag(cell)
+        return fractional
     return np.dot(fractional, cell)
 
 

@@ -181,3 +181,47 @@ def test_force_reuse_loop_is_bitwise_the_two_evaluation_solver():
         assert a_model.resets == 16 and b_model.resets == 9          # half the neighbor-list rebuilds
     c = NoseHooverChain(Toy(), s, T=1.0, num_chains=3, Q=5.0, topology_update_freq=3)
     assert odeint_reuse_force(c, tuple(c.get_inital_states(True)), t, "NH_verlet") is None
+
+
+def _wrap_published(positions, cell, pbc=(True, True, True), center=(0.5, 0.5, 0.5), eps=1e-7):
+    """ASE 3.20 `wrap_positions` as published (solve + per-column `%=`): the checker for the vectorised product path."""
+    shift = np.asarray(center, dtype=float) - 0.5 - eps
+    pbc = np.asarray(pbc, dtype=bool)
+    shift[~pbc] = 0.0
+    fractional = np.linalg.solve(np.asarray(cell, dtype=float).T, np.asarray(positions, dtype=float).T).T - shift
+    for i, periodic in enumerate(pbc):
+        if periodic:
+            fractional[:, i] %= 1.0
+            fractional[:, i] += shift[i]
+    return np.dot(fractional, cell)
+
+
+def test_wrap_positions_vectorised_path_matches_the_published_formula():
+    from mdgrad_b200._ase_compat import wrap_positions
+    rng = np.random.default_rng(7)
+    for trial in range(4):
+        L = rng.uniform(2.0, 90.0, 3)
+        cell = np.diag(L)
+        pos = (rng.random((20000, 3)) * 7 - 3) * L          # several boxes either side
+        pos[:8, 0] = [-0.0, 0.0, -1e-20, 1e-20, -L[0], L[0], 2.5 * L[0], -1e-300]
+        for pbc in [(True, True, True), (True, False, True)]:
+            got = wrap_positions(pos, cell, pbc=pbc)
+            ref = _wrap_published(pos, cell, pbc=pbc)
+            # the state that enters the device is the fp32 rounding of this array: it must not change; in fp64 allow the
+            # last bit (LAPACK's triangular solve may divide or multiply by the reciprocal, depending on the BLAS build)
+            assert np.array_equal(got.astype(np.float32), ref.astype(np.float32))
+            assert np.max(np.abs(got - ref)) <= 4 * np.finfo(float).eps * L.max()
+    # a sheared cell takes the published route itself
+    cell = np.array([[10.0, 0, 0], [2.0, 9.0, 0], [0, 1.0, 8.0]])
+    pos = rng.random((100, 3)) * 30 - 10
+    assert np.array_equal(wrap_positions(pos, cell), _wrap_published(pos, cell))
+
+
+def test_host_to_device_is_the_legacy_constructor_value_for_value():
+    from mdgrad_b200.md import _host_to_device
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((5000, 3)) * 50
+    assert torch.equal(_host_to_device(x, "cpu"), torch.Tensor(x))
+    x32 = x.astype(np.float32)[::2]                            # non-contiguous fp32 view
+    assert torch.equal(_host_to_device(x32, "cpu"), torch.Tensor(x32))
+    assert torch.equal(_host_to_device([0.0, 1.5], "cpu"), torch.Tensor([0.0, 1.5]))
