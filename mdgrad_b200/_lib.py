@@ -11,7 +11,9 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdgrad_b200.so")
+# MDG_LIB_VARIANT=<name> loads an experimental build (mdgrad_b200/build.py VARIANTS) for A/B measurements
+_VARIANT = os.environ.get("MDG_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "libmdgrad_b200%s.so" % (("_" + _VARIANT) if _VARIANT else ""))
 
 MDG_OK, MDG_E_BADARG, MDG_E_CUDA, MDG_E_CAPACITY, MDG_E_STATE, MDG_E_SKIN, MDG_E_NCCL = 0, -1, -2, -3, -4, -5, -6
 MDG_E_NUMERIC = -7

@@ -21,6 +21,15 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relax
           "-Xptxas", "-v"]
 # per-file extra flags
 EXTRA = {"engine.cu": ["-fmad=false"]}
+# Experimental build variants: the same sources with feature macros, linked to libmdgrad_b200_<name>.so and
+# selected at import time with MDG_LIB_VARIANT=<name> (A/B measurements on the GPU; the default library is "").
+VARIANTS = {
+    "x1": ["-DMDG_EXP_PURE=1"],
+    "x2": ["-DMDG_EXP_PURE=1", "-DMDG_EXP_T16=1"],
+    "x3": ["-DMDG_EXP_PURE=1", "-DMDG_EXP_CS=1"],
+    "x4": ["-DMDG_EXP_PURE=1", "-DMDG_EXP_T16=1", "-DMDG_EXP_CS=1"],
+    "x5": ["-DMDG_EXP_PURE=1", "-DMDG_EXP_T16=1", "-DMDG_EXP_CS=1", "-DMDG_EXP_MINB=8"],
+}
 
 
 def _sources():
@@ -37,10 +46,10 @@ def _stamp(path, flags):
     return h.hexdigest()
 
 
-def _compile(src, verbose):
-    flags = ARCH + COMMON + EXTRA.get(src, [])
+def _compile(src, verbose, variant=""):
+    flags = ARCH + COMMON + EXTRA.get(src, []) + VARIANTS.get(variant, [])
     path = os.path.join(CSRC, src)
-    obj = os.path.join(OBJ, src[:-3] + ".o")
+    obj = os.path.join(OBJ, src[:-3] + (("." + variant) if variant else "") + ".o")
     stamp_file = obj + ".stamp"
     stamp = _stamp(path, flags)
     if os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
@@ -56,14 +65,21 @@ def _compile(src, verbose):
     return obj, True, r.stderr
 
 
-def build(verbose=False, force=False):
+def lib_path(variant=""):
+    return os.path.join(HERE, "libmdgrad_b200%s.so" % (("_" + variant) if variant else ""))
+
+
+def build(verbose=False, force=False, variant=""):
+    if variant and variant not in VARIANTS:
+        raise ValueError("unknown build variant %r (have %s)" % (variant, sorted(VARIANTS)))
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
     srcs = _sources()
+    LIB = lib_path(variant)
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        results = list(ex.map(lambda s: _compile(s, verbose), srcs))
+        results = list(ex.map(lambda s: _compile(s, verbose, variant), srcs))
     objs = [r[0] for r in results]
     rebuilt = any(r[1] for r in results)
     if rebuilt or not os.path.exists(LIB):
@@ -98,6 +114,9 @@ def build_oracle():
 if __name__ == "__main__":
     lib = build(verbose="-v" in sys.argv, force="--force" in sys.argv)
     print("built", lib)
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):
+            print("built", build(verbose="-v" in sys.argv, variant=a.split("=", 1)[1]))
     o = build_oracle()
     if o:
         print("built", o)

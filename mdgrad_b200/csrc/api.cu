@@ -48,6 +48,9 @@ extern "C" int mdg_create(int device, mdg_ctx** out) {
     cudaMemset(c->flags.p, 0, sizeof(int) * 8);
     const char* fk = getenv("MDG_FORCE_KERNEL");
     c->want_stream_rows = fk && strcmp(fk, "cells") == 0;
+#if MDG_EXP_T16
+    c->want_stream_rows = false;     // the cell-staged kernel reads rows in storage order
+#endif
     const char* fg = getenv("MDG_FORCE_GROUP");
     c->force_group = (fg && (atoi(fg) == 8 || atoi(fg) == 2)) ? atoi(fg) : 4;
     *out = c;

@@ -31,6 +31,15 @@ __device__ __forceinline__ void local_coord(float x, float L, float invL, float 
     I = (int)nf + (int)r;
 }
 
+// Experimental build variants (see k_force_rows_x in force.cu).  MDG_EXP_T16: inside every aligned block of 16
+// entries, logical entry k is stored at slot 4*(k%4) + (k/4)%4, so that the four lanes that stream a row
+// (one uint4 = 4 slots each) gather four CONSECUTIVE neighbors per load instruction (same 128-byte line).
+#if MDG_EXP_T16
+__device__ __forceinline__ int fb_slot(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }
+#else
+__device__ __forceinline__ int fb_slot(int k) { return k; }
+#endif
+
 __device__ __forceinline__ uint32_t pack_img(int Ix, int Iy, int Iz) {
     return (uint32_t)((Ix + 512) & 1023) | ((uint32_t)((Iy + 512) & 1023) << 10) | ((uint32_t)((Iz + 512) & 1023) << 20);
 }
@@ -103,6 +112,12 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         const bool ctr_uniform = __all_sync(0xffffffffu, !act || imc == im0);
         uint32_t* row = rows + (size_t)(act ? s : a0) * cap;
         int cnt = 0;
+#if MDG_EXP_PURE
+        // a row is PURE when its single batch is uniform: bare indices, flagged in row_len (force kernel skips the
+        // index mask and the image-code test)
+        const bool pure_ok = (cell_local == nullptr) && (total <= FB_BATCH);
+        bool row_pure = false;
+#endif
         for (int B = 0; B < total; B += FB_BATCH) {
             const int nb = min(FB_BATCH, total - B);
             const int nch = (nb + 31) >> 5;
@@ -138,6 +153,12 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                 }
             }
             const bool uniform = ctr_uniform && __all_sync(0xffffffffu, cand_uniform) && !filt;
+#if MDG_EXP_PURE
+            row_pure = pure_ok && uniform;
+            const uint32_t uni_code = row_pure ? 0u : ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
+#else
+            const uint32_t uni_code = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
+#endif
             __syncwarp();
             // ---------------- phase 2: lane = atom ------------------------------------------------
             // One flattened loop per lane over ALL its set bits of the batch: lanes drift apart across
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     if (t == s) continue;                      // self
                     const uint32_t ref = local_idx ? (uint32_t)(B + al) : (uint32_t)t;   // stencil-stream index, or global index
                     if (uniform) {                             // interior cells: no pair crosses a periodic boundary
-                        if (cnt < cap) row[cnt] = ref | ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
+                        if (cnt < cap) row[fb_slot(cnt)] = ref | uni_code;
                         ++cnt;
                         continue;
                     }
@@ -170,15 +191,31 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     if ((unsigned)(mx + 1) > 2u || (unsigned)(my + 1) > 2u || (unsigned)(mz + 1) > 2u) continue;
                     if (filt && !pair_allowed(F, idi, __float_as_int(qs[t].w))) continue;
                     if (cnt < cap)
-                        row[cnt] = ref | ((uint32_t)((1 - mx) | ((1 - my) << 2) | ((1 - mz) << 4)) << MDG_IDX_BITS);
+                        row[fb_slot(cnt)] = ref | ((uint32_t)((1 - mx) | ((1 - my) << 2) | ((1 - mz) << 4)) << MDG_IDX_BITS);
                     ++cnt;
                 }
             }
         }
         if (act) {
             if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
+#if MDG_EXP_PURE || MDG_EXP_T16
+            {
+#if MDG_EXP_PURE
+                row_len[s] = cnt | (row_pure ? MDG_ROW_PURE : 0);
+                const uint32_t pad_code = row_pure ? 0u : ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
+#else
+                row_len[s] = cnt;
+                const uint32_t pad_code = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
+#endif
+                const uint32_t self_ref = local_idx ? (uint32_t)(s_pre[w][kself_slot] + pass + lane) : (uint32_t)s;
+                int end = (cnt + 31) & ~31;
+                if (end > cap) end = cap;
+                for (int k = cnt; k < end; ++k) row[fb_slot(k)] = self_ref | pad_code;
+            }
+#else
             row_len[s] = cnt;
             mdg_pad_row(row, cnt, cap, local_idx ? (uint32_t)(s_pre[w][kself_slot] + pass + lane) : (uint32_t)s);
+#endif
         }
         __syncwarp();
     }

@@ -66,6 +66,23 @@ struct DevBuf {
 #define MDG_IDX_BITS 26
 #define MDG_IDX_MASK ((1u << MDG_IDX_BITS) - 1u)
 #define MDG_MAX_ATOMS (1 << MDG_IDX_BITS)
+#define MDG_ROW_PURE 0x40000000        // row_len flag (experimental build variants): entries are bare indices, no image shifts
+#define MDG_ROW_LEN_MASK 0x3fffffff
+#ifndef MDG_EXP_PURE
+#define MDG_EXP_PURE 1
+#endif
+#ifndef MDG_EXP_T16
+#define MDG_EXP_T16 1
+#endif
+#ifndef MDG_EXP_CS
+#define MDG_EXP_CS 1
+#endif
+#ifndef MDG_EXP_MINB
+#define MDG_EXP_MINB 8
+#endif
+#if MDG_EXP_T16 && !MDG_EXP_PURE
+#error "MDG_EXP_T16 needs the block-streaming row kernel of MDG_EXP_PURE"
+#endif
 
 struct Box {
     float L[3];

@@ -134,6 +134,143 @@ __global__ void __launch_bounds__(256) k_force_rows(int s0, int n, const float4*
 }
 
 
+#if MDG_EXP_PURE
+// ---------------------------------------------------------------------------------------------
+// Experimental row kernel (build variant, -DMDG_EXP_PURE=1).  Same contract as k_force_rows, plus:
+//  * PURE rows: k_build_fast marks rows in which no entry carries an image shift (interior cells) with
+//    MDG_ROW_PURE in row_len and stores their entries as BARE indices - the loop over such a row has no
+//    index mask and no image-code test (6 of ~38 instructions per entry);
+//  * the LJ pair evaluation is if-converted: evaluated for every lane, only the four accumulations are
+//    predicated (with 32 lanes at ~61% acceptance the branch was never skipped anyway);
+//  * MDG_EXP_CS: the row stream is loaded with the evict-first (streaming) policy;
+//  * every lane streams whole 16-entry blocks (`kb < m`): rows are padded to 32 with self entries, so this
+//    is layout-agnostic and lets the builder permute entries inside a block (MDG_EXP_T16).
+// ---------------------------------------------------------------------------------------------
+template <int KIND, bool RETEST, bool WITH_DP, bool PURE, int GROUP>
+__device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, const uint32_t* __restrict__ row, int m,
+                                               int lane_in_group, const float4 qi, const Box& bx, float rc2,
+                                               const PotParams& P, float& fx, float& fy, float& fz, float& en, float* dpa) {
+    const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
+    constexpr bool IFCONV = (KIND == MDG_POT_LJ) && !WITH_DP;
+    for (int kb = 0; kb < m; kb += GROUP * 4) {
+#if MDG_EXP_CS
+        // the row stream (~100 MB per launch) is read once: evict-first, so that it does not push the gathered
+        // neighbor positions (4 MB, re-read ~90 times) out of L1/L2
+        const uint4 e4 = __ldcs(reinterpret_cast<const uint4*>(row + kb + lane_in_group * 4));
+#else
+        const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(row + kb + lane_in_group * 4));
+#endif
+        const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
+        float4 qj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qj[u] = mdg_gather4(qs, PURE ? es[u] : (es[u] & MDG_IDX_MASK));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t e = es[u];
+            float dx = __fsub_rn(qj[u].x, qi.x), dy = __fsub_rn(qj[u].y, qi.y), dz = __fsub_rn(qj[u].z, qi.z);
+            if (!PURE) {
+                if ((e & ~MDG_IDX_MASK) != ZERO_CODE) {         // rare: pair crosses the periodic boundary
+                    uint32_t code = e >> MDG_IDX_BITS;
+                    dx = __fadd_rn(dx, mdg_code_shift(code & 3u, bx.L[0]));
+                    dy = __fadd_rn(dy, mdg_code_shift((code >> 2) & 3u, bx.L[1]));
+                    dz = __fadd_rn(dz, mdg_code_shift((code >> 4) & 3u, bx.L[2]));
+                }
+            }
+            float d2;
+            bool in;
+            if (RETEST) {
+                d2 = mdg_d2_exact(dx, dy, dz);
+                in = (d2 < rc2) && (d2 != 0.0f);
+            } else {
+                d2 = dx * dx + dy * dy + dz * dz;
+                in = d2 != 0.0f;
+            }
+            if (IFCONV) {
+                float e_p, g, dp[MDG_MAX_POT_PARAMS];
+                pair_eval<KIND, false>(P, d2, e_p, g, dp);      // d2 == 0 gives inf/nan here; discarded by the predicate below
+                if (in) {
+                    fx -= g * dx;
+                    fy -= g * dy;
+                    fz -= g * dz;
+                    en += e_p;
+                }
+            } else if (in) {
+                float e_p, g, dp[MDG_MAX_POT_PARAMS];
+                pair_eval<KIND, WITH_DP>(P, d2, e_p, g, dp);
+                fx -= g * dx;
+                fy -= g * dy;
+                fz -= g * dz;
+                en += e_p;
+                if (WITH_DP) {
+#pragma unroll
+                    for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] += dp[q];
+                }
+            }
+        }
+    }
+}
+
+#ifndef MDG_EXP_MINB
+#define MDG_EXP_MINB 1
+#endif
+template <int KIND, bool RETEST, bool WITH_DP, int GROUP>
+__global__ void __launch_bounds__(256, MDG_EXP_MINB) k_force_rows_x(int s0, int n, const float4* __restrict__ qs,
+                                                                    const uint32_t* __restrict__ rows,
+                                                                    const int* __restrict__ row_len, int cap, Box bx, float rc2,
+                                                                    PotParams P, float4* __restrict__ fs,
+                                                                    double* __restrict__ dp_partials) {
+    const int lane_in_group = threadIdx.x % GROUP;
+    const int s = s0 + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+    float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
+    float dpa[MDG_MAX_POT_PARAMS] = {0.f, 0.f, 0.f, 0.f};
+    if (s < n) {
+        const float4 qi = qs[s];
+        const uint32_t* row = rows + (size_t)s * cap;
+        const int ml = row_len[s];
+        const int m = ml & MDG_ROW_LEN_MASK;
+        if (ml & MDG_ROW_PURE)
+            mdg_row_stream<KIND, RETEST, WITH_DP, true, GROUP>(qs, row, m, lane_in_group, qi, bx, rc2, P, fx, fy, fz, en, dpa);
+        else
+            mdg_row_stream<KIND, RETEST, WITH_DP, false, GROUP>(qs, row, m, lane_in_group, qi, bx, rc2, P, fx, fy, fz, en, dpa);
+        fx *= P.sg; fy *= P.sg; fz *= P.sg;
+        en *= 0.5f * P.se;
+        if (WITH_DP) {
+#pragma unroll
+            for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] *= 0.5f * P.sdp[q];
+        }
+    }
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        en += __shfl_xor_sync(0xffffffffu, en, o);
+    }
+    if (s < n && lane_in_group == 0) fs[s] = make_float4(fx, fy, fz, en);
+    if (WITH_DP) {
+        __shared__ double sm[8][MDG_MAX_POT_PARAMS];
+        double v[MDG_MAX_POT_PARAMS];
+#pragma unroll
+        for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) {
+            v[q] = (double)dpa[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        }
+        int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0)
+            for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) sm[w][q] = v[q];
+        __syncthreads();
+        if (threadIdx.x < MDG_MAX_POT_PARAMS) {
+            double t = 0;
+            for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) t += sm[ww][threadIdx.x];
+            dp_partials[(size_t)blockIdx.x * MDG_MAX_POT_PARAMS + threadIdx.x] = t;
+        }
+    }
+}
+#define k_force_rows k_force_rows_x
+#endif  // MDG_EXP_PURE
+
+
 // ---------------------------------------------------------------------------------------------
 // v2 force kernel for lists built by k_build_fast in STREAM-INDEX form: one CTA per cell.  The CTA
 // stages the cell's stencil stream (the atoms of its 27 stencil cells, concatenated in table order -
