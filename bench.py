@@ -390,7 +390,7 @@ def main():
     peak, peak_src = peaks()
     achieved = alg_bytes / (force_ms * 1e-3) / 1e9
     log("pair counts done: P_rc=%d P_list=%d force %.4f ms" % (P_rc, P_list, force_ms))
-    res["roofline"] = {"bound": "hbm", "kernel": "k_force_rows<LJ,RETEST,GROUP=4> (pair force over the fixed-capacity skin rows)", "achieved": achieved,
+    res["roofline"] = {"bound": "hbm", "kernel": "k_force_rows<LJ,RETEST,4 lanes/row> (pair force over the fixed-capacity skin rows)", "achieved": achieved,
                        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 104.2e6 + 4.8e6,
                        "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch "
                                          "(profiles/r01_ncu_summary.md, skin 0.45)",

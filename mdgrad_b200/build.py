@@ -21,15 +21,10 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relax
           "-Xptxas", "-v"]
 # per-file extra flags
 EXTRA = {"engine.cu": ["-fmad=false"]}
-# Experimental build variants: the same sources with feature macros, linked to libmdgrad_b200_<name>.so and
-# selected at import time with MDG_LIB_VARIANT=<name> (A/B measurements on the GPU; the default library is "").
-VARIANTS = {
-    "x1": ["-DMDG_EXP_PURE=1"],
-    "x2": ["-DMDG_EXP_PURE=1", "-DMDG_EXP_T16=1"],
-    "x3": ["-DMDG_EXP_PURE=1", "-DMDG_EXP_CS=1"],
-    "x4": ["-DMDG_EXP_PURE=1", "-DMDG_EXP_T16=1", "-DMDG_EXP_CS=1"],
-    "x5": ["-DMDG_EXP_PURE=1", "-DMDG_EXP_T16=1", "-DMDG_EXP_CS=1", "-DMDG_EXP_MINB=8"],
-}
+# Build variants for A/B measurements: the same sources with extra -D feature macros, linked to
+# libmdgrad_b200_<name>.so and selected at import time with MDG_LIB_VARIANT=<name> (tools/ab_variants.sh runs the
+# bench on each and the GPU suite on the fastest).  The default library is "" - add entries while experimenting.
+VARIANTS = {}
 
 
 def _sources():

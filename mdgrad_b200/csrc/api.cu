@@ -46,11 +46,6 @@ extern "C" int mdg_create(int device, mdg_ctx** out) {
     int s = c->flags.reserve(sizeof(int) * 8);
     if (s != MDG_OK) { cudaFreeHost(c->h_pinned); delete c; return s; }
     cudaMemset(c->flags.p, 0, sizeof(int) * 8);
-    const char* fk = getenv("MDG_FORCE_KERNEL");
-    c->want_stream_rows = fk && strcmp(fk, "cells") == 0;
-#if MDG_EXP_T16
-    c->want_stream_rows = false;     // the cell-staged kernel reads rows in storage order
-#endif
     const char* fg = getenv("MDG_FORCE_GROUP");
     c->force_group = (fg && (atoi(fg) == 8 || atoi(fg) == 2)) ? atoi(fg) : 4;
     *out = c;
@@ -63,7 +58,7 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
     DevBuf* bufs[] = {&c->cell_of, &c->slot_of, &c->cell_count, &c->cell_start, &c->perm, &c->perm_tmp, &c->stencil,
                       &c->qs_buf[0], &c->qs_buf[1], &c->rows, &c->row_len, &c->flags, &c->up_cnt, &c->up_off,
                       &c->scan_tmp, &c->fs, &c->partials, &c->v4, &c->vh4, &c->q4b, &c->f4b, &c->qref,
-                      &c->mass_sorted, &c->pvbuf, &c->kebuf, &c->dtbuf, &c->cell_local, &c->g_off, &c->g_cnt, &c->g_edge,
+                      &c->mass_sorted, &c->pvbuf, &c->kebuf, &c->dtbuf, &c->g_off, &c->g_cnt, &c->g_edge,
                       &c->g_other};
     for (DevBuf* b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);

@@ -31,14 +31,11 @@ __device__ __forceinline__ void local_coord(float x, float L, float invL, float 
     I = (int)nf + (int)r;
 }
 
-// Experimental build variants (see k_force_rows_x in force.cu).  MDG_EXP_T16: inside every aligned block of 16
-// entries, logical entry k is stored at slot 4*(k%4) + (k/4)%4, so that the four lanes that stream a row
-// (one uint4 = 4 slots each) gather four CONSECUTIVE neighbors per load instruction (same 128-byte line).
-#if MDG_EXP_T16
+// Row storage order: inside every aligned block of 16 entries, logical entry k is stored at slot
+// 4*(k%4) + (k/4)%4, so that the four lanes that stream a row in k_force_rows (one uint4 = 4 slots each) gather
+// four CONSECUTIVE neighbors per load instruction (same 128-byte line): 57.8 -> 53.4 us on the 256k-atom box.
+// (Only the engine's force kernel reads these rows; it is order-agnostic inside a block.)
 __device__ __forceinline__ int fb_slot(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }
-#else
-__device__ __forceinline__ int fb_slot(int k) { return k; }
-#endif
 
 __device__ __forceinline__ uint32_t pack_img(int Ix, int Iy, int Iz) {
     return (uint32_t)((Ix + 512) & 1023) | ((uint32_t)((Iy + 512) & 1023) << 10) | ((uint32_t)((Iz + 512) & 1023) << 20);
@@ -83,9 +80,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
     }
     __syncwarp();
     const int total = s_pre[w][27];
-    // Row entries reference the cell's STENCIL STREAM (the 27 stencil cells concatenated in table order) when it
-    // fits the force kernel's shared-memory stage; the force kernel stages the same stream and gathers from smem.
-    const bool local_idx = (cell_local != nullptr) && (total <= MDG_STREAM_CAP);   // only with MDG_FORCE_KERNEL=cells
+    // Stream-index form (entries index the cell's 27-cell STENCIL STREAM instead of the global sorted array, for a
+    // force kernel that stages the stream in shared memory): measured slower than the gather kernel (124 vs 66 us)
+    // and not used - the engine always passes cell_local == nullptr, so entries are global indices.
+    const bool local_idx = (cell_local != nullptr) && (total <= MDG_STREAM_CAP);
     if (cell_local && lane == 0) cell_local[c] = local_idx ? 1 : 0;
     const int cx = c % ncx, cy = (c / ncx) % ncy, cz = c / (ncx * ncy);
     const float ox = (float)cx / (float)ncx, oy = (float)cy / (float)ncy, oz = (float)cz / (float)ncz;
@@ -112,12 +110,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         const bool ctr_uniform = __all_sync(0xffffffffu, !act || imc == im0);
         uint32_t* row = rows + (size_t)(act ? s : a0) * cap;
         int cnt = 0;
-#if MDG_EXP_PURE
         // a row is PURE when its single batch is uniform: bare indices, flagged in row_len (force kernel skips the
         // index mask and the image-code test)
         const bool pure_ok = (cell_local == nullptr) && (total <= FB_BATCH);
         bool row_pure = false;
-#endif
         for (int B = 0; B < total; B += FB_BATCH) {
             const int nb = min(FB_BATCH, total - B);
             const int nch = (nb + 31) >> 5;
@@ -153,12 +149,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                 }
             }
             const bool uniform = ctr_uniform && __all_sync(0xffffffffu, cand_uniform) && !filt;
-#if MDG_EXP_PURE
             row_pure = pure_ok && uniform;
             const uint32_t uni_code = row_pure ? 0u : ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
-#else
-            const uint32_t uni_code = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
-#endif
             __syncwarp();
             // ---------------- phase 2: lane = atom ------------------------------------------------
             // One flattened loop per lane over ALL its set bits of the batch: lanes drift apart across
@@ -198,24 +190,14 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         }
         if (act) {
             if (cnt > cap) { atomicMax(&flags[2], cnt); flags[0] = 1; cnt = cap; }
-#if MDG_EXP_PURE || MDG_EXP_T16
-            {
-#if MDG_EXP_PURE
+            {   // length (+ PURE flag) and padding to a whole 32-entry block with self entries (see mdg_pad_row)
                 row_len[s] = cnt | (row_pure ? MDG_ROW_PURE : 0);
                 const uint32_t pad_code = row_pure ? 0u : ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
-#else
-                row_len[s] = cnt;
-                const uint32_t pad_code = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
-#endif
                 const uint32_t self_ref = local_idx ? (uint32_t)(s_pre[w][kself_slot] + pass + lane) : (uint32_t)s;
                 int end = (cnt + 31) & ~31;
                 if (end > cap) end = cap;
                 for (int k = cnt; k < end; ++k) row[fb_slot(k)] = self_ref | pad_code;
             }
-#else
-            row_len[s] = cnt;
-            mdg_pad_row(row, cnt, cap, local_idx ? (uint32_t)(s_pre[w][kself_slot] + pass + lane) : (uint32_t)s);
-#endif
         }
         __syncwarp();
     }

@@ -62,27 +62,12 @@ struct DevBuf {
 // 2 bits per axis holding off_k + 1 in {0,1,2} (off = reference `offsets` row-relative:
 // computed from d = x_j - x_i of the row atom i, topology.py:35,59-62)
 // ---------------------------------------------------------------------------------------------
-#define MDG_STREAM_CAP 1024   // max atoms of a 27-cell stencil stream staged in shared memory by k_force_cells
+#define MDG_STREAM_CAP 1024   // stream-index row form (unused, see build_fast.cuh): max atoms of a 27-cell stencil stream
 #define MDG_IDX_BITS 26
 #define MDG_IDX_MASK ((1u << MDG_IDX_BITS) - 1u)
 #define MDG_MAX_ATOMS (1 << MDG_IDX_BITS)
-#define MDG_ROW_PURE 0x40000000        // row_len flag (experimental build variants): entries are bare indices, no image shifts
+#define MDG_ROW_PURE 0x40000000        // row_len flag set by k_build_fast: entries are bare indices, no image shifts
 #define MDG_ROW_LEN_MASK 0x3fffffff
-#ifndef MDG_EXP_PURE
-#define MDG_EXP_PURE 1
-#endif
-#ifndef MDG_EXP_T16
-#define MDG_EXP_T16 1
-#endif
-#ifndef MDG_EXP_CS
-#define MDG_EXP_CS 1
-#endif
-#ifndef MDG_EXP_MINB
-#define MDG_EXP_MINB 8
-#endif
-#if MDG_EXP_T16 && !MDG_EXP_PURE
-#error "MDG_EXP_T16 needs the block-streaming row kernel of MDG_EXP_PURE"
-#endif
 
 struct Box {
     float L[3];
@@ -280,10 +265,7 @@ struct mdg_ctx {
     float4* qs_ptr = nullptr; //   the previous output), w = original index (int bits)
     // list
     DevBuf rows, row_len;     // uint32 [n*cap], int [n]
-    DevBuf cell_local;        // uchar [ncell]: 1 = the cell's rows hold stencil-stream indices (k_force_cells), 0 = global
     int    force_group = 4;            // lanes per row in k_force_rows (MDG_FORCE_GROUP=2|4|8)
-    bool   want_stream_rows = false;   // MDG_FORCE_KERNEL=cells: A/B switch for the shared-memory-staged force kernel
-    bool   rows_local = false; // the current list was built by k_build_fast in stream-index form
     DevBuf flags;             // int[8]: 0 = capacity overflow, 1 = skin violation
     // export scratch
     DevBuf up_cnt, up_off, scan_tmp;

@@ -27,10 +27,21 @@ PotParams mdg_make_pot(int kind, const float* h_params, int n_params) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// v1 list-streaming force kernel: GROUP lanes cooperate on one row (one atom); entries are
-// streamed with coalesced 4-byte loads, neighbor positions gathered from the sorted float4
-// array (L1/L2 resident), forces reduced with warp shuffles, one float4 store per atom.
-// RETEST: re-apply the reference membership test d2 < rc2 (exact arithmetic) to a skin list.
+// List-streaming force kernel: GROUP (4) lanes cooperate on one row (one atom).  Every lane streams whole
+// 16-entry blocks of the row with one 16-byte evict-first load per block (rows are 128-byte aligned, cap is a
+// multiple of 32, rows are padded to 32 with self entries whose d2 == 0 is dropped - no bounds guards),
+// issues its 4 position gathers (sorted float4 array, L1/L2 resident) back to back, and the row sums are
+// reduced with warp shuffles: one float4 store per atom.
+//  * RETEST: re-apply the reference membership test d2 < rc2 (exact arithmetic) to a skin list.
+//  * PURE rows: k_build_fast marks rows in which no entry carries an image shift (interior cells) with
+//    MDG_ROW_PURE in row_len and stores their entries as BARE indices - the loop over such a row has no
+//    index mask and no image-code test (28 instead of ~38 instructions per entry).
+//  * The LJ pair evaluation is if-converted: evaluated for every lane, only the four accumulations are
+//    predicated (with 32 lanes at ~61% acceptance a branch was never skipped anyway).
+//  * The loop is layout-agnostic inside a 16-entry block, which lets k_build_fast store the blocks transposed
+//    (build_fast.cuh fb_slot): the four lanes of a row then gather four CONSECUTIVE neighbors per load.
+// Measured on the 256k-atom box (profiles/r01_ab_*.json): 59.9 us -> 57.8 (pure rows + if-conversion) -> 53.4
+// (transposed blocks) -> 51.8 (evict-first row stream) -> 51.6 us (32 registers, 8 CTAs per SM).
 // ---------------------------------------------------------------------------------------------
 // float4 gather with a single mad.wide address computation
 __device__ __forceinline__ float4 mdg_gather4(const float4* __restrict__ base, uint32_t idx) {
@@ -39,113 +50,6 @@ __device__ __forceinline__ float4 mdg_gather4(const float4* __restrict__ base, u
     return __ldg(p);
 }
 
-template <int KIND, bool RETEST, bool WITH_DP, int GROUP>
-__global__ void __launch_bounds__(256) k_force_rows(int s0, int n, const float4* __restrict__ qs,
-                                                    const uint32_t* __restrict__ rows, const int* __restrict__ row_len,
-                                                    int cap, Box bx, float rc2, PotParams P, float4* __restrict__ fs,
-                                                    double* __restrict__ dp_partials) {
-    const int lane_in_group = threadIdx.x % GROUP;
-    const int s = s0 + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;      // rows [s0, n) (n = end of this rank's range)
-    float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
-    float dpa[MDG_MAX_POT_PARAMS] = {0.f, 0.f, 0.f, 0.f};
-    if (s < n) {
-        const float4 qi = qs[s];
-        const uint32_t* row = rows + (size_t)s * cap;
-        const int m = row_len[s];
-        const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;   // no image shift on any axis
-        // each lane streams 4 consecutive entries per iteration with one 16-byte load (rows are 128-byte
-        // aligned, cap is a multiple of 32) and issues the 4 position gathers back to back
-        // rows are padded to 32-entry blocks with self entries (d2 == 0 -> dropped): no bounds guards in the loop
-        for (int k0 = lane_in_group * 4; k0 < m; k0 += GROUP * 4) {
-            const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(row + k0));
-            const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
-            float4 qj[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) qj[u] = mdg_gather4(qs, es[u] & MDG_IDX_MASK);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t e = es[u];
-                // x_j - x_i: adding a zero image shift is a bit-wise no-op, so the common case skips it
-                float dx = __fsub_rn(qj[u].x, qi.x), dy = __fsub_rn(qj[u].y, qi.y), dz = __fsub_rn(qj[u].z, qi.z);
-                if ((e & ~MDG_IDX_MASK) != ZERO_CODE) {         // rare: pair crosses the periodic boundary
-                    uint32_t code = e >> MDG_IDX_BITS;
-                    dx = __fadd_rn(dx, mdg_code_shift(code & 3u, bx.L[0]));
-                    dy = __fadd_rn(dy, mdg_code_shift((code >> 2) & 3u, bx.L[1]));
-                    dz = __fadd_rn(dz, mdg_code_shift((code >> 4) & 3u, bx.L[2]));
-                }
-                float d2;
-                bool in;
-                if (RETEST) {
-                    d2 = mdg_d2_exact(dx, dy, dz);              // reference arithmetic: membership must be bit-exact
-                    in = (d2 < rc2) && (d2 != 0.0f);
-                } else {
-                    d2 = dx * dx + dy * dy + dz * dz;
-                    in = d2 != 0.0f;
-                }
-                if (in) {
-                    float e_p, g, dp[MDG_MAX_POT_PARAMS];
-                    pair_eval<KIND, WITH_DP>(P, d2, e_p, g, dp);
-                    fx -= g * dx;
-                    fy -= g * dy;
-                    fz -= g * dz;
-                    en += e_p;
-                    if (WITH_DP) {
-#pragma unroll
-                        for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] += dp[q];
-                    }
-                }
-            }
-        }
-        fx *= P.sg; fy *= P.sg; fz *= P.sg;
-        en *= 0.5f * P.se;
-        if (WITH_DP) {
-#pragma unroll
-            for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] *= 0.5f * P.sdp[q];
-        }
-    }
-#pragma unroll
-    for (int o = GROUP / 2; o > 0; o >>= 1) {
-        fx += __shfl_xor_sync(0xffffffffu, fx, o);
-        fy += __shfl_xor_sync(0xffffffffu, fy, o);
-        fz += __shfl_xor_sync(0xffffffffu, fz, o);
-        en += __shfl_xor_sync(0xffffffffu, en, o);
-    }
-    if (s < n && lane_in_group == 0) fs[s] = make_float4(fx, fy, fz, en);
-    if (WITH_DP) {
-        // block-level reduction of the parameter gradients (double), one partial row per block
-        __shared__ double sm[8][MDG_MAX_POT_PARAMS];
-        double v[MDG_MAX_POT_PARAMS];
-#pragma unroll
-        for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) {
-            v[q] = (double)dpa[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
-        }
-        int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0)
-            for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) sm[w][q] = v[q];
-        __syncthreads();
-        if (threadIdx.x < MDG_MAX_POT_PARAMS) {
-            double t = 0;
-            for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) t += sm[ww][threadIdx.x];
-            dp_partials[(size_t)blockIdx.x * MDG_MAX_POT_PARAMS + threadIdx.x] = t;
-        }
-    }
-}
-
-
-#if MDG_EXP_PURE
-// ---------------------------------------------------------------------------------------------
-// Experimental row kernel (build variant, -DMDG_EXP_PURE=1).  Same contract as k_force_rows, plus:
-//  * PURE rows: k_build_fast marks rows in which no entry carries an image shift (interior cells) with
-//    MDG_ROW_PURE in row_len and stores their entries as BARE indices - the loop over such a row has no
-//    index mask and no image-code test (6 of ~38 instructions per entry);
-//  * the LJ pair evaluation is if-converted: evaluated for every lane, only the four accumulations are
-//    predicated (with 32 lanes at ~61% acceptance the branch was never skipped anyway);
-//  * MDG_EXP_CS: the row stream is loaded with the evict-first (streaming) policy;
-//  * every lane streams whole 16-entry blocks (`kb < m`): rows are padded to 32 with self entries, so this
-//    is layout-agnostic and lets the builder permute entries inside a block (MDG_EXP_T16).
-// ---------------------------------------------------------------------------------------------
 template <int KIND, bool RETEST, bool WITH_DP, bool PURE, int GROUP>
 __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, const uint32_t* __restrict__ row, int m,
                                                int lane_in_group, const float4 qi, const Box& bx, float rc2,
@@ -153,13 +57,9 @@ __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, co
     const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
     constexpr bool IFCONV = (KIND == MDG_POT_LJ) && !WITH_DP;
     for (int kb = 0; kb < m; kb += GROUP * 4) {
-#if MDG_EXP_CS
         // the row stream (~100 MB per launch) is read once: evict-first, so that it does not push the gathered
         // neighbor positions (4 MB, re-read ~90 times) out of L1/L2
         const uint4 e4 = __ldcs(reinterpret_cast<const uint4*>(row + kb + lane_in_group * 4));
-#else
-        const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(row + kb + lane_in_group * 4));
-#endif
         const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
         float4 qj[4];
 #pragma unroll
@@ -210,11 +110,8 @@ __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, co
     }
 }
 
-#ifndef MDG_EXP_MINB
-#define MDG_EXP_MINB 1
-#endif
 template <int KIND, bool RETEST, bool WITH_DP, int GROUP>
-__global__ void __launch_bounds__(256, MDG_EXP_MINB) k_force_rows_x(int s0, int n, const float4* __restrict__ qs,
+__global__ void __launch_bounds__(256, 8) k_force_rows(int s0, int n, const float4* __restrict__ qs,
                                                                     const uint32_t* __restrict__ rows,
                                                                     const int* __restrict__ row_len, int cap, Box bx, float rc2,
                                                                     PotParams P, float4* __restrict__ fs,
@@ -267,135 +164,7 @@ __global__ void __launch_bounds__(256, MDG_EXP_MINB) k_force_rows_x(int s0, int 
         }
     }
 }
-#define k_force_rows k_force_rows_x
-#endif  // MDG_EXP_PURE
 
-
-// ---------------------------------------------------------------------------------------------
-// v2 force kernel for lists built by k_build_fast in STREAM-INDEX form: one CTA per cell.  The CTA
-// stages the cell's stencil stream (the atoms of its 27 stencil cells, concatenated in table order -
-// exactly the order the builder enumerated) into shared memory with coalesced float4 loads, then
-// 8 lanes per row stream the row (16-byte loads) and gather neighbor positions FROM SHARED MEMORY:
-// the row entries are stream indices, so no translation is needed.  Removes the L1 gather wavefronts
-// (~20 distinct lines per 32-lane gather) and the L1/L2 latency from the inner loop.
-// Cells whose stream exceeds MDG_STREAM_CAP keep global indices (cell_local[c] == 0) and gather from qs.
-// ---------------------------------------------------------------------------------------------
-template <int KIND>
-__global__ void __launch_bounds__(256) k_force_cells(int cell0, int cell1, const float4* __restrict__ qs,
-                                                     const int* __restrict__ cell_start, const int* __restrict__ stencil,
-                                                     const unsigned char* __restrict__ cell_local,
-                                                     const uint32_t* __restrict__ rows, const int* __restrict__ row_len, int cap,
-                                                     Box bx, float rc2, PotParams P, float4* __restrict__ fs) {
-    __shared__ float4 s_q[MDG_STREAM_CAP];
-    __shared__ int s_pre[28];
-    __shared__ int s_cs[27];
-    const int c = cell0 + blockIdx.x;
-    if (c >= cell1) return;
-    const int a0 = cell_start[c], na = cell_start[c + 1] - a0;
-    if (na == 0) return;
-    const bool local = cell_local[c] != 0;
-    if (local) {
-        if (threadIdx.x < 32) {
-            int lane = threadIdx.x;
-            int cc = lane < 27 ? stencil[c * 27 + lane] : 0;
-            int cs = lane < 27 ? cell_start[cc] : 0;
-            int x = lane < 27 ? cell_start[cc + 1] - cs : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            if (lane < 27) { s_pre[lane + 1] = x; s_cs[lane] = cs; }
-            if (lane == 0) s_pre[0] = 0;
-        }
-        __syncthreads();
-        const int total = s_pre[27];
-        for (int a = threadIdx.x; a < total; a += blockDim.x) {
-            int lo = 0, hi = 26;                      // largest k with s_pre[k] <= a
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if (s_pre[mid] <= a) lo = mid; else hi = mid - 1;
-            }
-            s_q[a] = qs[s_cs[lo] + (a - s_pre[lo])];
-        }
-        __syncthreads();
-    }
-    const int lane_in_group = threadIdx.x & 7;
-    const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
-    for (int r0 = 0; r0 < na; r0 += 32) {
-        const int r = r0 + (threadIdx.x >> 3);
-        float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
-        if (r < na) {
-            const int s = a0 + r;
-            const float4 qi = qs[s];
-            const uint32_t* row = rows + (size_t)s * cap;
-            const int m = row_len[s];
-            for (int k0 = lane_in_group * 4; k0 < m; k0 += 32) {
-                const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(row + k0));
-                const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
-                float4 qj[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t idx = es[u] & MDG_IDX_MASK;
-                    qj[u] = (k0 + u < m) ? (local ? s_q[idx] : qs[idx]) : qi;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u >= m) break;
-                    const uint32_t e = es[u];
-                    float dx = __fsub_rn(qj[u].x, qi.x), dy = __fsub_rn(qj[u].y, qi.y), dz = __fsub_rn(qj[u].z, qi.z);
-                    if ((e & ~MDG_IDX_MASK) != ZERO_CODE) {
-                        uint32_t code = e >> MDG_IDX_BITS;
-                        dx = __fadd_rn(dx, mdg_code_shift(code & 3u, bx.L[0]));
-                        dy = __fadd_rn(dy, mdg_code_shift((code >> 2) & 3u, bx.L[1]));
-                        dz = __fadd_rn(dz, mdg_code_shift((code >> 4) & 3u, bx.L[2]));
-                    }
-                    float d2 = mdg_d2_exact(dx, dy, dz);       // reference arithmetic: membership must be bit-exact
-                    if ((d2 < rc2) && (d2 != 0.0f)) {
-                        float e_p, g, dp[MDG_MAX_POT_PARAMS];
-                        pair_eval<KIND, false>(P, d2, e_p, g, dp);
-                        fx -= g * dx;
-                        fy -= g * dy;
-                        fz -= g * dz;
-                        en += e_p;
-                    }
-                }
-            }
-            fx *= P.sg; fy *= P.sg; fz *= P.sg;
-            en *= 0.5f * P.se;
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o);
-            fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o);
-            en += __shfl_xor_sync(0xffffffffu, en, o);
-        }
-        if (r < na && lane_in_group == 0) fs[a0 + r] = make_float4(fx, fy, fz, en);
-    }
-}
-
-static int launch_force_cells(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, int c0, int c1, cudaStream_t st) {
-    if (c1 <= c0) return MDG_OK;
-    const uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
-#define LC(K)                                                                                                          \
-    k_force_cells<K><<<c1 - c0, 256, 0, st>>>(c0, c1, qs, c->cell_start.as<int>(), c->stencil.as<int>(),               \
-                                             c->cell_local.as<unsigned char>(), rows_base, c->row_len.as<int>(), c->cap, \
-                                             c->box, c->rc2, P, fs)
-    switch (P.kind) {
-        case MDG_POT_LJ: LC(MDG_POT_LJ); break;
-        case MDG_POT_LJFAM: LC(MDG_POT_LJFAM); break;
-        case MDG_POT_LJ69: LC(MDG_POT_LJ69); break;
-        case MDG_POT_EXV: LC(MDG_POT_EXV); break;
-        case MDG_POT_BUCK: LC(MDG_POT_BUCK); break;
-        case MDG_POT_MORSE: LC(MDG_POT_MORSE); break;
-        default: mdg_set_error("unknown potential kind %d", P.kind); return MDG_E_BADARG;
-    }
-#undef LC
-    c->stat_launches++;
-    MDG_KERNEL_CHECK();
-    return MDG_OK;
-}
 
 template <bool RETEST, bool WITH_DP, int GROUP>
 static int launch_force_g(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
@@ -449,12 +218,6 @@ int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4
 int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, bool with_dp,
                        double* d_dp_partials, cudaStream_t st) {
     if (c->n == 0) return MDG_OK;
-    if (c->rows_local) {
-        // stream-index rows (k_build_fast): only the cell-staged kernel can read them
-        if (!retest || with_dp) { mdg_set_error("stream-index lists support the re-testing engine path only"); return MDG_E_STATE; }
-        int c0 = c->force_s0 >= 0 ? c->force_c0 : c->own_c0, c1 = c->force_s0 >= 0 ? c->force_c1 : c->own_c1;
-        return launch_force_cells(c, P, d_qs, d_fs, c0, c1, st);
-    }
     if (retest) {
         if (with_dp) return launch_force<true, true>(c, P, d_qs, d_fs, d_dp_partials, st);
         return launch_force<true, false>(c, P, d_qs, d_fs, d_dp_partials, st);

@@ -629,8 +629,6 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         if (c->rows_wanted) {
             MDG_TRY(c->rows.reserve(sizeof(uint32_t) * (size_t)(c->own_s1 - c->own_s0 + 1) * c->cap));
             uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
-            MDG_TRY(c->cell_local.reserve((size_t)ncell + 16));
-            c->rows_local = false;
             bool roomy = g.nc[0] >= 5 && g.nc[1] >= 5 && g.nc[2] >= 5;   // stencil extent < half a box
             if (c->fast_build && rlist > cutoff && roomy) {
                 int ncl = c->own_c1 - c->own_c0;
@@ -638,8 +636,7 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
                     k_build_fast<<<(ncl + FB_WARPS - 1) / FB_WARPS, FB_WARPS * 32, 0, st>>>(
                         c->own_c0, c->own_c1, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box, g.nc[0], g.nc[1], g.nc[2],
                         c->rlist2, c->cap, F, rows_base, c->row_len.as<int>(), c->flags.as<int>(),
-                        c->want_stream_rows ? c->cell_local.as<unsigned char>() : nullptr);
-                c->rows_local = c->want_stream_rows;
+                        nullptr);
             } else {
                 int nl = c->own_s1 - c->own_s0;
                 if (nl > 0)
@@ -654,7 +651,6 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         k_iota<<<nb, T, 0, st>>>(c->perm.as<int>(), n);
         c->own_s0 = 0; c->own_s1 = n; c->own_c0 = 0; c->own_c1 = ncell; c->rows_s0 = 0;
         if (c->rows_wanted) MDG_TRY(c->rows.reserve(sizeof(uint32_t) * (size_t)n * c->cap));
-        c->rows_local = false;
         if (c->rows_wanted)
             k_build_allpairs<<<(n + AP_TILE - 1) / AP_TILE, AP_TILE, 0, st>>>(n, qs, c->box, c->rlist2, c->cap, F,
                                                                             c->rows.as<uint32_t>(), c->row_len.as<int>(),
