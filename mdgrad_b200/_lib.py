@@ -68,7 +68,12 @@ def load():
         raise RuntimeError(
             "libmdgrad_b200.so not found at %s - build it with `python -m mdgrad_b200.build` "
             "(nvcc, sm_100a).  There is no CPU fallback for the MD hot path." % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+    _lib = bind(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+def bind(lib):
+    """Declares the argument / result types of every entry point of include/mdgrad_b200.h on a loaded library."""
     vp, ip, dbl, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64
     fp = ctypes.POINTER(ctypes.c_float)
     lib.mdg_version.restype = ip
@@ -97,7 +102,6 @@ def load():
         if name not in ("mdg_last_error",):
             getattr(lib, name).restype = ip
     lib.mdg_last_error.restype = ctypes.c_char_p
-    _lib = lib
     return lib
 
 
@@ -130,6 +134,22 @@ def _ptr(t):
 class Context:
     """One mdg_ctx per (device, use).  Not thread-safe."""
 
+    # hooks (the CPU emulation harness under tests/cuemu subclasses these; the product path is CUDA only)
+    def _api(self):
+        return load()
+
+    def _check(self, status):
+        check(status)
+
+    def _require(self, t, name="tensor"):
+        require_cuda(t, name)
+
+    def _stream(self, device):
+        return _stream(device)
+
+    def _guard(self, device):
+        return torch.cuda.device(device)
+
     def __init__(self, device):
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -137,12 +157,12 @@ class Context:
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", idx)
         self._h = ctypes.c_void_p()
-        check(load().mdg_create(idx, ctypes.byref(self._h)))
+        self._check(self._api().mdg_create(idx, ctypes.byref(self._h)))
 
     def __del__(self):
         try:
             if getattr(self, "_h", None) and self._h.value:
-                load().mdg_destroy(self._h)
+                self._api().mdg_destroy(self._h)
                 self._h = ctypes.c_void_p()
         except Exception:
             pass
@@ -150,47 +170,47 @@ class Context:
     # -- K1 ---------------------------------------------------------------------------------
     def nbr_list(self, xyz, cell3, cutoff, sel_a=None, sel_b=None, ex_keys=None, get_dis=False):
         """generate_nbr_list for one frame: returns (nbr int64 (P,2), offsets fp32 (P,3)[, dis (P,)])."""
-        require_cuda(xyz, "xyz")
+        self._require(xyz, "xyz")
         xyz = xyz.detach().to(torch.float32).contiguous()
         n = xyz.shape[0]
         dev = xyz.device
         npairs = ctypes.c_int64(0)
-        with torch.cuda.device(dev):
-            check(load().mdg_nbr_build(self._h, _ptr(xyz), n, _farr(cell3, 3), float(cutoff), _ptr(sel_a), _ptr(sel_b),
-                                       _ptr(ex_keys), 0 if ex_keys is None else int(ex_keys.numel()), _stream(dev),
+        with self._guard(dev):
+            self._check(self._api().mdg_nbr_build(self._h, _ptr(xyz), n, _farr(cell3, 3), float(cutoff), _ptr(sel_a), _ptr(sel_b),
+                                       _ptr(ex_keys), 0 if ex_keys is None else int(ex_keys.numel()), self._stream(dev),
                                        ctypes.byref(npairs)))
             P = npairs.value
             nbr = torch.empty((P, 2), dtype=torch.int64, device=dev)
             off = torch.empty((P, 3), dtype=torch.float32, device=dev)
             dis = torch.empty((P,), dtype=torch.float32, device=dev) if get_dis else None
-            check(load().mdg_nbr_export(self._h, _ptr(nbr), _ptr(off), _ptr(dis), _stream(dev)))
+            self._check(self._api().mdg_nbr_export(self._h, _ptr(nbr), _ptr(off), _ptr(dis), self._stream(dev)))
         self._keepalive = (xyz, sel_a, sel_b, ex_keys)
         return (nbr, off, dis) if get_dis else (nbr, off)
 
     # -- K2+K3 ------------------------------------------------------------------------------
     def pair_force(self, kind, params, xyz, want_force=True, want_dparams=False):
         """E (0-d), F (N,3) or None, dE/dparams (4,) or None over the list of the last nbr_list()."""
-        require_cuda(xyz, "xyz")
+        self._require(xyz, "xyz")
         xyz = xyz.detach().to(torch.float32).contiguous()
         n = xyz.shape[0]
         dev = xyz.device
         e = torch.empty((), dtype=torch.float32, device=dev)
         f = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_force else None
         dp = torch.empty((MAX_POT_PARAMS,), dtype=torch.float32, device=dev) if want_dparams else None
-        with torch.cuda.device(dev):
-            check(load().mdg_pair_force(self._h, int(kind), _farr(params, MAX_POT_PARAMS), len(params), _ptr(xyz), n,
-                                        _ptr(e), _ptr(f), _ptr(dp), _stream(dev)))
+        with self._guard(dev):
+            self._check(self._api().mdg_pair_force(self._h, int(kind), _farr(params, MAX_POT_PARAMS), len(params), _ptr(xyz), n,
+                                        _ptr(e), _ptr(f), _ptr(dp), self._stream(dev)))
         return e, f, dp
 
     # -- K6 ---------------------------------------------------------------------------------
     def rdf_accumulate(self, xyz, cell3, start, end, nbins, width, count, sel_a=None, sel_b=None):
-        require_cuda(xyz, "xyz")
+        self._require(xyz, "xyz")
         xyz = xyz.detach().to(torch.float32).contiguous()
         dev = xyz.device
-        with torch.cuda.device(dev):
-            check(load().mdg_rdf_accumulate(self._h, _ptr(xyz), xyz.shape[0], _farr(cell3, 3), float(start), float(end),
+        with self._guard(dev):
+            self._check(self._api().mdg_rdf_accumulate(self._h, _ptr(xyz), xyz.shape[0], _farr(cell3, 3), float(start), float(end),
                                             int(nbins), float(width) if width else 0.0, _ptr(sel_a), _ptr(sel_b),
-                                            _ptr(count), _stream(dev)))
+                                            _ptr(count), self._stream(dev)))
         self._keepalive = (xyz, sel_a, sel_b)
 
     # -- K4 + driver ------------------------------------------------------------------------
@@ -198,7 +218,7 @@ class Context:
         """Runs one epoch; returns (traj_v, traj_q, traj_pv or None, last_energy or None).
         `out=(traj_v, traj_q)` reuses caller-allocated (n_frames, N, 3) fp32 CUDA buffers."""
         for t, nm in ((mass, "mass"), (v0, "v0"), (q0, "q0")):
-            require_cuda(t, nm)
+            self._require(t, nm)
         dev = q0.device
         n = q0.shape[0]
         n_grid = len(tgrid)
@@ -215,42 +235,42 @@ class Context:
         hpv0 = _farr(pv0 if M else [0.0], max(1, M))
         tg = _farr(tgrid)
         e = ctypes.c_float(0.0)
-        with torch.cuda.device(dev):
-            check(load().mdg_md_run(self._h, ctypes.byref(params), n, _ptr(mass), _ptr(v0), _ptr(q0), hpv0, tg, n_grid,
+        with self._guard(dev):
+            self._check(self._api().mdg_md_run(self._h, ctypes.byref(params), n, _ptr(mass), _ptr(v0), _ptr(q0), hpv0, tg, n_grid,
                                     _ptr(tv), _ptr(tq), hpv if M else None,
-                                    ctypes.byref(e) if want_energy else None, _stream(dev)))
+                                    ctypes.byref(e) if want_energy else None, self._stream(dev)))
         tpv = None
         if M:
             tpv = torch.tensor(list(hpv), dtype=torch.float32).reshape(n_frames, M).to(dev)
         return tv, tq, tpv, (e.value if want_energy else None)
 
     def set_pair_filter(self, sel_a=None, sel_b=None, ex_keys=None):
-        check(load().mdg_set_pair_filter(self._h, _ptr(sel_a), _ptr(sel_b), _ptr(ex_keys),
+        self._check(self._api().mdg_set_pair_filter(self._h, _ptr(sel_a), _ptr(sel_b), _ptr(ex_keys),
                                          0 if ex_keys is None else int(ex_keys.numel())))
         self._filter_keepalive = (sel_a, sel_b, ex_keys)
 
     # -- K5: SchNet cfconv aggregation ---------------------------------------------------------
     def graph_build(self, nbr, n):
-        require_cuda(nbr, "nbr_list")
+        self._require(nbr, "nbr_list")
         nbr = nbr.to(torch.int64).contiguous()
-        with torch.cuda.device(nbr.device):
-            check(load().mdg_graph_build(self._h, _ptr(nbr), nbr.shape[0], int(n), _stream(nbr.device)))
+        with self._guard(nbr.device):
+            self._check(self._api().mdg_graph_build(self._h, _ptr(nbr), nbr.shape[0], int(n), self._stream(nbr.device)))
         self._graph_keepalive = nbr
         self._graph_n = int(n)
 
     def cfconv_agg(self, h, W):
-        require_cuda(h, "h")
+        self._require(h, "h")
         h, W = h.contiguous(), W.contiguous()
         out = torch.empty_like(h)
-        with torch.cuda.device(h.device):
-            check(load().mdg_cfconv_agg(self._h, _ptr(h), _ptr(W), h.shape[0], h.shape[1], _ptr(out), _stream(h.device)))
+        with self._guard(h.device):
+            self._check(self._api().mdg_cfconv_agg(self._h, _ptr(h), _ptr(W), h.shape[0], h.shape[1], _ptr(out), self._stream(h.device)))
         return out
 
     def cfconv_edge_grad(self, h, g, n_edges):
         h, g = h.contiguous(), g.contiguous()
         gW = torch.empty((n_edges, h.shape[1]), dtype=torch.float32, device=h.device)
-        with torch.cuda.device(h.device):
-            check(load().mdg_cfconv_edge_grad(self._h, _ptr(h), _ptr(g), h.shape[0], h.shape[1], _ptr(gW), _stream(h.device)))
+        with self._guard(h.device):
+            self._check(self._api().mdg_cfconv_edge_grad(self._h, _ptr(h), _ptr(g), h.shape[0], h.shape[1], _ptr(gW), self._stream(h.device)))
         return gW
 
     # -- multi-GPU ----------------------------------------------------------------------------
@@ -263,30 +283,30 @@ class Context:
         path = nccl_library_path().encode()
         buf = ctypes.create_string_buffer(128)
         if rank == 0:
-            check(load().mdg_dist_unique_id(path, buf))
+            self._check(self._api().mdg_dist_unique_id(path, buf))
         t = torch.tensor(list(buf.raw), dtype=torch.uint8)
         if dist.get_backend(group) == "nccl":
             t = t.to(self.device)
         dist.broadcast(t, src=0, group=group)
         ident = bytes(t.cpu().tolist())
-        with torch.cuda.device(self.device):
-            check(load().mdg_dist_init(self._h, path, ident, rank, world))
+        with self._guard(self.device):
+            self._check(self._api().mdg_dist_init(self._h, path, ident, rank, world))
         self.rank, self.world = rank, world
 
     def dist_finalize(self):
-        check(load().mdg_dist_finalize(self._h))
+        self._check(self._api().mdg_dist_finalize(self._h))
 
     def set_profile(self, enable):
-        check(load().mdg_set_profile(self._h, int(bool(enable))))
+        self._check(self._api().mdg_set_profile(self._h, int(bool(enable))))
 
     def get_profile(self):
         out = (ctypes.c_double * 2)()
-        check(load().mdg_get_profile(self._h, out))
+        self._check(self._api().mdg_get_profile(self._h, out))
         return {"force_ms": out[0], "force_launches": int(out[1])}
 
     def stats(self):
         out = (ctypes.c_int64 * 8)()
-        check(load().mdg_get_stats(self._h, out))
+        self._check(self._api().mdg_get_stats(self._h, out))
         keys = ["launches", "rebuilds", "entries", "maxrow_or_K", "ncx", "ncy", "ncz", "path"]
         return dict(zip(keys, list(out)))
 

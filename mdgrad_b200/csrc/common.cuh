@@ -139,9 +139,13 @@ __device__ __forceinline__ float mdg_ipow(float x, int n) {
 
 // 1-ulp reciprocal on the SFU (MUFU.RCP); energies/forces are tolerance-parity (1e-5), membership is not affected
 __device__ __forceinline__ float mdg_rcp(float x) {
+#ifdef MDG_EMU       // CPU emulation harness (tests/cuemu): no PTX
+    return 1.0f / x;
+#else
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 
 // Per-pair values are returned UNSCALED for the hot kinds; the per-atom sums are multiplied once by

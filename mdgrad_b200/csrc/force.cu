@@ -45,9 +45,13 @@ PotParams mdg_make_pot(int kind, const float* h_params, int n_params) {
 // ---------------------------------------------------------------------------------------------
 // float4 gather with a single mad.wide address computation
 __device__ __forceinline__ float4 mdg_gather4(const float4* __restrict__ base, uint32_t idx) {
+#ifdef MDG_EMU       // CPU emulation harness (tests/cuemu): no PTX
+    return base[idx];
+#else
     const float4* p;
     asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(p) : "r"(idx), "l"(base));
     return __ldg(p);
+#endif
 }
 
 template <int KIND, bool RETEST, bool WITH_DP, bool PURE, int GROUP>
