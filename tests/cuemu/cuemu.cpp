@@ -4,8 +4,37 @@
 #include "cuda_runtime.h"
 
 #include <stdio.h>
-#include <ucontext.h>
 #include <vector>
+
+// Context switch: callee-saved registers only (x86-64 SysV), ~2 ns; ucontext's swapcontext makes a sigprocmask system
+// call per switch, which dominated the ballot-heavy kernels.
+#if defined(__x86_64__)
+extern "C" void cuemu_switch(void** save_sp, void* new_sp);
+asm(R"(
+.text
+.globl cuemu_switch
+.type cuemu_switch,@function
+cuemu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size cuemu_switch,.-cuemu_switch
+)");
+#else
+#error "cuemu: context switch implemented for x86-64 only"
+#endif
 
 namespace cuemu {
 
@@ -17,7 +46,7 @@ static const size_t STACK_BYTES = 256 * 1024;
 static const int    MAX_THREADS = 1024;
 
 struct Fiber {
-    ucontext_t  ctx;
+    void*       sp = nullptr;
     char*       stack = nullptr;
     ThreadState ts;
     bool        done = false;
@@ -30,7 +59,7 @@ struct Warp {
 
 static std::vector<Fiber> g_fibers;
 static std::vector<Warp>  g_warps;
-static ucontext_t         g_main;
+static void*              g_main_sp = nullptr;
 static Fiber*             g_fiber = nullptr;
 static const std::function<void()>* g_body = nullptr;
 static uint64_t g_progress = 0;
@@ -38,7 +67,7 @@ static int      g_live = 0, g_bar_arrived = 0;
 static uint64_t g_bar_gen = 0;
 static std::vector<char> g_dyn_smem;
 
-static void yield() { swapcontext(&g_fiber->ctx, &g_main); }
+static void yield() { cuemu_switch(&g_fiber->sp, g_main_sp); }
 
 static void trampoline() {
     (*g_body)();
@@ -47,7 +76,8 @@ static void trampoline() {
     g_live--;
     g_warps[f->ts.lin >> 5].live &= ~(1u << (f->ts.lin & 31));
     g_progress++;
-    swapcontext(&f->ctx, &g_main);
+    cuemu_switch(&f->sp, g_main_sp);
+    abort();     // a finished fiber is never resumed
 }
 
 int lane_id() { return g_cur->lin & 31; }
@@ -157,11 +187,12 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
                     f.ts.tid.y = (t / block.x) % block.y;
                     f.ts.tid.z = t / (block.x * block.y);
                     g_warps[t >> 5].live |= 1u << (t & 31);
-                    getcontext(&f.ctx);
-                    f.ctx.uc_stack.ss_sp = f.stack;
-                    f.ctx.uc_stack.ss_size = STACK_BYTES;
-                    f.ctx.uc_link = nullptr;
-                    makecontext(&f.ctx, trampoline, 0);
+                    // initial frame: six callee-saved register slots, then the entry point as the return address
+                    void** top = (void**)(f.stack + STACK_BYTES);
+                    top[-1] = nullptr;
+                    top[-2] = (void*)trampoline;
+                    for (int r = 3; r <= 8; ++r) top[-r] = nullptr;
+                    f.sp = (void*)(top - 8);
                 }
                 int remaining = nt;
                 while (remaining > 0) {
@@ -172,7 +203,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
                         if (f.done) continue;
                         g_fiber = &f;
                         g_cur = &f.ts;
-                        swapcontext(&g_main, &f.ctx);
+                        cuemu_switch(&g_main_sp, f.sp);
                         if (!f.done) remaining++;
                     }
                     if (remaining > 0 && g_progress == p0) {
