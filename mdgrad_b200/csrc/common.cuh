@@ -270,6 +270,7 @@ struct mdg_ctx {
     // list
     DevBuf rows, row_len;     // uint32 [n*cap], int [n]
     int    force_group = 4;            // lanes per row in k_force_rows (MDG_FORCE_GROUP=2|4|8)
+    bool   force_energy = true;        // false: the next force launches skip the per-atom energy (engine inner steps)
     DevBuf flags;             // int[8]: 0 = capacity overflow, 1 = skin violation
     // export scratch
     DevBuf up_cnt, up_off, scan_tmp;

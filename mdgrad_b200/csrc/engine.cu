@@ -496,7 +496,11 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     int nown = A.s1 - A.s0;
     int ib = (nown + T - 1) / T;
     ib = ib < 1 ? 1 : (ib > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : ib);
+    // the per-atom energy is only read after the LAST force evaluation of the epoch (h_last_energy)
+    const bool energy_free = getenv("MDG_FORCE_ENERGY_ALWAYS") == nullptr;
+    c->force_energy = !(energy_free && n_grid > 1);
     MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
+    c->force_energy = true;
     if (nhc) { k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, vbuf[vsel], ke_v_cur); c->stat_launches++; }
     if (!dist) {   // frame 0 = the initial state, verbatim
         MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -552,6 +556,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         const double* ke_a = ke_v_cur;
         const double* ke_b = ke_h_cur;
         int n_part = ib_prev;
+        c->force_energy = !(energy_free && g + 1 < nsteps);
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (c->prof_enable) {
             std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
@@ -607,6 +612,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
             if (nhc) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_ke, 0));
         }
+        c->force_energy = true;
         int gp = g + 1;
         bool keep = (gp % stride) == 0;
         size_t fr = (size_t)(gp / stride);
@@ -692,6 +698,7 @@ extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float
         c->prof_used = 0;
         int s = run_once(c, p, n, d_mass, d_v0, d_q0, h_pv0, h_tgrid, n_grid, d_traj_v, d_traj_q, h_traj_pv,
                          h_last_energy, K, st);
+        c->force_energy = true;     // (an error return inside the loop must not leak the force-only mode)
         if (s == MDG_E_CAPACITY) {
             int need = c->h_pinned[2];
             int cap = ((need + need / 8 + 31) / 32) * 32;

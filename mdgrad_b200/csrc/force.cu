@@ -54,16 +54,18 @@ __device__ __forceinline__ float4 mdg_gather4(const float4* __restrict__ base, u
 #endif
 }
 
-template <int KIND, bool RETEST, bool WITH_DP, bool PURE, int GROUP>
+template <int KIND, bool RETEST, bool WITH_DP, bool PURE, int GROUP, bool WITH_E>
 __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, const uint32_t* __restrict__ row, int m,
                                                int lane_in_group, const float4 qi, const Box& bx, float rc2,
                                                const PotParams& P, float& fx, float& fy, float& fz, float& en, float* dpa) {
     const uint32_t ZERO_CODE = (1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS;
     constexpr bool IFCONV = (KIND == MDG_POT_LJ) && !WITH_DP;
-    for (int kb = 0; kb < m; kb += GROUP * 4) {
+    // (down-counting loop: no loop-bound register - at the 32-register budget the bound was spilled to local memory)
+    const uint32_t* rp = row + lane_in_group * 4;
+    for (int rem = m; rem > 0; rem -= GROUP * 4, rp += GROUP * 4) {
         // the row stream (~100 MB per launch) is read once: evict-first, so that it does not push the gathered
         // neighbor positions (4 MB, re-read ~90 times) out of L1/L2
-        const uint4 e4 = __ldcs(reinterpret_cast<const uint4*>(row + kb + lane_in_group * 4));
+        const uint4 e4 = __ldcs(reinterpret_cast<const uint4*>(rp));
         const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
         float4 qj[4];
 #pragma unroll
@@ -96,7 +98,7 @@ __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, co
                     fx -= g * dx;
                     fy -= g * dy;
                     fz -= g * dz;
-                    en += e_p;
+                    if (WITH_E) en += e_p;
                 }
             } else if (in) {
                 float e_p, g, dp[MDG_MAX_POT_PARAMS];
@@ -104,7 +106,7 @@ __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, co
                 fx -= g * dx;
                 fy -= g * dy;
                 fz -= g * dz;
-                en += e_p;
+                if (WITH_E) en += e_p;
                 if (WITH_DP) {
 #pragma unroll
                     for (int q = 0; q < MDG_MAX_POT_PARAMS; ++q) dpa[q] += dp[q];
@@ -114,7 +116,9 @@ __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, co
     }
 }
 
-template <int KIND, bool RETEST, bool WITH_DP, int GROUP>
+// WITH_E = false: the per-atom energy (fs.w) is not accumulated (written as 0) - the MD loop only needs it after
+// the last step of an epoch, and the energy costs 3 of the 28 instructions of a pure-row entry.
+template <int KIND, bool RETEST, bool WITH_DP, int GROUP, bool WITH_E>
 __global__ void __launch_bounds__(256, 8) k_force_rows(int s0, int n, const float4* __restrict__ qs,
                                                                     const uint32_t* __restrict__ rows,
                                                                     const int* __restrict__ row_len, int cap, Box bx, float rc2,
@@ -130,9 +134,9 @@ __global__ void __launch_bounds__(256, 8) k_force_rows(int s0, int n, const floa
         const int ml = row_len[s];
         const int m = ml & MDG_ROW_LEN_MASK;
         if (ml & MDG_ROW_PURE)
-            mdg_row_stream<KIND, RETEST, WITH_DP, true, GROUP>(qs, row, m, lane_in_group, qi, bx, rc2, P, fx, fy, fz, en, dpa);
+            mdg_row_stream<KIND, RETEST, WITH_DP, true, GROUP, WITH_E>(qs, row, m, lane_in_group, qi, bx, rc2, P, fx, fy, fz, en, dpa);
         else
-            mdg_row_stream<KIND, RETEST, WITH_DP, false, GROUP>(qs, row, m, lane_in_group, qi, bx, rc2, P, fx, fy, fz, en, dpa);
+            mdg_row_stream<KIND, RETEST, WITH_DP, false, GROUP, WITH_E>(qs, row, m, lane_in_group, qi, bx, rc2, P, fx, fy, fz, en, dpa);
         fx *= P.sg; fy *= P.sg; fz *= P.sg;
         en *= 0.5f * P.se;
         if (WITH_DP) {
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(256, 8) k_force_rows(int s0, int n, const floa
         fx += __shfl_xor_sync(0xffffffffu, fx, o);
         fy += __shfl_xor_sync(0xffffffffu, fy, o);
         fz += __shfl_xor_sync(0xffffffffu, fz, o);
-        en += __shfl_xor_sync(0xffffffffu, en, o);
+        if (WITH_E) en += __shfl_xor_sync(0xffffffffu, en, o);
     }
     if (s < n && lane_in_group == 0) fs[s] = make_float4(fx, fy, fz, en);
     if (WITH_DP) {
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(256, 8) k_force_rows(int s0, int n, const floa
 }
 
 
-template <bool RETEST, bool WITH_DP, int GROUP>
+template <bool RETEST, bool WITH_DP, int GROUP, bool WITH_E>
 static int launch_force_g(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
     const int T = 256;
     int s0 = c->force_s0 >= 0 ? c->force_s0 : c->own_s0, n = c->force_s0 >= 0 ? c->force_s1 : c->own_s1;
@@ -179,7 +183,7 @@ static int launch_force_g(mdg_ctx* c, const PotParams& P, const float4* qs, floa
     // rows are allocated for the own range only: address them by the global sorted index
     const uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
 #define LF(K)                                                                                                  \
-    k_force_rows<K, RETEST, WITH_DP, GROUP><<<nb, T, 0, st>>>(s0, n, qs, rows_base, c->row_len.as<int>(),      \
+    k_force_rows<K, RETEST, WITH_DP, GROUP, WITH_E><<<nb, T, 0, st>>>(s0, n, qs, rows_base, c->row_len.as<int>(),      \
                                                               c->cap, c->box, c->rc2, P, fs, dpp)
     switch (P.kind) {
         case MDG_POT_LJ: LF(MDG_POT_LJ); break;
@@ -199,9 +203,11 @@ static int launch_force_g(mdg_ctx* c, const PotParams& P, const float4* qs, floa
 // lanes per row: 4 (default; measured 60.0 us vs 65.8 us with 8 on the 256k-atom box) - MDG_FORCE_GROUP=2|4|8
 template <bool RETEST, bool WITH_DP>
 static int launch_force(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
-    if (c->force_group == 8) return launch_force_g<RETEST, WITH_DP, 8>(c, P, qs, fs, dpp, st);
-    if (c->force_group == 2 && RETEST && !WITH_DP) return launch_force_g<RETEST, WITH_DP, 2>(c, P, qs, fs, dpp, st);
-    return launch_force_g<RETEST, WITH_DP, 4>(c, P, qs, fs, dpp, st);
+    if (c->force_group == 8) return launch_force_g<RETEST, WITH_DP, 8, true>(c, P, qs, fs, dpp, st);
+    if (c->force_group == 2 && RETEST && !WITH_DP) return launch_force_g<RETEST, WITH_DP, 2, true>(c, P, qs, fs, dpp, st);
+    // engine steps whose energy nobody reads (all but the last of an epoch): force-only specialisation
+    if (RETEST && !WITH_DP && !c->force_energy) return launch_force_g<RETEST, WITH_DP, 4, false>(c, P, qs, fs, dpp, st);
+    return launch_force_g<RETEST, WITH_DP, 4, true>(c, P, qs, fs, dpp, st);
 }
 
 int mdg_i_force_blocks(mdg_ctx* c) { return (int)(((int64_t)(c->own_s1 - c->own_s0) * c->force_group + 255) / 256); }
