@@ -18,9 +18,16 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mdgrad_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libmdgrad_b200_emu.so")
-CXX = os.environ.get("CXX", "g++")
-FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
-         "-Wno-unused-function", "-DMDG_EMU=1", "-I", HERE, "-I", CSRC]
+CXX = os.environ.get("CUEMU_CXX", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++")
+# CUEMU_SANITIZE=1: AddressSanitizer + UBSan build (out-of-bounds / misaligned vector accesses of the kernels); run the
+# tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0
+SANITIZE = os.environ.get("CUEMU_SANITIZE", "") not in ("", "0")
+if SANITIZE:
+    OUT = os.path.join(HERE, "_build_san")
+    LIB = os.path.join(OUT, "libmdgrad_b200_emu.so")
+FLAGS = (["-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if SANITIZE else ["-O2"]) + [
+    "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
+    "-Wno-unused-function", "-DMDG_EMU=1", "-I", HERE, "-I", CSRC]
 
 
 def _match_back_template(src, i):
@@ -167,7 +174,8 @@ def build(verbose=False):
             raise RuntimeError("cuemu build failed for %s:\n%s" % (name, out))
         if verbose and out.strip():
             print(out)
-    r = subprocess.run([CXX, "-shared", "-o", LIB] + objs + ["-ldl", "-lm"], capture_output=True, text=True)
+    r = subprocess.run([CXX, "-shared", "-o", LIB] + (["-fsanitize=address,undefined"] if SANITIZE else []) + objs + ["-ldl", "-lm"],
+                       capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("cuemu link failed:\n" + r.stdout + r.stderr)
     with open(stamp_file, "w") as f:
