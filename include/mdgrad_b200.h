@@ -206,6 +206,46 @@ int mdg_cfconv_agg(mdg_ctx* ctx, const float* d_h, const float* d_W, int n, int 
 int mdg_cfconv_edge_grad(mdg_ctx* ctx, const float* d_h, const float* d_g, int n, int n_filters, float* d_gW, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5'  SchNet energy + forces in one call - replaces SchNet.forward (nff/nn/models/schnet.py:113-171:
+ *     convolve -> atomwisereadout -> batch_and_sum) over a given neighbor list together with the autograd
+ *     force F = -dE/dxyz (torchmd/md.py:227-228) for a GNNPotentials model (torchmd/interface.py:125-136).
+ *
+ * The model is described by DEVICE pointers to its parameters in the reference's `state_dict` layout (torch
+ * Linear weight = out x in, row-major):
+ *   embed  : atom_embed.weight (100 x A)
+ *   layer l: mu/width = convolutions.l.moduledict.message_edge_filter.0.{offsets,width} (G)
+ *            We1,be1  = ...message_edge_filter.1.{weight,bias}   (G x G, G)
+ *            We2,be2  = ...message_edge_filter.3.{weight,bias}   (F x G, F)
+ *            Wn,bn    = ...message_node_filter.{weight,bias}     (F x A, F)
+ *            Wu1,bu1  = ...update_function.0.{weight,bias}       (A x F, A)
+ *            Wu2,bu2  = ...update_function.2.{weight,bias}       (A x A, A)
+ *   readout: Wr1,br1  = atomwisereadout.readout.energy.linear0   (R x A, R),  Wr2,br2 = ...linear2 (1 x R, 1)
+ * Inputs: d_z (N int64 atomic numbers), d_xyz (N x 3), the list in the reference layout (d_nbr E x 2 int64 with
+ * i < j, d_offsets E x 3 fp32) and h_off_scale3: edge vector = x_i - x_j - offsets * h_off_scale3 - (1,1,1)
+ * reproduces the reference's raw-offset quirk (schnet.py:140-142), the cell lengths give true PBC.
+ * Outputs: d_energy (1 fp32), d_force (N x 3 fp32, may be NULL = energy only).  Asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------------ */
+#define MDG_SCHNET_MAX_LAYERS 8
+typedef struct mdg_schnet_layer {
+    const float *mu, *width;
+    const float *We1, *be1, *We2, *be2;
+    const float *Wn, *bn;
+    const float *Wu1, *bu1, *Wu2, *bu2;
+} mdg_schnet_layer;
+
+typedef struct mdg_schnet_model {
+    int n_atom_basis, n_filters, n_gaussians, n_convolutions, n_readout;   /* A, F, G, L, R */
+    const float* embed;
+    mdg_schnet_layer layers[MDG_SCHNET_MAX_LAYERS];
+    const float *Wr1, *br1, *Wr2, *br2;
+} mdg_schnet_model;
+
+int mdg_schnet_energy_force(mdg_ctx* ctx, const mdg_schnet_model* h_model, const int64_t* d_z,
+                            const float* d_xyz, int n, const int64_t* d_nbr, const float* d_offsets,
+                            int64_t n_edges, const float* h_off_scale3,
+                            float* d_energy, float* d_force, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The reference has no distributed code; this is the
  * spatial decomposition of SURVEY 8e: slabs of whole z-layers of cells in the global cell-sorted
  * index space, per-step ghost-position halo (ncclSend/ncclRecv of two contiguous ranges), one

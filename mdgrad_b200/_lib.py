@@ -28,7 +28,7 @@ SYMBOLS = [
     "mdg_pair_force", "mdg_pair_dis_fwd", "mdg_pair_dis_bwd", "mdg_rdf_accumulate", "mdg_md_run",
     "mdg_get_stats", "mdg_set_pair_filter", "mdg_set_profile", "mdg_get_profile",
     "mdg_slab_plan", "mdg_dist_unique_id", "mdg_dist_init", "mdg_dist_finalize",
-    "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad",
+    "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad", "mdg_schnet_energy_force",
 ]
 
 
@@ -48,6 +48,58 @@ class MdParams(ctypes.Structure):
         ("rebuild_every", ctypes.c_int),
         ("traj_stride", ctypes.c_int),
     ]
+
+
+SCHNET_MAX_LAYERS = 8
+
+
+class SchnetLayer(ctypes.Structure):
+    """mirror of struct mdg_schnet_layer (device pointers)"""
+    _fields_ = [(k, ctypes.c_void_p) for k in
+                ("mu", "width", "We1", "be1", "We2", "be2", "Wn", "bn", "Wu1", "bu1", "Wu2", "bu2")]
+
+
+class SchnetModel(ctypes.Structure):
+    """mirror of struct mdg_schnet_model"""
+    _fields_ = [("n_atom_basis", ctypes.c_int), ("n_filters", ctypes.c_int), ("n_gaussians", ctypes.c_int),
+                ("n_convolutions", ctypes.c_int), ("n_readout", ctypes.c_int),
+                ("embed", ctypes.c_void_p), ("layers", SchnetLayer * SCHNET_MAX_LAYERS),
+                ("Wr1", ctypes.c_void_p), ("br1", ctypes.c_void_p), ("Wr2", ctypes.c_void_p), ("br2", ctypes.c_void_p)]
+
+
+def schnet_model_struct(sd, device):
+    """mdg_schnet_model from a reference-layout SchNet `state_dict` (nff/nn/models/schnet.py); returns the struct and
+    the list of fp32 contiguous tensors it points into (keep them alive while the struct is used)."""
+    keep = []
+
+    def dp(key):
+        t = sd[key].detach().to(device, torch.float32).contiguous()
+        keep.append(t)
+        return t.data_ptr()
+
+    L = len({k.split(".")[1] for k in sd if k.startswith("convolutions.")})
+    if L > SCHNET_MAX_LAYERS:
+        raise ValueError("SchNet with %d convolutions: the native path supports up to %d" % (L, SCHNET_MAX_LAYERS))
+    m = SchnetModel()
+    m.n_atom_basis = sd["atom_embed.weight"].shape[1]
+    m.n_convolutions = L
+    m.embed = dp("atom_embed.weight")
+    for l in range(L):
+        pre = "convolutions.%d.moduledict." % l
+        y = m.layers[l]
+        y.mu, y.width = dp(pre + "message_edge_filter.0.offsets"), dp(pre + "message_edge_filter.0.width")
+        y.We1, y.be1 = dp(pre + "message_edge_filter.1.weight"), dp(pre + "message_edge_filter.1.bias")
+        y.We2, y.be2 = dp(pre + "message_edge_filter.3.weight"), dp(pre + "message_edge_filter.3.bias")
+        y.Wn, y.bn = dp(pre + "message_node_filter.weight"), dp(pre + "message_node_filter.bias")
+        y.Wu1, y.bu1 = dp(pre + "update_function.0.weight"), dp(pre + "update_function.0.bias")
+        y.Wu2, y.bu2 = dp(pre + "update_function.2.weight"), dp(pre + "update_function.2.bias")
+    m.n_gaussians = sd["convolutions.0.moduledict.message_edge_filter.1.weight"].shape[1]
+    m.n_filters = sd["convolutions.0.moduledict.message_edge_filter.3.weight"].shape[0]
+    ro = "atomwisereadout.readout.energy."
+    m.n_readout = sd[ro + "linear0.weight"].shape[0]
+    m.Wr1, m.br1 = dp(ro + "linear0.weight"), dp(ro + "linear0.bias")
+    m.Wr2, m.br2 = dp(ro + "linear2.weight"), dp(ro + "linear2.bias")
+    return m, keep
 
 
 class MdgError(RuntimeError):
@@ -98,6 +150,7 @@ def bind(lib):
     lib.mdg_cfconv_agg.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     lib.mdg_cfconv_edge_grad.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     lib.mdg_get_profile.argtypes = [vp, ctypes.POINTER(dbl)]
+    lib.mdg_schnet_energy_force.argtypes = [vp, ctypes.POINTER(SchnetModel), vp, vp, ip, vp, vp, i64, fp, vp, vp, vp]
     for name in SYMBOLS:
         if name not in ("mdg_last_error",):
             getattr(lib, name).restype = ip
@@ -272,6 +325,24 @@ class Context:
         with self._guard(h.device):
             self._check(self._api().mdg_cfconv_edge_grad(self._h, _ptr(h), _ptr(g), h.shape[0], h.shape[1], _ptr(gW), self._stream(h.device)))
         return gW
+
+    def schnet_energy_force(self, model, z, xyz, nbr, offsets, off_scale=(1.0, 1.0, 1.0), want_force=True):
+        """SchNet energy (0-d) and forces (N,3) over the given reference-layout list; `model` = (SchnetModel, keepalive)
+        from schnet_model_struct().  off_scale (1,1,1) = the reference's raw-offset quirk, cell lengths = true PBC."""
+        self._require(xyz, "xyz")
+        xyz = xyz.detach().to(torch.float32).contiguous()
+        z = z.to(xyz.device, torch.int64).contiguous()
+        nbr = nbr.to(xyz.device, torch.int64).contiguous()
+        offsets = offsets.detach().to(xyz.device, torch.float32).contiguous()
+        n = xyz.shape[0]
+        e = torch.empty((), dtype=torch.float32, device=xyz.device)
+        f = torch.empty((n, 3), dtype=torch.float32, device=xyz.device) if want_force else None
+        with self._guard(xyz.device):
+            self._check(self._api().mdg_schnet_energy_force(self._h, ctypes.byref(model[0]), _ptr(z), _ptr(xyz), n, _ptr(nbr),
+                                                         _ptr(offsets), nbr.shape[0], _farr(off_scale, 3), _ptr(e), _ptr(f),
+                                                         self._stream(xyz.device)))
+        self._schnet_keepalive = (z, xyz, nbr, offsets)
+        return e, f
 
     # -- multi-GPU ----------------------------------------------------------------------------
     def dist_init(self, group=None):

@@ -291,6 +291,7 @@ struct mdg_ctx {
 
     // SchNet graph (graph.cu): node -> incident-edge CSR of the last mdg_graph_build
     DevBuf g_off, g_cnt, g_edge, g_other;
+    DevBuf sn_ws;             // SchNet activations / workspace (schnet.cu)
     int     g_n = -1;
     int64_t g_edges = 0;
     const int64_t* g_nbr = nullptr;

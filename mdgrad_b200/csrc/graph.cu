@@ -83,10 +83,17 @@ __global__ void k_cfconv_edge_grad(int64_t E, int F, const int64_t* __restrict__
     gW[idx] = h[a0 * F + f] * g[a1 * F + f] + h[a1 * F + f] * g[a0 * F + f];
 }
 
+int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st);
+int mdg_i_cfconv_agg(mdg_ctx* c, const float* d_h, const float* d_W, int n, int F, float* d_out, cudaStream_t st);
+
 extern "C" int mdg_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, void* stream) {
-    if (!c || (n_edges > 0 && !d_nbr) || n < 0 || n_edges < 0 || 2 * n_edges > 0x7fffffffLL) { mdg_set_error("mdg_graph_build: bad arguments"); return MDG_E_BADARG; }
+    if (!c) { mdg_set_error("mdg_graph_build: null ctx"); return MDG_E_BADARG; }
     MDG_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    return mdg_i_graph_build(c, d_nbr, n_edges, n, (cudaStream_t)stream);
+}
+
+int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st) {
+    if ((n_edges > 0 && !d_nbr) || n < 0 || n_edges < 0 || 2 * n_edges > 0x7fffffffLL) { mdg_set_error("mdg_graph_build: bad arguments"); return MDG_E_BADARG; }
     c->g_n = n;
     c->g_edges = n_edges;
     c->g_nbr = d_nbr;
@@ -111,7 +118,10 @@ extern "C" int mdg_cfconv_agg(mdg_ctx* c, const float* d_h, const float* d_W, in
     if (!c || !d_h || !d_out || F <= 0) { mdg_set_error("mdg_cfconv_agg: bad arguments"); return MDG_E_BADARG; }
     if (n != c->g_n) { mdg_set_error("mdg_cfconv_agg: graph was built for %d nodes, got %d", c->g_n, n); return MDG_E_STATE; }
     MDG_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    return mdg_i_cfconv_agg(c, d_h, d_W, n, F, d_out, (cudaStream_t)stream);
+}
+
+int mdg_i_cfconv_agg(mdg_ctx* c, const float* d_h, const float* d_W, int n, int F, float* d_out, cudaStream_t st) {
     if (n == 0) return MDG_OK;
     int nb = (int)(((int64_t)n * 32 + 255) / 256);
     if ((F & 3) == 0 && (((uintptr_t)d_h | (uintptr_t)d_W | (uintptr_t)d_out) & 15) == 0)

@@ -11,6 +11,7 @@ offsets @ cell instead.
 """
 import torch
 
+from . import _lib
 from .interface import GeneralInteraction
 from .topology import _exclusion_keys, cell_lengths, generate_nbr_list
 
@@ -41,6 +42,44 @@ class GNNPotentials(GeneralInteraction):
         self.inputs["nbr_list"] = nbr
         self.inputs["offsets"] = offsets if self.pbc_mode == "reference" else offsets * torch.tensor(self._L, device=offsets.device)
         self.inputs.pop("_native_graph", None)
+
+    # -- native force route (no autograd tape): used by the solvers whenever no graph is being recorded -----------
+    def native_ready(self):
+        """True when `native_force` covers this model: our SchNet mirror with the default energy readout."""
+        from .nffm.schnet import SchNet, shifted_softplus
+        g = self.gnn
+        if type(g) is not SchNet or self.second_order or g.atomwisereadout.post_readout is not None:
+            return False
+        ro = g.atomwisereadout.readout
+        if list(ro.keys()) != ["energy"] or len(ro["energy"]) != 3:
+            return False
+        l0, act, l2 = ro["energy"][0], ro["energy"][1], ro["energy"][2]
+        if not (isinstance(l0, torch.nn.Linear) and isinstance(act, shifted_softplus) and isinstance(l2, torch.nn.Linear)):
+            return False
+        if l2.out_features != 1 or l0.bias is None or l2.bias is None:
+            return False
+        G = g.convolutions[0].moduledict["message_edge_filter"][1].in_features
+        return len(g.convolutions) <= _lib.SCHNET_MAX_LAYERS and G <= 64
+
+    def _native_model(self):
+        sd = self.gnn.state_dict()
+        key = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+        if getattr(self, "_nm_key", None) != key:
+            self._nm = _lib.schnet_model_struct(sd, self.inputs["nxyz"].device)
+            self._nm_key = key
+        return self._nm
+
+    def native_energy_force(self, xyz, want_force=True):
+        """(energy 0-d, forces (N,3)) of the stored list at xyz from ONE native program (mdg_schnet_energy_force):
+        SchNet.forward (nff/nn/models/schnet.py:113-171) + the autograd force of md.py:227-228."""
+        if getattr(self, "_sn_ctx", None) is None:
+            self._sn_ctx = _lib.Context(xyz.device)
+            self._z = self.inputs["nxyz"][:, 0].to(torch.int64).contiguous()
+        return self._sn_ctx.schnet_energy_force(self._native_model(), self._z, xyz, self.inputs["nbr_list"],
+                                                self.inputs["offsets"], (1.0, 1.0, 1.0), want_force=want_force)
+
+    def native_force(self, xyz):
+        return self.native_energy_force(xyz)[1]
 
     def forward(self, xyz):
         if hasattr(self.gnn, "second_order"):

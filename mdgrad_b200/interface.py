@@ -89,6 +89,15 @@ class PairPotentials(GeneralInteraction):
         self.offsets = off
         return nbr, dis, off
 
+    # -- native force route (no autograd tape) ---------------------------------------------------------------------
+    def native_ready(self):
+        return type(self) is PairPotentials and self.native_kind() is not None and not self.second_order
+
+    def native_force(self, xyz):
+        """-dE/dxyz over the stored list straight from the force kernel (mdg_pair_force)."""
+        kind, values, _ = self.native_kind()
+        return self._ctx.pair_force(kind, values, xyz, want_force=True)[1]
+
     def forward(self, xyz):
         """sum_pairs u(|x_i - x_j - offsets@cell|) over the STORED list (reference :284-300)."""
         spec = self.native_kind()
@@ -130,6 +139,16 @@ class Stack(torch.nn.Module):
     def _reset_topology(self, x):
         for key in self.models.keys():
             self.models[key]._reset_topology(x)
+
+    def native_ready(self):
+        return all(hasattr(m, "native_ready") and m.native_ready() for m in self.models.values())
+
+    def native_force(self, x):
+        f = None
+        for m in self.models.values():
+            fm = m.native_force(x)
+            f = fm if f is None else f + fm
+        return f
 
     def forward(self, x):
         result = None

@@ -132,6 +132,11 @@ class _EOM(torch.nn.Module):
 
     def force(self, q):
         """-dU/dq at q with the reference's side effects (requires_grad on q, topology update, md.py:216-228)."""
+        if not torch.is_grad_enabled() and q.is_cuda and getattr(self.model, "native_ready", lambda: False)():
+            # nobody records a graph (forward pass of the adjoint solver, plain MD): forces come straight from the
+            # native programs (pair-force kernel / SchNet energy+force), no autograd tape
+            self.update_topology(q)
+            return self.model.native_force(q.detach())
         with torch.set_grad_enabled(True):
             if self.adjoint:
                 q.requires_grad = True

@@ -29,6 +29,7 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __constant__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 // ---------------------------------------------------------------------------------------------
 // vector types

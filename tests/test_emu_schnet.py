@@ -1,0 +1,76 @@
+"""CPU-emulated run (tests/cuemu) of the native SchNet energy+force program against the oracle (autograd forces) and
+against the reference fixtures.  Test infrastructure - the GPU parity test of the same op is in test_schnet.py."""
+import numpy as np
+import pytest
+import torch
+
+from emu_lib import EmuContext
+from mdgrad_b200 import _lib
+from oracle import oracle_torch as O
+from test_schnet import _fixture
+
+
+@pytest.fixture(scope="module")
+def ectx():
+    return EmuContext()
+
+
+def _rand_sd(A, F, G, L, R, cutoff, seed, bias=True):
+    g = torch.Generator().manual_seed(seed)
+    sd = {"atom_embed.weight": torch.randn(100, A, generator=g)}
+    mu = torch.linspace(0.0, cutoff, G)
+    lin = lambda o, i: torch.randn(o, i, generator=g) * (1.5 / np.sqrt(i))      # noqa: E731
+    b = lambda o: (torch.randn(o, generator=g) * 0.3 if bias else torch.zeros(o))  # noqa: E731
+    for l in range(L):
+        pre = "convolutions.%d.moduledict." % l
+        sd[pre + "message_edge_filter.0.width"] = (mu[1] - mu[0]) * torch.ones(G)
+        sd[pre + "message_edge_filter.0.offsets"] = mu.clone()
+        sd[pre + "message_edge_filter.1.weight"], sd[pre + "message_edge_filter.1.bias"] = lin(G, G), b(G)
+        sd[pre + "message_edge_filter.3.weight"], sd[pre + "message_edge_filter.3.bias"] = lin(F, G), b(F)
+        sd[pre + "message_node_filter.weight"], sd[pre + "message_node_filter.bias"] = lin(F, A), b(F)
+        sd[pre + "update_function.0.weight"], sd[pre + "update_function.0.bias"] = lin(A, F), b(A)
+        sd[pre + "update_function.2.weight"], sd[pre + "update_function.2.bias"] = lin(A, A), b(A)
+    ro = "atomwisereadout.readout.energy."
+    sd[ro + "linear0.weight"], sd[ro + "linear0.bias"] = lin(R, A), b(R)
+    sd[ro + "linear2.weight"], sd[ro + "linear2.bias"] = lin(1, R), b(1)
+    return sd
+
+
+@pytest.mark.parametrize("n,A,F,G,L,R,mode", [
+    (40, 16, 24, 7, 1, 8, "reference"),          # ragged sizes: every tile guard of the GEMM / edge kernels
+    (97, 36, 52, 13, 2, 18, "correct"),
+    (150, 64, 64, 29, 3, 32, "reference"),
+])
+def test_emu_schnet_random_model(ectx, n, A, F, G, L, R, mode):
+    rng = np.random.default_rng(n)
+    box = 9.0
+    xyz = torch.tensor(rng.uniform(0, box, (n, 3)), dtype=torch.float32)
+    z = torch.tensor(rng.integers(1, 9, n), dtype=torch.long)
+    cell = torch.tensor([box, box * 1.1, box * 0.95])
+    rc = 3.2
+    nbr, off = O.neighbor_list(xyz, rc, cell)
+    sd = _rand_sd(A, F, G, L, R, rc, seed=n)
+    x = xyz.clone().requires_grad_(True)
+    e_o = O.schnet_energy(sd, z, x, nbr, off, cell=torch.diag(cell), pbc_mode=mode)
+    f_o = -torch.autograd.grad(e_o, x)[0]
+    model = _lib.schnet_model_struct(sd, "cpu")
+    scale = (1.0, 1.0, 1.0) if mode == "reference" else tuple(cell.tolist())
+    e, f = ectx.schnet_energy_force(model, z, xyz, nbr, off, scale)
+    assert abs(e.item() - e_o.item()) <= 1e-5 * max(1.0, abs(e_o.item()))
+    assert (f - f_o).abs().max().item() <= 2e-5 * f_o.abs().max().item()
+    e2, _ = ectx.schnet_energy_force(model, z, xyz, nbr, off, scale, want_force=False)
+    assert e2.item() == e.item()
+
+
+@pytest.mark.parametrize("tag", ["water"])
+def test_emu_schnet_vs_reference_fixture(ectx, tag):
+    g, params, sd = _fixture(tag)
+    xyz = torch.Tensor(g["positions"])
+    cell = torch.Tensor(g["cell"])
+    nbr, off = O.neighbor_list(xyz, params["cutoff"], cell)
+    z = torch.tensor(g["numbers"], dtype=torch.long)
+    model = _lib.schnet_model_struct(sd, "cpu")
+    e, f = ectx.schnet_energy_force(model, z, xyz, nbr, off)
+    eref = float(g["energy"].reshape(-1)[0])
+    assert abs(e.item() - eref) <= 1e-5 * abs(eref)
+    assert np.abs(f.numpy() - g["forces"]).max() <= 1e-5 * np.abs(g["forces"]).max()

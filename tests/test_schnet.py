@@ -126,3 +126,67 @@ def test_schnet_md_through_generic_route():
     v, q, pv = sim.simulate(steps=6, frequency=6, dt=0.5 * units.fs)
     assert q.shape == (6, 192, 3) and torch.isfinite(q).all() and torch.isfinite(v).all()
     assert integ.update_count == 10 and integ.last_engine_stats is None        # generic route: 2 evaluations per step
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["water", "si"])
+def test_native_schnet_energy_force_vs_reference_fixture(tag):
+    """mdg_schnet_energy_force (one native program: forward + analytic backward, no autograd) vs the reference's
+    energy and autograd forces, 1e-5 relative; and vs the op-by-op autograd route of the mirror on the same list."""
+    from nff.nn.models.schnet import SchNet
+    from torchmd.interface import GNNPotentials
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms
+    g, params, sd = _fixture(tag)
+    system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device=0)
+    model = SchNet(params)
+    model.load_state_dict(sd)
+    gnn = GNNPotentials(system, model.cuda(), cutoff=params["cutoff"])
+    assert gnn.native_ready()
+    xyz = torch.Tensor(system.get_positions()).cuda()
+    e, f = gnn.native_energy_force(xyz)
+    eref = float(g["energy"].reshape(-1)[0])
+    assert abs(e.item() - eref) <= 1e-5 * abs(eref)
+    assert np.abs(f.cpu().numpy() - g["forces"]).max() <= 1e-5 * np.abs(g["forces"]).max()
+    x = xyz.clone().requires_grad_(True)
+    ea = gnn(x)
+    fa = -torch.autograd.grad(ea.sum(), x)[0]
+    assert (f - fa).abs().max().item() <= 1e-5 * fa.abs().max().item()
+    # perturbed positions on the SAME (now stale) list, and determinism
+    x2 = xyz + 0.01 * torch.randn_like(xyz)
+    e2, f2 = gnn.native_energy_force(x2)
+    xa = x2.clone().requires_grad_(True)
+    fb = -torch.autograd.grad(gnn(xa).sum(), xa)[0]
+    assert (f2 - fb).abs().max().item() <= 1e-5 * fb.abs().max().item()
+    assert torch.equal(gnn.native_energy_force(x2)[1], f2)
+
+
+@pytest.mark.gpu
+def test_schnet_md_native_force_equals_autograd_route():
+    """The no-grad solver route takes forces from the native programs; the same epoch with the autograd route
+    (grad mode on) must give the same short trajectory."""
+    from nff.nn.models.schnet import SchNet
+    from torchmd.interface import GNNPotentials, PairPotentials, Stack
+    from torchmd.potentials import ExcludedVolume
+    from torchmd.md import NoseHooverChain
+    from torchmd.sovlers import odeint, odeint_reuse_force
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms, units
+    g, params, sd = _fixture("water")
+    system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device=0)
+    np.random.seed(0)
+    system.set_temperature(298.0 * units.kB)
+    model = SchNet(params)
+    model.load_state_dict(sd)
+    gnn = GNNPotentials(system, model.cuda(), cutoff=params["cutoff"])
+    oxy = [int(i) for i in np.nonzero(g["numbers"] == 8)[0]]
+    prior = PairPotentials(system, ExcludedVolume(2.6, 0.015, 12).cuda(), cutoff=params["cutoff"], index_tuple=(oxy, oxy))
+    integ = NoseHooverChain(Stack({"gnn": gnn, "prior": prior}), system, T=298.0 * units.kB, num_chains=5, Q=50.0, adjoint=True)
+    assert integ.model.native_ready()
+    y0 = tuple(integ.get_inital_states(True))
+    t = torch.Tensor([0.5 * units.fs * i for i in range(6)]).cuda()
+    with torch.no_grad():
+        a = odeint_reuse_force(integ, y0, t, "NH_verlet")            # native forces
+    b = odeint(integ, tuple(v.clone() for v in y0), t, method="NH_verlet")   # autograd forces, two evaluations per step
+    for xa, xb in zip(a, b):
+        assert (xa - xb.detach()).abs().max().item() <= 2e-5 * max(1e-3, xb.detach().abs().max().item())
