@@ -112,6 +112,22 @@ int mdg_pair_force(mdg_ctx* ctx, int kind, const float* h_params, int n_params,
                    const float* d_xyz, int n,
                    float* d_energy, float* d_force, float* d_dparams, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Adjoint support: analytic second-order products of the listed-pair force - replaces the
+ * DOUBLE backward through compute_dis / u(r) that OdeintAdjointMethod.backward (torchmd/sovlers.py:211-293, with the
+ * len(y)==8 branch of NHverlet_update :129-164) performs via torch.autograd.grad(..., create_graph=True) on
+ * NoseHooverChain.forward / NVE.forward (torchmd/md.py:210-240 / :131-148).
+ * Over the list held by ctx (last mdg_nbr_build, stored image offsets, no re-test - as mdg_pair_force) and a given
+ * adjoint vector d_avec (N x 3):
+ *   d_hv     (N x 3)  = (dF/dxyz)^T a   ( = -Hessian(E) a )
+ *   d_dtheta (MDG_MAX_POT_PARAMS, may be NULL) = (dF/dparam)^T a  for (sigma, epsilon)
+ * Power-law kinds only (MDG_POT_LJ, _LJFAM, _LJ69, _EXV); other kinds return MDG_E_BADARG and the caller keeps its
+ * autograd route.
+ * ------------------------------------------------------------------------------------------ */
+int mdg_pair_hvp(mdg_ctx* ctx, int kind, const float* h_params, int n_params,
+                 const float* d_xyz, int n, const float* d_avec,
+                 float* d_hv, float* d_dtheta, void* stream);
+
 /* Generic listed-pair distance op for learned u(r) (pairMLP etc.): replaces compute_dis
  * (torchmd/topology.py:5-12) and its autograd backward.  The list is given explicitly in the
  * reference layout (d_nbr P x 2 int64, d_offsets P x 3 fp32).

@@ -28,7 +28,7 @@ SYMBOLS = [
     "mdg_pair_force", "mdg_pair_dis_fwd", "mdg_pair_dis_bwd", "mdg_rdf_accumulate", "mdg_md_run",
     "mdg_get_stats", "mdg_set_pair_filter", "mdg_set_profile", "mdg_get_profile",
     "mdg_slab_plan", "mdg_dist_unique_id", "mdg_dist_init", "mdg_dist_finalize",
-    "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad", "mdg_schnet_energy_force",
+    "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad", "mdg_schnet_energy_force", "mdg_pair_hvp",
 ]
 
 
@@ -150,6 +150,7 @@ def bind(lib):
     lib.mdg_cfconv_agg.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     lib.mdg_cfconv_edge_grad.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     lib.mdg_get_profile.argtypes = [vp, ctypes.POINTER(dbl)]
+    lib.mdg_pair_hvp.argtypes = [vp, ip, fp, ip, vp, ip, vp, vp, vp, vp]
     lib.mdg_schnet_energy_force.argtypes = [vp, ctypes.POINTER(SchnetModel), vp, vp, ip, vp, vp, i64, fp, vp, vp, vp]
     for name in SYMBOLS:
         if name not in ("mdg_last_error",):
@@ -176,8 +177,18 @@ def require_cuda(t, name="tensor"):
             "only and has no CPU fallback" % (name, getattr(t, "device", type(t))))
 
 
+def on_device(t):
+    """True for tensors the native path can take (CUDA).  One function so that the CPU emulation harness of the test
+    suite (tests/cuemu) can run the unmodified Python layer on host tensors."""
+    return bool(t.is_cuda)
+
+
 def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _guard(device):
+    return torch.cuda.device(device)
 
 
 def _ptr(t):
@@ -201,7 +212,7 @@ class Context:
         return _stream(device)
 
     def _guard(self, device):
-        return torch.cuda.device(device)
+        return _guard(device)
 
     def __init__(self, device):
         self.device = torch.device(device)
@@ -254,6 +265,20 @@ class Context:
             self._check(self._api().mdg_pair_force(self._h, int(kind), _farr(params, MAX_POT_PARAMS), len(params), _ptr(xyz), n,
                                         _ptr(e), _ptr(f), _ptr(dp), self._stream(dev)))
         return e, f, dp
+
+    def pair_hvp(self, kind, params, xyz, avec, want_dtheta=True):
+        """((dF/dxyz)^T a (N,3), (dF/dparams)^T a (4,) or None) over the list of the last nbr_list() - analytic
+        second-order products for the adjoint solver (power-law kinds; raises MdgError(BADARG) otherwise)."""
+        self._require(xyz, "xyz")
+        xyz = xyz.detach().to(torch.float32).contiguous()
+        avec = avec.detach().to(xyz.device, torch.float32).contiguous()
+        n = xyz.shape[0]
+        hv = torch.empty((n, 3), dtype=torch.float32, device=xyz.device)
+        dth = torch.empty((MAX_POT_PARAMS,), dtype=torch.float32, device=xyz.device) if want_dtheta else None
+        with self._guard(xyz.device):
+            self._check(self._api().mdg_pair_hvp(self._h, int(kind), _farr(params, MAX_POT_PARAMS), len(params), _ptr(xyz), n,
+                                              _ptr(avec), _ptr(hv), _ptr(dth), self._stream(xyz.device)))
+        return hv, dth
 
     # -- K6 ---------------------------------------------------------------------------------
     def rdf_accumulate(self, xyz, cell3, start, end, nbins, width, count, sel_a=None, sel_b=None):
@@ -400,7 +425,7 @@ def pair_dis_fwd(xyz, nbr, offsets, cell3):
     require_cuda(xyz, "xyz")
     P = nbr.shape[0]
     dis = torch.empty((P,), dtype=torch.float32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with _guard(xyz.device):
         check(load().mdg_pair_dis_fwd(_ptr(xyz), xyz.shape[0], _ptr(nbr), _ptr(offsets), P, _farr(cell3, 3), _ptr(dis),
                                       _stream(xyz.device)))
     return dis
@@ -409,7 +434,7 @@ def pair_dis_fwd(xyz, nbr, offsets, cell3):
 def pair_dis_bwd(xyz, nbr, offsets, cell3, dis, grad_dis):
     require_cuda(xyz, "xyz")
     g = torch.empty_like(xyz)
-    with torch.cuda.device(xyz.device):
+    with _guard(xyz.device):
         check(load().mdg_pair_dis_bwd(_ptr(xyz), xyz.shape[0], _ptr(nbr), _ptr(offsets), nbr.shape[0], _farr(cell3, 3),
                                       _ptr(dis), _ptr(grad_dis), _ptr(g), _stream(xyz.device)))
     return g

@@ -132,7 +132,7 @@ class _EOM(torch.nn.Module):
 
     def force(self, q):
         """-dU/dq at q with the reference's side effects (requires_grad on q, topology update, md.py:216-228)."""
-        if not torch.is_grad_enabled() and q.is_cuda and getattr(self.model, "native_ready", lambda: False)():
+        if not torch.is_grad_enabled() and _lib.on_device(q) and getattr(self.model, "native_ready", lambda: False)():
             # nobody records a graph (forward pass of the adjoint solver, plain MD): forces come straight from the
             # native programs (pair-force kernel / SchNet energy+force), no autograd tape
             self.update_topology(q)
@@ -143,6 +143,44 @@ class _EOM(torch.nn.Module):
             self.update_topology(q)
             u = self.model(q)
             return -compute_grad(inputs=q, output=u.sum(-1), create_graph=_needs_graph(self.model))
+
+    # -- analytic adjoint dynamics -----------------------------------------------------------------------------------
+    _POWER_LAW = (_lib.POT_LJ, _lib.POT_LJFAM, _lib.POT_LJ69, _lib.POT_EXV)
+
+    def _native_second_order(self, q):
+        """The pair model when its force has closed-form second-order products (mdg_pair_hvp), else None."""
+        from .interface import PairPotentials
+        m = self.model
+        if type(m) is not PairPotentials or not _lib.on_device(q) or getattr(self, "disable_native_adjoint", False):
+            return None
+        spec = m.native_kind()
+        return m if spec is not None and spec[0] in self._POWER_LAW else None
+
+    def native_augmented(self, tt, y_aug, n):
+        """Augmented adjoint dynamics (f, vjp_y, vjp_t, vjp_params) at (y, adj) WITHOUT autograd: the reference
+        differentiates the autograd force a second time (sovlers.py:216-236); here the force comes from the force
+        kernel, (dF/dq)^T a and (dF/dtheta)^T a from the analytic Hessian-vector kernel, the thermostat algebra is
+        written out.  Returns None when this configuration is not covered (the caller then uses autograd)."""
+        y, adj = y_aug[:n], y_aug[n:2 * n]
+        m = self._native_second_order(y[1])
+        if m is None:
+            return None
+        with torch.no_grad():
+            v, q = y[0], y[1]
+            self.update_topology(q)                      # same evaluation count / list refresh as func(t, y)
+            kind, values, ptensors = m.native_kind()
+            F = m.native_force(q)
+            f = self.derivative(tt, y, F)
+            cot = tuple(-a for a in adj)
+            a_q, gv, gpv = self._vjp_algebra(y, cot)
+            hv, dth = m._ctx.pair_hvp(kind, values, q, a_q)
+            vjp_y = (gv, hv) + ((gpv,) if gpv is not None else ())
+            parts = []
+            for p_ in self.parameters():
+                hit = [k for k, pt in enumerate(ptensors) if pt is p_]
+                parts.append(dth[hit[0]].reshape(-1) if hit else torch.zeros(p_.numel(), device=q.device))
+            vjp_p = torch.cat(parts) if parts else torch.tensor(0.).to(q)
+            return (*f, *vjp_y, torch.zeros_like(tt), vjp_p)
 
     # -- fused engine -------------------------------------------------------------------------
     def _native_spec(self, method):
@@ -165,7 +203,7 @@ class _EOM(torch.nn.Module):
         if len(t) > 1 and not bool((t[1:] > t[:-1]).all()):
             return None
         v0, q0 = y0[0], y0[1]
-        if not v0.is_cuda:
+        if not _lib.on_device(v0):
             _lib.require_cuda(v0, "state tensors")
         kind, values, _ = m.native_kind()
         n = q0.shape[0]
@@ -227,6 +265,10 @@ class NVE(_EOM):
     def derivative(self, t, state, f):
         return (f, state[0])
 
+    def _vjp_algebra(self, y, cot):
+        """dv/dt = F(q), dq/dt = v:  vector for the force products = c_v;  d/dv = c_q"""
+        return cot[0], cot[1], None
+
     def get_inital_states(self, wrap=True):
         states = [self.system.get_velocities(), self.system.get_positions(wrap=wrap)]
         return [_host_to_device(var, self.system.device) for var in states]
@@ -270,9 +312,34 @@ class NoseHooverChain(_EOM):
             dvdt = dpdt / m
         return (dvdt, v, torch.cat((d0[None], dmid, dlast[None])))
 
+    def _vjp_algebra(self, y, cot):
+        """Vector-Jacobian products of `derivative` (md.py:221-240) w.r.t. (v, p_v) for cotangents (c_v, c_q, c_p), and
+        the vector a_q = c_v / m that multiplies dF/dq and dF/dtheta:
+            dv    = F/m - (p_0/Q_0) v                 dp_0 = 2 (ke - T ndof/2) - p_0 p_1 / Q_1,  ke = 1/2 sum m v^2
+            dp_k  = (p_{k-1}^2/Q_{k-1} - T) - p_{k+1} p_k / Q_{k+1}        dp_last = p_{M-2}^2/Q_{M-2} - T"""
+        return nhc_vjp_algebra(y[0], y[2], self.mass[:, None], self.Q, cot[0], cot[1], cot[2])
+
     def get_inital_states(self, wrap=True):
         states = [self.system.get_velocities(), self.system.get_positions(wrap=wrap), [0.0] * self.num_chains]
         return [_host_to_device(var, self.system.device) for var in states]
+
+
+def nhc_vjp_algebra(v, pv, m, Q, cv, cq, cp):
+    """(a_q, g_v, g_pv) for NoseHooverChain.derivative - see NoseHooverChain._vjp_algebra.  Pure tensor algebra
+    (device agnostic) so that it can be checked against autograd on the CPU (tests/test_cabi_and_host.py)."""
+    M = pv.shape[0]
+    a_q = cv / m
+    g_v = cq - (pv[0] / Q[0]) * cv + (2.0 * cp[0]) * (m * v)
+    g_pv = torch.zeros_like(pv)
+    g_pv[0] = -(cv * v).sum() / Q[0] - cp[0] * pv[1] / Q[1] + cp[1] * 2.0 * pv[0] / Q[0]
+    for k in range(1, M):
+        t = -cp[k - 1] * pv[k - 1] / Q[k]
+        if k <= M - 2:
+            t = t - cp[k] * pv[k + 1] / Q[k + 1]
+        if k + 1 <= M - 1:
+            t = t + cp[k + 1] * 2.0 * pv[k] / Q[k]
+        g_pv[k] = t
+    return a_q, g_v, g_pv
 
 
 def _needs_graph(model):

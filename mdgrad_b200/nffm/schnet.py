@@ -245,7 +245,7 @@ class SchNet(nn.Module):
         N = batch["num_atoms"].reshape(-1).tolist()
         a = batch["nbr_list"]
         offsets = batch.get("offsets", 0)
-        native = xyz.is_cuda and not (self.second_order and torch.is_grad_enabled())
+        native = _lib.on_device(xyz) and not (self.second_order and torch.is_grad_enabled())
         if native and torch.is_tensor(offsets):
             # |x_i - x_j - offsets| : the distance kernel with a unit "cell" reproduces the reference's raw subtraction
             from ..topology import _PairDis

@@ -220,7 +220,13 @@ class OdeintAdjointMethod(torch.autograd.Function):
         n = len(ans)
         params = tuple(func.parameters())
 
+        native_aug = getattr(func, "native_augmented", None)
+
         def augmented(tt, y_aug):
+            if native_aug is not None:            # closed-form second-order products (pair power laws): no autograd
+                out = native_aug(tt.to(y_aug[0].device), y_aug, n)
+                if out is not None:
+                    return out
             y, adj = y_aug[:n], y_aug[n:2 * n]
             with torch.set_grad_enabled(True), second_order(func):
                 tt = tt.to(y[0].device).detach().requires_grad_(True)

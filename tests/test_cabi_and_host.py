@@ -225,3 +225,25 @@ def test_host_to_device_is_the_legacy_constructor_value_for_value():
     x32 = x.astype(np.float32)[::2]                            # non-contiguous fp32 view
     assert torch.equal(_host_to_device(x32, "cpu"), torch.Tensor(x32))
     assert torch.equal(_host_to_device([0.0, 1.5], "cpu"), torch.Tensor([0.0, 1.5]))
+
+
+def test_nhc_vjp_algebra_vs_autograd():
+    """The written-out vector-Jacobian products of the Nose-Hoover-chain derivative (used by the analytic adjoint
+    route, md.py nhc_vjp_algebra) against torch autograd of the oracle's restatement of md.py:221-240."""
+    from mdgrad_b200.md import nhc_vjp_algebra
+    from oracle import oracle_torch as O
+    torch.manual_seed(0)
+    for M in (2, 3, 5):
+        n = 7
+        v = torch.randn(n, 3, dtype=torch.float64, requires_grad=True)
+        pv = torch.randn(M, dtype=torch.float64, requires_grad=True)
+        F = torch.randn(n, 3, dtype=torch.float64)
+        mass = torch.rand(n, dtype=torch.float64) + 0.5
+        Qb = torch.rand(M, dtype=torch.float64) + 0.5
+        dv, dq, dpv = O.nhc_derivative(v, F, pv, mass, Qb, 0.7, 3 * n)
+        cv, cq, cp = torch.randn(n, 3, dtype=torch.float64), torch.randn(n, 3, dtype=torch.float64), torch.randn(M, dtype=torch.float64)
+        gv_o, gpv_o = torch.autograd.grad((dv * cv).sum() + (dq * cq).sum() + (dpv * cp).sum(), (v, pv))
+        a_q, gv, gpv = nhc_vjp_algebra(v.detach(), pv.detach(), mass[:, None], Qb, cv, cq, cp)
+        torch.testing.assert_close(gv, gv_o, rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(gpv, gpv_o, rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(a_q, cv / mass[:, None])       # dv = F/m + ...: the force enters through c_v / m

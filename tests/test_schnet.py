@@ -187,6 +187,7 @@ def test_schnet_md_native_force_equals_autograd_route():
     t = torch.Tensor([0.5 * units.fs * i for i in range(6)]).cuda()
     with torch.no_grad():
         a = odeint_reuse_force(integ, y0, t, "NH_verlet")            # native forces
-    b = odeint(integ, tuple(v.clone() for v in y0), t, method="NH_verlet")   # autograd forces, two evaluations per step
+    integ.adjoint = False                                          # plain autograd solve (reference md.py:88-91)
+    b = odeint(integ, tuple(v.clone().requires_grad_(True) for v in y0), t, method="NH_verlet")   # autograd forces, two evaluations per step
     for xa, xb in zip(a, b):
         assert (xa - xb.detach()).abs().max().item() <= 2e-5 * max(1e-3, xb.detach().abs().max().item())
