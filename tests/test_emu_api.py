@@ -14,7 +14,7 @@ import pytest
 import torch
 
 import emu_lib
-from mdgrad_b200 import _lib, topology
+from mdgrad_b200 import _lib, observable, topology
 from oracle import oracle_torch as O
 
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -29,7 +29,9 @@ def emulated_backend(monkeypatch):
     monkeypatch.setattr(_lib, "_stream", lambda device: ctypes.c_void_p(0))
     monkeypatch.setattr(_lib, "_guard", lambda device: contextlib.nullcontext())
     ctxs = {}
-    monkeypatch.setattr(topology, "context_for", lambda device, key="default": ctxs.setdefault(key, emu_lib.EmuContext()))
+    emu_context_for = lambda device, key="default": ctxs.setdefault(key, emu_lib.EmuContext())    # noqa: E731
+    monkeypatch.setattr(topology, "context_for", emu_context_for)
+    monkeypatch.setattr(observable, "context_for", emu_context_for)     # (imported by name there)
     yield
 
 
