@@ -436,9 +436,11 @@ def main():
         e2e_steps = n_epochs * per_epoch
         state_bytes = n * 3 * 4 * 2 + CHAINS * 4
         res["e2e"] = {"value": e2e_steps / el, "unit": "steps/s",
-                      "h2d_bytes_per_step": state_bytes / per_epoch, "d2h_bytes_per_step": state_bytes / per_epoch,
-                      "api": "Simulations.simulate(steps=%d, frequency=%d, dt=0.005): %d epochs x %d steps, host numpy "
-                             "state -> H2D each epoch, last frame D2H + fp64 host wrap each epoch"
+                      "h2d_bytes_per_step": state_bytes / e2e_steps, "d2h_bytes_per_step": state_bytes / per_epoch,
+                      "api": "Simulations.simulate(steps=%d, frequency=%d, dt=0.005): %d epochs x %d steps; host numpy state "
+                             "(System) -> H2D at the start of the call, every epoch's last frame D2H into the host log and "
+                             "System update before the call returns; between epochs the state is handed over on the device "
+                             "(fp64 wrap there, bit-identical to the reference's host wrap)"
                              % (freq * n_epochs, freq, n_epochs, per_epoch)}
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only)

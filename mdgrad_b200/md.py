@@ -41,6 +41,30 @@ def _host_to_device(x, device):
     return torch.Tensor(x).to(device)
 
 
+def _device_wrap(q, cell, eps=1e-7):
+    """`wrap_positions(q, cell)` of the epoch hand-off (reference md.py:60-71 -> ase.geometry.wrap_positions, center 0.5,
+    eps 1e-7, all axes periodic) evaluated ON THE DEVICE, bit for bit: the host version is six separately rounded fp64
+    elementwise operations (x * (1/L), - shift, - floor, + shift, * L) on the fp32 frame and a final rounding to fp32;
+    the same six IEEE operations as separate fp64 tensor ops give the same bits (no fusion between eager ops), so the
+    state never has to leave the device between the epochs of one `simulate()` call
+    (tests/test_cabi_and_host.py::test_device_wrap_is_bit_identical).  Orthorhombic cells only -> None otherwise."""
+    c = np.asarray(cell, dtype=float)
+    if c.shape == (3,):
+        c = np.diag(c)
+    if c.shape != (3, 3) or (c - np.diag(np.diag(c))).any() or not np.all(np.diag(c) != 0):
+        return None
+    L = np.diag(c)
+    shift = np.asarray((0.5, 0.5, 0.5), dtype=float) - 0.5 - eps
+    t64 = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=q.device)      # noqa: E731
+    f = q.detach().to(torch.float64) * t64(1.0 / L)
+    sh = t64(shift)
+    f -= sh
+    f -= torch.floor(f)
+    f += sh
+    f *= t64(L)
+    return f.to(torch.float32)
+
+
 def _torch_device(device):
     return torch.device("cuda:%d" % device) if isinstance(device, int) else torch.device(device)
 
@@ -91,6 +115,12 @@ class Simulations():
             states = self.get_check_point()
         sim_epochs = int(steps // frequency)
         t = torch.Tensor([dt * i for i in range(frequency)]).to(self.device)
+        # Epoch hand-off.  The reference logs the last frame to the host, updates the System and re-reads the log
+        # (fp64 wrap on the host) after EVERY epoch (md.py:92-95).  None of that is observable before simulate()
+        # returns, and the next epoch's start state is a pure function of the last frame, so between epochs the
+        # state stays on the device (bit-identical fp64 wrap there) and the host-side log / System are brought up to
+        # date in one flush - same log, same System, same trajectory, without a host round trip per epoch.
+        pending = []
         for epoch in range(sim_epochs):
             if self.integrator.adjoint:
                 trajs = odeint_adjoint(self.integrator, states, t, method=self.solvemethod)
@@ -98,10 +128,43 @@ class Simulations():
                 for var in states:
                     var.requires_grad = True
                 trajs = odeint(self.integrator, tuple(states), t, method=self.solvemethod)
-            self.update_log(trajs)
-            self.update_states()
-            states = self.get_check_point()
+            nxt = self._device_check_point(trajs) if self.device_handoff else None
+            if nxt is None:                           # reference order of operations, on the host
+                self._flush_log(pending)
+                self.update_log(trajs)
+                self.update_states()
+                states = self.get_check_point()
+                continue
+            pending.append([tr[-1].detach().clone() for tr in trajs])
+            if len(pending) >= 64:                    # bound the device memory held by un-logged frames
+                self._flush_log(pending)
+            states = nxt
+        self._flush_log(pending)
         return trajs
+
+    device_handoff = True     # False: host round trip after every epoch, literally as the reference
+
+    def _device_check_point(self, trajs):
+        """The states `get_check_point()` would return after logging `trajs`, computed on the device; None if the
+        configuration needs the host path (non-orthorhombic cell)."""
+        last = [tr[-1].detach().clone() for tr in trajs]
+        if self.wrap and "positions" in self.keys:
+            k = self.keys.index("positions")
+            wrapped = _device_wrap(last[k], self.system.get_cell())
+            if wrapped is None:
+                return None
+            last[k] = wrapped
+        return last
+
+    def _flush_log(self, pending):
+        """append the deferred last frames to the log (numpy, as update_log) and update the System once"""
+        if not pending:
+            return
+        for frames in pending:
+            for key, fr in zip(self.keys, frames):
+                self.log[key].append(fr.cpu().numpy())
+        pending.clear()
+        self.update_states()
 
 
 class _EOM(torch.nn.Module):

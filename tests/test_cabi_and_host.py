@@ -247,3 +247,18 @@ def test_nhc_vjp_algebra_vs_autograd():
         torch.testing.assert_close(gv, gv_o, rtol=1e-12, atol=1e-12)
         torch.testing.assert_close(gpv, gpv_o, rtol=1e-12, atol=1e-12)
         torch.testing.assert_close(a_q, cv / mass[:, None])       # dv = F/m + ...: the force enters through c_v / m
+
+
+def test_device_wrap_is_bit_identical():
+    """The epoch hand-off wraps positions with separate fp64 tensor ops instead of the host numpy path: same bits."""
+    from mdgrad_b200.md import _device_wrap, _host_to_device
+    from mdgrad_b200._ase_compat import wrap_positions
+    rng = np.random.default_rng(5)
+    for L in ([67.16363, 67.16363, 67.16363], [5.037, 6.1, 4.4]):
+        q = (rng.uniform(-2.5, 3.5, (20000, 3)) * np.array(L)).astype(np.float32)
+        q[:50] = np.array([0.0, L[1], -L[2]], dtype=np.float32)          # exact boundaries
+        q[50:60] = np.float32(-1e-7)
+        host = _host_to_device(wrap_positions(q, np.diag(L)), "cpu")
+        dev = _device_wrap(torch.from_numpy(q), np.diag(L))
+        assert dev.dtype == torch.float32 and torch.equal(dev, host)
+    assert _device_wrap(torch.zeros(4, 3), np.array([[5.0, 0.1, 0], [0, 5.0, 0], [0, 0, 5.0]])) is None

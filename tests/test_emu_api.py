@@ -157,3 +157,31 @@ def test_emu_schnet_md_native_force_equals_autograd_route():
     b = odeint(integ, tuple(v.clone().requires_grad_(True) for v in y0), t, method="NH_verlet")
     for xa, xb in zip(a, b):
         assert (xa - xb.detach()).abs().max().item() <= 2e-5 * max(1e-3, xb.detach().abs().max().item())
+
+
+def test_emu_simulate_device_handoff_equals_host_roundtrip():
+    """Simulations.simulate over several epochs: state kept on the device between epochs (bit-identical fp64 wrap)
+    vs the reference's host round trip after every epoch - identical log, System and trajectories."""
+    from torchmd.interface import PairPotentials
+    from torchmd.potentials import LennardJones
+    from torchmd.md import NoseHooverChain, Simulations
+    g = np.load(os.path.join(G, "c1_traj.npz"))
+    runs = []
+    for handoff in (True, False):
+        system = _fcc_system()
+        system.set_positions(g["q0"] + 7.0)                 # several atoms outside the box: the wrap matters
+        system.set_velocities(g["v0"])
+        integ = NoseHooverChain(PairPotentials(system, LennardJones(1.0, 1.0), cutoff=2.5), system, T=1.0, num_chains=5, Q=50.0)
+        sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+        sim.device_handoff = handoff
+        v, q, pv = sim.simulate(steps=4 * 6, frequency=6, dt=0.01)
+        v2, q2, pv2 = sim.simulate(steps=6, frequency=6, dt=0.01)          # continues from the logged check point
+        runs.append((sim.log, system.get_positions(), system.get_velocities(), v.detach(), q.detach(), pv.detach(), q2.detach()))
+    a, b = runs
+    assert len(a[0]["positions"]) == 5 and len(b[0]["positions"]) == 5
+    for key in ("velocities", "positions", "baths"):
+        for x, y in zip(a[0][key], b[0][key]):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for k in range(3, 7):
+        assert torch.equal(a[k], b[k])

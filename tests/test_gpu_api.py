@@ -203,3 +203,39 @@ def test_simulate_frequency_one_integrates_zero_steps():
     assert np.allclose(system.get_positions(), q_before, atol=1e-5)
     with pytest.raises(UnboundLocalError):
         sim.simulate(steps=2, frequency=5, dt=0.01)
+
+
+def test_device_wrap_bit_identical_on_gpu():
+    """epoch hand-off: the fp64 wrap as separate CUDA tensor ops gives the bits of the host (ASE) wrap"""
+    from mdgrad_b200.md import _device_wrap, _host_to_device
+    from mdgrad_b200._ase_compat import wrap_positions
+    rng = np.random.default_rng(5)
+    for L in ([67.16363, 67.16363, 67.16363], [5.037, 6.1, 4.4]):
+        q = (rng.uniform(-2.5, 3.5, (200000, 3)) * np.array(L)).astype(np.float32)
+        q[:50] = np.array([0.0, L[1], -L[2]], dtype=np.float32)
+        host = _host_to_device(wrap_positions(q, np.diag(L)), "cpu")
+        dev = _device_wrap(torch.from_numpy(q).cuda(), np.diag(L))
+        assert torch.equal(dev.cpu(), host)
+
+
+def test_simulate_device_handoff_equals_host_roundtrip():
+    from torchmd.interface import PairPotentials
+    from torchmd.potentials import LennardJones
+    from torchmd.md import NoseHooverChain, Simulations
+    g = np.load(os.path.join(G, "c1_traj.npz"))
+    runs = []
+    for handoff in (True, False):
+        system = _fcc_system()
+        system.set_positions(g["q0"] + 7.0)
+        system.set_velocities(g["v0"])
+        integ = NoseHooverChain(PairPotentials(system, LennardJones(1.0, 1.0), cutoff=2.5), system, T=1.0, num_chains=5, Q=50.0)
+        sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+        sim.device_handoff = handoff
+        v, q, pv = sim.simulate(steps=4 * 6, frequency=6, dt=0.01)
+        runs.append((sim.log, system.get_positions(), system.get_velocities(), q.detach()))
+    a, b = runs
+    for key in ("velocities", "positions", "baths"):
+        assert len(a[0][key]) == 4
+        for x, y in zip(a[0][key], b[0][key]):
+            assert np.array_equal(x, y)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and torch.equal(a[3], b[3])
