@@ -262,6 +262,52 @@ int mdg_schnet_energy_force(mdg_ctx* ctx, const mdg_schnet_model* h_model, const
                             float* d_energy, float* d_force, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K4 + K5  fused MD epoch with a SchNet force field (+ analytic pair priors) - the epoch loop of
+ *     Simulations.simulate (torchmd/md.py:73-96 -> tinydiffeq.py:56-76 -> sovlers.py:110-127 / :25-40 ->
+ *     md.py:210-240 / :131-148) for a model = GNNPotentials (torchmd/interface.py:86-136) or a Stack
+ *     (:364-403) of one GNNPotentials and PairPotentials priors, topology_update_freq = 1: every step rebuilds
+ *     each member's exact neighbor list at the current positions (mdg_nbr_build semantics, each member with its
+ *     own cutoff / species selection / exclusions), evaluates SchNet energy+forces (mdg_schnet_energy_force) and
+ *     the priors (mdg_pair_force), and applies the fused integrator kernels - all from one host call, no Python
+ *     and no autograd inside the loop.  Same trajectory outputs as mdg_md_run.  One SYNC per list build (pair
+ *     count read-back) and one at the end.
+ *     ctx owns the GNN list and the SchNet workspace; every prior brings the context that owns its list.
+ * ------------------------------------------------------------------------------------------ */
+#define MDG_MAX_PRIORS 4
+typedef struct mdg_prior_spec {
+    mdg_ctx*       ctx;
+    int            kind;                          /* MDG_POT_*                                   */
+    float          params[MDG_MAX_POT_PARAMS];
+    int            n_params;
+    double         cutoff;
+    const uint8_t* d_sel_a;                       /* index_tuple flags or NULL (as mdg_nbr_build) */
+    const uint8_t* d_sel_b;
+    const int64_t* d_ex_keys;
+    int            n_ex;
+} mdg_prior_spec;
+
+typedef struct mdg_gnn_md_params {
+    int     integrator;                           /* MDG_INT_NVE | MDG_INT_NHC                   */
+    int     n_chains;
+    float   Q[MDG_MAX_CHAINS];
+    double  T;
+    int     ndof;
+    float   cell[3];
+    double  cutoff;                               /* GNNPotentials(cutoff=)                      */
+    float   off_scale[3];                         /* see mdg_schnet_energy_force                 */
+    const int64_t* d_ex_keys;                     /* GNNPotentials(ex_pairs=) as sorted keys     */
+    int     n_ex;
+    int     n_priors;
+    mdg_prior_spec priors[MDG_MAX_PRIORS];
+    int     traj_stride;
+} mdg_gnn_md_params;
+
+int mdg_md_run_gnn(mdg_ctx* ctx, const mdg_gnn_md_params* p, const mdg_schnet_model* h_model,
+                   const int64_t* d_z, int n, const float* d_mass, const float* d_v0, const float* d_q0,
+                   const float* h_pv0, const float* h_tgrid, int n_grid,
+                   float* d_traj_v, float* d_traj_q, float* h_traj_pv, float* h_last_energy, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The reference has no distributed code; this is the
  * spatial decomposition of SURVEY 8e: slabs of whole z-layers of cells in the global cell-sorted
  * index space, per-step ghost-position halo (ncclSend/ncclRecv of two contiguous ranges), one

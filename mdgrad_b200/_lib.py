@@ -28,7 +28,7 @@ SYMBOLS = [
     "mdg_pair_force", "mdg_pair_dis_fwd", "mdg_pair_dis_bwd", "mdg_rdf_accumulate", "mdg_md_run",
     "mdg_get_stats", "mdg_set_pair_filter", "mdg_set_profile", "mdg_get_profile",
     "mdg_slab_plan", "mdg_dist_unique_id", "mdg_dist_init", "mdg_dist_finalize",
-    "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad", "mdg_schnet_energy_force", "mdg_pair_hvp",
+    "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad", "mdg_schnet_energy_force", "mdg_pair_hvp", "mdg_md_run_gnn",
 ]
 
 
@@ -65,6 +65,24 @@ class SchnetModel(ctypes.Structure):
                 ("n_convolutions", ctypes.c_int), ("n_readout", ctypes.c_int),
                 ("embed", ctypes.c_void_p), ("layers", SchnetLayer * SCHNET_MAX_LAYERS),
                 ("Wr1", ctypes.c_void_p), ("br1", ctypes.c_void_p), ("Wr2", ctypes.c_void_p), ("br2", ctypes.c_void_p)]
+
+
+MAX_PRIORS = 4
+
+
+class PriorSpec(ctypes.Structure):
+    """mirror of struct mdg_prior_spec"""
+    _fields_ = [("ctx", ctypes.c_void_p), ("kind", ctypes.c_int), ("params", ctypes.c_float * MAX_POT_PARAMS),
+                ("n_params", ctypes.c_int), ("cutoff", ctypes.c_double), ("d_sel_a", ctypes.c_void_p),
+                ("d_sel_b", ctypes.c_void_p), ("d_ex_keys", ctypes.c_void_p), ("n_ex", ctypes.c_int)]
+
+
+class GnnMdParams(ctypes.Structure):
+    """mirror of struct mdg_gnn_md_params"""
+    _fields_ = [("integrator", ctypes.c_int), ("n_chains", ctypes.c_int), ("Q", ctypes.c_float * MAX_CHAINS),
+                ("T", ctypes.c_double), ("ndof", ctypes.c_int), ("cell", ctypes.c_float * 3), ("cutoff", ctypes.c_double),
+                ("off_scale", ctypes.c_float * 3), ("d_ex_keys", ctypes.c_void_p), ("n_ex", ctypes.c_int),
+                ("n_priors", ctypes.c_int), ("priors", PriorSpec * MAX_PRIORS), ("traj_stride", ctypes.c_int)]
 
 
 def schnet_model_struct(sd, device):
@@ -150,6 +168,8 @@ def bind(lib):
     lib.mdg_cfconv_agg.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     lib.mdg_cfconv_edge_grad.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     lib.mdg_get_profile.argtypes = [vp, ctypes.POINTER(dbl)]
+    lib.mdg_md_run_gnn.argtypes = [vp, ctypes.POINTER(GnnMdParams), ctypes.POINTER(SchnetModel), vp, ip, vp, vp, vp, fp, fp, ip,
+                                   vp, vp, fp, fp, vp]
     lib.mdg_pair_hvp.argtypes = [vp, ip, fp, ip, vp, ip, vp, vp, vp, vp]
     lib.mdg_schnet_energy_force.argtypes = [vp, ctypes.POINTER(SchnetModel), vp, vp, ip, vp, vp, i64, fp, vp, vp, vp]
     for name in SYMBOLS:
@@ -321,6 +341,29 @@ class Context:
         if M:
             tpv = torch.tensor(list(hpv), dtype=torch.float32).reshape(n_frames, M).to(dev)
         return tv, tq, tpv, (e.value if want_energy else None)
+
+    def md_run_gnn(self, params, model, z, mass, v0, q0, pv0, tgrid):
+        """One epoch with a SchNet (+ pair priors) force field on the device engine (mdg_md_run_gnn); `params` is a
+        filled GnnMdParams, `model` = (SchnetModel, keepalive).  Returns (traj_v, traj_q, traj_pv or None)."""
+        for t, nm in ((mass, "mass"), (v0, "v0"), (q0, "q0")):
+            self._require(t, nm)
+        dev = q0.device
+        n = q0.shape[0]
+        n_grid = len(tgrid)
+        stride = max(1, params.traj_stride)
+        n_frames = (n_grid - 1) // stride + 1
+        tv = torch.empty((n_frames, n, 3), dtype=torch.float32, device=dev)
+        tq = torch.empty((n_frames, n, 3), dtype=torch.float32, device=dev)
+        M = params.n_chains if params.integrator == INT_NHC else 0
+        hpv = (ctypes.c_float * max(1, n_frames * M))()
+        hpv0 = _farr(pv0 if M else [0.0], max(1, M))
+        z = z.to(dev, torch.int64).contiguous()
+        with self._guard(dev):
+            self._check(self._api().mdg_md_run_gnn(self._h, ctypes.byref(params), ctypes.byref(model[0]), _ptr(z), n, _ptr(mass),
+                                                _ptr(v0), _ptr(q0), hpv0, _farr(tgrid), n_grid, _ptr(tv), _ptr(tq),
+                                                hpv if M else None, None, self._stream(dev)))
+        tpv = torch.tensor(list(hpv), dtype=torch.float32).reshape(n_frames, M).to(dev) if M else None
+        return tv, tq, tpv
 
     def set_pair_filter(self, sel_a=None, sel_b=None, ex_keys=None):
         self._check(self._api().mdg_set_pair_filter(self._h, _ptr(sel_a), _ptr(sel_b), _ptr(ex_keys),

@@ -720,6 +720,185 @@ extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float
     return status;
 }
 
+// ---------------------------------------------------------------------------------------------
+// GNN epoch: SchNet (+ pair priors) force provider under the same integrator kernels.
+// State stays in ORIGINAL atom order (q4.w = id = index): the lists are rebuilt from scratch at every step anyway
+// (reference semantics, topology_update_freq = 1) and each member sorts privately inside its own context.
+// ---------------------------------------------------------------------------------------------
+int mdg_i_export_count(mdg_ctx* c, cudaStream_t st, int64_t* h_npairs);
+int mdg_i_export_fill(mdg_ctx* c, int64_t* d_nbr, float* d_offsets, float* d_dis, cudaStream_t st);
+
+__global__ void k_gnn_init(int n, const float* __restrict__ v0, const float* __restrict__ q0, const float* __restrict__ mass,
+                           float4* __restrict__ v4, float4* __restrict__ q4, float4* __restrict__ vh4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    v4[i] = make_float4(v0[3 * i], v0[3 * i + 1], v0[3 * i + 2], mass[i]);
+    q4[i] = make_float4(q0[3 * i], q0[3 * i + 1], q0[3 * i + 2], __int_as_float(i));
+    vh4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void k_gnn_q_to_xyz(int n, const float4* __restrict__ q4, float* __restrict__ xyz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 q = q4[i];
+    xyz[3 * i] = q.x; xyz[3 * i + 1] = q.y; xyz[3 * i + 2] = q.z;
+}
+
+// f4 = f_gnn + sum of the prior forces (fp3 holds n_priors consecutive N x 3 blocks), summed in member order like
+// Stack.forward (interface.py:397-403) followed by one autograd pass
+__global__ void k_gnn_sum_forces(int n, const float* __restrict__ f3, const float* __restrict__ fp3, int n_priors,
+                                 float4* __restrict__ f4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float fx = f3[3 * i], fy = f3[3 * i + 1], fz = f3[3 * i + 2];
+    for (int k = 0; k < n_priors; ++k) {
+        const float* f = fp3 + (size_t)k * 3 * n;
+        fx += f[3 * i]; fy += f[3 * i + 1]; fz += f[3 * i + 2];
+    }
+    f4[i] = make_float4(fx, fy, fz, 0.f);
+}
+
+static int gnn_force(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_model* model, const int64_t* d_z, int n,
+                     const float4* q4, float4* f4, float* d_e_gnn, int64_t* launches, cudaStream_t st) {
+    const int T = 256, nb = (n + T - 1) / T;
+    *launches += c->stat_launches;               // (mdg_nbr_build restarts the context's counter)
+    float* xyz = c->gnn_xyz.as<float>();
+    float* f3 = c->gnn_f3.as<float>();
+    float* fp3 = c->gnn_fp3.as<float>();
+    k_gnn_q_to_xyz<<<nb, T, 0, st>>>(n, q4, xyz);
+    // GNN list at the current positions (exact membership, reference layout)
+    int64_t P = 0;
+    MDG_TRY(mdg_nbr_build(c, xyz, n, p->cell, p->cutoff, nullptr, nullptr, p->d_ex_keys, p->n_ex, (void*)st, &P));
+    MDG_TRY(c->gnn_nbr.reserve(sizeof(int64_t) * 2 * (size_t)(P + 1)));
+    MDG_TRY(c->gnn_off.reserve(sizeof(float) * 3 * (size_t)(P + 1)));
+    MDG_TRY(mdg_i_export_fill(c, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), nullptr, st));
+    MDG_TRY(mdg_schnet_energy_force(c, model, d_z, xyz, n, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), P, p->off_scale,
+                                    d_e_gnn, f3, (void*)st));
+    for (int k = 0; k < p->n_priors; ++k) {
+        const mdg_prior_spec& R = p->priors[k];
+        int64_t Pk = 0;
+        MDG_TRY(mdg_nbr_build(R.ctx, xyz, n, p->cell, R.cutoff, R.d_sel_a, R.d_sel_b, R.d_ex_keys, R.n_ex, (void*)st, &Pk));
+        MDG_TRY(mdg_pair_force(R.ctx, R.kind, R.params, R.n_params, xyz, n, nullptr, fp3 + (size_t)k * 3 * n, nullptr, (void*)st));
+    }
+    k_gnn_sum_forces<<<nb, T, 0, st>>>(n, f3, fp3, p->n_priors, f4);
+    c->stat_launches += 2;
+    for (int k = 0; k < p->n_priors; ++k) *launches += p->priors[k].ctx->stat_launches;
+    c->stat_rebuilds++;
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_model* model, const int64_t* d_z, int n,
+                              const float* d_mass, const float* d_v0, const float* d_q0, const float* h_pv0,
+                              const float* h_tgrid, int n_grid, float* d_traj_v, float* d_traj_q, float* h_traj_pv,
+                              float* h_last_energy, void* stream) {
+    if (!c || !p || !model || !d_z) { mdg_set_error("mdg_md_run_gnn: null argument"); return MDG_E_BADARG; }
+    if (n <= 0 || n_grid < 1) { mdg_set_error("mdg_md_run_gnn: n=%d n_grid=%d", n, n_grid); return MDG_E_BADARG; }
+    if (p->integrator != MDG_INT_NHC && p->integrator != MDG_INT_NVE) { mdg_set_error("bad integrator"); return MDG_E_BADARG; }
+    if (p->integrator == MDG_INT_NHC && (p->n_chains < 2 || p->n_chains > MDG_MAX_CHAINS)) {
+        mdg_set_error("NHC needs 2 <= n_chains <= %d (got %d)", MDG_MAX_CHAINS, p->n_chains);
+        return MDG_E_BADARG;
+    }
+    if (p->n_priors < 0 || p->n_priors > MDG_MAX_PRIORS) { mdg_set_error("mdg_md_run_gnn: n_priors=%d", p->n_priors); return MDG_E_BADARG; }
+    for (int k = 0; k < p->n_priors; ++k)
+        if (!p->priors[k].ctx || p->priors[k].ctx == c) { mdg_set_error("mdg_md_run_gnn: prior %d needs its own context", k); return MDG_E_BADARG; }
+    if (c->dist_world > 1) { mdg_set_error("mdg_md_run_gnn: single GPU only"); return MDG_E_BADARG; }
+    MDG_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nhc = p->integrator == MDG_INT_NHC;
+    const int M = nhc ? p->n_chains : 0;
+    const int stride = p->traj_stride < 1 ? 1 : p->traj_stride;
+    const int n_frames = (n_grid - 1) / stride + 1;
+    const int T = 256, nb = (n + T - 1) / T;
+    c->stat_launches = 0;
+    c->stat_rebuilds = 0;
+
+    IntArgs A;
+    memset(&A, 0, sizeof(A));
+    A.s0 = 0; A.s1 = n;
+    A.integrator = p->integrator;
+    A.M = M;
+    for (int k = 0; k < M; ++k) A.Q[k] = p->Q[k];
+    A.T = (float)p->T;
+    A.target = (float)(p->T * (double)p->ndof * 0.5);
+    A.half_skin2 = 0.f;
+
+    MDG_TRY(c->v4.reserve(sizeof(float4) * (size_t)n));
+    MDG_TRY(c->vh4.reserve(sizeof(float4) * (size_t)n));
+    MDG_TRY(c->f4b.reserve(sizeof(float4) * (size_t)n));
+    MDG_TRY(c->gnn_xyz.reserve(sizeof(float) * 3 * (size_t)n));
+    MDG_TRY(c->gnn_f3.reserve(sizeof(float) * 3 * (size_t)n));
+    MDG_TRY(c->gnn_fp3.reserve(sizeof(float) * 3 * (size_t)n * (p->n_priors > 0 ? p->n_priors : 1)));
+    MDG_TRY(c->pvbuf.reserve(sizeof(Scalars) + sizeof(float) * (size_t)n_frames * MDG_MAX_CHAINS + 64));
+    MDG_TRY(c->kebuf.reserve(sizeof(double) * (5 * INT_MAX_BLOCKS + 8)));
+    MDG_TRY(c->flags.reserve(sizeof(int) * 8));
+    float4 *v4 = c->v4.as<float4>(), *vh4 = c->vh4.as<float4>(), *f4 = c->f4b.as<float4>();
+    // positions: `qref` (free here - no skin list).  The list builds of this context use q4b / qs_buf / rows / ..., the
+    // SchNet program sn_ws, so v4 / vh4 / f4b / qref are untouched by the force evaluation.
+    MDG_TRY(c->qref.reserve(sizeof(float4) * (size_t)n));
+    float4* q4 = c->qref.as<float4>();
+    Scalars* sc = c->pvbuf.as<Scalars>();
+    float* d_traj_pv = (float*)(sc + 1);
+    float* d_e_gnn = d_traj_pv + (size_t)n_frames * MDG_MAX_CHAINS;
+    double* kb = c->kebuf.as<double>();
+    double *ke_v_cur = kb, *ke_h_cur = kb + INT_MAX_BLOCKS, *ke_v_nxt = kb + 2 * INT_MAX_BLOCKS, *ke_h_nxt = kb + 3 * INT_MAX_BLOCKS;
+
+    Scalars hs;
+    memset(&hs, 0, sizeof(hs));
+    for (int k = 0; k < M; ++k) hs.pv[0][k] = h_pv0 ? h_pv0[k] : 0.f;
+    MDG_CUDA(cudaMemcpyAsync(sc, &hs, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 8, st));
+    k_gnn_init<<<nb, T, 0, st>>>(n, d_v0, d_q0, d_mass, v4, q4, vh4);
+    int ib = nb < 1 ? 1 : (nb > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : nb);
+    int64_t launches = 0;
+    int64_t rebuilds0 = 0;
+    MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, st));
+    if (nhc) k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, v4, ke_v_cur);
+    MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    MDG_CUDA(cudaMemcpyAsync(d_traj_q, d_q0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (M) MDG_CUDA(cudaMemcpyAsync(d_traj_pv, sc->pv[0], sizeof(float) * M, cudaMemcpyDeviceToDevice, st));
+    c->stat_launches += 2;
+
+    int pv_sel = 0;
+    const int nsteps = n_grid - 1;
+    for (int g = 0; g < nsteps; ++g) {
+        float dt = h_tgrid[g + 1] - h_tgrid[g];
+        if (g == 0) {
+            k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, v4, vh4, q4, f4, nullptr, 0, ke_h_cur, c->flags.as<int>());
+            c->stat_launches++;
+        }
+        MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, st));
+        int gp = g + 1;
+        bool keep = (gp % stride) == 0;
+        size_t fr = (size_t)(gp / stride);
+        float* tv = keep ? d_traj_v + fr * 3 * (size_t)n : nullptr;
+        float* tq = keep ? d_traj_q + fr * 3 * (size_t)n : nullptr;
+        float* tp = (keep && M) ? d_traj_pv + fr * M : nullptr;
+        if (g + 1 < nsteps) {
+            float dt_next = h_tgrid[g + 2] - h_tgrid[g + 1];
+            k_step_ba<<<ib, INT_THREADS, 0, st>>>(A, dt, dt_next, pv_sel, sc, v4, vh4, q4, f4, ke_v_cur, ke_h_cur, ib, ke_v_nxt,
+                                                  ke_h_nxt, tv, tq, tp, nullptr, 0, c->flags.as<int>());
+            { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
+            { double* t2 = ke_h_cur; ke_h_cur = ke_h_nxt; ke_h_nxt = t2; }
+        } else {
+            k_step_b<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, v4, vh4, q4, f4, ke_v_cur, ke_h_cur, ib, ke_v_nxt, tv, tq, tp);
+            { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
+        }
+        c->stat_launches++;
+        pv_sel ^= 1;
+    }
+    MDG_KERNEL_CHECK();
+    float h_e = 0.f;
+    if (h_last_energy) MDG_CUDA(cudaMemcpyAsync(&h_e, d_e_gnn, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (M && h_traj_pv)
+        MDG_CUDA(cudaMemcpyAsync(h_traj_pv, d_traj_pv, sizeof(float) * (size_t)n_frames * M, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA(cudaStreamSynchronize(st));
+    if (h_last_energy) *h_last_energy = h_e;      // SchNet energy of the last evaluation (priors not included)
+    c->stat_launches += launches;
+    (void)rebuilds0;
+    return MDG_OK;
+}
+
 void mdg_i_release_profile(mdg_ctx* c) {
     std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
     if (!pool) return;

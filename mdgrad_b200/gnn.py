@@ -43,6 +43,12 @@ class GNNPotentials(GeneralInteraction):
         self.inputs["offsets"] = offsets if self.pbc_mode == "reference" else offsets * torch.tensor(self._L, device=offsets.device)
         self.inputs.pop("_native_graph", None)
 
+    def _ex_keys(self, device):
+        """GNNPotentials(ex_pairs=) as the sorted unique int64 keys of mdg_nbr_build (cached)"""
+        if getattr(self, "_exk_cache", None) is None:
+            self._exk_cache = (_exclusion_keys(self.inputs["nxyz"].shape[0], self.ex_pairs, device),)
+        return self._exk_cache[0]
+
     # -- native force route (no autograd tape): used by the solvers whenever no graph is being recorded -----------
     def native_ready(self):
         """True when `native_force` covers this model: our SchNet mirror with the default energy readout."""

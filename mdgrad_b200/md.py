@@ -257,11 +257,89 @@ class _EOM(torch.nn.Module):
             return None
         return m
 
+    def _gnn_members(self, method):
+        """(GNNPotentials, [PairPotentials priors]) when the model is a native-ready GNNPotentials or a Stack of exactly
+        one GNNPotentials and analytic PairPotentials priors, else None (device engine mdg_md_run_gnn)."""
+        from .gnn import GNNPotentials
+        from .interface import PairPotentials, Stack
+        if self.topology_update_freq != 1 or method != self._native_method or getattr(self, "disable_gnn_engine", False):
+            return None
+        members = list(self.model.models.values()) if type(self.model) is Stack else [self.model]
+        gnns = [m for m in members if type(m) is GNNPotentials]
+        priors = [m for m in members if type(m) is PairPotentials]
+        if len(gnns) != 1 or len(gnns) + len(priors) != len(members) or len(priors) > _lib.MAX_PRIORS:
+            return None
+        if not all(m.native_ready() for m in members):
+            return None
+        if any(p.requires_grad and p.grad_fn is not None for p in self.model.parameters()):
+            return None
+        return gnns[0], priors
+
+    def _native_forward_gnn(self, y0, t, method):
+        mem = self._gnn_members(method)
+        if mem is None or len(t) < 1 or (len(t) > 1 and not bool((t[1:] > t[:-1]).all())):
+            return None
+        gnn, priors = mem
+        v0, q0 = y0[0], y0[1]
+        if not _lib.on_device(q0):
+            return None
+        p = _lib.GnnMdParams()
+        p.integrator = self._native_integrator
+        if self._native_integrator == _lib.INT_NHC:
+            p.n_chains = int(self.num_chains)
+            Qh = self.Q.detach().cpu()
+            for k in range(self.num_chains):
+                p.Q[k] = float(Qh[k])
+            p.T = float(self.T)
+        p.ndof = int(self.N_dof)
+        for k in range(3):
+            p.cell[k] = gnn._L[k]
+            p.off_scale[k] = 1.0            # reference quirk: raw integer offsets, not multiplied by the cell (SURVEY 3c)
+        p.cutoff = float(gnn.cutoff)
+        if gnn.pbc_mode != "reference":
+            for k in range(3):
+                p.off_scale[k] = gnn._L[k]
+        exk = gnn._ex_keys(q0.device)
+        p.d_ex_keys = 0 if exk is None else exk.data_ptr()
+        p.n_ex = 0 if exk is None else int(exk.numel())
+        p.n_priors = len(priors)
+        for k, pr in enumerate(priors):
+            kind, values, _ = pr.native_kind()
+            s_ = p.priors[k]
+            s_.ctx = pr._ctx._h.value
+            s_.kind = kind
+            for i, v in enumerate(values):
+                s_.params[i] = float(v)
+            s_.n_params = len(values)
+            s_.cutoff = float(pr.cutoff)
+            s_.d_sel_a = 0 if pr._sel[0] is None else pr._sel[0].data_ptr()
+            s_.d_sel_b = 0 if pr._sel[1] is None else pr._sel[1].data_ptr()
+            s_.d_ex_keys = 0 if pr._exk is None else pr._exk.data_ptr()
+            s_.n_ex = 0 if pr._exk is None else int(pr._exk.numel())
+        p.traj_stride = 1
+        if self._engine_ctx is None:
+            self._engine_ctx = _lib.Context(q0.device)
+        ctx = self._engine_ctx
+        tl = [float(x) for x in t.detach().cpu()]
+        pv0 = [float(x) for x in y0[2].detach().cpu()] if len(y0) > 2 else []
+        mass = self.mass.to(q0.device, torch.float32).contiguous()
+        z = gnn.inputs["nxyz"][:, 0].to(torch.int64).contiguous()
+        tv, tq, tpv = ctx.md_run_gnn(p, gnn._native_model(), z, mass, v0.detach().to(torch.float32).contiguous(),
+                                     q0.detach().to(torch.float32).contiguous(), pv0, tl)
+        self._gnn_keepalive = (exk, z, mass)
+        self.last_engine_stats = ctx.stats()
+        if len(tl) > 1:
+            self.update_count += 2 * (len(tl) - 1)       # two evaluations per step in the reference
+            self.model._reset_topology(tq[-1])            # python-visible lists = those of the reference's last evaluation
+        return (tv, tq, tpv) if tpv is not None else (tv, tq)
+
     def _native_forward(self, y0, t, method):
         """Run the epoch on the fused engine; returns the stacked trajectory or None if this
         configuration is not covered (caller then takes the generic route)."""
         m = self._native_spec(method)
-        if m is None or len(t) < 1:
+        if m is None:
+            return self._native_forward_gnn(y0, t, method)
+        if len(t) < 1:
             return None
         if len(t) > 1 and not bool((t[1:] > t[:-1]).all()):
             return None

@@ -185,3 +185,44 @@ def test_emu_simulate_device_handoff_equals_host_roundtrip():
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     for k in range(3, 7):
         assert torch.equal(a[k], b[k])
+
+
+def test_emu_gnn_engine_epoch_equals_op_level_solver():
+    """Simulations.simulate with Stack(GNNPotentials + prior): device engine epoch (mdg_md_run_gnn) vs the op-level
+    solver with native forces; NoseHooverChain and NVE"""
+    from nff.nn.models.schnet import SchNet
+    from test_schnet import _fixture
+    from torchmd.interface import GNNPotentials, PairPotentials, Stack
+    from torchmd.potentials import ExcludedVolume
+    from torchmd.md import NVE, NoseHooverChain, Simulations
+    from torchmd.sovlers import odeint_reuse_force
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms, units
+    g, params, sd = _fixture("water")
+    for which in ("nhc", "nve"):
+        system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device="cpu")
+        np.random.seed(0)
+        system.set_temperature(298.0 * units.kB)
+        model = SchNet(params)
+        model.load_state_dict(sd)
+        gnn = GNNPotentials(system, model, cutoff=params["cutoff"])
+        oxy = [int(i) for i in np.nonzero(g["numbers"] == 8)[0]]
+        prior = PairPotentials(system, ExcludedVolume(2.6, 0.015, 12), cutoff=params["cutoff"], index_tuple=(oxy, oxy))
+        stack = Stack({"gnn": gnn, "prior": prior})
+        if which == "nhc":
+            integ = NoseHooverChain(stack, system, T=298.0 * units.kB, num_chains=5, Q=50.0, adjoint=True)
+            method = "NH_verlet"
+        else:
+            integ = NVE(stack, system, adjoint=True)
+            method = "verlet"
+        sim = Simulations(system, integ, wrap=True, method=method)
+        out = sim.simulate(steps=5, frequency=5, dt=0.5 * units.fs)
+        assert integ.last_engine_stats is not None and integ.update_count == 8
+        nbr_after = gnn.inputs["nbr_list"].clone()
+        integ.disable_gnn_engine = True
+        t = torch.Tensor([0.5 * units.fs * i for i in range(5)])
+        with torch.no_grad():
+            ref = odeint_reuse_force(integ, tuple(o[0].detach() for o in out), t, method)
+        for a, b in zip(out, ref):
+            assert (a.detach() - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
+        assert torch.equal(nbr_after, gnn.inputs["nbr_list"])          # python-visible list = list at the last frame

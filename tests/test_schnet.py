@@ -103,9 +103,9 @@ def test_gnn_potentials_vs_reference_fixture(tag):
 
 
 @pytest.mark.gpu
-def test_schnet_md_through_generic_route():
-    """Stack(GNN + ExcludedVolume prior) under NoseHooverChain, a few steps through the op-level solver
-    (configs[2] shape: water box, SchNet force field): finite, deterministic, energy decreasing under the prior."""
+def test_schnet_md_on_device_engine():
+    """Stack(GNN + ExcludedVolume prior) under NoseHooverChain through Simulations.simulate (configs[2] shape: water
+    box, SchNet force field): the epoch runs on the device engine (mdg_md_run_gnn) and equals the op-level solver."""
     from nff.nn.models.schnet import SchNet
     from torchmd.interface import GNNPotentials, PairPotentials, Stack
     from torchmd.potentials import ExcludedVolume
@@ -125,7 +125,14 @@ def test_schnet_md_through_generic_route():
     sim = Simulations(system, integ, wrap=True, method="NH_verlet")
     v, q, pv = sim.simulate(steps=6, frequency=6, dt=0.5 * units.fs)
     assert q.shape == (6, 192, 3) and torch.isfinite(q).all() and torch.isfinite(v).all()
-    assert integ.update_count == 10 and integ.last_engine_stats is None        # generic route: 2 evaluations per step
+    assert integ.update_count == 10 and integ.last_engine_stats is not None    # device engine; 2 evaluations per step counted
+    # same epoch through the op-level solver (native forces, PyTorch loop)
+    from torchmd.sovlers import odeint_reuse_force
+    integ.disable_gnn_engine = True
+    with torch.no_grad():
+        vg, qg, pg = odeint_reuse_force(integ, (v[0].detach(), q[0].detach(), pv[0].detach()),
+                                        torch.Tensor([0.5 * units.fs * i for i in range(6)]).cuda(), "NH_verlet")
+    assert (q.detach() - qg).abs().max().item() <= 2e-5 and (v.detach() - vg).abs().max().item() <= 2e-5 * vg.abs().max().item() + 1e-6
 
 
 @pytest.mark.gpu
