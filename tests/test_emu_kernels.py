@@ -88,3 +88,79 @@ def test_emu_edges(ectx):
     G.test_edge_empty_and_single_atom(ectx)
     G.test_edge_zero_step_epoch(ectx)
     G.test_edge_dense_cluster_grows_row_capacity(ectx)
+
+
+# ------------------------------------------------------------------------------------------
+# engine corner cases that the GPU suite only touches at the op level: fast builder + pair filters, non-cubic boxes,
+# unwrapped coordinates, other potential kinds under the re-test kernel, capacity growth and the skin retry
+# ------------------------------------------------------------------------------------------
+def _oracle_filtered_force(cell, rc, kind_name, params, index_tuple=None, ex_pairs=None):
+    def force(q):
+        nbr, off = O.neighbor_list(q.detach(), rc, cell, index_tuple=index_tuple, ex_pairs=ex_pairs)
+        return O.pair_energy_forces(q.detach(), nbr, off, cell, kind_name, params)[1]
+    return force
+
+
+@pytest.mark.parametrize("kind_name,kind,pp", [("lj", 0, (1.0, 1.0)), ("lj69", 2, (1.05, 0.8)), ("exv", 3, (1.0, 0.5, 12))])
+def test_emu_engine_skin_list_noncubic_unwrapped_filtered(ectx, kind_name, kind, pp):
+    rng = np.random.default_rng(7)
+    pos, vel, L = O.lj_system(12, jitter=0.03, seed=2)
+    n = pos.shape[0]
+    scale = np.array([1.0, 1.07, 0.94])
+    Ls = (np.float32(L) * scale).astype(np.float32)
+    pos = pos * scale
+    pos = pos + rng.integers(-2, 3, (n, 1)) * Ls          # whole-box displacements: raw coordinates far outside
+    q0 = torch.tensor(pos, dtype=torch.float32)
+    v0 = torch.tensor(vel, dtype=torch.float32)
+    mass = torch.full((n,), 1.008)
+    A = list(range(0, n, 2))
+    B = list(range(0, n, 3))
+    ex = rng.integers(0, n, (300, 2))
+    ex = ex[ex[:, 0] != ex[:, 1]]
+    sa = torch.zeros(n, dtype=torch.uint8); sa[A] = 1
+    sb = torch.zeros(n, dtype=torch.uint8); sb[B] = 1
+    lo, hi = np.minimum(ex[:, 0], ex[:, 1]), np.maximum(ex[:, 0], ex[:, 1])
+    keys = torch.tensor(np.unique(lo.astype(np.int64) * n + hi), dtype=torch.int64)
+    p, Qb = G._md_params(1, 1.0, n, skin=0.35, K=3, kind=kind, pp=pp)
+    for k in range(3):
+        p.cell[k] = float(Ls[k])
+    t = O.time_grid(0.004, 7)
+    cell = torch.tensor(Ls)
+    force = _oracle_filtered_force(cell, 2.5, kind_name, pp, index_tuple=(A, B), ex_pairs=torch.tensor(ex))
+    vo, qo, po = O.nh_verlet_trajectory(force, v0, q0, torch.zeros(5), t, mass, Qb, 1.0, 3 * n)
+    ectx.set_pair_filter(sa, sb, keys)
+    try:
+        tv, tq, tpv, _ = ectx.md_run(p, mass, v0, q0, [0.0] * 5, t.tolist())
+    finally:
+        ectx.set_pair_filter(None, None, None)
+    assert ectx.stats()["rebuilds"] >= 2 and ectx.stats()["path"] == 0
+    vs = vo.abs().max().item()
+    assert (tv[1] - vo[1]).abs().max().item() <= 3e-6 * vs
+    assert (tv[-1] - vo[-1]).abs().max().item() <= 1e-4 * vs
+    assert (tq[-1] - qo[-1]).abs().max().item() <= 2e-5 * float(Ls.max()) * 3
+
+
+def test_emu_engine_capacity_growth_and_skin_retry(ectx):
+    """a dense blob makes the row-capacity estimate overflow (grow + redo); a far too optimistic rebuild interval with fast
+    atoms violates the skin criterion (halve K + redo) - both inside mdg_md_run, the result still equals the oracle"""
+    rng = np.random.default_rng(3)
+    blob = rng.normal(20.0, 1.1, (500, 3))
+    gas = rng.uniform(0, 40.0, (3300, 3))
+    pos = np.concatenate([blob, gas])
+    # push apart overlapping pairs a little so that forces stay finite-ish
+    q0 = torch.tensor(pos, dtype=torch.float32)
+    n = q0.shape[0]
+    v0 = torch.tensor(rng.normal(0, 1.0, (n, 3)), dtype=torch.float32)
+    v0[:20] *= 40.0                                        # a few very fast atoms: skin violation with K = 16
+    mass = torch.full((n,), 1.0)
+    L = 40.0
+    p, Qb = G._md_params(0, L, n, skin=0.3, K=16, kind=3, pp=(1.0, 0.01, 4))     # soft ExcludedVolume: overlaps are harmless
+    t = O.time_grid(0.002, 9)
+    cell = torch.tensor([L] * 3)
+    force = _oracle_filtered_force(cell, 2.5, "exv", (1.0, 0.01, 4))
+    vo, qo = O.verlet_trajectory(force, v0, q0, t)
+    tv, tq, tpv, _ = ectx.md_run(p, mass, v0, q0, [], t.tolist())
+    st = ectx.stats()
+    assert st["maxrow_or_K"] < 16                          # the engine had to shorten the rebuild interval
+    assert (tq[-1] - qo[-1]).abs().max().item() <= 2e-5 * L
+    assert (tv[-1] - vo[-1]).abs().max().item() <= 2e-4 * vo.abs().max().item()
