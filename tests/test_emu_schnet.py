@@ -40,6 +40,8 @@ def _rand_sd(A, F, G, L, R, cutoff, seed, bias=True):
     (40, 16, 24, 7, 1, 8, "reference"),          # ragged sizes: every tile guard of the GEMM / edge kernels
     (97, 36, 52, 13, 2, 18, "correct"),
     (150, 64, 64, 29, 3, 32, "reference"),
+    (64, 512, 256, 33, 3, 256, "correct"),       # the layer widths of configs[4] (a-Si: A512 F256 G33 L3)
+    (50, 64, 512, 64, 1, 32, "reference"),       # F > one block of threads, G at the supported maximum
 ])
 def test_emu_schnet_random_model(ectx, n, A, F, G, L, R, mode):
     rng = np.random.default_rng(n)
@@ -62,7 +64,7 @@ def test_emu_schnet_random_model(ectx, n, A, F, G, L, R, mode):
     assert e2.item() == e.item()
 
 
-@pytest.mark.parametrize("tag", ["water"])
+@pytest.mark.parametrize("tag", ["water", "si"])
 def test_emu_schnet_vs_reference_fixture(ectx, tag):
     g, params, sd = _fixture(tag)
     xyz = torch.Tensor(g["positions"])
