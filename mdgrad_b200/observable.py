@@ -90,6 +90,5 @@ class vacf(Observable):
 
     def forward(self, vel):
         vacf = [(vel * vel).mean()[None]]
-        average_vel_sq = (vel * vel).mean() + 1e-6
         vacf += [(vel[t:] * vel[:-t]).mean()[None] for t in self.t_window]
-        return torch.stack(vacf).reshape(-1) / average_vel_sq
+        return torch.stack(vacf).reshape(-1)          # un-normalised, exactly as the reference

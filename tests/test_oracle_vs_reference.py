@@ -42,3 +42,16 @@ def test_adjoint_solver_live():
             res.append((v.detach(), q.detach(), pv.detach(), lj.sigma.grad.clone(), lj.epsilon.grad.clone()))
         for a, b in zip(*res):
             assert torch.equal(a, b)
+
+
+def test_vacf_live():
+    """the vacf mirror (device-agnostic tensor algebra) returns the reference's un-normalised values bit for bit"""
+    from mdgrad_b200 import observable as Ob
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    from mdgrad_b200.system import System
+    with ref_import.active() as ref:
+        atoms = FaceCenteredCubic(symbol="H", size=(2, 2, 2), latticeconstant=1.679, pbc=True)
+        vel = torch.randn(40, 32, 3, generator=torch.Generator().manual_seed(3))
+        a = ref.observable.vacf(ref.system.System(atoms, device="cpu"), t_range=15)(vel)
+    b = Ob.vacf(System(atoms, device="cpu"), t_range=15)(vel)
+    assert a.shape == (15,) and torch.equal(a, b)
