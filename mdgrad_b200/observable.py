@@ -12,7 +12,9 @@ import torch
 
 from . import _lib
 from .system import check_system
-from .topology import _selection_flags, cell_lengths, compute_dis_torch, context_for, generate_nbr_list
+from .potentials import GaussianSmearing
+from .topology import (_selection_flags, cell_lengths, compute_dis_torch, context_for, generate_angle_list,
+                       generate_nbr_list, get_offsets)
 
 
 def generate_vol_bins(start, end, nbins, dim):
@@ -79,6 +81,55 @@ class rdf(Observable):
         count = count / count.sum()
         g = count / (self.vol_bins / self.V)
         return count, self.bins, g
+
+
+def compute_angle(xyz, angle_list, cell, N):
+    """cos of the angle a-b-c at the centre b with minimum-image bond vectors (reference observable.py:166-179)"""
+    device = xyz.device
+    xyz = xyz.reshape(-1, N, 3)
+    bond_vec1 = xyz[angle_list[:, 0], angle_list[:, 1]] - xyz[angle_list[:, 0], angle_list[:, 2]]
+    bond_vec2 = xyz[angle_list[:, 0], angle_list[:, 3]] - xyz[angle_list[:, 0], angle_list[:, 2]]
+    bond_vec1 = bond_vec1 + get_offsets(bond_vec1, cell, device) * cell
+    bond_vec2 = bond_vec2 + get_offsets(bond_vec2, cell, device) * cell
+    angle_dot = (bond_vec1 * bond_vec2).sum(-1)
+    norm = (bond_vec1.pow(2).sum(-1) * bond_vec2.pow(2).sum(-1)).sqrt()
+    return angle_dot / norm
+
+
+class Angles(Observable):
+    """cos(angle) of every bonded triple within `cutoff` (reference observable.py:78-110); the neighbor list comes
+    from the native cell-list kernels, the triples are enumerated on the device (topology.generate_angle_list)."""
+
+    def __init__(self, system, nbins, angle_range, cutoff=3.0, index_tuple=None, width=None):
+        super().__init__(system)
+        start, end = angle_range[0], angle_range[1]
+        self.bins = torch.linspace(start, end, nbins + 1).to(self.device)
+        self.smear = GaussianSmearing(start=start, stop=self.bins[-1], n_gaussians=nbins, width=width,
+                                      trainable=False).to(self.device)
+        self.width = (self.smear.width[0]).item()
+        self.cutoff = cutoff
+        self.index_tuple = index_tuple
+
+    def _cos_angles(self, xyz):
+        xyz = xyz.reshape(-1, self.natoms, 3)
+        nbr_list, _ = generate_nbr_list(xyz, self.cutoff, self.cell, index_tuple=self.index_tuple, get_dis=False,
+                                        _ctx_key="angles")
+        angle_list = generate_angle_list(nbr_list)
+        return compute_angle(xyz, angle_list, self.cell, N=self.natoms)
+
+    def forward(self, xyz):
+        return self._cos_angles(xyz)
+
+
+class angle_distribution(Angles):
+    """Gaussian-smeared, normalised histogram of the bond angles (reference observable.py:112-151):
+    returns (bins, count, angles)."""
+
+    def forward(self, xyz):
+        angles = self._cos_angles(xyz).acos()
+        count = self.smear(angles.reshape(-1).squeeze()[..., None]).sum(0)
+        count = count / count.sum()
+        return self.bins, count, angles
 
 
 class vacf(Observable):

@@ -149,3 +149,36 @@ def compute_dis_torch(xyz, nbr_list, offsets, cell):
 def get_offsets(vecs, cell, device):
     """reference topology.py:75-80"""
     return -vecs.ge(0.5 * cell).to(torch.float).to(device) + vecs.lt(-0.5 * cell).to(torch.float).to(device)
+
+
+def make_directed(nbr_list):
+    """both directions of every listed pair: rows (f, a, b) followed by rows (f, b, a)  (reference topology.py:108-122)"""
+    rev = torch.stack([nbr_list[:, 0], nbr_list[:, 2], nbr_list[:, 1]], dim=-1)
+    return torch.cat([nbr_list, rev], dim=0)
+
+
+def generate_angle_list(nbr_list):
+    """All angle triples (frame, a, b, c): directed bond a->b followed by a directed bond b->c with c != a, in the
+    reference's row order (reference topology.py:83-106).  The reference materialises a (2P x 2P) boolean mask on the
+    CPU (numpy repeat); here the same list is enumerated on the tensor's own device from a per-(frame, atom) CSR of
+    the directed list: O(#angles) memory, no host round trip."""
+    assert nbr_list.shape[1] == 3
+    d = make_directed(nbr_list)
+    R = d.shape[0]
+    dev = d.device
+    if R == 0:
+        return torch.zeros((0, 4), dtype=d.dtype, device=dev)
+    n = int(d[:, 1:].max()) + 1
+    key_first = d[:, 0] * n + d[:, 1]                       # (frame, first atom) of every directed row
+    order = torch.argsort(key_first, stable=True)           # CSR order = ascending row index inside a segment
+    nseg = int(key_first.max()) + 1
+    counts = torch.bincount(key_first, minlength=nseg)
+    start = torch.cumsum(counts, 0) - counts
+    key_second = d[:, 0] * n + d[:, 2]                      # rows q with (frame, first atom) == (frame_p, b_p)
+    cnt_p = counts[key_second]
+    rep = torch.repeat_interleave(torch.arange(R, device=dev), cnt_p)
+    within = torch.arange(rep.shape[0], device=dev) - torch.repeat_interleave(torch.cumsum(cnt_p, 0) - cnt_p, cnt_p)
+    q = order[start[key_second][rep] + within]
+    third = d[q, 2]
+    keep = third != d[rep, 1]                               # c != a
+    return torch.cat([d[rep[keep]], third[keep].reshape(-1, 1)], dim=1)

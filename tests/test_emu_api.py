@@ -226,3 +226,31 @@ def test_emu_gnn_engine_epoch_equals_op_level_solver():
         for a, b in zip(out, ref):
             assert (a.detach() - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
         assert torch.equal(nbr_after, gnn.inputs["nbr_list"])          # python-visible list = list at the last frame
+
+
+def test_emu_angle_distribution_vs_live_reference():
+    """angle_distribution (native neighbor list -> device-side triple enumeration -> smeared histogram) against the
+    unmodified reference observable (authoring container only)"""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    from torchmd.observable import angle_distribution
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms
+    rng = np.random.default_rng(4)
+    n, L = 81, 9.3
+    pos = rng.uniform(0, L, (n, 3))
+    numbers = np.array(([8, 1, 1] * n)[:n])
+    atoms = Atoms(numbers=numbers, positions=pos, cell=[L] * 3, pbc=True)
+    oxy = [int(i) for i in np.nonzero(numbers == 8)[0]]
+    xyz = torch.tensor(np.stack([pos, pos + 0.1 * rng.standard_normal((n, 3))]), dtype=torch.float32)
+    obs = angle_distribution(System(atoms, device="cpu"), nbins=32, angle_range=(0.0, np.pi), cutoff=3.3, index_tuple=(oxy, oxy))
+    bins, count, angles = obs(xyz)
+    with ref_import.active() as ref:
+        robs = ref.observable.angle_distribution(ref.system.System(atoms, device="cpu"), nbins=32, angle_range=(0.0, np.pi),
+                                                 cutoff=3.3, index_tuple=(oxy, oxy))
+        rbins, rcount, rangles = robs(xyz)
+    assert angles.shape == rangles.shape and angles.shape[0] > 50
+    assert torch.equal(bins, rbins)
+    torch.testing.assert_close(angles, rangles, rtol=0, atol=2e-6)
+    torch.testing.assert_close(count, rcount, rtol=1e-5, atol=1e-7)

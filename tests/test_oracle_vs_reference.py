@@ -55,3 +55,27 @@ def test_vacf_live():
         a = ref.observable.vacf(ref.system.System(atoms, device="cpu"), t_range=15)(vel)
     b = Ob.vacf(System(atoms, device="cpu"), t_range=15)(vel)
     assert a.shape == (15,) and torch.equal(a, b)
+
+
+def test_angle_list_and_angles_live():
+    """generate_angle_list enumerated from a CSR on the device == the reference's (2P x 2P) mask construction, row for
+    row; compute_angle / the smeared angle histogram agree with the reference on the same list"""
+    from mdgrad_b200 import observable as Ob
+    from mdgrad_b200 import topology as T
+    ref = ref_import.load()
+    rng = np.random.default_rng(2)
+    n, L = 60, 7.0
+    xyz = torch.tensor(rng.uniform(0, L, (3, n, 3)), dtype=torch.float32)          # 3 frames
+    cell = torch.tensor([L, L, L])
+    frames = []
+    for f in range(3):
+        nb, _ = O.neighbor_list(xyz[f], 2.2, cell)
+        frames.append(torch.cat([torch.full((nb.shape[0], 1), f, dtype=torch.int64), nb], 1))
+    nbr = torch.cat(frames)
+    a = ref.topology.generate_angle_list(nbr)
+    b = T.generate_angle_list(nbr)
+    assert a.shape[0] > 500 and torch.equal(a, b)
+    ca = ref.observable.compute_angle(xyz, a, cell, N=n)
+    cb = Ob.compute_angle(xyz, b, cell, N=n)
+    assert torch.equal(ca, cb)
+    assert T.generate_angle_list(nbr[:0]).shape == (0, 4)
