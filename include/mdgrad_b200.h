@@ -272,6 +272,8 @@ int mdg_schnet_energy_force(mdg_ctx* ctx, const mdg_schnet_model* h_model, const
  *     and no autograd inside the loop.  Same trajectory outputs as mdg_md_run.  One SYNC per list build (pair
  *     count read-back) and one at the end.
  *     ctx owns the GNN list and the SchNet workspace; every prior brings the context that owns its list.
+ *     h_model == NULL: a Stack of analytic PairPotentials only (e.g. the three species-pair members of
+ *     scripts/fit_2_comp.py:182), every member evaluated on its own exact per-step list.
  * ------------------------------------------------------------------------------------------ */
 #define MDG_MAX_PRIORS 4
 typedef struct mdg_prior_spec {

@@ -357,9 +357,10 @@ class Context:
         M = params.n_chains if params.integrator == INT_NHC else 0
         hpv = (ctypes.c_float * max(1, n_frames * M))()
         hpv0 = _farr(pv0 if M else [0.0], max(1, M))
-        z = z.to(dev, torch.int64).contiguous()
+        z = z.to(dev, torch.int64).contiguous() if z is not None else None
         with self._guard(dev):
-            self._check(self._api().mdg_md_run_gnn(self._h, ctypes.byref(params), ctypes.byref(model[0]), _ptr(z), n, _ptr(mass),
+            self._check(self._api().mdg_md_run_gnn(self._h, ctypes.byref(params),
+                                                ctypes.byref(model[0]) if model is not None else None, _ptr(z), n, _ptr(mass),
                                                 _ptr(v0), _ptr(q0), hpv0, _farr(tgrid), n_grid, _ptr(tv), _ptr(tq),
                                                 hpv if M else None, None, self._stream(dev)))
         tpv = torch.tensor(list(hpv), dtype=torch.float32).reshape(n_frames, M).to(dev) if M else None

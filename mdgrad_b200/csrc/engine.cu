@@ -766,14 +766,19 @@ static int gnn_force(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_mo
     float* f3 = c->gnn_f3.as<float>();
     float* fp3 = c->gnn_fp3.as<float>();
     k_gnn_q_to_xyz<<<nb, T, 0, st>>>(n, q4, xyz);
-    // GNN list at the current positions (exact membership, reference layout)
-    int64_t P = 0;
-    MDG_TRY(mdg_nbr_build(c, xyz, n, p->cell, p->cutoff, nullptr, nullptr, p->d_ex_keys, p->n_ex, (void*)st, &P));
-    MDG_TRY(c->gnn_nbr.reserve(sizeof(int64_t) * 2 * (size_t)(P + 1)));
-    MDG_TRY(c->gnn_off.reserve(sizeof(float) * 3 * (size_t)(P + 1)));
-    MDG_TRY(mdg_i_export_fill(c, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), nullptr, st));
-    MDG_TRY(mdg_schnet_energy_force(c, model, d_z, xyz, n, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), P, p->off_scale,
-                                    d_e_gnn, f3, (void*)st));
+    if (model) {
+        // GNN list at the current positions (exact membership, reference layout)
+        int64_t P = 0;
+        MDG_TRY(mdg_nbr_build(c, xyz, n, p->cell, p->cutoff, nullptr, nullptr, p->d_ex_keys, p->n_ex, (void*)st, &P));
+        MDG_TRY(c->gnn_nbr.reserve(sizeof(int64_t) * 2 * (size_t)(P + 1)));
+        MDG_TRY(c->gnn_off.reserve(sizeof(float) * 3 * (size_t)(P + 1)));
+        MDG_TRY(mdg_i_export_fill(c, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), nullptr, st));
+        MDG_TRY(mdg_schnet_energy_force(c, model, d_z, xyz, n, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), P, p->off_scale,
+                                        d_e_gnn, f3, (void*)st));
+    } else {    // Stack of analytic pair members only
+        MDG_CUDA(cudaMemsetAsync(f3, 0, sizeof(float) * 3 * (size_t)n, st));
+        MDG_CUDA(cudaMemsetAsync(d_e_gnn, 0, sizeof(float), st));
+    }
     for (int k = 0; k < p->n_priors; ++k) {
         const mdg_prior_spec& R = p->priors[k];
         int64_t Pk = 0;
@@ -792,7 +797,8 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
                               const float* d_mass, const float* d_v0, const float* d_q0, const float* h_pv0,
                               const float* h_tgrid, int n_grid, float* d_traj_v, float* d_traj_q, float* h_traj_pv,
                               float* h_last_energy, void* stream) {
-    if (!c || !p || !model || !d_z) { mdg_set_error("mdg_md_run_gnn: null argument"); return MDG_E_BADARG; }
+    if (!c || !p || (model && !d_z)) { mdg_set_error("mdg_md_run_gnn: null argument"); return MDG_E_BADARG; }
+    if (!model && p->n_priors < 1) { mdg_set_error("mdg_md_run_gnn: no SchNet model and no pair member"); return MDG_E_BADARG; }
     if (n <= 0 || n_grid < 1) { mdg_set_error("mdg_md_run_gnn: n=%d n_grid=%d", n, n_grid); return MDG_E_BADARG; }
     if (p->integrator != MDG_INT_NHC && p->integrator != MDG_INT_NVE) { mdg_set_error("bad integrator"); return MDG_E_BADARG; }
     if (p->integrator == MDG_INT_NHC && (p->n_chains < 2 || p->n_chains > MDG_MAX_CHAINS)) {

@@ -267,13 +267,15 @@ class _EOM(torch.nn.Module):
         members = list(self.model.models.values()) if type(self.model) is Stack else [self.model]
         gnns = [m for m in members if type(m) is GNNPotentials]
         priors = [m for m in members if type(m) is PairPotentials]
-        if len(gnns) != 1 or len(gnns) + len(priors) != len(members) or len(priors) > _lib.MAX_PRIORS:
+        if len(gnns) > 1 or len(gnns) + len(priors) != len(members) or len(priors) > _lib.MAX_PRIORS:
             return None
+        if not gnns and (type(self.model) is not Stack or not priors):
+            return None                               # a single PairPotentials runs on the skin-list engine (mdg_md_run)
         if not all(m.native_ready() for m in members):
             return None
         if any(p.requires_grad and p.grad_fn is not None for p in self.model.parameters()):
             return None
-        return gnns[0], priors
+        return (gnns[0] if gnns else None), priors
 
     def _native_forward_gnn(self, y0, t, method):
         mem = self._gnn_members(method)
@@ -292,14 +294,17 @@ class _EOM(torch.nn.Module):
                 p.Q[k] = float(Qh[k])
             p.T = float(self.T)
         p.ndof = int(self.N_dof)
+        L = gnn._L if gnn is not None else priors[0]._L
         for k in range(3):
-            p.cell[k] = gnn._L[k]
+            p.cell[k] = L[k]
             p.off_scale[k] = 1.0            # reference quirk: raw integer offsets, not multiplied by the cell
-        p.cutoff = float(gnn.cutoff)
-        if gnn.pbc_mode != "reference":
-            for k in range(3):
-                p.off_scale[k] = gnn._L[k]
-        exk = gnn._ex_keys(q0.device)
+        exk = None
+        if gnn is not None:
+            p.cutoff = float(gnn.cutoff)
+            if gnn.pbc_mode != "reference":
+                for k in range(3):
+                    p.off_scale[k] = L[k]
+            exk = gnn._ex_keys(q0.device)
         p.d_ex_keys = 0 if exk is None else exk.data_ptr()
         p.n_ex = 0 if exk is None else int(exk.numel())
         p.n_priors = len(priors)
@@ -323,8 +328,9 @@ class _EOM(torch.nn.Module):
         tl = [float(x) for x in t.detach().cpu()]
         pv0 = [float(x) for x in y0[2].detach().cpu()] if len(y0) > 2 else []
         mass = self.mass.to(q0.device, torch.float32).contiguous()
-        z = gnn.inputs["nxyz"][:, 0].to(torch.int64).contiguous()
-        tv, tq, tpv = ctx.md_run_gnn(p, gnn._native_model(), z, mass, v0.detach().to(torch.float32).contiguous(),
+        z = gnn.inputs["nxyz"][:, 0].to(torch.int64).contiguous() if gnn is not None else None
+        tv, tq, tpv = ctx.md_run_gnn(p, gnn._native_model() if gnn is not None else None, z, mass,
+                                     v0.detach().to(torch.float32).contiguous(),
                                      q0.detach().to(torch.float32).contiguous(), pv0, tl)
         self._gnn_keepalive = (exk, z, mass)
         self.last_engine_stats = ctx.stats()

@@ -254,3 +254,30 @@ def test_emu_angle_distribution_vs_live_reference():
     assert torch.equal(bins, rbins)
     torch.testing.assert_close(angles, rangles, rtol=0, atol=2e-6)
     torch.testing.assert_close(count, rcount, rtol=1e-5, atol=1e-7)
+
+
+def test_emu_stack_of_pair_potentials_on_device_engine():
+    """scripts/fit_2_comp.py shape: Stack of three species-pair PairPotentials (index_tuples) under NoseHooverChain -
+    the epoch runs on the device engine (no SchNet member) and equals the op-level solver"""
+    from torchmd.interface import PairPotentials, Stack
+    from torchmd.potentials import LennardJones
+    from torchmd.md import NoseHooverChain, Simulations
+    from torchmd.sovlers import odeint_reuse_force
+    system = _fcc_system(size=4)
+    n = len(system)
+    np.random.seed(1)
+    system.set_temperature(1.0)
+    A, B = list(range(0, n, 2)), list(range(1, n, 2))
+    stack = Stack({"aa": PairPotentials(system, LennardJones(1.0, 1.0), cutoff=2.5, index_tuple=(A, A)),
+                   "bb": PairPotentials(system, LennardJones(0.9, 0.8), cutoff=2.2, index_tuple=(B, B)),
+                   "ab": PairPotentials(system, LennardJones(0.95, 1.1), cutoff=2.5, index_tuple=(A, B))})
+    integ = NoseHooverChain(stack, system, T=1.0, num_chains=3, Q=20.0, adjoint=True)
+    sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+    out = sim.simulate(steps=6, frequency=6, dt=0.005)
+    assert integ.last_engine_stats is not None and integ.update_count == 10
+    integ.disable_gnn_engine = True
+    t = torch.Tensor([0.005 * i for i in range(6)])
+    with torch.no_grad():
+        ref = odeint_reuse_force(integ, tuple(o[0].detach() for o in out), t, "NH_verlet")
+    for a, b in zip(out, ref):
+        assert (a.detach() - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
