@@ -76,3 +76,18 @@ def test_emu_schnet_vs_reference_fixture(ectx, tag):
     eref = float(g["energy"].reshape(-1)[0])
     assert abs(e.item() - eref) <= 1e-5 * abs(eref)
     assert np.abs(f.numpy() - g["forces"]).max() <= 1e-5 * np.abs(g["forces"]).max()
+
+
+def test_emu_schnet_no_edges_and_single_atom(ectx):
+    """isolated atoms: energy = sum of the per-atom readout of the embedding path, zero forces"""
+    sd = _rand_sd(16, 24, 7, 2, 8, 3.0, seed=1)
+    model = _lib.schnet_model_struct(sd, "cpu")
+    for n in (1, 5):
+        xyz = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) * 50.0
+        z = torch.arange(1, n + 1, dtype=torch.long)
+        nbr = torch.zeros((0, 2), dtype=torch.int64)
+        off = torch.zeros((0, 3), dtype=torch.float32)
+        e_o = O.schnet_energy(sd, z, xyz, nbr, off)
+        e, f = ectx.schnet_energy_force(model, z, xyz, nbr, off)
+        assert abs(e.item() - e_o.item()) <= 1e-5 * max(1.0, abs(e_o.item()))
+        assert float(f.abs().max()) == 0.0
