@@ -24,7 +24,10 @@ EXTRA = {"engine.cu": ["-fmad=false"]}
 # Build variants for A/B measurements: the same sources with extra -D feature macros, linked to
 # libmdgrad_b200_<name>.so and selected at import time with MDG_LIB_VARIANT=<name> (tools/ab_variants.sh runs the
 # bench on each and the GPU suite on the fastest).  The default library is "" - add entries while experimenting.
-VARIANTS = {}
+VARIANTS = {
+    # int8 (VABSDIFF4 + IDP.4A) screening in the skin-list builder - build_fast.cuh; to be A/B-measured on a GPU (round 2)
+    "i8": ["-DMDG_BUILD_INT8_SCREEN=1"],
+}
 
 
 def _sources():

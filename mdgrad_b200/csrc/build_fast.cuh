@@ -37,6 +37,22 @@ __device__ __forceinline__ void local_coord(float x, float L, float invL, float 
 // (Only the engine's force kernel reads these rows; it is order-agnostic inside a block.)
 __device__ __forceinline__ int fb_slot(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }
 
+// ---- experimental build variant MDG_BUILD_INT8_SCREEN (mdgrad_b200/build.py VARIANTS["i8"]; NOT the default) -------------
+// Phase 1 screens candidates on cell-local coordinates quantised to 8 bits per axis: one VABSDIFF4.U8 + one IDP.4A.U8.U8
+// give the squared distance in quantisation units (both single SASS instructions on sm_100a) instead of 3 FADD + FMUL +
+// 2 FFMA.  Local coordinates lie in [-c, 2c) per axis (the cell and its +-1 neighbours), so with ONE scale S = 255 / (3 c_max)
+// for all axes q = floor((l + c) S) fits a byte and |dq_k| < |dl_k| S + 1, hence
+//      sum dq^2 < (S d + sqrt(3))^2   for every pair with true distance d,
+// and the threshold T = (S r_list + sqrt(3) + 0.05)^2 can never lose a pair inside r_list (0.05: fp32 slack of the quantiser).
+// The price: pairs up to ~2 sqrt(3)/S (0.12 sigma at the benchmark geometry) beyond r_list also pass - ~6% longer rows, which the
+// force kernel's exact re-test discards.  Whether the cheaper phase 1 pays for the longer rows is a GPU measurement (round 2).
+__device__ __forceinline__ uint32_t fb_quant(float lx, float ly, float lz, float cx, float cy, float cz, float S) {
+    int qx = min(max((int)floorf((lx + cx) * S), 0), 255);
+    int qy = min(max((int)floorf((ly + cy) * S), 0), 255);
+    int qz = min(max((int)floorf((lz + cz) * S), 0), 255);
+    return (uint32_t)qx | ((uint32_t)qy << 8) | ((uint32_t)qz << 16);
+}
+
 __device__ __forceinline__ uint32_t pack_img(int Ix, int Iy, int Iz) {
     return (uint32_t)((Ix + 512) & 1023) | ((uint32_t)((Iy + 512) & 1023) << 10) | ((uint32_t)((Iz + 512) & 1023) << 20);
 }
@@ -51,6 +67,13 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
     __shared__ uint32_t s_img[FB_WARPS][FB_BATCH];
     __shared__ int s_t[FB_WARPS][FB_BATCH];                     // sorted index of each staged candidate
     __shared__ float4 s_ctr[FB_WARPS][32];                     // local coords of the cell's atoms, w = packed image
+#ifdef MDG_BUILD_INT8_SCREEN
+    __shared__ uint32_t s_cq[FB_WARPS][32];                    // the same, quantised (fb_quant)
+    const float i8_cx = bx.L[0] / (float)ncx, i8_cy = bx.L[1] / (float)ncy, i8_cz = bx.L[2] / (float)ncz;
+    const float i8_S = 255.0f / (3.0f * fmaxf(i8_cx, fmaxf(i8_cy, i8_cz)));
+    const float i8_t = i8_S * sqrtf(r2list) + 1.7820508f;      // sqrt(3) + 0.05
+    const uint32_t i8_T = (uint32_t)ceilf(i8_t * i8_t);
+#endif
     __shared__ int s_pre[FB_WARPS][28];                        // candidate-index prefix over the 27 stencil cells
     __shared__ int s_cs[FB_WARPS][27];                         // cell_start of the stencil cells
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,6 +126,9 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
             local_coord(qi.y, bx.L[1], bx.invL[1], oy, ly, Iiy);
             local_coord(qi.z, bx.L[2], bx.invL[2], oz, lz, Iiz);
             s_ctr[w][lane] = make_float4(lx, ly, lz, 0.f);
+#ifdef MDG_BUILD_INT8_SCREEN
+            s_cq[w][lane] = fb_quant(lx, ly, lz, i8_cx, i8_cy, i8_cz, i8_S);
+#endif
             imc = pack_img(Iix, Iiy, Iiz);
         }
         // image of the pass: if every atom of the cell and every candidate share it, all codes are "no shift"
@@ -139,6 +165,17 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     s_t[w][a - B] = t;
                     cand_uniform = cand_uniform && (imj == im0);
                 }
+#ifdef MDG_BUILD_INT8_SCREEN
+                const uint32_t cq = valid ? fb_quant(lx, ly, lz, i8_cx, i8_cy, i8_cz, i8_S) : 0u;
+                const uint32_t thr = valid ? i8_T : 0u;        // lanes past the end of the stream never pass
+#pragma unroll 4
+                for (int i = 0; i < np; ++i) {          // (the self pair passes here and is dropped in phase 2)
+                    uint32_t d = __vabsdiffu4(cq, s_cq[w][i]);
+                    uint32_t d2 = __dp4a(d, d, 0u);
+                    uint32_t m = __ballot_sync(0xffffffffu, d2 < thr);
+                    if (lane == 0) s_mask[w][i][ch] = m;
+                }
+#else
 #pragma unroll 4
                 for (int i = 0; i < np; ++i) {          // (the self pair passes here and is dropped in phase 2)
                     float4 ci = s_ctr[w][i];
@@ -147,6 +184,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     uint32_t m = __ballot_sync(0xffffffffu, d2 < r2list);
                     if (lane == 0) s_mask[w][i][ch] = m;
                 }
+#endif
             }
             const bool uniform = ctr_uniform && __all_sync(0xffffffffu, cand_uniform) && !filt;
             row_pure = pure_ok && uniform;

@@ -22,12 +22,14 @@ CXX = os.environ.get("CUEMU_CXX", "/usr/bin/g++" if os.path.exists("/usr/bin/g++
 # CUEMU_SANITIZE=1: AddressSanitizer + UBSan build (out-of-bounds / misaligned vector accesses of the kernels); run the
 # tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0
 SANITIZE = os.environ.get("CUEMU_SANITIZE", "") not in ("", "0")
-if SANITIZE:
-    OUT = os.path.join(HERE, "_build_san")
+# CUEMU_DEFINES="-DMDG_BUILD_INT8_SCREEN=1": emulate an experimental build variant (mdgrad_b200/build.py VARIANTS)
+DEFINES = os.environ.get("CUEMU_DEFINES", "").split()
+if SANITIZE or DEFINES:
+    OUT = os.path.join(HERE, "_build_san" if SANITIZE else "_build_var")
     LIB = os.path.join(OUT, "libmdgrad_b200_emu.so")
 FLAGS = (["-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if SANITIZE else ["-O2"]) + [
     "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
-    "-Wno-unused-function", "-DMDG_EMU=1", "-I", HERE, "-I", CSRC]
+    "-Wno-unused-function", "-DMDG_EMU=1"] + DEFINES + ["-I", HERE, "-I", CSRC]
 
 
 def _match_back_template(src, i):

@@ -188,6 +188,18 @@ static inline int   __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int   __ffs(int x) { return __builtin_ffs(x); }
 static inline int   __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int   __float2int_rn(float x) { return (int)rintf(x); }
+static inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k) {
+        int x = (a >> (8 * k)) & 255, y = (b >> (8 * k)) & 255;
+        r |= (unsigned)(x > y ? x - y : y - x) << (8 * k);
+    }
+    return r;
+}
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+    for (int k = 0; k < 4; ++k) c += ((a >> (8 * k)) & 255) * ((b >> (8 * k)) & 255);
+    return c;
+}
 
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
