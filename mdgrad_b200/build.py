@@ -27,6 +27,14 @@ EXTRA = {"engine.cu": ["-fmad=false"]}
 VARIANTS = {
     # int8 (VABSDIFF4 + IDP.4A) screening in the skin-list builder - build_fast.cuh; to be A/B-measured on a GPU (round 2)
     "i8": ["-DMDG_BUILD_INT8_SCREEN=1"],
+    # register budget of the force kernel (default 8 CTAs/SM = 32 registers) and CTA shape of the list builder
+    "mb6": ["-DMDG_FORCE_MINBLOCKS=6"],
+    "mb4": ["-DMDG_FORCE_MINBLOCKS=4"],
+    "u2mb6": ["-DMDG_FORCE_UNROLL=2", "-DMDG_FORCE_MINBLOCKS=6"],
+    "u2mb4": ["-DMDG_FORCE_UNROLL=2", "-DMDG_FORCE_MINBLOCKS=4"],
+    "fbw2": ["-DFB_WARPS=2"],
+    "fbw8": ["-DFB_WARPS=8"],
+    "i8fbw8": ["-DMDG_BUILD_INT8_SCREEN=1", "-DFB_WARPS=8"],
 }
 
 

@@ -18,7 +18,9 @@
 // Requires >= 5 cells per axis (stencil extent < half a box), else the exact builder is used.
 #pragma once
 
-#define FB_WARPS 4
+#ifndef FB_WARPS
+#define FB_WARPS 4                // cells (warps) per CTA; build variants fbw2 / fbw8
+#endif
 #define FB_BATCH 736             // candidates per batch (23 chunks of 32; a 27-cell stencil holds ~650 at liquid density)
 #define FB_CHUNKS (FB_BATCH / 32)
 

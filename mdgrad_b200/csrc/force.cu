@@ -54,23 +54,36 @@ __device__ __forceinline__ float4 mdg_gather4(const float4* __restrict__ base, u
 #endif
 }
 
+#ifndef MDG_FORCE_UNROLL
+#define MDG_FORCE_UNROLL 1
+#endif
+#ifndef MDG_FORCE_MINBLOCKS
+#define MDG_FORCE_MINBLOCKS 8      // 32-register budget (measured best of the round); build variants mb6 / mb4 relax it
+#endif
 template <int KIND, bool RETEST, bool WITH_DP, bool PURE, int GROUP, bool WITH_E>
 __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, const uint32_t* __restrict__ row, int m,
                                                int lane_in_group, const float4 qi, const Box& bx, float rc2,
                                                const PotParams& P, float& fx, float& fy, float& fz, float& en, float* dpa) {
     constexpr bool IFCONV = (KIND == MDG_POT_LJ) && !WITH_DP;
     // (down-counting loop: no loop-bound register - at the 32-register budget the bound was spilled to local memory)
+    // MDG_FORCE_UNROLL = 2 (build variants u2*): two 16-entry blocks per iteration, 8 gathers in flight per lane; rows are
+    // padded to 32 entries, so this is valid for GROUP * 4 * 2 <= 32 only.
+    constexpr int U = (GROUP * 4 * MDG_FORCE_UNROLL <= 32) ? MDG_FORCE_UNROLL : 1;
     const uint32_t* rp = row + lane_in_group * 4;
-    for (int rem = m; rem > 0; rem -= GROUP * 4, rp += GROUP * 4) {
+    for (int rem = m; rem > 0; rem -= GROUP * 4 * U, rp += GROUP * 4 * U) {
         // the row stream (~100 MB per launch) is read once: evict-first, so that it does not push the gathered
         // neighbor positions (4 MB, re-read ~90 times) out of L1/L2
-        const uint4 e4 = __ldcs(reinterpret_cast<const uint4*>(rp));
-        const uint32_t es[4] = {e4.x, e4.y, e4.z, e4.w};
-        float4 qj[4];
+        uint32_t es[4 * U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) qj[u] = mdg_gather4(qs, PURE ? es[u] : (es[u] & MDG_IDX_MASK));
+        for (int b = 0; b < U; ++b) {
+            const uint4 e4 = __ldcs(reinterpret_cast<const uint4*>(rp + b * GROUP * 4));
+            es[4 * b] = e4.x; es[4 * b + 1] = e4.y; es[4 * b + 2] = e4.z; es[4 * b + 3] = e4.w;
+        }
+        float4 qj[4 * U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 4 * U; ++u) qj[u] = mdg_gather4(qs, PURE ? es[u] : (es[u] & MDG_IDX_MASK));
+#pragma unroll
+        for (int u = 0; u < 4 * U; ++u) {
             const uint32_t e = es[u];
             float dx = __fsub_rn(qj[u].x, qi.x), dy = __fsub_rn(qj[u].y, qi.y), dz = __fsub_rn(qj[u].z, qi.z);
             if (!PURE) {
@@ -121,7 +134,7 @@ __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, co
 // WITH_E = false: the per-atom energy (fs.w) is not accumulated (written as 0) - the MD loop only needs it after
 // the last step of an epoch, and the energy costs 3 of the 28 instructions of a pure-row entry.
 template <int KIND, bool RETEST, bool WITH_DP, int GROUP, bool WITH_E>
-__global__ void __launch_bounds__(256, 8) k_force_rows(int s0, int n, const float4* __restrict__ qs,
+__global__ void __launch_bounds__(256, MDG_FORCE_MINBLOCKS) k_force_rows(int s0, int n, const float4* __restrict__ qs,
                                                                     const uint32_t* __restrict__ rows,
                                                                     const int* __restrict__ row_len, int cap, Box bx, float rc2,
                                                                     PotParams P, float4* __restrict__ fs,

@@ -4,7 +4,7 @@
 # usage (under gpurun): bash tools/ab_variants.sh x1 x2 x3 x4
 mkdir -p gpurun_out
 for v in "$@"; do
-  MDG_LIB_VARIANT=$v timeout 25 python bench.py --steps 600 --warmup 30 --no-e2e --no-cpu-baseline \
+  MDG_LIB_VARIANT=$v timeout 150 python bench.py --steps 600 --warmup 30 --no-e2e --no-cpu-baseline \
       > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || echo "variant $v: bench failed rc=$?"
 done
 best=$(python - "$@" <<'PY'
@@ -24,6 +24,6 @@ PY
 )
 echo "best variant: '$best'"
 if [ -n "$best" ]; then
-  MDG_LIB_VARIANT=$best timeout 70 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/ab_pytest_$best.log
+  MDG_LIB_VARIANT=$best timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/ab_pytest_$best.log
   cat gpurun_out/ab_pytest_$best.log
 fi
