@@ -292,6 +292,7 @@ struct mdg_ctx {
     // SchNet graph (graph.cu): node -> incident-edge CSR of the last mdg_graph_build
     DevBuf g_off, g_cnt, g_edge, g_other;
     DevBuf sn_ws;             // SchNet activations / workspace (schnet.cu)
+    DevBuf sn_wt;             // transposed weight scratch of the tensor-core dense layers (schnet_tc.cuh)
     DevBuf gnn_nbr, gnn_off, gnn_xyz, gnn_f3, gnn_fp3;   // GNN epoch (engine.cu): exported list, xyz / force staging
     int     g_n = -1;
     int64_t g_edges = 0;

@@ -19,6 +19,7 @@
 // fp32 throughout (reference dtype), plain FMA arithmetic: parity with the reference is a tolerance (1e-5), not bits.
 // The dense node-side layers use a shared-memory tiled SIMT GEMM here; they are the part the tcgen05 path replaces
 // (DESIGN.md section 7).  Weight gradients are not produced: training goes through the autograd route of the mirror.
+#include <stdlib.h>
 #include "common.cuh"
 
 int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st);
@@ -315,10 +316,36 @@ __global__ void __launch_bounds__(256) k_sn_gemm(int M, int N, int K, const floa
     }
 }
 
+#include "schnet_tc.cuh"
+
+// MDG_SCHNET_TC=1: route the dense layers through the tcgen05 kernel (experimental, see schnet_tc.cuh)
+static bool sn_tc_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MDG_SCHNET_TC");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 template <bool TRANSB, int EPI>
-static int sn_gemm(int M, int N, int K, const float* A, const float* B, int ldb, const float* bias, float* aux, float* C,
+static int sn_gemm(mdg_ctx* c, int M, int N, int K, const float* A, const float* B, int ldb, const float* bias, float* aux, float* C,
                    cudaStream_t st) {
     if (M <= 0 || N <= 0) return MDG_OK;
+#ifndef MDG_EMU
+    if (sn_tc_enabled()) {
+        const float* Bt = B;                     // the tensor-core kernel wants B as (N x K) row-major = K-major
+        if (!TRANSB) {                           // backward layers multiply by W (K x N): transpose the (small) weight first
+            MDG_TRY(c->sn_wt.reserve(sizeof(float) * (size_t)K * N));
+            k_sn_transpose<<<(K * N + 255) / 256, 256, 0, st>>>(K, N, B, c->sn_wt.as<float>());
+            Bt = c->sn_wt.as<float>();
+        }
+        if ((TRANSB ? ldb == K : ldb == N)) {
+            int r = sn_gemm_tc<EPI>(M, N, K, A, Bt, bias, aux, C, st);
+            if (r != MDG_E_STATE) return r;
+        }
+    }
+#endif
     dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
     k_sn_gemm<TRANSB, EPI><<<grid, 256, 0, st>>>(M, N, K, A, B, ldb, bias, aux, C);
     MDG_KERNEL_CHECK();
@@ -424,12 +451,12 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
         k_sn_transpose<<<(F * G + T - 1) / T, T, 0, st>>>(F, G, Y.We2, We2T[l]);
         if (E > 0)
             k_sn_edge_fwd<<<eb, 256, 0, st>>>(E, G, F, dis, Y.mu, Y.width, We1T[l], Y.be1, We2T[l], Y.be2, preT1[l], W[l]);
-        MDG_TRY((sn_gemm<true, SN_EPI_BIAS>(n, F, A, r, Y.Wn, A, Y.bn, nullptr, h[l], st)));
+        MDG_TRY((sn_gemm<true, SN_EPI_BIAS>(c, n, F, A, r, Y.Wn, A, Y.bn, nullptr, h[l], st)));
         MDG_TRY(mdg_i_cfconv_agg(c, h[l], W[l], n, F, agg, st));
-        MDG_TRY((sn_gemm<true, SN_EPI_BIAS_SSP>(n, A, F, agg, Y.Wu1, F, Y.bu1, preU1[l], u1, st)));
-        MDG_TRY((sn_gemm<true, SN_EPI_BIAS_ADD>(n, A, A, u1, Y.Wu2, A, Y.bu2, nullptr, r, st)));
+        MDG_TRY((sn_gemm<true, SN_EPI_BIAS_SSP>(c, n, A, F, agg, Y.Wu1, F, Y.bu1, preU1[l], u1, st)));
+        MDG_TRY((sn_gemm<true, SN_EPI_BIAS_ADD>(c, n, A, A, u1, Y.Wu2, A, Y.bu2, nullptr, r, st)));
     }
-    MDG_TRY((sn_gemm<true, SN_EPI_BIAS_SSP>(n, R, A, r, m->Wr1, A, m->br1, preY, y, st)));
+    MDG_TRY((sn_gemm<true, SN_EPI_BIAS_SSP>(c, n, R, A, r, m->Wr1, A, m->br1, preY, y, st)));
     int rb = (n + 7) / 8;
     if (rb > 256) rb = 256;
     k_sn_readout<<<rb, 256, 0, st>>>(n, R, y, preY, m->Wr2, m->br2, gy, epart);
@@ -439,7 +466,7 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
     if (!d_force) return MDG_OK;
 
     // ---- backward (dE/dxyz) ----------------------------------------------------------------------------------
-    MDG_TRY((sn_gemm<false, SN_EPI_STORE>(n, A, R, gy, m->Wr1, A, nullptr, nullptr, gr, st)));
+    MDG_TRY((sn_gemm<false, SN_EPI_STORE>(c, n, A, R, gy, m->Wr1, A, nullptr, nullptr, gr, st)));
     if (E > 0) MDG_CUDA(cudaMemsetAsync(gd, 0, sizeof(float) * (size_t)E, st));
     const unsigned ebb = (unsigned)((E + SN_TEB - 1) / SN_TEB);
     const size_t bwd_smem = sizeof(float) * (size_t)F * SN_TEB;
@@ -449,15 +476,15 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
     }
     for (int l = L - 1; l >= 0; --l) {
         const mdg_schnet_layer& Y = m->layers[l];
-        MDG_TRY((sn_gemm<false, SN_EPI_MUL_SIG>(n, A, A, gr, Y.Wu2, A, nullptr, preU1[l], gu, st)));
-        MDG_TRY((sn_gemm<false, SN_EPI_STORE>(n, F, A, gu, Y.Wu1, F, nullptr, nullptr, gagg, st)));
+        MDG_TRY((sn_gemm<false, SN_EPI_MUL_SIG>(c, n, A, A, gr, Y.Wu2, A, nullptr, preU1[l], gu, st)));
+        MDG_TRY((sn_gemm<false, SN_EPI_STORE>(c, n, F, A, gu, Y.Wu1, F, nullptr, nullptr, gagg, st)));
         if (E > 0) {
             k_sn_edge_bwd<<<ebb, 256, bwd_smem, st>>>(E, G, F, d_nbr, h[l], gagg, dis, Y.mu, Y.width, Y.We1,
                                                                              Y.We2, preT1[l], gd);
         }
         if (l > 0) {     // the embedding below layer 0 does not depend on the positions
             MDG_TRY(mdg_i_cfconv_agg(c, gagg, W[l], n, F, gh, st));
-            MDG_TRY((sn_gemm<false, SN_EPI_ADD>(n, A, F, gh, Y.Wn, A, nullptr, nullptr, gr, st)));
+            MDG_TRY((sn_gemm<false, SN_EPI_ADD>(c, n, A, F, gh, Y.Wn, A, nullptr, nullptr, gr, st)));
         }
     }
     k_sn_edge_force<<<(n + 127) / 128, 128, 0, st>>>(n, c->g_off.as<int>(), c->g_edge.as<int>(), d_nbr, d_offsets, h_off_scale3[0],

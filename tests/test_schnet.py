@@ -198,3 +198,21 @@ def test_schnet_md_native_force_equals_autograd_route():
     b = odeint(integ, tuple(v.clone().requires_grad_(True) for v in y0), t, method="NH_verlet")   # autograd forces, two evaluations per step
     for xa, xb in zip(a, b):
         assert (xa - xb.detach()).abs().max().item() <= 2e-5 * max(1e-3, xb.detach().abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("MDG_TEST_TC") != "1",
+                    reason="tcgen05 dense layers are opt-in until validated on hardware: MDG_TEST_TC=1 (tools/tc_check.py)")
+def test_tc_gemm_dense_layers_equal_simt(tmp_path):
+    """MDG_SCHNET_TC=1 (tcgen05, 3xTF32) vs the default SIMT dense layers on the fixtures and the configs[4] widths,
+    each in its own process and under a timeout (the tensor-core kernel had never run on hardware when this was written)."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "tc_check.py")
+    a, b = str(tmp_path / "simt.npz"), str(tmp_path / "tc.npz")
+    env = dict(os.environ)
+    env.pop("MDG_SCHNET_TC", None)
+    subprocess.run([sys.executable, tool, "simt", a], check=True, timeout=300, env=env)
+    env["MDG_SCHNET_TC"] = "1"
+    subprocess.run([sys.executable, tool, "tc", b], check=True, timeout=300, env=env)
+    assert subprocess.run([sys.executable, tool, "compare", a, b], timeout=60).returncode == 0
