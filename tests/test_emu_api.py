@@ -281,3 +281,39 @@ def test_emu_stack_of_pair_potentials_on_device_engine():
         ref = odeint_reuse_force(integ, tuple(o[0].detach() for o in out), t, "NH_verlet")
     for a, b in zip(out, ref):
         assert (a.detach() - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
+
+
+def test_emu_gnn_engine_cell_list_path_4096_atoms():
+    """configs[4] geometry (4096-atom diamond Si, rc 4.9: the cell-list path of the per-step list builds) with a narrow
+    SchNet: device engine epoch vs op-level solver"""
+    from nff.train import get_model
+    from torchmd.interface import GNNPotentials, PairPotentials, Stack
+    from torchmd.potentials import ExcludedVolume
+    from torchmd.md import NoseHooverChain, Simulations
+    from torchmd.sovlers import odeint_reuse_force
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms, units
+    a, nc = 5.45933, 8
+    basis = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]])
+    basis = np.concatenate([basis, basis + 0.25])
+    cells = np.array([[i, j, k] for i in range(nc) for j in range(nc) for k in range(nc)])
+    pos = ((cells[:, None, :] + basis[None, :, :]).reshape(-1, 3)) * a
+    pos = pos + np.random.default_rng(3).normal(0, 0.05, pos.shape)
+    system = System(Atoms(numbers=[14] * len(pos), positions=pos, cell=[a * nc] * 3, pbc=True), device="cpu")
+    np.random.seed(0)
+    system.set_temperature(100.0 * units.kB)
+    torch.manual_seed(0)
+    model = get_model({"n_atom_basis": 16, "n_filters": 12, "n_gaussians": 9, "n_convolutions": 2, "cutoff": 4.9, "trainable_gauss": False})
+    gnn = GNNPotentials(system, model, cutoff=4.9)
+    assert gnn.inputs["nbr_list"].shape[0] == 57344 or gnn.inputs["nbr_list"].shape[0] > 50000        # SURVEY 8: E = 57 344 on the perfect lattice
+    prior = PairPotentials(system, ExcludedVolume(1.9, 0.015, 12), cutoff=4.9)
+    integ = NoseHooverChain(Stack({"gnn": gnn, "prior": prior}), system, T=100.0 * units.kB, num_chains=5, Q=50.0, adjoint=True)
+    sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+    out = sim.simulate(steps=3, frequency=3, dt=1.0 * units.fs)
+    assert integ.last_engine_stats is not None and integ.last_engine_stats["path"] == 0
+    integ.disable_gnn_engine = True
+    t = torch.Tensor([1.0 * units.fs * i for i in range(3)])
+    with torch.no_grad():
+        ref = odeint_reuse_force(integ, tuple(o[0].detach() for o in out), t, "NH_verlet")
+    for x, y in zip(out, ref):
+        assert (x.detach() - y).abs().max().item() <= 2e-6 * max(1.0, y.abs().max().item())
