@@ -164,3 +164,35 @@ def test_emu_engine_capacity_growth_and_skin_retry(ectx):
     assert st["maxrow_or_K"] < 16                          # the engine had to shorten the rebuild interval
     assert (tq[-1] - qo[-1]).abs().max().item() <= 2e-5 * L
     assert (tv[-1] - vo[-1]).abs().max().item() <= 2e-4 * vo.abs().max().item()
+
+
+def test_emu_nbr_list_fuzz(ectx):
+    """seeded random sweep over atom counts (around the all-pairs / cell-list switch), densities, anisotropic boxes, cutoffs,
+    unwrapped coordinates, coincident atoms, species selections and exclusions: indices, order and offsets bit-exact"""
+    rng = np.random.default_rng(11)
+    for it in range(14):
+        n = int(rng.choice([1, 3, 33, 500, 3072, 3073, 3500, 4200]))
+        dens = rng.uniform(0.05, 1.1)
+        L = max(1.5, (n / dens) ** (1 / 3))
+        Ls = np.array([L, L * rng.uniform(0.7, 1.4), L * rng.uniform(0.7, 1.4)], dtype=np.float32)
+        rc = float(rng.uniform(0.3, max(0.35, min(4.5, 0.49 * Ls.min()))))
+        spread = float(rng.choice([0.0, 0.3, 2.5]))
+        xyz = torch.tensor(rng.uniform(-spread * Ls, (1 + spread) * Ls, (n, 3)), dtype=torch.float32)
+        if n > 10:
+            xyz[3] = xyz[8]
+        kw, sel, keys = {}, (None, None), None
+        if n > 10 and rng.random() < 0.5:
+            A = sorted(set(rng.integers(0, n, n // 2).tolist()))
+            B = sorted(set(rng.integers(0, n, n // 3).tolist()))
+            sa = torch.zeros(n, dtype=torch.uint8); sa[A] = 1
+            sb = torch.zeros(n, dtype=torch.uint8); sb[B] = 1
+            kw["index_tuple"], sel = (A, B), (sa, sb)
+        if n > 10 and rng.random() < 0.5:
+            ex = rng.integers(0, n, (50, 2))
+            ex = ex[ex[:, 0] != ex[:, 1]]
+            kw["ex_pairs"] = torch.tensor(ex)
+            lo, hi = np.minimum(ex[:, 0], ex[:, 1]), np.maximum(ex[:, 0], ex[:, 1])
+            keys = torch.tensor(np.unique(lo.astype(np.int64) * n + hi), dtype=torch.int64)
+        nbr_o, off_o = O.neighbor_list(xyz, rc, torch.tensor(Ls), block=256, **kw)
+        nbr, off = ectx.nbr_list(xyz, Ls.tolist(), rc, sel_a=sel[0], sel_b=sel[1], ex_keys=keys)
+        assert torch.equal(nbr, nbr_o) and torch.equal(off, off_o), (it, n, Ls, rc, spread)
