@@ -857,7 +857,6 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
     k_gnn_init<<<nb, T, 0, st>>>(n, d_v0, d_q0, d_mass, v4, q4, vh4);
     int ib = nb < 1 ? 1 : (nb > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : nb);
     int64_t launches = 0;
-    int64_t rebuilds0 = 0;
     MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, st));
     if (nhc) k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, v4, ke_v_cur);
     MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -901,7 +900,6 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
     MDG_CUDA(cudaStreamSynchronize(st));
     if (h_last_energy) *h_last_energy = h_e;      // SchNet energy of the last evaluation (priors not included)
     c->stat_launches += launches;
-    (void)rebuilds0;
     return MDG_OK;
 }
 

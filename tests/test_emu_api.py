@@ -15,7 +15,6 @@ import torch
 
 import emu_lib
 from mdgrad_b200 import _lib, observable, topology
-from oracle import oracle_torch as O
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 
