@@ -316,3 +316,39 @@ def test_emu_gnn_engine_cell_list_path_4096_atoms():
         ref = odeint_reuse_force(integ, tuple(o[0].detach() for o in out), t, "NH_verlet")
     for x, y in zip(out, ref):
         assert (x.detach() - y).abs().max().item() <= 2e-6 * max(1.0, y.abs().max().item())
+
+
+def test_emu_thermo_temperature_and_virial_pressure():
+    """Temperature = the reference's algebra; Pressure (working replacement of the reference's broken class) = ideal part
+    minus dE/dV of the pair energy, checked against a finite difference under uniform scaling of the box"""
+    from torchmd.interface import PairPotentials
+    from torchmd.potentials import LennardJones
+    from torchmd.thermo import Pressure, Temperature
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    rng = np.random.default_rng(0)
+
+    def energy(scale):
+        atoms = FaceCenteredCubic(symbol="H", size=(4, 4, 4), latticeconstant=1.679 * scale, pbc=True)
+        system = System(atoms, device="cpu")
+        pos = (base_frac * scale)
+        system.set_positions(pos)
+        pair = PairPotentials(system, LennardJones(1.0, 1.0), cutoff=2.5 * scale)      # same pair set under scaling
+        q = torch.Tensor(pos)
+        pair._reset_topology(q)
+        return system, pair, q, float(pair(q).detach())
+
+    atoms0 = FaceCenteredCubic(symbol="H", size=(4, 4, 4), latticeconstant=1.679, pbc=True)
+    base_frac = atoms0.get_positions() + 0.05 * rng.standard_normal((len(atoms0), 3))
+    system, pair, q, e0 = energy(1.0)
+    n = len(system)
+    v = torch.tensor(rng.standard_normal((n, 3)), dtype=torch.float32)
+    T = Temperature(system)(v)
+    m = torch.Tensor(system.get_masses())
+    assert abs(T.item() - float((m[:, None] * v * v).sum() / (3 * n))) <= 1e-5 * T.item()
+    P = Pressure(system, pair)(q, v).item()
+    h = 1e-3
+    ep, em = energy(1.0 + h)[3], energy(1.0 - h)[3]
+    V = system.get_volume()
+    dEdV = (ep - em) / (V * ((1 + h) ** 3 - (1 - h) ** 3))
+    assert abs(P - (n * T.item() / V - dEdV)) <= 2e-3 * abs(P)

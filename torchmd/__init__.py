@@ -7,7 +7,7 @@ implementation (SURVEY.md 8b Python surface).
 import importlib
 import sys
 
-_MAP = ["system", "topology", "potentials", "interface", "md", "sovlers", "observable"]
+_MAP = ["system", "topology", "potentials", "interface", "md", "sovlers", "observable", "thermo"]
 for _name in _MAP:
     _mod = importlib.import_module("mdgrad_b200." + _name)
     sys.modules[__name__ + "." + _name] = _mod
