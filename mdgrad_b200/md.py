@@ -208,7 +208,7 @@ class _EOM(torch.nn.Module):
             return -compute_grad(inputs=q, output=u.sum(-1), create_graph=_needs_graph(self.model))
 
     # -- analytic adjoint dynamics -----------------------------------------------------------------------------------
-    _POWER_LAW = (_lib.POT_LJ, _lib.POT_LJFAM, _lib.POT_LJ69, _lib.POT_EXV)
+    _POWER_LAW = (_lib.POT_LJ, _lib.POT_LJFAM, _lib.POT_LJ69, _lib.POT_EXV, _lib.POT_BUCK, _lib.POT_MORSE)   # kinds with closed-form second order
 
     def _native_second_order(self, q):
         """The pair model when its force has closed-form second-order products (mdg_pair_hvp), else None."""

@@ -352,3 +352,25 @@ def test_emu_thermo_temperature_and_virial_pressure():
     V = system.get_volume()
     dEdV = (ep - em) / (V * ((1 + h) ** 3 - (1 - h) ** 3))
     assert abs(P - (n * T.item() / V - dEdV)) <= 2e-3 * abs(P)
+
+
+def test_emu_buck_adjoint_native_vs_autograd():
+    """three-parameter potential (Buck A, B, C): analytic reverse dynamics == the double-backward route"""
+    from torchmd.interface import PairPotentials
+    from torchmd.potentials import Buck
+    from torchmd.md import NoseHooverChain, Simulations
+    g = np.load(os.path.join(G, "c1_traj.npz"))
+    out = []
+    for native in (True, False):
+        system = _fcc_system()
+        system.set_positions(g["q0"])
+        system.set_velocities(g["v0"])
+        pot = Buck(900.0, 3.2, 1.5)
+        integ = NoseHooverChain(PairPotentials(system, pot, cutoff=2.5), system, T=1.0, num_chains=3, Q=20.0, adjoint=True)
+        integ.disable_native_adjoint = not native
+        sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+        v, q, pv = sim.simulate(steps=7, frequency=7, dt=0.005)
+        ((q[-1] ** 2).sum() + (v[2] * v[5]).sum() + pv[-1].sum()).backward()
+        out.append([p.grad.item() for p in (pot.A, pot.B, pot.C)])
+    for x, y in zip(*out):
+        assert abs(x - y) <= 3e-4 * max(1.0, abs(y)), out
