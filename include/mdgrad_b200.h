@@ -120,9 +120,9 @@ int mdg_pair_force(mdg_ctx* ctx, int kind, const float* h_params, int n_params,
  * Over the list held by ctx (last mdg_nbr_build, stored image offsets, no re-test - as mdg_pair_force) and a given
  * adjoint vector d_avec (N x 3):
  *   d_hv     (N x 3)  = (dF/dxyz)^T a   ( = -Hessian(E) a )
- *   d_dtheta (MDG_MAX_POT_PARAMS, may be NULL) = (dF/dparam)^T a  for (sigma, epsilon)
- * Power-law kinds only (MDG_POT_LJ, _LJFAM, _LJ69, _EXV); other kinds return MDG_E_BADARG and the caller keeps its
- * autograd route.
+ *   d_dtheta (MDG_MAX_POT_PARAMS, may be NULL) = (dF/dparam)^T a  for the kind's parameters, in mdg_pair_force order
+ * All analytic kinds: the power-law family (MDG_POT_LJ, _LJFAM, _LJ69, _EXV: sigma, epsilon), MDG_POT_BUCK (A, B, C) and
+ * MDG_POT_MORSE (no differentiable parameters).  Learned u(r) keeps the autograd route in the Python layer.
  * ------------------------------------------------------------------------------------------ */
 int mdg_pair_hvp(mdg_ctx* ctx, int kind, const float* h_params, int n_params,
                  const float* d_xyz, int n, const float* d_avec,
