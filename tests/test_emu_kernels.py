@@ -196,3 +196,14 @@ def test_emu_nbr_list_fuzz(ectx):
         nbr_o, off_o = O.neighbor_list(xyz, rc, torch.tensor(Ls), block=256, **kw)
         nbr, off = ectx.nbr_list(xyz, Ls.tolist(), rc, sel_a=sel[0], sel_b=sel[1], ex_keys=keys)
         assert torch.equal(nbr, nbr_o) and torch.equal(off, off_o), (it, n, Ls, rc, spread)
+
+
+def test_emu_fullsize_property_checks_at_reduced_size(ectx):
+    """the property checks of tests/test_gpu_zfullsize.py (run there at 256 000 atoms) executed here on a 4 000-atom box"""
+    import fullsize_checks as F
+    cpu = torch.device("cpu")
+    P = F.check_list_structure(ectx, cpu, 10)
+    assert 100_000 < P < 120_000
+    F.check_forces_against_c_oracle(ectx, cpu, 10, nrows=512)
+    F.check_engine_invariants(ectx, cpu, 10, nsteps=12)
+    F.check_rdf_two_paths(ectx, cpu, 10)
