@@ -35,6 +35,8 @@ VARIANTS = {
     "fbw2": ["-DFB_WARPS=2"],
     "fbw8": ["-DFB_WARPS=8"],
     "i8fbw8": ["-DMDG_BUILD_INT8_SCREEN=1", "-DFB_WARPS=8"],
+    "lean": ["-DMDG_BUILD_LEAN=1"],
+    "i8lean": ["-DMDG_BUILD_INT8_SCREEN=1", "-DMDG_BUILD_LEAN=1"],
 }
 
 

@@ -108,8 +108,12 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
     // Stream-index form (entries index the cell's 27-cell STENCIL STREAM instead of the global sorted array, for a
     // force kernel that stages the stream in shared memory): measured slower than the gather kernel (124 vs 66 us)
     // and not used - the engine always passes cell_local == nullptr, so entries are global indices.
+#ifdef MDG_BUILD_LEAN      // build variants "lean*": the unused stream-index form is compiled out of the phase-2 loop
+    constexpr bool local_idx = false;
+#else
     const bool local_idx = (cell_local != nullptr) && (total <= MDG_STREAM_CAP);
     if (cell_local && lane == 0) cell_local[c] = local_idx ? 1 : 0;
+#endif
     const int cx = c % ncx, cy = (c / ncx) % ncy, cz = c / (ncx * ncy);
     const float ox = (float)cx / (float)ncx, oy = (float)cy / (float)ncy, oz = (float)cz / (float)ncz;
     const bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
@@ -140,7 +144,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         int cnt = 0;
         // a row is PURE when its single batch is uniform: bare indices, flagged in row_len (force kernel skips the
         // index mask and the image-code test)
+#ifdef MDG_BUILD_LEAN
+        const bool pure_ok = (total <= FB_BATCH);
+#else
         const bool pure_ok = (cell_local == nullptr) && (total <= FB_BATCH);
+#endif
         bool row_pure = false;
         for (int B = 0; B < total; B += FB_BATCH) {
             const int nb = min(FB_BATCH, total - B);
