@@ -254,6 +254,9 @@ typedef struct mdg_schnet_model {
     const float* embed;
     mdg_schnet_layer layers[MDG_SCHNET_MAX_LAYERS];
     const float *Wr1, *br1, *Wr2, *br2;
+    uint64_t weights_tag;   /* 0 = unknown: derived weight layouts are rebuilt at every call.  Non-zero: the caller promises to
+                               change the tag whenever any parameter VALUE changed, so the library may cache the transposed
+                               filter weights it derives (the Python layer hashes the tensors' data pointers and version counters) */
 } mdg_schnet_model;
 
 int mdg_schnet_energy_force(mdg_ctx* ctx, const mdg_schnet_model* h_model, const int64_t* d_z,

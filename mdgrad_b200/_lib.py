@@ -64,7 +64,8 @@ class SchnetModel(ctypes.Structure):
     _fields_ = [("n_atom_basis", ctypes.c_int), ("n_filters", ctypes.c_int), ("n_gaussians", ctypes.c_int),
                 ("n_convolutions", ctypes.c_int), ("n_readout", ctypes.c_int),
                 ("embed", ctypes.c_void_p), ("layers", SchnetLayer * SCHNET_MAX_LAYERS),
-                ("Wr1", ctypes.c_void_p), ("br1", ctypes.c_void_p), ("Wr2", ctypes.c_void_p), ("br2", ctypes.c_void_p)]
+                ("Wr1", ctypes.c_void_p), ("br1", ctypes.c_void_p), ("Wr2", ctypes.c_void_p), ("br2", ctypes.c_void_p),
+                ("weights_tag", ctypes.c_uint64)]
 
 
 MAX_PRIORS = 4
@@ -117,6 +118,8 @@ def schnet_model_struct(sd, device):
     m.n_readout = sd[ro + "linear0.weight"].shape[0]
     m.Wr1, m.br1 = dp(ro + "linear0.weight"), dp(ro + "linear0.bias")
     m.Wr2, m.br2 = dp(ro + "linear2.weight"), dp(ro + "linear2.bias")
+    # value tag: changes whenever a parameter tensor is replaced or modified in place (torch bumps `_version`)
+    m.weights_tag = (hash(tuple((sd[k].data_ptr(), sd[k]._version) for k in sd)) & 0x7FFFFFFFFFFFFFFF) | 1
     return m, keep
 
 

@@ -292,6 +292,9 @@ struct mdg_ctx {
     // SchNet graph (graph.cu): node -> incident-edge CSR of the last mdg_graph_build
     DevBuf g_off, g_cnt, g_edge, g_other;
     DevBuf sn_ws;             // SchNet activations / workspace (schnet.cu)
+    DevBuf sn_wcache;         // cached transposed filter weights of the last model (schnet.cu), valid for sn_wtag
+    uint64_t sn_wtag = 0;
+    const float* sn_wkey[2 * MDG_SCHNET_MAX_LAYERS] = {nullptr};
     DevBuf sn_wt;             // transposed weight scratch of the tensor-core dense layers (schnet_tc.cuh)
     DevBuf gnn_nbr, gnn_off, gnn_xyz, gnn_f3, gnn_fp3;   // GNN epoch (engine.cu): exported list, xyz / force staging
     int     g_n = -1;

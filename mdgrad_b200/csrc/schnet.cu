@@ -415,7 +415,7 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
     // workspace carve-up (floats)
     const size_t sE = al((size_t)E), sEG = al((size_t)E * G), sEF = al((size_t)E * F);
     const size_t sNA = al((size_t)n * A), sNF = al((size_t)n * F), sNR = al((size_t)n * R);
-    const size_t sWt = al((size_t)G * G) + al((size_t)G * F);
+    const size_t sWt = 0;       // transposed filter weights live in their own cached buffer (sn_wcache)
     size_t total = 2 * sE + (size_t)L * (sEG + sEF + sNF + sNA + sWt) + 4 * sNA + 3 * sNF + 3 * sNR + 1024;
     MDG_TRY(c->sn_ws.reserve(total * sizeof(float)));
     float* p = c->sn_ws.as<float>();
@@ -426,7 +426,27 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
     float *We1T[MDG_SCHNET_MAX_LAYERS], *We2T[MDG_SCHNET_MAX_LAYERS];
     for (int l = 0; l < L; ++l) {
         preT1[l] = take(sEG); W[l] = take(sEF); h[l] = take(sNF); preU1[l] = take(sNA);
-        We1T[l] = take(al((size_t)G * G)); We2T[l] = take(al((size_t)G * F));
+    }
+    // transposed filter weights: rebuilt only when the model's weights_tag (or a weight pointer) changed
+    {
+        const size_t per = al((size_t)G * G) + al((size_t)G * F);
+        MDG_TRY(c->sn_wcache.reserve(sizeof(float) * per * (size_t)L));
+        bool fresh = m->weights_tag != 0 && m->weights_tag == c->sn_wtag;
+        for (int l = 0; l < L; ++l) {
+            We1T[l] = c->sn_wcache.as<float>() + per * (size_t)l;
+            We2T[l] = We1T[l] + al((size_t)G * G);
+            fresh = fresh && c->sn_wkey[2 * l] == m->layers[l].We1 && c->sn_wkey[2 * l + 1] == m->layers[l].We2;
+        }
+        if (!fresh) {
+            for (int l = 0; l < L; ++l) {
+                k_sn_transpose<<<(G * G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(G, G, m->layers[l].We1, We1T[l]);
+                k_sn_transpose<<<(F * G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(F, G, m->layers[l].We2, We2T[l]);
+                c->sn_wkey[2 * l] = m->layers[l].We1;
+                c->sn_wkey[2 * l + 1] = m->layers[l].We2;
+            }
+            c->sn_wtag = m->weights_tag;
+            c->stat_launches += 2 * L;
+        }
     }
     float* r = take(sNA);
     float* u1 = take(sNA);
@@ -447,8 +467,6 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
     const unsigned eb = (unsigned)((E + SN_TE - 1) / SN_TE);
     for (int l = 0; l < L; ++l) {
         const mdg_schnet_layer& Y = m->layers[l];
-        k_sn_transpose<<<(G * G + T - 1) / T, T, 0, st>>>(G, G, Y.We1, We1T[l]);
-        k_sn_transpose<<<(F * G + T - 1) / T, T, 0, st>>>(F, G, Y.We2, We2T[l]);
         if (E > 0)
             k_sn_edge_fwd<<<eb, 256, 0, st>>>(E, G, F, dis, Y.mu, Y.width, We1T[l], Y.be1, We2T[l], Y.be2, preT1[l], W[l]);
         MDG_TRY((sn_gemm<true, SN_EPI_BIAS>(c, n, F, A, r, Y.Wn, A, Y.bn, nullptr, h[l], st)));
@@ -461,7 +479,7 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
     if (rb > 256) rb = 256;
     k_sn_readout<<<rb, 256, 0, st>>>(n, R, y, preY, m->Wr2, m->br2, gy, epart);
     k_sn_energy_final<<<1, 32, 0, st>>>(rb, epart, d_energy);
-    c->stat_launches += 4 + 9 * L;
+    c->stat_launches += 4 + 5 * L;
     MDG_KERNEL_CHECK();
     if (!d_force) return MDG_OK;
 

@@ -374,3 +374,34 @@ def test_emu_buck_adjoint_native_vs_autograd():
         out.append([p.grad.item() for p in (pot.A, pot.B, pot.C)])
     for x, y in zip(*out):
         assert abs(x - y) <= 3e-4 * max(1.0, abs(y)), out
+
+
+def test_emu_native_schnet_sees_in_place_weight_updates():
+    """the library caches derived weight layouts per weights_tag: an optimiser step (in-place update, version bump) must be
+    picked up by the next native evaluation"""
+    from nff.nn.models.schnet import SchNet
+    from test_schnet import _fixture
+    from torchmd.interface import GNNPotentials
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms
+    from oracle import oracle_torch as O
+    g, params, sd = _fixture("water")
+    system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device="cpu")
+    model = SchNet(params)
+    model.load_state_dict(sd)
+    gnn = GNNPotentials(system, model, cutoff=params["cutoff"])
+    xyz = torch.Tensor(system.get_positions())
+    e0, _ = gnn.native_energy_force(xyz)
+    e0b, _ = gnn.native_energy_force(xyz)
+    assert e0.item() == e0b.item()
+    with torch.no_grad():
+        model.convolutions[0].moduledict["message_edge_filter"][3].weight.mul_(1.05)
+        model.convolutions[1].moduledict["message_edge_filter"][1].weight.add_(0.01)
+    e1, f1 = gnn.native_energy_force(xyz)
+    z = torch.tensor(g["numbers"], dtype=torch.long)
+    x = xyz.clone().requires_grad_(True)
+    eo = O.schnet_energy(model.state_dict(), z, x, gnn.inputs["nbr_list"], gnn.inputs["offsets"])
+    fo = -torch.autograd.grad(eo, x)[0]
+    assert abs(e1.item() - e0.item()) > 1e-4 * abs(e0.item())
+    assert abs(e1.item() - eo.item()) <= 1e-5 * abs(eo.item())
+    assert (f1 - fo).abs().max().item() <= 2e-5 * fo.abs().max().item()
