@@ -113,8 +113,10 @@ def rewrite_launches(src):
         q = _match_paren(src, p)
         args = src[p + 1:q]
         out.append(src[pos:start])
-        out.append("cuemu::launch(dim3(%s), dim3(%s), (size_t)(%s), [&, _cuemu_args = std::make_tuple(%s)]() { "
-                   "std::apply([](auto... _a) { %s(_a...); }, _cuemu_args); })" % (cfg[0], cfg[1], smem, args, kernel))
+        stream = cfg[3] if len(cfg) > 3 else "nullptr"
+        ktext = "".join(kernel.split()).replace('"', "")
+        out.append("cuemu::launch(\"%s\", dim3(%s), dim3(%s), (size_t)(%s), (cudaStream_t)(%s), [_cuemu_args = std::make_tuple(%s)]() { "
+                   "std::apply([](auto... _a) { %s(_a...); }, _cuemu_args); })" % (ktext, cfg[0], cfg[1], smem, stream, args, kernel))
         pos = q + 1
     return "".join(out)
 
@@ -183,6 +185,25 @@ def build(verbose=False):
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return LIB
+
+
+def build_selftest():
+    """tests/cuemu/selftest.cu -> _build/selftest (the emulator checking itself, tests/test_emu_selftest.py)"""
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "selftest")
+    srcs = [os.path.join(HERE, f) for f in ("selftest.cu", "cuemu.cpp", "cuda_runtime.h", "build_emu.py")]
+    if os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(f) for f in srcs):
+        return exe
+    cpp = os.path.join(OUT, "selftest.emu.cpp")
+    with open(srcs[0]) as fh:
+        t = translate(fh.read())
+    with open(cpp, "w") as fh:
+        fh.write('#line 1 "%s"\n' % srcs[0])
+        fh.write(t)
+    r = subprocess.run([CXX] + FLAGS + [cpp, srcs[1], "-o", exe, "-rdynamic", "-ldl", "-lm"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("cuemu selftest build failed:\n" + r.stdout + r.stderr)
+    return exe
 
 
 if __name__ == "__main__":

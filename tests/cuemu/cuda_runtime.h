@@ -60,6 +60,7 @@ static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y
 // ---------------------------------------------------------------------------------------------
 // the fiber runtime (cuemu.cpp)
 // ---------------------------------------------------------------------------------------------
+struct cuemu_stream_st;
 namespace cuemu {
 struct ThreadState {
     uint3 tid;
@@ -68,7 +69,7 @@ struct ThreadState {
 extern ThreadState* g_cur;
 extern uint3 g_blockIdx;
 extern dim3  g_blockDim, g_gridDim;
-void  launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void  launch(const char* kernel_text, dim3 grid, dim3 block, size_t smem, struct ::cuemu_stream_st* stream, std::function<void()> body);
 void  sync_block();
 // warp collective: deposit (value, pred) for this lane, wait for all live lanes of `mask`; the returned arrays stay
 // valid until coll_leave()
@@ -226,17 +227,33 @@ template <typename T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return 
 template <typename T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
 // ---------------------------------------------------------------------------------------------
-// runtime API (synchronous, host memory)
+// runtime API (cuemu.cpp).  Two modes, chosen at run time by CUEMU_STRICT (default 1):
+//   strict: GPU-like ASYNCHRONOUS semantics.  Launches / async copies / memsets are queued per stream and only run
+//           when the host synchronises (stream / event / device sync, a blocking copy, cudaFree) - and then only
+//           what that synchronisation guarantees (the stream, plus what its event waits and the legacy-default-stream
+//           rules drag in).  A host read of a result before its synchronisation, a pinned staging buffer rewritten
+//           before its queued copy ran, or a missing cudaStreamWaitEvent therefore FAIL here as they would on a GPU.
+//           cudaMalloc memory comes from an arena that is PROT_NONE while no device operation is executing: host
+//           code dereferencing a device pointer takes a SIGSEGV with a diagnostic; freed device memory stays
+//           inaccessible for good (use after free), every allocation ends at a guard page.
+//   relaxed (CUEMU_STRICT=0, and the sanitizer build): the old synchronous behaviour on plain malloc memory.
+// Launch configurations are checked like the driver does (zero / oversized grid or block dimensions, dynamic shared
+// memory above 48 KB without cudaFuncSetAttribute, above 227 KB at all): the launch is dropped and
+// cudaGetLastError() returns cudaErrorInvalidConfiguration / cudaErrorInvalidValue.
 // ---------------------------------------------------------------------------------------------
 typedef int cudaError_t;
 #define cudaSuccess 0
+#define cudaErrorInvalidValue 1
 #define cudaErrorMemoryAllocation 2
+#define cudaErrorInvalidConfiguration 9
+#define cudaErrorNotReady 600
 typedef struct cuemu_stream_st* cudaStream_t;
 typedef struct cuemu_event_st*  cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 #define cudaEventDisableTiming 2
 #define cudaEventDefault 0
 #define cudaStreamNonBlocking 1
+#define cudaStreamDefault 0
 
 struct cudaDeviceProp {
     char name[256];
@@ -244,9 +261,9 @@ struct cudaDeviceProp {
     size_t totalGlobalMem, sharedMemPerBlockOptin;
 };
 
-static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cuemu error"; }
-static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e);
+cudaError_t cudaGetLastError();
+cudaError_t cudaPeekAtLastError();
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
@@ -258,38 +275,45 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     p->sharedMemPerBlockOptin = 227 * 1024;
     return cudaSuccess;
 }
-static inline cudaError_t cudaMalloc(void** p, size_t bytes) {
-    size_t b = (bytes + 255) & ~(size_t)255;
-    *p = aligned_alloc(256, b ? b : 256);
-    if (*p) memset(*p, 0xCD, b ? b : 256);   // poison: uninitialised device memory must not look like zeros
-    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
-}
+cudaError_t cudaMalloc(void** p, size_t bytes);
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc((void**)p, bytes); }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-static inline cudaError_t cudaMallocHost(void** p, size_t bytes) { return cudaMalloc(p, bytes); }
-template <typename T> inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return cudaMalloc((void**)p, bytes); }
-static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
-static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
-    for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
-    return cudaSuccess;
-}
-static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
-static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
-static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
-static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+cudaError_t cudaFree(void* p);
+cudaError_t cudaMallocHost(void** p, size_t bytes);
+template <typename T> inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return cudaMallocHost((void**)p, bytes); }
+cudaError_t cudaFreeHost(void* p);
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind k);
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t st = nullptr);
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind k, cudaStream_t st = nullptr);
+cudaError_t cudaMemset(void* d, int v, size_t n);
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = nullptr);
+cudaError_t cudaStreamSynchronize(cudaStream_t st);
+cudaError_t cudaStreamQuery(cudaStream_t st);
+cudaError_t cudaDeviceSynchronize();
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned flags, int prio);
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
+cudaError_t cudaStreamCreate(cudaStream_t* s);
+cudaError_t cudaStreamDestroy(cudaStream_t s);
 static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -5; return cudaSuccess; }
-static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
-static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
-static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
-static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
-static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
-template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned flags = 0);
+cudaError_t cudaEventCreate(cudaEvent_t* e);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags);
+cudaError_t cudaEventDestroy(cudaEvent_t e);
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);
+cudaError_t cudaEventSynchronize(cudaEvent_t e);
+cudaError_t cudaEventQuery(cudaEvent_t e);
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
+namespace cuemu {
+cudaError_t func_set_attr(const char* call_text, int attr, int value);
+template <typename F> inline cudaError_t func_set_attr2(const char* call_text, F, int attr, int value) { return func_set_attr(call_text, attr, value); }
+}
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
+// the kernel is identified by its source text (the same text the launch rewriter records), template commas included
+#define cudaFuncSetAttribute(...) cuemu::func_set_attr2(#__VA_ARGS__, __VA_ARGS__)
+
+// test hooks (exported, C linkage): what a following operation on the caller's stream would observe / leftovers
+extern "C" {
+int  cuemu_api_return(void* user_stream);   // synchronise the caller's stream; returns the number of OTHER streams with pending work
+void cuemu_flush_all();
+int  cuemu_strict();
+long cuemu_counter(int which);              // 0 launches run, 1 launches rejected, 2 ops deferred past their enqueue call
+}

@@ -21,12 +21,42 @@ from mdgrad_b200 import _lib as L  # noqa: E402
 _emu = None
 
 
+class _AsyncBoundary:
+    """Every entry point of the emulated library returns the way it would on a GPU: work may still be QUEUED on the
+    caller's stream (the emulator defers launches and async copies until something synchronises, see
+    cuemu/cuda_runtime.h).  The test then reads the output tensors the way a following torch op on the same stream
+    would - after everything queued on THAT stream, and only that: `cuemu_api_return` runs the caller's stream and
+    reports streams that still hold work nobody joined (an error: the call returned with an unjoined side stream)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        lib.cuemu_api_return.argtypes = [ctypes.c_void_p]
+        lib.cuemu_api_return.restype = ctypes.c_int
+        lib.cuemu_counter.argtypes = [ctypes.c_int]
+        lib.cuemu_counter.restype = ctypes.c_long
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("mdg_") or name in ("mdg_last_error", "mdg_version"):
+            return fn
+        lib = self._lib
+
+        def call(*args):
+            status = fn(*args)
+            left = lib.cuemu_api_return(None)
+            if left:
+                raise AssertionError("%s returned with work pending on %d side stream(s) that the caller's stream never joined" % (name, left))
+            return status
+        call.__name__ = name
+        return call
+
+
 def load():
     global _emu
     if _emu is None:
         sys.path.insert(0, os.path.join(ROOT, "tests", "cuemu"))
         import build_emu
-        _emu = L.bind(ctypes.CDLL(build_emu.build()))
+        _emu = _AsyncBoundary(L.bind(ctypes.CDLL(build_emu.build())))
     return _emu
 
 
