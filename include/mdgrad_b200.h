@@ -279,6 +279,35 @@ int mdg_schnet_energy_force(mdg_ctx* ctx, const mdg_schnet_model* h_model, const
  *     scripts/fit_2_comp.py:182), every member evaluated on its own exact per-step list.
  * ------------------------------------------------------------------------------------------ */
 #define MDG_MAX_PRIORS 4
+
+/* ------------------------------------------------------------------------------------------
+ * Bonded terms: BondPotentials.forward (torchmd/interface.py:436-451) and AnglePotentials.forward
+ *     (:489-510) with their autograd forces (md.py:227-228) - the `prior` member of demo/fold.py:131.
+ *     bond (i, j):     v = x_i - x_j + get_offsets(v) * L (topology.py:74-80),  b = |v|^2 (SQUARED, as the reference),
+ *                      E = 0.5 k sum (b - ro)^2
+ *     angle (a, c, e): E = 0.5 k sum (acos(v1.v2 / sqrt(|v1|^2 |v2|^2)) - theta0)^2,  v1 = x_a - x_c, v2 = x_e - x_c
+ *     d_energy2 = (E_bond, E_angle); d_force (n,3) = -dE/dx of both (overwritten); d_dparams4 = dE/d(k_bond, ro,
+ *     k_angle, theta0); each may be NULL.  Forces need the atom -> term reference list of the (static) topology:
+ *     d_ref_start (n+1) and d_refs, refs of atom i = d_refs[d_ref_start[i] .. d_ref_start[i+1]), each
+ *     ref = slot * 4 + role with slot = t for bond t, n_bonds + 2 t for angle t; role 0 = first atom of a bond /
+ *     first atom of an angle (and, with slot + 1, its third atom), 1 = second atom of a bond, 2 = centre atom of an
+ *     angle (mdgrad_b200/interface.py builds it once per topology).  Terms naming atoms outside [0, n) contribute
+ *     nothing.  Deterministic (no atomics).  Asynchronous.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mdg_bonded_terms {
+    const int64_t* d_bond_top;                    /* (n_bonds, 2) int64 or NULL                  */
+    int            n_bonds;
+    float          k_bond, r0;
+    const int64_t* d_angle_top;                   /* (n_angles, 3) int64 or NULL                 */
+    int            n_angles;
+    float          k_angle, theta0;
+    const int32_t* d_ref_start;                   /* (n + 1)                                      */
+    const int32_t* d_refs;
+} mdg_bonded_terms;
+
+int mdg_bonded_force(mdg_ctx* ctx, const mdg_bonded_terms* h_terms, const float* d_xyz, int n, const float* h_cell3,
+                     float* d_energy2, float* d_force, float* d_dparams4, void* stream);
+
 typedef struct mdg_prior_spec {
     mdg_ctx*       ctx;
     int            kind;                          /* MDG_POT_*                                   */
@@ -305,6 +334,8 @@ typedef struct mdg_gnn_md_params {
     int     n_priors;
     mdg_prior_spec priors[MDG_MAX_PRIORS];
     int     traj_stride;
+    mdg_bonded_terms bonded;                      /* BondPotentials / AnglePotentials members of the Stack
+                                                     (n_bonds = n_angles = 0: none)               */
 } mdg_gnn_md_params;
 
 int mdg_md_run_gnn(mdg_ctx* ctx, const mdg_gnn_md_params* p, const mdg_schnet_model* h_model,

@@ -29,6 +29,7 @@ SYMBOLS = [
     "mdg_get_stats", "mdg_set_pair_filter", "mdg_set_profile", "mdg_get_profile",
     "mdg_slab_plan", "mdg_dist_unique_id", "mdg_dist_init", "mdg_dist_finalize",
     "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad", "mdg_schnet_energy_force", "mdg_pair_hvp", "mdg_md_run_gnn",
+    "mdg_bonded_force",
 ]
 
 
@@ -78,12 +79,20 @@ class PriorSpec(ctypes.Structure):
                 ("d_sel_b", ctypes.c_void_p), ("d_ex_keys", ctypes.c_void_p), ("n_ex", ctypes.c_int)]
 
 
+class BondedTerms(ctypes.Structure):
+    """mirror of struct mdg_bonded_terms"""
+    _fields_ = [("d_bond_top", ctypes.c_void_p), ("n_bonds", ctypes.c_int), ("k_bond", ctypes.c_float), ("r0", ctypes.c_float),
+                ("d_angle_top", ctypes.c_void_p), ("n_angles", ctypes.c_int), ("k_angle", ctypes.c_float),
+                ("theta0", ctypes.c_float), ("d_ref_start", ctypes.c_void_p), ("d_refs", ctypes.c_void_p)]
+
+
 class GnnMdParams(ctypes.Structure):
     """mirror of struct mdg_gnn_md_params"""
     _fields_ = [("integrator", ctypes.c_int), ("n_chains", ctypes.c_int), ("Q", ctypes.c_float * MAX_CHAINS),
                 ("T", ctypes.c_double), ("ndof", ctypes.c_int), ("cell", ctypes.c_float * 3), ("cutoff", ctypes.c_double),
                 ("off_scale", ctypes.c_float * 3), ("d_ex_keys", ctypes.c_void_p), ("n_ex", ctypes.c_int),
-                ("n_priors", ctypes.c_int), ("priors", PriorSpec * MAX_PRIORS), ("traj_stride", ctypes.c_int)]
+                ("n_priors", ctypes.c_int), ("priors", PriorSpec * MAX_PRIORS), ("traj_stride", ctypes.c_int),
+                ("bonded", BondedTerms)]
 
 
 def schnet_model_struct(sd, device):
@@ -174,6 +183,7 @@ def bind(lib):
     lib.mdg_md_run_gnn.argtypes = [vp, ctypes.POINTER(GnnMdParams), ctypes.POINTER(SchnetModel), vp, ip, vp, vp, vp, fp, fp, ip,
                                    vp, vp, fp, fp, vp]
     lib.mdg_pair_hvp.argtypes = [vp, ip, fp, ip, vp, ip, vp, vp, vp, vp]
+    lib.mdg_bonded_force.argtypes = [vp, ctypes.POINTER(BondedTerms), vp, ip, fp, vp, vp, vp, vp]
     lib.mdg_schnet_energy_force.argtypes = [vp, ctypes.POINTER(SchnetModel), vp, vp, ip, vp, vp, i64, fp, vp, vp, vp]
     for name in SYMBOLS:
         if name not in ("mdg_last_error",):
@@ -415,6 +425,21 @@ class Context:
                                                          self._stream(xyz.device)))
         self._schnet_keepalive = (z, xyz, nbr, offsets)
         return e, f
+
+    # -- bonded terms -------------------------------------------------------------------------
+    def bonded_force(self, terms, xyz, cell3, want_force=True, want_dparams=False):
+        """(E (2,) = (E_bond, E_angle), F (N,3) or None, dE/d(k_bond, ro, k_angle, theta0) (4,) or None) for a filled
+        BondedTerms struct (its tensors kept alive by the caller) - mdg_bonded_force."""
+        self._require(xyz, "xyz")
+        xyz = xyz.detach().to(torch.float32).contiguous()
+        n = xyz.shape[0]
+        e = torch.empty((2,), dtype=torch.float32, device=xyz.device)
+        f = torch.empty((n, 3), dtype=torch.float32, device=xyz.device) if want_force else None
+        dp = torch.empty((4,), dtype=torch.float32, device=xyz.device) if want_dparams else None
+        with self._guard(xyz.device):
+            self._check(self._api().mdg_bonded_force(self._h, ctypes.byref(terms), _ptr(xyz), n, _farr(cell3, 3), _ptr(e), _ptr(f),
+                                                  _ptr(dp), self._stream(xyz.device)))
+        return e, f, dp
 
     # -- multi-GPU ----------------------------------------------------------------------------
     def dist_init(self, group=None):

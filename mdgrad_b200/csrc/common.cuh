@@ -297,6 +297,7 @@ struct mdg_ctx {
     const float* sn_wkey[2 * MDG_SCHNET_MAX_LAYERS] = {nullptr};
     DevBuf sn_wt;             // transposed weight scratch of the tensor-core dense layers (schnet_tc.cuh)
     DevBuf gnn_nbr, gnn_off, gnn_xyz, gnn_f3, gnn_fp3;   // GNN epoch (engine.cu): exported list, xyz / force staging
+    DevBuf bd_slots, bd_part;  // bonded terms (bonded.cu): per-term gradient slots, block partial sums
     int     g_n = -1;
     int64_t g_edges = 0;
     const int64_t* g_nbr = nullptr;

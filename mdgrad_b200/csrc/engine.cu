@@ -785,7 +785,12 @@ static int gnn_force(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_mo
         MDG_TRY(mdg_nbr_build(R.ctx, xyz, n, p->cell, R.cutoff, R.d_sel_a, R.d_sel_b, R.d_ex_keys, R.n_ex, (void*)st, &Pk));
         MDG_TRY(mdg_pair_force(R.ctx, R.kind, R.params, R.n_params, xyz, n, nullptr, fp3 + (size_t)k * 3 * n, nullptr, (void*)st));
     }
-    k_gnn_sum_forces<<<nb, T, 0, st>>>(n, f3, fp3, p->n_priors, f4);
+    int n_extra = p->n_priors;
+    if (p->bonded.n_bonds + p->bonded.n_angles > 0) {      // bonded members of the Stack (bonded.cu)
+        MDG_TRY(mdg_bonded_force(c, &p->bonded, xyz, n, p->cell, nullptr, fp3 + (size_t)n_extra * 3 * n, nullptr, (void*)st));
+        n_extra++;
+    }
+    k_gnn_sum_forces<<<nb, T, 0, st>>>(n, f3, fp3, n_extra, f4);
     c->stat_launches += 2;
     for (int k = 0; k < p->n_priors; ++k) *launches += p->priors[k].ctx->stat_launches;
     c->stat_rebuilds++;
@@ -798,7 +803,10 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
                               const float* h_tgrid, int n_grid, float* d_traj_v, float* d_traj_q, float* h_traj_pv,
                               float* h_last_energy, void* stream) {
     if (!c || !p || (model && !d_z)) { mdg_set_error("mdg_md_run_gnn: null argument"); return MDG_E_BADARG; }
-    if (!model && p->n_priors < 1) { mdg_set_error("mdg_md_run_gnn: no SchNet model and no pair member"); return MDG_E_BADARG; }
+    if (!model && p->n_priors < 1 && p->bonded.n_bonds + p->bonded.n_angles < 1) {
+        mdg_set_error("mdg_md_run_gnn: no SchNet model, no pair member and no bonded term");
+        return MDG_E_BADARG;
+    }
     if (n <= 0 || n_grid < 1) { mdg_set_error("mdg_md_run_gnn: n=%d n_grid=%d", n, n_grid); return MDG_E_BADARG; }
     if (p->integrator != MDG_INT_NHC && p->integrator != MDG_INT_NVE) { mdg_set_error("bad integrator"); return MDG_E_BADARG; }
     if (p->integrator == MDG_INT_NHC && (p->n_chains < 2 || p->n_chains > MDG_MAX_CHAINS)) {
@@ -834,7 +842,7 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
     MDG_TRY(c->f4b.reserve(sizeof(float4) * (size_t)n));
     MDG_TRY(c->gnn_xyz.reserve(sizeof(float) * 3 * (size_t)n));
     MDG_TRY(c->gnn_f3.reserve(sizeof(float) * 3 * (size_t)n));
-    MDG_TRY(c->gnn_fp3.reserve(sizeof(float) * 3 * (size_t)n * (p->n_priors > 0 ? p->n_priors : 1)));
+    MDG_TRY(c->gnn_fp3.reserve(sizeof(float) * 3 * (size_t)n * (size_t)(p->n_priors + 1)));
     MDG_TRY(c->pvbuf.reserve(sizeof(Scalars) + sizeof(float) * (size_t)n_frames * MDG_MAX_CHAINS + 64));
     MDG_TRY(c->kebuf.reserve(sizeof(double) * (5 * INT_MAX_BLOCKS + 8)));
     MDG_TRY(c->flags.reserve(sizeof(int) * 8));

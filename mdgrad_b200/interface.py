@@ -1,6 +1,6 @@
 """Interaction wrappers - mirror of reference torchmd/interface.py: GeneralInteraction :33-57,
 PairPotentials :217-300, TPairPotentials :139-215, Stack :364-403 (GNNPotentials :86-136 lives in
-gnn.py once the SchNet path is native).
+gnn.py; BondPotentials :406-454, AnglePotentials :456-510, Electrostatics :303-361 in bonded.py).
 
 Same constructor signatures, attributes (.nbr_list .offsets .cell .cutoff .model .index_tuple
 .ex_pairs .nbr_list_device) and `forward(xyz) -> energy`, `_reset_topology(xyz)`.  The list is
@@ -162,4 +162,7 @@ def __getattr__(name):
     if name == "GNNPotentials":          # lives in gnn.py (imports this module)
         from .gnn import GNNPotentials
         return GNNPotentials
+    if name in ("BondPotentials", "AnglePotentials", "Electrostatics"):      # bonded.py
+        from . import bonded
+        return getattr(bonded, name)
     raise AttributeError(name)

@@ -264,17 +264,23 @@ class _EOM(torch.nn.Module):
         from .interface import PairPotentials, Stack
         if self.topology_update_freq != 1 or method != self._native_method or getattr(self, "disable_gnn_engine", False):
             return None
+        from .bonded import AnglePotentials, BondPotentials
         members = list(self.model.models.values()) if type(self.model) is Stack else [self.model]
         gnns = [m for m in members if type(m) is GNNPotentials]
         priors = [m for m in members if type(m) is PairPotentials]
-        if len(gnns) > 1 or len(gnns) + len(priors) != len(members) or len(priors) > _lib.MAX_PRIORS:
+        bonds = [m for m in members if type(m) is BondPotentials]
+        angles = [m for m in members if type(m) is AnglePotentials]
+        if len(gnns) > 1 or len(bonds) > 1 or len(angles) > 1 or len(priors) > _lib.MAX_PRIORS:
             return None
-        if not gnns and (type(self.model) is not Stack or not priors):
+        if len(gnns) + len(priors) + len(bonds) + len(angles) != len(members):
+            return None
+        if not gnns and (type(self.model) is not Stack or not (priors or bonds or angles)):
             return None                               # a single PairPotentials runs on the skin-list engine (mdg_md_run)
         if not all(m.native_ready() for m in members):
             return None
         if any(p.requires_grad and p.grad_fn is not None for p in self.model.parameters()):
             return None
+        self._bonded_members = (bonds[0] if bonds else None, angles[0] if angles else None)
         return (gnns[0] if gnns else None), priors
 
     def _native_forward_gnn(self, y0, t, method):
@@ -294,7 +300,8 @@ class _EOM(torch.nn.Module):
                 p.Q[k] = float(Qh[k])
             p.T = float(self.T)
         p.ndof = int(self.N_dof)
-        L = gnn._L if gnn is not None else priors[0]._L
+        bond, angle = self._bonded_members
+        L = next(m._L for m in (gnn, *priors, bond, angle) if m is not None)
         for k in range(3):
             p.cell[k] = L[k]
             p.off_scale[k] = 1.0            # reference quirk: raw integer offsets, not multiplied by the cell
@@ -322,6 +329,28 @@ class _EOM(torch.nn.Module):
             s_.d_ex_keys = 0 if pr._exk is None else pr._exk.data_ptr()
             s_.n_ex = 0 if pr._exk is None else int(pr._exk.numel())
         p.traj_stride = 1
+        bonded_keep = None
+        if bond is not None or angle is not None:
+            # one reference list over both members: bond slots first, then two slots per angle (include/mdgrad_b200.h)
+            from .bonded import term_refs
+            key = (id(bond), id(angle))
+            if getattr(self, "_bonded_cache", (None,))[0] != key:
+                bt = bond.top.cpu().numpy() if bond is not None else None
+                at = angle.top.cpu().numpy() if angle is not None else None
+                rs, rf = term_refs(q0.shape[0], bt, at)
+                self._bonded_cache = (key, torch.from_numpy(rs).to(q0.device), torch.from_numpy(rf).to(q0.device),
+                                      bond.top.contiguous() if bond is not None else None,
+                                      angle.top.contiguous() if angle is not None else None)
+            _, rs_d, rf_d, bt_d, at_d = self._bonded_cache
+            b_ = p.bonded
+            if bond is not None:
+                b_.d_bond_top, b_.n_bonds = bt_d.data_ptr(), int(bt_d.shape[0])
+                b_.k_bond, b_.r0 = bond._scalars()
+            if angle is not None:
+                b_.d_angle_top, b_.n_angles = at_d.data_ptr(), int(at_d.shape[0])
+                b_.k_angle, b_.theta0 = angle._scalars()
+            b_.d_ref_start, b_.d_refs = rs_d.data_ptr(), (rf_d.data_ptr() if rf_d.numel() else 0)
+            bonded_keep = self._bonded_cache
         if self._engine_ctx is None:
             self._engine_ctx = _lib.Context(q0.device)
         ctx = self._engine_ctx
@@ -332,7 +361,7 @@ class _EOM(torch.nn.Module):
         tv, tq, tpv = ctx.md_run_gnn(p, gnn._native_model() if gnn is not None else None, z, mass,
                                      v0.detach().to(torch.float32).contiguous(),
                                      q0.detach().to(torch.float32).contiguous(), pv0, tl)
-        self._gnn_keepalive = (exk, z, mass)
+        self._gnn_keepalive = (exk, z, mass, bonded_keep)
         self.last_engine_stats = ctx.stats()
         if len(tl) > 1:
             self.update_count += 2 * (len(tl) - 1)       # two evaluations per step in the reference

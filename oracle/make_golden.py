@@ -102,7 +102,7 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
-if __name__ == "__main__" and "--schnet" not in sys.argv:
+if __name__ == "__main__" and "--schnet" not in sys.argv and "--bonded" not in sys.argv:
     main()
 
 
@@ -145,5 +145,82 @@ def schnet_golden():
             print(tag, "E", e.item(), "edges", gnn.inputs["nbr_list"].shape[0], "|F|max", f.abs().max().item())
 
 
+def chain_system(n_beads=24, bond_len=1.1, L=6.0, seed=5):
+    """a bead chain wound through a periodic box (bonds and angles cross the boundary), fold.py-style (demo/fold.py:116-119)"""
+    from mdgrad_b200._ase_compat import Atoms
+    rng = np.random.default_rng(seed)
+    pos = np.zeros((n_beads, 3))
+    pos[0] = [0.4, 4.0, 8.7]
+    d = np.array([1.0, 0.3, 0.2])
+    for i in range(1, n_beads):
+        d = d + rng.normal(0, 0.45, 3)
+        d /= np.linalg.norm(d)
+        pos[i] = pos[i - 1] + d * bond_len * (1.0 + rng.normal(0, 0.04))
+    atoms = Atoms(numbers=[1] * n_beads, positions=pos, cell=[L, L, L], pbc=True)
+    bond_top = np.stack([np.arange(n_beads - 1), np.arange(1, n_beads)], axis=1)
+    angle_top = np.stack([np.arange(n_beads - 2), np.arange(1, n_beads - 1), np.arange(2, n_beads)], axis=1)
+    return atoms, bond_top, angle_top
+
+
+def bonded_golden():
+    """G5: BondPotentials / AnglePotentials / Electrostatics (reference torchmd/interface.py:406-510, :303-361) energies and
+    autograd forces on a bead chain, and an NHC trajectory of Stack{bond, pair(ex_pairs=bonds)} (the force field of
+    demo/fold.py:130-160 without its GNN member)."""
+    with ref_import.active() as ref:
+        atoms, bond_top, angle_top = chain_system()
+        system = ref.system.System(atoms, device="cpu")
+        n = len(atoms)
+        xyz0 = torch.Tensor(system.get_positions())          # UNWRAPPED: several beads lie outside [0, L)
+        xyzw = torch.Tensor(system.get_positions(wrap=True))
+        out = {"positions": system.get_positions(), "cell": np.diag(system.get_cell()), "bond_top": bond_top, "angle_top": angle_top}
+        kb, ro, ka, th0 = 3.0, 1.3, 2.0, 1.9
+        bond = ref.interface.BondPotentials(system, torch.LongTensor(bond_top), kb, ro)
+        angle = ref.interface.AnglePotentials(system, torch.LongTensor(angle_top), ka, th0)
+        for tag, x in (("raw", xyz0), ("wrap", xyzw)):
+            for name, mod in (("bond", bond), ("angle", angle)):
+                q = x.clone().requires_grad_(True)
+                e = mod(q)
+                out["e_%s_%s" % (name, tag)] = e.detach().numpy()
+                out["f_%s_%s" % (name, tag)] = (-torch.autograd.grad(e, q)[0]).numpy()
+        # parameter derivatives (k, ro | thetao as tensors)
+        kt, rt = torch.tensor(kb, requires_grad=True), torch.tensor(ro, requires_grad=True)
+        e = ref.interface.BondPotentials(system, torch.LongTensor(bond_top), kt, rt)(xyzw)
+        out["dp_bond"] = np.array([g.item() for g in torch.autograd.grad(e, [kt, rt])])
+        kt, tt = torch.tensor(ka, requires_grad=True), torch.tensor(th0, requires_grad=True)
+        e = ref.interface.AnglePotentials(system, torch.LongTensor(angle_top), kt, tt)(xyzw)
+        out["dp_angle"] = np.array([g.item() for g in torch.autograd.grad(e, [kt, tt])])
+        out["params"] = np.array([kb, ro, ka, th0])
+        # Electrostatics (reference arithmetic incl. the overwritten first charge)
+        rng = np.random.default_rng(9)
+        charges = torch.tensor(rng.normal(0, 0.5, n), dtype=torch.float32)
+        es = ref.interface.Electrostatics(charges, np.diag(system.get_cell()), device="cpu", cutoff=2.5,
+                                          ex_pairs=torch.LongTensor(bond_top))
+        q = xyzw.clone().requires_grad_(True)
+        e = es(q)
+        out["charges"] = charges.numpy()
+        out["e_coul"] = e.detach().numpy()
+        out["f_coul"] = (-torch.autograd.grad(e, q)[0]).numpy()
+        out["coul_conversion"] = np.array(es.conversion)
+        # Stack{bond, pair} NoseHooverChain trajectory
+        np.random.seed(3)
+        system.set_temperature(0.6)
+        v0 = system.get_velocities().copy()
+        q0 = system.get_positions(wrap=True).copy()
+        pair = ref.interface.PairPotentials(system, ref.potentials.ExcludedVolume(1.0, 0.8, 10), cutoff=2.5,
+                                            ex_pairs=torch.LongTensor(bond_top))
+        # (the reference's AnglePotentials has no _reset_topology: it cannot be a Stack member under md.py:203)
+        ff = ref.interface.Stack({"prior": bond, "pair": pair})
+        integ = ref.md.NoseHooverChain(ff, system, Q=50.0, T=0.6, num_chains=5, adjoint=True)
+        sim = ref.md.Simulations(system, integ, wrap=True, method="NH_verlet")
+        v, q, pv = sim.simulate(steps=30, frequency=30, dt=0.002)
+        out.update(v0=v0, q0=q0, traj_v=v.detach().numpy(), traj_q=q.detach().numpy(), traj_pv=pv.detach().numpy(),
+                   masses=system.get_masses())
+        np.savez_compressed(os.path.join(OUT, "bonded_chain.npz"), **out)
+        print("bonded: E_bond %.6f E_angle %.6f E_coul %.6f" % (out["e_bond_wrap"], out["e_angle_wrap"], out["e_coul"]),
+              "outside box:", int(((xyz0 < 0) | (xyz0 > 6.0)).any(1).sum()))
+
+
 if __name__ == "__main__" and "--schnet" in sys.argv:
     schnet_golden()
+if __name__ == "__main__" and "--bonded" in sys.argv:
+    bonded_golden()

@@ -1,0 +1,127 @@
+"""Bodies of the bonded / electrostatic member checks, shared by the emulated (CPU, tests/test_emu_bonded.py)
+and the GPU (tests/test_gpu_zz_bonded.py) suites.  Everything is compared with tests/golden/bonded_chain.npz, written by
+oracle/make_golden.py --bonded from the unmodified reference (torchmd/interface.py:303-361, :406-510).
+Tolerance: 1e-5 relative to the largest component (fp32), as for the pair terms."""
+import os
+
+import numpy as np
+import torch
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-5
+
+
+def _system(dev):
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms
+    g = np.load(os.path.join(G, "bonded_chain.npz"))
+    atoms = Atoms(numbers=[1] * len(g["positions"]), positions=g["positions"], cell=g["cell"], pbc=True)
+    return System(atoms, device=dev), g
+
+
+def _close(a, b, rtol=RTOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert np.abs(a - b).max() <= rtol * max(np.abs(b).max(), 1e-30), (np.abs(a - b).max(), np.abs(b).max())
+
+
+def check_bond_angle_energy_force(dev):
+    from torchmd.interface import AnglePotentials, BondPotentials
+    system, g = _system(dev)
+    kb, ro, ka, th0 = [float(x) for x in g["params"]]
+    bond = BondPotentials(system, torch.LongTensor(g["bond_top"]), kb, ro)
+    angle = AnglePotentials(system, torch.LongTensor(g["angle_top"]), ka, th0)
+    raw = torch.tensor(g["positions"], dtype=torch.float32)
+    L = torch.tensor(g["cell"], dtype=torch.float32)
+    from mdgrad_b200._ase_compat import wrap_positions
+    wrap = torch.tensor(wrap_positions(g["positions"], np.diag(g["cell"])), dtype=torch.float32)
+    for tag, x in (("raw", raw), ("wrap", wrap)):
+        for name, mod in (("bond", bond), ("angle", angle)):
+            q = x.to(dev).clone().requires_grad_(True)
+            e = mod(q)
+            assert e.dim() == 0
+            f = -torch.autograd.grad(e, q)[0]
+            _close(e.item(), g["e_%s_%s" % (name, tag)])
+            _close(f.cpu().numpy(), g["f_%s_%s" % (name, tag)])
+            # native force route (what the no-grad solver path and the device engine use)
+            _close(mod.native_force(x.to(dev)).cpu().numpy(), g["f_%s_%s" % (name, tag)])
+            # pure-torch restatement (double-backward route) agrees
+            _close(mod.forward_torch(x.to(dev)).item(), g["e_%s_%s" % (name, tag)])
+    assert L.shape == (3,)
+
+
+def check_bonded_param_grads(dev):
+    from torchmd.interface import AnglePotentials, BondPotentials
+    from mdgrad_b200._ase_compat import wrap_positions
+    system, g = _system(dev)
+    kb, ro, ka, th0 = [float(x) for x in g["params"]]
+    x = torch.tensor(wrap_positions(g["positions"], np.diag(g["cell"])), dtype=torch.float32).to(dev)
+    kt, rt = torch.tensor(kb, requires_grad=True, device=dev), torch.tensor(ro, requires_grad=True, device=dev)
+    e = BondPotentials(system, torch.LongTensor(g["bond_top"]), kt, rt)(x)
+    _close([t.item() for t in torch.autograd.grad(e, [kt, rt])], g["dp_bond"])
+    kt, tt = torch.tensor(ka, requires_grad=True, device=dev), torch.tensor(th0, requires_grad=True, device=dev)
+    e = AnglePotentials(system, torch.LongTensor(g["angle_top"]), kt, tt)(x)
+    _close([t.item() for t in torch.autograd.grad(e, [kt, tt])], g["dp_angle"])
+
+
+def check_bonded_second_order_route(dev):
+    """double backward goes through the pure-torch restatement (adjoint reverse sweep), same numbers"""
+    from torchmd.interface import BondPotentials
+    system, g = _system(dev)
+    kb, ro = float(g["params"][0]), float(g["params"][1])
+    bond = BondPotentials(system, torch.LongTensor(g["bond_top"]), kb, ro)
+    bond.second_order = True
+    q = torch.tensor(g["positions"], dtype=torch.float32).to(dev).requires_grad_(True)
+    f = -torch.autograd.grad(bond(q), q, create_graph=True)[0]
+    _close(f.detach().cpu().numpy(), g["f_bond_raw"])
+    h = torch.autograd.grad((f ** 2).sum(), q)[0]
+    assert torch.isfinite(h).all() and float(h.abs().max()) > 0
+
+
+def check_electrostatics(dev):
+    from torchmd.interface import Electrostatics
+    from mdgrad_b200._ase_compat import wrap_positions
+    system, g = _system(dev)
+    x = torch.tensor(wrap_positions(g["positions"], np.diag(g["cell"])), dtype=torch.float32).to(dev)
+    es = Electrostatics(torch.tensor(g["charges"]), g["cell"], device=dev, cutoff=2.5, ex_pairs=torch.LongTensor(g["bond_top"]))
+    _close(es.conversion, g["coul_conversion"], 1e-12)
+    q = x.clone().requires_grad_(True)
+    e = es(q)
+    _close(e.item(), g["e_coul"])
+    _close((-torch.autograd.grad(e, q)[0]).cpu().numpy(), g["f_coul"])
+    # the physical product differs from the reference's q_j^2 (and is what a user should ask for)
+    ep = Electrostatics(torch.tensor(g["charges"]), g["cell"], device=dev, cutoff=2.5, ex_pairs=torch.LongTensor(g["bond_top"]),
+                        charge_product="physical")(x)
+    assert abs(ep.item() - e.item()) > 1e-3 * abs(e.item())
+
+
+def _stack_sim(dev, engine):
+    from torchmd.interface import BondPotentials, PairPotentials, Stack
+    from torchmd.potentials import ExcludedVolume
+    from torchmd.md import NoseHooverChain, Simulations
+    system, g = _system(dev)
+    system.set_positions(g["q0"])
+    system.set_velocities(g["v0"])
+    kb, ro = float(g["params"][0]), float(g["params"][1])
+    bond = BondPotentials(system, torch.LongTensor(g["bond_top"]), kb, ro)
+    pair = PairPotentials(system, ExcludedVolume(1.0, 0.8, 10), cutoff=2.5, ex_pairs=torch.LongTensor(g["bond_top"])).to(dev)
+    ff = Stack({"prior": bond, "pair": pair})
+    integ = NoseHooverChain(ff, system, Q=50.0, T=0.6, num_chains=5, adjoint=True).to(dev)
+    integ.disable_gnn_engine = not engine
+    sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+    v, q, pv = sim.simulate(steps=30, frequency=30, dt=0.002)
+    return integ, v.detach().cpu().numpy(), q.detach().cpu().numpy(), pv.detach().cpu().numpy(), g
+
+
+def check_fold_stack_on_device_engine(dev):
+    """Stack{BondPotentials, PairPotentials(ex_pairs=bonds)} NoseHooverChain epoch (the force field of demo/fold.py:130-160
+    without its GNN member) on the device engine, against the reference trajectory"""
+    integ, v, q, pv, g = _stack_sim(dev, engine=True)
+    assert integ.last_engine_stats is not None, "the epoch did not run on the device engine"
+    assert np.array_equal(q[0], g["traj_q"][0].astype(np.float32))
+    for k, tol in ((1, 3e-6), (10, 5e-5), (29, 5e-4)):
+        assert np.abs(q[k] - g["traj_q"][k]).max() < tol, (k, np.abs(q[k] - g["traj_q"][k]).max())
+        assert np.abs(v[k] - g["traj_v"][k]).max() < 20 * tol
+        assert np.abs(pv[k] - g["traj_pv"][k]).max() < 50 * tol
+    # and the op-level solver (bonded autograd Function + pair kernel) gives the same epoch
+    integ2, v2, q2, pv2, _ = _stack_sim(dev, engine=False)
+    assert np.abs(q2 - q).max() < 2e-5 and np.abs(v2 - v).max() < 2e-4

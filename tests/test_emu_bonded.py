@@ -1,0 +1,13 @@
+"""Bonded / electrostatic Stack members (BondPotentials, AnglePotentials, Electrostatics - SURVEY 8f-4) through the
+CPU-emulated kernels against the reference fixture.  TEST INFRASTRUCTURE; the GPU run of the same bodies is
+tests/test_gpu_zz_bonded.py."""
+import pytest
+
+import bonded_checks as B
+from test_emu_api import emulated_backend  # noqa: F401  (autouse fixture: swaps the four binding hooks)
+
+
+@pytest.mark.parametrize("check", [B.check_bond_angle_energy_force, B.check_bonded_param_grads, B.check_bonded_second_order_route,
+                                   B.check_electrostatics, B.check_fold_stack_on_device_engine], ids=lambda f: f.__name__)
+def test_emu_bonded(check):
+    check("cpu")

@@ -1,0 +1,13 @@
+"""GPU: bonded / electrostatic Stack members against the reference fixture (same bodies as tests/test_emu_bonded.py).
+Sorted after the suites that already ran on hardware."""
+import pytest
+
+import bonded_checks as B
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("check", [B.check_bond_angle_energy_force, B.check_bonded_param_grads, B.check_bonded_second_order_route,
+                                   B.check_electrostatics, B.check_fold_stack_on_device_engine], ids=lambda f: f.__name__)
+def test_gpu_bonded(check):
+    check("cuda")
