@@ -215,6 +215,24 @@ def bonded_golden():
         v, q, pv = sim.simulate(steps=30, frequency=30, dt=0.002)
         out.update(v0=v0, q0=q0, traj_v=v.detach().numpy(), traj_q=q.detach().numpy(), traj_pv=pv.detach().numpy(),
                    masses=system.get_masses())
+        # the whole force field of demo/fold.py:130-160: Stack{gnn: GNNPotentials(SchNet), prior: bond, pair}, NHC epoch
+        system2 = ref.system.System(chain_system()[0], device="cpu")
+        system2.set_positions(q0)
+        system2.set_velocities(v0)
+        gp = {"n_atom_basis": 32, "n_filters": 32, "n_gaussians": 16, "n_convolutions": 2, "cutoff": 2.5, "trainable_gauss": False}
+        torch.manual_seed(4)
+        schnet = ref.schnet.SchNet(gp)
+        gnn = ref.interface.GNNPotentials(system2, schnet, cutoff=gp["cutoff"])
+        bond2 = ref.interface.BondPotentials(system2, torch.LongTensor(bond_top), kb, ro)
+        pair2 = ref.interface.PairPotentials(system2, ref.potentials.ExcludedVolume(1.0, 0.8, 10), cutoff=2.5,
+                                             ex_pairs=torch.LongTensor(bond_top))
+        ff2 = ref.interface.Stack({"gnn": gnn, "prior": bond2, "pair": pair2})
+        integ2 = ref.md.NoseHooverChain(ff2, system2, Q=50.0, T=0.6, num_chains=5, adjoint=True)
+        sim2 = ref.md.Simulations(system2, integ2, wrap=True, method="NH_verlet")
+        v2, q2, pv2 = sim2.simulate(steps=12, frequency=12, dt=0.002)
+        out.update(fold_v=v2.detach().numpy(), fold_q=q2.detach().numpy(), fold_pv=pv2.detach().numpy(),
+                   **{("gnnp_" + k): np.array(v) for k, v in gp.items() if k != "trainable_gauss"},
+                   **{("w_" + k): v.numpy() for k, v in schnet.state_dict().items()})
         np.savez_compressed(os.path.join(OUT, "bonded_chain.npz"), **out)
         print("bonded: E_bond %.6f E_angle %.6f E_coul %.6f" % (out["e_bond_wrap"], out["e_angle_wrap"], out["e_coul"]),
               "outside box:", int(((xyz0 < 0) | (xyz0 > 6.0)).any(1).sum()))

@@ -125,3 +125,38 @@ def check_fold_stack_on_device_engine(dev):
     # and the op-level solver (bonded autograd Function + pair kernel) gives the same epoch
     integ2, v2, q2, pv2, _ = _stack_sim(dev, engine=False)
     assert np.abs(q2 - q).max() < 2e-5 and np.abs(v2 - v).max() < 2e-4
+
+
+def _fold_sim(dev, engine):
+    from torchmd.interface import BondPotentials, GNNPotentials, PairPotentials, Stack
+    from torchmd.potentials import ExcludedVolume
+    from torchmd.md import NoseHooverChain, Simulations
+    from nff.nn.models.schnet import SchNet
+    system, g = _system(dev)
+    system.set_positions(g["q0"])
+    system.set_velocities(g["v0"])
+    params = {k[5:]: (float(g[k]) if k == "gnnp_cutoff" else int(g[k])) for k in g.files if k.startswith("gnnp_")}
+    params["trainable_gauss"] = False
+    model = SchNet(params)
+    model.load_state_dict({k[2:]: torch.tensor(g[k]) for k in g.files if k.startswith("w_")})
+    model = model.to(dev)
+    kb, ro = float(g["params"][0]), float(g["params"][1])
+    gnn = GNNPotentials(system, model, cutoff=params["cutoff"])
+    bond = BondPotentials(system, torch.LongTensor(g["bond_top"]), kb, ro)
+    pair = PairPotentials(system, ExcludedVolume(1.0, 0.8, 10), cutoff=2.5, ex_pairs=torch.LongTensor(g["bond_top"])).to(dev)
+    integ = NoseHooverChain(Stack({"gnn": gnn, "prior": bond, "pair": pair}), system, Q=50.0, T=0.6, num_chains=5, adjoint=True).to(dev)
+    integ.disable_gnn_engine = not engine
+    sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+    v, q, pv = sim.simulate(steps=12, frequency=12, dt=0.002)
+    return integ, v.detach().cpu().numpy(), q.detach().cpu().numpy(), pv.detach().cpu().numpy(), g
+
+
+def check_fold_force_field_with_gnn(dev):
+    """the whole force field of demo/fold.py:130-160 - Stack{gnn: GNNPotentials(SchNet), prior: BondPotentials,
+    pair: PairPotentials(ExcludedVolume, ex_pairs=bonds)} - as one device-engine epoch, against the reference trajectory"""
+    integ, v, q, pv, g = _fold_sim(dev, engine=True)
+    assert integ.last_engine_stats is not None, "the epoch did not run on the device engine"
+    for k, tol in ((1, 3e-6), (11, 1e-4)):
+        assert np.abs(q[k] - g["fold_q"][k]).max() < tol, (k, np.abs(q[k] - g["fold_q"][k]).max())
+        assert np.abs(v[k] - g["fold_v"][k]).max() < 20 * tol
+        assert np.abs(pv[k] - g["fold_pv"][k]).max() < 50 * tol
