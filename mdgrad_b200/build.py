@@ -32,6 +32,10 @@ VARIANTS = {
     "mb4": ["-DMDG_FORCE_MINBLOCKS=4"],
     "u2mb6": ["-DMDG_FORCE_UNROLL=2", "-DMDG_FORCE_MINBLOCKS=6"],
     "u2mb4": ["-DMDG_FORCE_UNROLL=2", "-DMDG_FORCE_MINBLOCKS=4"],
+    # software-pipelined row stream (next index block requested one iteration ahead), at three register budgets
+    "pf": ["-DMDG_FORCE_PREFETCH=1"],
+    "pfmb6": ["-DMDG_FORCE_PREFETCH=1", "-DMDG_FORCE_MINBLOCKS=6"],
+    "pfmb4": ["-DMDG_FORCE_PREFETCH=1", "-DMDG_FORCE_MINBLOCKS=4"],
     "fbw2": ["-DFB_WARPS=2"],
     "fbw8": ["-DFB_WARPS=8"],
     "i8fbw8": ["-DMDG_BUILD_INT8_SCREEN=1", "-DFB_WARPS=8"],

@@ -54,8 +54,14 @@ __device__ __forceinline__ float4 mdg_gather4(const float4* __restrict__ base, u
 #endif
 }
 
+#ifndef MDG_FORCE_PREFETCH
+#define MDG_FORCE_PREFETCH 0
+#endif
 #ifndef MDG_FORCE_UNROLL
 #define MDG_FORCE_UNROLL 1
+#endif
+#if MDG_FORCE_PREFETCH && MDG_FORCE_UNROLL != 1
+#error "MDG_FORCE_PREFETCH needs MDG_FORCE_UNROLL == 1"
 #endif
 #ifndef MDG_FORCE_MINBLOCKS
 #define MDG_FORCE_MINBLOCKS 8      // 32-register budget (measured best of the round); build variants mb6 / mb4 relax it
@@ -70,15 +76,26 @@ __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, co
     // padded to 32 entries, so this is valid for GROUP * 4 * 2 <= 32 only.
     constexpr int U = (GROUP * 4 * MDG_FORCE_UNROLL <= 32) ? MDG_FORCE_UNROLL : 1;
     const uint32_t* rp = row + lane_in_group * 4;
+#if MDG_FORCE_PREFETCH
+    // build variant pf*: the index block of the NEXT iteration is requested before this iteration's gathers are consumed
+    // (register double buffer), so the row-stream latency overlaps a whole iteration instead of heading its dependency
+    // chain (index load -> gather -> arithmetic).  U = 1 only.
+    uint4 nxt = __ldcs(reinterpret_cast<const uint4*>(rp));
+#endif
     for (int rem = m; rem > 0; rem -= GROUP * 4 * U, rp += GROUP * 4 * U) {
         // the row stream (~100 MB per launch) is read once: evict-first, so that it does not push the gathered
         // neighbor positions (4 MB, re-read ~90 times) out of L1/L2
         uint32_t es[4 * U];
+#if MDG_FORCE_PREFETCH
+        es[0] = nxt.x; es[1] = nxt.y; es[2] = nxt.z; es[3] = nxt.w;
+        if (rem > GROUP * 4) nxt = __ldcs(reinterpret_cast<const uint4*>(rp + GROUP * 4));
+#else
 #pragma unroll
         for (int b = 0; b < U; ++b) {
             const uint4 e4 = __ldcs(reinterpret_cast<const uint4*>(rp + b * GROUP * 4));
             es[4 * b] = e4.x; es[4 * b + 1] = e4.y; es[4 * b + 2] = e4.z; es[4 * b + 3] = e4.w;
         }
+#endif
         float4 qj[4 * U];
 #pragma unroll
         for (int u = 0; u < 4 * U; ++u) qj[u] = mdg_gather4(qs, PURE ? es[u] : (es[u] & MDG_IDX_MASK));

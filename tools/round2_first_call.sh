@@ -13,7 +13,7 @@ echo "== 3. build variants (device-resident steps/s, force-kernel us)" | tee -a 
 python -c "
 from mdgrad_b200 import build as b
 for v in b.VARIANTS: b.build(variant=v)" 2>&1 | tail -2
-for v in i8 lean i8lean mb6 mb4 u2mb6 u2mb4 fbw2 fbw8 i8fbw8; do
+for v in pf pfmb6 pfmb4 i8 lean i8lean mb6 mb4 u2mb6 u2mb4 fbw2 fbw8 i8fbw8; do
   MDG_LIB_VARIANT=$v timeout 200 python bench.py --steps 600 --warmup 60 --no-e2e --no-cpu-baseline \
       > gpurun_out/r2_ab_$v.json 2> gpurun_out/r2_ab_$v.err
   python - "$v" <<'PY' | tee -a gpurun_out/r2_summary.txt
