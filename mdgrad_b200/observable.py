@@ -143,3 +143,18 @@ class vacf(Observable):
         vacf = [(vel * vel).mean()[None]]
         vacf += [(vel[t:] * vel[:-t]).mean()[None] for t in self.t_window]
         return torch.stack(vacf).reshape(-1)          # un-normalised, exactly as the reference
+
+
+def compute_dihe(xyz, dihes):
+    """cos(phi) of the listed dihedrals for every frame (reference observable.py:181-197), without the reference's
+    (frames, N, N, 3) difference tensor: only the four bond vectors of each dihedral are formed.  No periodic images (as the
+    reference)."""
+    assert len(xyz.shape) == 3
+    dihes = torch.as_tensor(dihes).to(xyz.device)
+    p0, p1, p2, p3 = (xyz[:, dihes[:, k]] for k in range(4))
+    vec1, vec2 = p1 - p0, p1 - p2          # D[:, d1, d0] = x[d1] - x[d0],  D[:, d1, d2] = x[d1] - x[d2]
+    vec3, vec4 = p2 - p1, p2 - p3
+    cross1 = torch.cross(vec1, vec2, dim=-1)
+    cross2 = torch.cross(vec3, vec4, dim=-1)
+    norm = (cross1.pow(2).sum(-1) * cross2.pow(2).sum(-1)).sqrt()
+    return 1.0 * ((cross1 * cross2).sum(-1) / norm)

@@ -218,6 +218,52 @@ class MLP(nn.Module):
         return u_ex + x
 
 
+class pairTab(nn.Module):
+    """pairTab(nbins=1000, rc=2.5, device='cpu'): tabulated u(r), `tab` (nbins,) a Parameter on the knots
+    x = linspace(0, rc, nbins), evaluated by cubic-spline interpolation (reference potentials.py:152-160, which calls
+    `xitorch.interpolate.Interp1D(x, tab)(r)`).
+
+    xitorch is an un-vendored dependency that is not installed here: PARITY UNPINNED.  This class restates
+    Interp1D's documented default - a C2 cubic spline with not-a-knot end conditions (the same algorithm as
+    scipy.interpolate.CubicSpline, against which tests/test_cabi_and_host.py checks it) - as torch ops: the spline's
+    second derivatives are LINEAR in the table, so one (nbins x nbins) solve at construction gives a fixed matrix and
+    every forward is a matmul + a gather, differentiable in both `tab` and r (to any order - the adjoint route works).
+    r outside [0, rc] is extrapolated with the end polynomials (the list cutoff keeps r <= rc)."""
+
+    def __init__(self, nbins=1000, rc=2.5, device="cpu"):
+        super().__init__()
+        self.tab = nn.Parameter(torch.zeros(nbins).to(device))
+        self.x = torch.linspace(0.0, rc, nbins).to(device)
+        n = int(nbins)
+        if n < 4:
+            raise ValueError("pairTab needs at least 4 knots")
+        x = torch.linspace(0.0, rc, nbins, dtype=torch.float64)
+        h = x[1:] - x[:-1]
+        A = torch.zeros(n, n, dtype=torch.float64)       # A m = B y,  m = second derivatives at the knots
+        B = torch.zeros(n, n, dtype=torch.float64)
+        for i in range(1, n - 1):
+            A[i, i - 1], A[i, i], A[i, i + 1] = h[i - 1], 2 * (h[i - 1] + h[i]), h[i]
+            B[i, i - 1], B[i, i], B[i, i + 1] = 6 / h[i - 1], -6 / h[i - 1] - 6 / h[i], 6 / h[i]
+        # not-a-knot: the third derivative is continuous across the second and the second-to-last knot
+        A[0, 0], A[0, 1], A[0, 2] = h[1], -(h[0] + h[1]), h[0]
+        A[n - 1, n - 3], A[n - 1, n - 2], A[n - 1, n - 1] = h[n - 2], -(h[n - 3] + h[n - 2]), h[n - 3]
+        self.register_buffer("_m_of_y", torch.linalg.solve(A, B).to(torch.float32).to(device), persistent=False)
+
+    def forward(self, r):
+        shape = r.shape
+        rq = r.reshape(-1)
+        x = self.x.to(rq.device)
+        y = self.tab
+        m = self._m_of_y.to(rq.device) @ y
+        n = x.shape[0]
+        i = torch.clamp(torch.searchsorted(x, rq.detach(), right=True) - 1, 0, n - 2)
+        h = x[i + 1] - x[i]
+        a = (x[i + 1] - rq) / h
+        b = (rq - x[i]) / h
+        u = a * y[i] + b * y[i + 1] + ((a ** 3 - a) * m[i] + (b ** 3 - b) * m[i + 1]) * (h * h) / 6.0
+        return u.reshape(shape) if len(shape) and shape[-1] == 1 else u.unsqueeze(-1)
+
+
 def __getattr__(name):
     # `PairPotentials` lives in interface.py in the reference, but BASELINE.json / README name it
     # `torchmd.potentials.PairPotentials` (SURVEY naming trap): export it from both.

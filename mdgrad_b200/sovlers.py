@@ -125,6 +125,42 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
     return out[0] if tensor_input else out
 
 
+class FixedGridODESolver(object):
+    """Class form of the grid loop (reference tinydiffeq.py:13-85): `Solver(func, y0, step_size=None).integrate(t)`.
+    The output grid IS the integration grid (the reference's default grid constructor, :22-27); `step_size` sub-stepping is
+    not used anywhere on the path and raises."""
+    step_name = None
+
+    def __init__(self, func, y0, step_size=None, grid_constructor=None, **unused_kwargs):
+        if step_size is not None or grid_constructor is not None:
+            raise NotImplementedError("mdgrad_b200: sub-stepped grids are not supported; pass the integration grid as t")
+        self.func, self.y0 = func, y0
+
+    @property
+    def order(self):
+        return 4 if self.step_name == "rk4" else 2
+
+    def step_func(self, func, t, dt, y):
+        return STEPPERS[self.step_name](func, t, dt, y)
+
+    def integrate(self, t):
+        return odeint(self.func, self.y0, t, method=self.step_name)
+
+
+class RK4(FixedGridODESolver):
+    step_name = "rk4"
+
+
+class NHVerlet(FixedGridODESolver):
+    """reference sovlers.py:11-14"""
+    step_name = "NH_verlet"
+
+
+class Verlet(FixedGridODESolver):
+    """reference sovlers.py:16-19"""
+    step_name = "verlet"
+
+
 # ---------------------------------------------------------------------------------------------
 # forward-only fast loop: ONE force evaluation per step
 # ---------------------------------------------------------------------------------------------

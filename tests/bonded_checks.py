@@ -160,3 +160,37 @@ def check_fold_force_field_with_gnn(dev):
         assert np.abs(q[k] - g["fold_q"][k]).max() < tol, (k, np.abs(q[k] - g["fold_q"][k]).max())
         assert np.abs(v[k] - g["fold_v"][k]).max() < 20 * tol
         assert np.abs(pv[k] - g["fold_pv"][k]).max() < 50 * tol
+
+
+def check_pair_tab_through_pair_potentials(dev):
+    """PairPotentials(system, pairTab(...)): tabulated u(r) on the native list + distance op (generic route), energy and
+    forces and d/dtab against the oracle's list / distances with the same table"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle_torch as O
+    from torchmd.interface import PairPotentials
+    from torchmd.potentials import pairTab
+    from mdgrad_b200._ase_compat import wrap_positions
+    system, g = _system(dev)
+    tab = pairTab(nbins=64, rc=2.5, device=dev)
+    with torch.no_grad():
+        tab.tab.copy_(4.0 * ((1.0 / (tab.x + 0.6)) ** 8 - (1.0 / (tab.x + 0.6)) ** 4))
+    pair = PairPotentials(system, tab, cutoff=2.5)
+    xw = torch.tensor(wrap_positions(g["positions"], np.diag(g["cell"])), dtype=torch.float32)
+    pair._reset_topology(xw.to(dev))
+    q = xw.to(dev).clone().requires_grad_(True)
+    e = pair(q)
+    gq, gt = torch.autograd.grad(e, [q, tab.tab])
+    # oracle: reference-order list and distances on the CPU, same spline module on the CPU
+    cell = torch.tensor(g["cell"], dtype=torch.float32)
+    nbr, off = O.neighbor_list(xw, 2.5, cell)
+    assert torch.equal(pair.nbr_list.cpu(), nbr)
+    tab_c = pairTab(nbins=64, rc=2.5)
+    with torch.no_grad():
+        tab_c.tab.copy_(tab.tab.detach().cpu())
+    qc = xw.clone().requires_grad_(True)
+    ec = tab_c(O.pair_distance(qc, nbr, off, torch.diag(cell))).sum()
+    gqc, gtc = torch.autograd.grad(ec, [qc, tab_c.tab])
+    _close(e.item(), ec.item())
+    _close(gq.cpu().numpy(), gqc.numpy())
+    _close(gt.cpu().numpy(), gtc.numpy())
