@@ -272,8 +272,12 @@ int mdg_schnet_energy_force(mdg_ctx* ctx, const mdg_schnet_model* h_model, const
  *     each member's exact neighbor list at the current positions (mdg_nbr_build semantics, each member with its
  *     own cutoff / species selection / exclusions), evaluates SchNet energy+forces (mdg_schnet_energy_force) and
  *     the priors (mdg_pair_force), and applies the fused integrator kernels - all from one host call, no Python
- *     and no autograd inside the loop.  Same trajectory outputs as mdg_md_run.  One SYNC per list build (pair
- *     count read-back) and one at the end.
+ *     and no autograd inside the loop.  Same trajectory outputs as mdg_md_run.  SYNC: the FIRST evaluation of an
+ *     epoch reads its pair counts back (they size the edge buffers, +25%); every later step is enqueued without any
+ *     read-back - the pair count is consumed on the device, a capacity that turns out too small is latched on the
+ *     device, read once at the end of the epoch, and the epoch is then repeated with a read-back per list build
+ *     (inputs are never modified; MDG_GNN_SYNC=1 forces that path).  mdg_get_stats slot 3 = 1 if the epoch
+ *     completed on the asynchronous path.
  *     ctx owns the GNN list and the SchNet workspace; every prior brings the context that owns its list.
  *     h_model == NULL: a Stack of analytic PairPotentials only (e.g. the three species-pair members of
  *     scripts/fit_2_comp.py:182), every member evaluated on its own exact per-step list.

@@ -307,6 +307,7 @@ struct mdg_ctx {
 
     // stats
     int64_t stat_launches = 0, stat_rebuilds = 0, stat_entries = 0, stat_maxrow = 0;
+    int64_t stat_async_retries = 0;   // GNN epochs repeated on the synchronous path after a latched overflow (engine.cu)
     // optional per-kernel timing of the engine's force launches (mdg_set_profile)
     int     prof_enable = 0;
     void*   prof_events = nullptr;   // std::vector<cudaEvent_t>* (pairs)

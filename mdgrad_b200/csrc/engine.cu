@@ -758,10 +758,25 @@ __global__ void k_gnn_sum_forces(int n, const float* __restrict__ f3, const floa
     f4[i] = make_float4(fx, fy, fz, 0.f);
 }
 
+int mdg_i_nbr_build_async(mdg_ctx* c, const float* d_xyz, int n, const float* h_cell3, double cutoff, const uint8_t* d_sel_a,
+                          const uint8_t* d_sel_b, const int64_t* d_ex_keys, int n_ex, bool want_export, int64_t cap_pairs,
+                          int64_t* d_nbr, float* d_offsets, cudaStream_t st);
+int mdg_i_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, const int64_t* d_z, const float* d_xyz, int n,
+                              const int64_t* d_nbr, const float* d_offsets, int64_t E, const int* d_E, const float* h_off_scale3,
+                              float* d_energy, float* d_force, void* stream);
+
+// One force evaluation of the GNN / Stack model.
+//   cap_pairs <  0 (synchronous): every list build reads its pair count back (one SYNC per member), buffers are sized
+//                  exactly; *pairs_out = the GNN list's pair count.
+//   cap_pairs >= 0 (asynchronous): NOTHING is read back.  The GNN list is exported into buffers of cap_pairs pairs (sized by
+//                  the caller from an earlier, synchronous evaluation), its count stays in flags[4] and is consumed on the
+//                  device; overflows are latched in flags[3] of the member's context (mdg_i_nbr_build_async).
 static int gnn_force(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_model* model, const int64_t* d_z, int n,
-                     const float4* q4, float4* f4, float* d_e_gnn, int64_t* launches, cudaStream_t st) {
+                     const float4* q4, float4* f4, float* d_e_gnn, int64_t* launches, int64_t cap_pairs, int64_t* pairs_out,
+                     cudaStream_t st) {
     const int T = 256, nb = (n + T - 1) / T;
-    *launches += c->stat_launches;               // (mdg_nbr_build restarts the context's counter)
+    const bool async = cap_pairs >= 0;
+    *launches += c->stat_launches;               // (the list builds restart the context's counter)
     float* xyz = c->gnn_xyz.as<float>();
     float* f3 = c->gnn_f3.as<float>();
     float* fp3 = c->gnn_fp3.as<float>();
@@ -769,20 +784,33 @@ static int gnn_force(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_mo
     if (model) {
         // GNN list at the current positions (exact membership, reference layout)
         int64_t P = 0;
-        MDG_TRY(mdg_nbr_build(c, xyz, n, p->cell, p->cutoff, nullptr, nullptr, p->d_ex_keys, p->n_ex, (void*)st, &P));
-        MDG_TRY(c->gnn_nbr.reserve(sizeof(int64_t) * 2 * (size_t)(P + 1)));
-        MDG_TRY(c->gnn_off.reserve(sizeof(float) * 3 * (size_t)(P + 1)));
-        MDG_TRY(mdg_i_export_fill(c, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), nullptr, st));
-        MDG_TRY(mdg_schnet_energy_force(c, model, d_z, xyz, n, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), P, p->off_scale,
-                                        d_e_gnn, f3, (void*)st));
+        if (!async) {
+            MDG_TRY(mdg_nbr_build(c, xyz, n, p->cell, p->cutoff, nullptr, nullptr, p->d_ex_keys, p->n_ex, (void*)st, &P));
+            MDG_TRY(c->gnn_nbr.reserve(sizeof(int64_t) * 2 * (size_t)(P + 1)));
+            MDG_TRY(c->gnn_off.reserve(sizeof(float) * 3 * (size_t)(P + 1)));
+            MDG_TRY(mdg_i_export_fill(c, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), nullptr, st));
+            MDG_TRY(mdg_schnet_energy_force(c, model, d_z, xyz, n, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), P, p->off_scale,
+                                            d_e_gnn, f3, (void*)st));
+            if (pairs_out) *pairs_out = P;
+        } else {
+            MDG_TRY(mdg_i_nbr_build_async(c, xyz, n, p->cell, p->cutoff, nullptr, nullptr, p->d_ex_keys, p->n_ex, true, cap_pairs,
+                                          c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), st));
+            MDG_TRY(mdg_i_schnet_energy_force(c, model, d_z, xyz, n, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), cap_pairs,
+                                              c->flags.as<int>() + 4, p->off_scale, d_e_gnn, f3, (void*)st));
+        }
     } else {    // Stack of analytic pair members only
         MDG_CUDA(cudaMemsetAsync(f3, 0, sizeof(float) * 3 * (size_t)n, st));
         MDG_CUDA(cudaMemsetAsync(d_e_gnn, 0, sizeof(float), st));
     }
     for (int k = 0; k < p->n_priors; ++k) {
         const mdg_prior_spec& R = p->priors[k];
-        int64_t Pk = 0;
-        MDG_TRY(mdg_nbr_build(R.ctx, xyz, n, p->cell, R.cutoff, R.d_sel_a, R.d_sel_b, R.d_ex_keys, R.n_ex, (void*)st, &Pk));
+        if (!async) {
+            int64_t Pk = 0;
+            MDG_TRY(mdg_nbr_build(R.ctx, xyz, n, p->cell, R.cutoff, R.d_sel_a, R.d_sel_b, R.d_ex_keys, R.n_ex, (void*)st, &Pk));
+        } else {    // the force kernel streams the member's rows: no export, no count
+            MDG_TRY(mdg_i_nbr_build_async(R.ctx, xyz, n, p->cell, R.cutoff, R.d_sel_a, R.d_sel_b, R.d_ex_keys, R.n_ex, false, 0,
+                                          nullptr, nullptr, st));
+        }
         MDG_TRY(mdg_pair_force(R.ctx, R.kind, R.params, R.n_params, xyz, n, nullptr, fp3 + (size_t)k * 3 * n, nullptr, (void*)st));
     }
     int n_extra = p->n_priors;
@@ -797,6 +825,11 @@ static int gnn_force(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_mo
     MDG_KERNEL_CHECK();
     return MDG_OK;
 }
+
+static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_model* model, const int64_t* d_z, int n,
+                        const float* d_mass, const float* d_v0, const float* d_q0, const float* h_pv0, const float* h_tgrid,
+                        int n_grid, float* d_traj_v, float* d_traj_q, float* h_traj_pv, float* h_last_energy, bool async,
+                        int* latched, cudaStream_t st);
 
 extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_model* model, const int64_t* d_z, int n,
                               const float* d_mass, const float* d_v0, const float* d_q0, const float* h_pv0,
@@ -818,7 +851,26 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
         if (!p->priors[k].ctx || p->priors[k].ctx == c) { mdg_set_error("mdg_md_run_gnn: prior %d needs its own context", k); return MDG_E_BADARG; }
     if (c->dist_world > 1) { mdg_set_error("mdg_md_run_gnn: single GPU only"); return MDG_E_BADARG; }
     MDG_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    // Steps after the first run ASYNCHRONOUSLY (no pair-count read-back, see gnn_force); if a capacity sized from the first
+    // evaluation turns out too small during the epoch, the latched flags say so at the end and the epoch is repeated on
+    // the synchronous path (inputs are never modified).  MDG_GNN_SYNC=1 forces the synchronous path.
+    const bool try_async = getenv("MDG_GNN_SYNC") == nullptr && n_grid > 2;
+    if (try_async) {
+        int latched = 0;
+        MDG_TRY(gnn_run_once(c, p, model, d_z, n, d_mass, d_v0, d_q0, h_pv0, h_tgrid, n_grid, d_traj_v, d_traj_q, h_traj_pv,
+                             h_last_energy, true, &latched, (cudaStream_t)stream));
+        if (!latched) { c->stat_maxrow = 1; return MDG_OK; }     // stats slot 3: 1 = the epoch completed on the asynchronous path
+        c->stat_async_retries++;
+    }
+    c->stat_maxrow = 0;
+    return gnn_run_once(c, p, model, d_z, n, d_mass, d_v0, d_q0, h_pv0, h_tgrid, n_grid, d_traj_v, d_traj_q, h_traj_pv, h_last_energy,
+                        false, nullptr, (cudaStream_t)stream);
+}
+
+static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_model* model, const int64_t* d_z, int n,
+                        const float* d_mass, const float* d_v0, const float* d_q0, const float* h_pv0, const float* h_tgrid,
+                        int n_grid, float* d_traj_v, float* d_traj_q, float* h_traj_pv, float* h_last_energy, bool async,
+                        int* latched, cudaStream_t st) {
     const int nhc = p->integrator == MDG_INT_NHC;
     const int M = nhc ? p->n_chains : 0;
     const int stride = p->traj_stride < 1 ? 1 : p->traj_stride;
@@ -862,10 +914,22 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
     for (int k = 0; k < M; ++k) hs.pv[0][k] = h_pv0 ? h_pv0[k] : 0.f;
     MDG_CUDA(cudaMemcpyAsync(sc, &hs, sizeof(Scalars), cudaMemcpyHostToDevice, st));
     MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 8, st));
+    for (int k = 0; k < p->n_priors; ++k)      // the members' overflow latches
+        MDG_CUDA(cudaMemsetAsync(p->priors[k].ctx->flags.as<int>() + 3, 0, sizeof(int), st));
     k_gnn_init<<<nb, T, 0, st>>>(n, d_v0, d_q0, d_mass, v4, q4, vh4);
     int ib = nb < 1 ? 1 : (nb > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : nb);
     int64_t launches = 0;
-    MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, st));
+    // the first evaluation is synchronous: its pair count sizes the edge buffers of the asynchronous steps
+    int64_t P0 = 0, cap_pairs = -1;
+    MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, -1, &P0, st));
+    if (async) {
+        const char* mg = getenv("MDG_GNN_MARGIN");             // (tests force the overflow / retry path with a tiny margin)
+        cap_pairs = P0 + (mg ? (int64_t)atoll(mg) : P0 / 4 + 256);
+        if (model) {
+            MDG_TRY(c->gnn_nbr.reserve(sizeof(int64_t) * 2 * (size_t)(cap_pairs + 1)));
+            MDG_TRY(c->gnn_off.reserve(sizeof(float) * 3 * (size_t)(cap_pairs + 1)));
+        }
+    }
     if (nhc) k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, v4, ke_v_cur);
     MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
     MDG_CUDA(cudaMemcpyAsync(d_traj_q, d_q0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -880,7 +944,7 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
             k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, v4, vh4, q4, f4, nullptr, 0, ke_h_cur, c->flags.as<int>());
             c->stat_launches++;
         }
-        MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, st));
+        MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, cap_pairs, nullptr, st));
         int gp = g + 1;
         bool keep = (gp % stride) == 0;
         size_t fr = (size_t)(gp / stride);
@@ -905,7 +969,18 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
     if (h_last_energy) MDG_CUDA(cudaMemcpyAsync(&h_e, d_e_gnn, sizeof(float), cudaMemcpyDeviceToHost, st));
     if (M && h_traj_pv)
         MDG_CUDA(cudaMemcpyAsync(h_traj_pv, d_traj_pv, sizeof(float) * (size_t)n_frames * M, cudaMemcpyDeviceToHost, st));
+    if (async) {    // the overflow latches of all members -> pinned slots 8.., read after the one synchronisation of the epoch
+        MDG_CUDA(cudaMemcpyAsync(c->h_pinned + 8, c->flags.as<int>() + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+        for (int k = 0; k < p->n_priors; ++k)
+            MDG_CUDA(cudaMemcpyAsync(c->h_pinned + 9 + k, p->priors[k].ctx->flags.as<int>() + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     MDG_CUDA(cudaStreamSynchronize(st));
+    if (async) {
+        int any = c->h_pinned[8];
+        for (int k = 0; k < p->n_priors; ++k) any |= c->h_pinned[9 + k];
+        *latched = any;
+        if (any & 2) { mdg_set_error("mdg_md_run_gnn: non-finite coordinates or collapsed cell during the epoch"); return MDG_E_NUMERIC; }
+    }
     if (h_last_energy) *h_last_energy = h_e;      // SchNet energy of the last evaluation (priors not included)
     c->stat_launches += launches;
     return MDG_OK;

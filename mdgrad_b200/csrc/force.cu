@@ -365,9 +365,12 @@ int mdg_i_pair_force_op(mdg_ctx* c, const PotParams& P, const float* d_xyz, int 
 // ---------------------------------------------------------------------------------------------
 // generic listed-pair distance op (compute_dis, reference torchmd/topology.py:5-12) fwd/bwd
 // ---------------------------------------------------------------------------------------------
+// dP != nullptr: the pair count lives on the device (asynchronous engine steps); P is then only the launch bound
 __global__ void k_pair_dis_fwd(const float* __restrict__ xyz, const int64_t* __restrict__ nbr,
-                               const float* __restrict__ off, int64_t P, Box bx, float* __restrict__ dis) {
+                               const float* __restrict__ off, int64_t P, const int* __restrict__ dP, Box bx,
+                               float* __restrict__ dis) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (dP) P = min(P, (int64_t)*dP);
     if (p >= P) return;
     int64_t i = nbr[2 * p], j = nbr[2 * p + 1];
     float dx = (xyz[3 * i] - xyz[3 * j]) - off[3 * p] * bx.L[0];
@@ -401,14 +404,19 @@ static Box make_box(const float* h_cell3) {
     return b;
 }
 
+int mdg_i_pair_dis_fwd(const float* d_xyz, const int64_t* d_nbr, const float* d_offsets, int64_t n_pairs, const int* d_n_pairs,
+                       const float* h_cell3, float* d_dis, cudaStream_t st) {
+    if (n_pairs <= 0) return MDG_OK;
+    k_pair_dis_fwd<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(d_xyz, d_nbr, d_offsets, n_pairs, d_n_pairs, make_box(h_cell3),
+                                                                     d_dis);
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
 extern "C" int mdg_pair_dis_fwd(const float* d_xyz, int n, const int64_t* d_nbr, const float* d_offsets,
                                 int64_t n_pairs, const float* h_cell3, float* d_dis, void* stream) {
     (void)n;
-    if (n_pairs <= 0) return MDG_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    k_pair_dis_fwd<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(d_xyz, d_nbr, d_offsets, n_pairs, make_box(h_cell3), d_dis);
-    MDG_KERNEL_CHECK();
-    return MDG_OK;
+    return mdg_i_pair_dis_fwd(d_xyz, d_nbr, d_offsets, n_pairs, nullptr, h_cell3, d_dis, (cudaStream_t)stream);
 }
 
 extern "C" int mdg_pair_dis_bwd(const float* d_xyz, int n, const int64_t* d_nbr, const float* d_offsets,

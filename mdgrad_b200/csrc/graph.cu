@@ -12,17 +12,20 @@
 // tcgen05 path is the planned replacement.
 #include "common.cuh"
 
-__global__ void k_inc_count(const int64_t* __restrict__ nbr, int64_t E, int n, int* __restrict__ cnt) {
+// dE != nullptr: the edge count lives on the device (asynchronous engine steps); E is then only the launch bound
+__global__ void k_inc_count(const int64_t* __restrict__ nbr, int64_t E, const int* __restrict__ dE, int n, int* __restrict__ cnt) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (dE) E = min(E, (int64_t)*dE);
     if (e >= E) return;
     int a0 = (int)nbr[2 * e], a1 = (int)nbr[2 * e + 1];
     if ((unsigned)a0 < (unsigned)n) atomicAdd(&cnt[a0], 1);
     if ((unsigned)a1 < (unsigned)n) atomicAdd(&cnt[a1], 1);
 }
 
-__global__ void k_inc_fill(const int64_t* __restrict__ nbr, int64_t E, int n, const int* __restrict__ off,
+__global__ void k_inc_fill(const int64_t* __restrict__ nbr, int64_t E, const int* __restrict__ dE, int n, const int* __restrict__ off,
                            int* __restrict__ cursor, int* __restrict__ inc_edge, int* __restrict__ inc_other) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (dE) E = min(E, (int64_t)*dE);
     if (e >= E) return;
     int a0 = (int)nbr[2 * e], a1 = (int)nbr[2 * e + 1];
     if ((unsigned)a0 < (unsigned)n) { int p = off[a0] + atomicAdd(&cursor[a0], 1); inc_edge[p] = (int)e; inc_other[p] = a1; }
@@ -83,7 +86,7 @@ __global__ void k_cfconv_edge_grad(int64_t E, int F, const int64_t* __restrict__
     gW[idx] = h[a0 * F + f] * g[a1 * F + f] + h[a1 * F + f] * g[a0 * F + f];
 }
 
-int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st);
+int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st, const int* d_n_edges = nullptr);
 int mdg_i_cfconv_agg(mdg_ctx* c, const float* d_h, const float* d_W, int n, int F, float* d_out, cudaStream_t st);
 
 extern "C" int mdg_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, void* stream) {
@@ -92,7 +95,8 @@ extern "C" int mdg_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges
     return mdg_i_graph_build(c, d_nbr, n_edges, n, (cudaStream_t)stream);
 }
 
-int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st) {
+// d_n_edges != nullptr: n_edges is an upper bound (buffer capacity), the actual count is read on the device
+int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st, const int* d_n_edges) {
     if ((n_edges > 0 && !d_nbr) || n < 0 || n_edges < 0 || 2 * n_edges > 0x7fffffffLL) { mdg_set_error("mdg_graph_build: bad arguments"); return MDG_E_BADARG; }
     c->g_n = n;
     c->g_edges = n_edges;
@@ -102,11 +106,11 @@ int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, 
     MDG_TRY(c->g_edge.reserve(sizeof(int) * (size_t)(2 * n_edges + 1)));
     MDG_TRY(c->g_other.reserve(sizeof(int) * (size_t)(2 * n_edges + 1)));
     MDG_CUDA(cudaMemsetAsync(c->g_cnt.p, 0, sizeof(int) * (size_t)(n + 1), st));
-    if (n_edges > 0) k_inc_count<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(d_nbr, n_edges, n, c->g_cnt.as<int>());
+    if (n_edges > 0) k_inc_count<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(d_nbr, n_edges, d_n_edges, n, c->g_cnt.as<int>());
     MDG_TRY(mdg_i_scan_exclusive(c, c->g_cnt.as<int>(), c->g_off.as<int>(), n + 1, nullptr, st));
     MDG_CUDA(cudaMemsetAsync(c->g_cnt.p, 0, sizeof(int) * (size_t)(n + 1), st));
     if (n_edges > 0) {
-        k_inc_fill<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(d_nbr, n_edges, n, c->g_off.as<int>(), c->g_cnt.as<int>(),
+        k_inc_fill<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(d_nbr, n_edges, d_n_edges, n, c->g_off.as<int>(), c->g_cnt.as<int>(),
                                                                    c->g_edge.as<int>(), c->g_other.as<int>());
         k_inc_sort<<<(n + 127) / 128, 128, 0, st>>>(n, c->g_off.as<int>(), c->g_edge.as<int>(), c->g_other.as<int>());
     }

@@ -683,7 +683,8 @@ __global__ void k_export_count(int n, const float4* __restrict__ qs, const uint3
 
 __global__ void k_export_fill(int n, const float4* __restrict__ qs, const uint32_t* __restrict__ rows,
                               const int* __restrict__ row_len, int cap, const int* __restrict__ up_off, Box bx,
-                              int64_t* __restrict__ nbr, float* __restrict__ offsets, float* __restrict__ dis) {
+                              int64_t* __restrict__ nbr, float* __restrict__ offsets, float* __restrict__ dis,
+                              int64_t cap_pairs) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     float4 qi = qs[s];
@@ -703,6 +704,7 @@ __global__ void k_export_fill(int n, const float4* __restrict__ qs, const uint32
             rank += (id2 > idi && id2 < idj);
         }
         int64_t p = base + rank;
+        if (p >= cap_pairs) continue;      // asynchronous export into a buffer sized from an earlier count (k_latch reports it)
         nbr[2 * p] = idi;
         nbr[2 * p + 1] = idj;
         uint32_t code = e >> MDG_IDX_BITS;
@@ -749,7 +751,55 @@ int mdg_i_export_fill(mdg_ctx* c, int64_t* d_nbr, float* d_offsets, float* d_dis
     if (n == 0 || c->npairs == 0) return MDG_OK;
     const int T = 128;
     k_export_fill<<<(n + T - 1) / T, T, 0, st>>>(n, c->qs_ptr, c->rows.as<uint32_t>(), c->row_len.as<int>(),
-                                                 c->cap, c->up_off.as<int>(), c->box, d_nbr, d_offsets, d_dis);
+                                                 c->cap, c->up_off.as<int>(), c->box, d_nbr, d_offsets, d_dis, INT64_MAX);
+    c->stat_launches++;
+    MDG_KERNEL_CHECK();
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Asynchronous list build for the device engine's GNN / Stack epochs (engine.cu): the same exact list as
+// mdg_nbr_build, but NOTHING is read back - the host keeps enqueueing the step while the list is being built.
+//   * the pair count stays on the device (flags[4]); consumers take it from there, bounded by `cap_pairs`, the size of
+//     the buffers the host allocated from an EARLIER step's count;
+//   * a row-capacity overflow, non-finite input or a pair count above cap_pairs is LATCHED in flags[3] (bit 0 / 1 / 2),
+//     which survives later builds; the engine reads it once, at the end of the epoch, and repeats the epoch on the
+//     synchronous path (which grows the capacities) if it is set.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_latch(int* __restrict__ flags, int check_total, int64_t cap_pairs) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int v = 0;
+        if (flags[0]) v |= 1;
+        if (flags[6] | flags[7]) v |= 2;
+        if (check_total && (int64_t)flags[4] > cap_pairs) v |= 4;
+        if (v) flags[3] |= v;
+    }
+}
+
+int mdg_i_nbr_build_async(mdg_ctx* c, const float* d_xyz, int n, const float* h_cell3, double cutoff, const uint8_t* d_sel_a,
+                          const uint8_t* d_sel_b, const int64_t* d_ex_keys, int n_ex, bool want_export, int64_t cap_pairs,
+                          int64_t* d_nbr, float* d_offsets, cudaStream_t st) {
+    c->sel_a = d_sel_a;
+    c->sel_b = d_sel_b;
+    c->ex_keys = d_ex_keys;
+    c->n_ex = d_ex_keys ? n_ex : 0;
+    c->rows_wanted = true;
+    c->fast_build = false;       // exact membership, as mdg_nbr_build
+    c->stat_launches = 0;
+    MDG_TRY(mdg_i_build_list(c, d_xyz, nullptr, n, h_cell3, cutoff, cutoff, st));
+    if (n == 0) return MDG_OK;
+    if (want_export) {
+        MDG_TRY(c->up_cnt.reserve(sizeof(int) * (size_t)(n + 1)));
+        MDG_TRY(c->up_off.reserve(sizeof(int) * (size_t)(n + 2)));
+        const int T = 256;
+        k_export_count<<<(n + T - 1) / T, T, 0, st>>>(n, c->qs_ptr, c->rows.as<uint32_t>(), c->row_len.as<int>(), c->cap,
+                                                     c->up_cnt.as<int>());
+        MDG_TRY(mdg_i_scan_exclusive(c, c->up_cnt.as<int>(), c->up_off.as<int>(), n, c->flags.as<int>() + 4, st));
+        k_export_fill<<<(n + 127) / 128, 128, 0, st>>>(n, c->qs_ptr, c->rows.as<uint32_t>(), c->row_len.as<int>(), c->cap,
+                                                      c->up_off.as<int>(), c->box, d_nbr, d_offsets, nullptr, cap_pairs);
+        c->stat_launches += 2;
+    }
+    k_latch<<<1, 32, 0, st>>>(c->flags.as<int>(), want_export ? 1 : 0, cap_pairs);
     c->stat_launches++;
     MDG_KERNEL_CHECK();
     return MDG_OK;

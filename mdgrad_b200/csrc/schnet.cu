@@ -22,7 +22,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 
-int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st);
+int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, cudaStream_t st, const int* d_n_edges = nullptr);
 int mdg_i_cfconv_agg(mdg_ctx* c, const float* d_h, const float* d_W, int n, int F, float* d_out, cudaStream_t st);
 
 #define SN_GMAX 64          // max gaussians (29 / 33 in the reference configs)
@@ -59,14 +59,16 @@ __global__ void k_sn_transpose(int rows, int cols, const float* __restrict__ W, 
 // FMAs with the same weight; weights come pre-transposed ([in][out]) so that the lanes of a warp (consecutive output
 // index) read one coalesced line per k.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sn_edge_fwd(int64_t E, int G, int F, const float* __restrict__ dis,
+__global__ void __launch_bounds__(256) k_sn_edge_fwd(int64_t E, const int* __restrict__ dE, int G, int F, const float* __restrict__ dis,
                                                      const float* __restrict__ mu, const float* __restrict__ width,
                                                      const float* __restrict__ We1T, const float* __restrict__ be1,
                                                      const float* __restrict__ We2T, const float* __restrict__ be2,
                                                      float* __restrict__ preT1, float* __restrict__ W) {
     __shared__ __align__(16) float s_g[SN_GMAX][SN_TE];
     __shared__ __align__(16) float s_a[SN_GMAX][SN_TE];
+    if (dE) E = min(E, (int64_t)*dE);          // asynchronous engine steps: E is the launch bound, the count is on the device
     const int64_t e0 = (int64_t)blockIdx.x * SN_TE;
+    if (e0 >= E) return;                       // (block-uniform)
     const int t = threadIdx.x;
     for (int idx = t; idx < G * SN_TE; idx += blockDim.x) {
         int k = idx / SN_TE, e = idx - k * SN_TE;
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256) k_sn_edge_fwd(int64_t E, int G, int F, co
 //   gd[e]    += sum_k' gg[e][k'] * gauss_k'(d) * 2 coeff_k' (d - mu_k')
 // dynamic shared memory: F x SN_TEB floats (gW transposed).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sn_edge_bwd(int64_t E, int G, int F, const int64_t* __restrict__ nbr,
+__global__ void __launch_bounds__(256) k_sn_edge_bwd(int64_t E, const int* __restrict__ dE, int G, int F, const int64_t* __restrict__ nbr,
                                                      const float* __restrict__ h, const float* __restrict__ g,
                                                      const float* __restrict__ dis, const float* __restrict__ mu,
                                                      const float* __restrict__ width, const float* __restrict__ We1,
@@ -142,7 +144,9 @@ __global__ void __launch_bounds__(256) k_sn_edge_bwd(int64_t E, int G, int F, co
     __shared__ __align__(16) float s_gt[SN_GMAX][SN_TEB];         // [k][edge]
     __shared__ float s_out[SN_TEB];
     __shared__ int s_i[SN_TEB], s_j[SN_TEB];
+    if (dE) E = min(E, (int64_t)*dE);
     const int64_t e0 = (int64_t)blockIdx.x * SN_TEB;
+    if (e0 >= E) return;                       // (block-uniform)
     const int t = threadIdx.x;
     if (t < SN_TEB) {
         bool ok = e0 + t < E;
@@ -392,12 +396,23 @@ __global__ void k_sn_energy_final(int np, const double* __restrict__ part, float
 // ---------------------------------------------------------------------------------------------
 static inline size_t al(size_t x) { return (x + 63) & ~(size_t)63; }   // floats, 256-byte granules
 
-extern "C" int mdg_pair_dis_fwd(const float* d_xyz, int n, const int64_t* d_nbr, const float* d_offsets,
-                                int64_t n_pairs, const float* h_cell3, float* d_dis, void* stream);
+int mdg_i_pair_dis_fwd(const float* d_xyz, const int64_t* d_nbr, const float* d_offsets, int64_t n_pairs, const int* d_n_pairs,
+                       const float* h_cell3, float* d_dis, cudaStream_t st);
+int mdg_i_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, const int64_t* d_z, const float* d_xyz, int n,
+                              const int64_t* d_nbr, const float* d_offsets, int64_t E, const int* d_E, const float* h_off_scale3,
+                              float* d_energy, float* d_force, void* stream);
 
 extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, const int64_t* d_z, const float* d_xyz, int n,
                                        const int64_t* d_nbr, const float* d_offsets, int64_t E, const float* h_off_scale3,
                                        float* d_energy, float* d_force, void* stream) {
+    return mdg_i_schnet_energy_force(c, m, d_z, d_xyz, n, d_nbr, d_offsets, E, nullptr, h_off_scale3, d_energy, d_force, stream);
+}
+
+// d_E != nullptr (asynchronous engine steps, engine.cu): E is the CAPACITY of the edge buffers / the launch bound, the
+// actual edge count is read on the device (flags[4] of the list build); nothing here depends on it on the host.
+int mdg_i_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, const int64_t* d_z, const float* d_xyz, int n,
+                              const int64_t* d_nbr, const float* d_offsets, int64_t E, const int* d_E, const float* h_off_scale3,
+                              float* d_energy, float* d_force, void* stream) {
     if (!c || !m || !d_energy || (n > 0 && (!d_z || !d_xyz)) || (E > 0 && (!d_nbr || !d_offsets)) || !h_off_scale3) {
         mdg_set_error("mdg_schnet_energy_force: null argument");
         return MDG_E_BADARG;
@@ -410,7 +425,7 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
     MDG_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { MDG_CUDA(cudaMemsetAsync(d_energy, 0, sizeof(float), st)); return MDG_OK; }
-    MDG_TRY(mdg_i_graph_build(c, d_nbr, E, n, st));
+    MDG_TRY(mdg_i_graph_build(c, d_nbr, E, n, st, d_E));
 
     // workspace carve-up (floats)
     const size_t sE = al((size_t)E), sEG = al((size_t)E * G), sEF = al((size_t)E * F);
@@ -462,13 +477,13 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
 
     const int T = 256;
     // ---- forward ---------------------------------------------------------------------------------------------
-    if (E > 0) MDG_TRY(mdg_pair_dis_fwd(d_xyz, n, d_nbr, d_offsets, E, h_off_scale3, dis, stream));
+    if (E > 0) MDG_TRY(mdg_i_pair_dis_fwd(d_xyz, d_nbr, d_offsets, E, d_E, h_off_scale3, dis, st));
     k_sn_embed<<<(unsigned)(((int64_t)n * A + T - 1) / T), T, 0, st>>>(n, A, d_z, m->embed, r);
     const unsigned eb = (unsigned)((E + SN_TE - 1) / SN_TE);
     for (int l = 0; l < L; ++l) {
         const mdg_schnet_layer& Y = m->layers[l];
         if (E > 0)
-            k_sn_edge_fwd<<<eb, 256, 0, st>>>(E, G, F, dis, Y.mu, Y.width, We1T[l], Y.be1, We2T[l], Y.be2, preT1[l], W[l]);
+            k_sn_edge_fwd<<<eb, 256, 0, st>>>(E, d_E, G, F, dis, Y.mu, Y.width, We1T[l], Y.be1, We2T[l], Y.be2, preT1[l], W[l]);
         MDG_TRY((sn_gemm<true, SN_EPI_BIAS>(c, n, F, A, r, Y.Wn, A, Y.bn, nullptr, h[l], st)));
         MDG_TRY(mdg_i_cfconv_agg(c, h[l], W[l], n, F, agg, st));
         MDG_TRY((sn_gemm<true, SN_EPI_BIAS_SSP>(c, n, A, F, agg, Y.Wu1, F, Y.bu1, preU1[l], u1, st)));
@@ -497,7 +512,7 @@ extern "C" int mdg_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, co
         MDG_TRY((sn_gemm<false, SN_EPI_MUL_SIG>(c, n, A, A, gr, Y.Wu2, A, nullptr, preU1[l], gu, st)));
         MDG_TRY((sn_gemm<false, SN_EPI_STORE>(c, n, F, A, gu, Y.Wu1, F, nullptr, nullptr, gagg, st)));
         if (E > 0) {
-            k_sn_edge_bwd<<<ebb, 256, bwd_smem, st>>>(E, G, F, d_nbr, h[l], gagg, dis, Y.mu, Y.width, Y.We1,
+            k_sn_edge_bwd<<<ebb, 256, bwd_smem, st>>>(E, d_E, G, F, d_nbr, h[l], gagg, dis, Y.mu, Y.width, Y.We1,
                                                                              Y.We2, preT1[l], gd);
         }
         if (l > 0) {     // the embedding below layer 0 does not depend on the positions

@@ -315,5 +315,5 @@ extern "C" {
 int  cuemu_api_return(void* user_stream);   // synchronise the caller's stream; returns the number of OTHER streams with pending work
 void cuemu_flush_all();
 int  cuemu_strict();
-long cuemu_counter(int which);              // 0 launches run, 1 launches rejected, 2 ops deferred past their enqueue call
+long cuemu_counter(int which);              // 0 launches run, 1 launches rejected, 2 ops deferred past their enqueue call, 3 host-blocking synchronisations
 }

@@ -507,6 +507,7 @@ cudaError_t cudaMalloc(void** p, size_t bytes) {
 cudaError_t cudaFree(void* p) {
     if (!p) return cudaSuccess;
     if (!strict()) { free(p); return cudaSuccess; }
+    g_counters[3]++;
     flush_all();                                   // cudaFree synchronises the device
     Alloc* a = find_alloc(p);
     if (!a || a->user != (char*)p || !a->live) { fprintf(stderr, "cuemu: cudaFree of %p which is not a live device allocation\n", p); abort(); }
@@ -550,7 +551,7 @@ static cudaError_t copy_async(void* d, const void* s, size_t n, cudaMemcpyKind k
     } else {
         enqueue(st, [d, s, n]() { memmove(d, s, n); });
     }
-    if (blocking || (dst_host && !is_pinned(d))) run_until(st, st->last_seq);
+    if (blocking || (dst_host && !is_pinned(d))) { g_counters[3]++; run_until(st, st->last_seq); }
     return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind k) { return copy_async(d, s, n, k, stream_of(nullptr), true); }
@@ -569,9 +570,9 @@ cudaError_t cudaMemset(void* d, int v, size_t n) {
     run_until(s, s->last_seq);
     return cudaSuccess;
 }
-cudaError_t cudaStreamSynchronize(cudaStream_t st) { Stream* s = stream_of(st); run_until(s, s->last_seq); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t st) { Stream* s = stream_of(st); g_counters[3]++; run_until(s, s->last_seq); return cudaSuccess; }
 cudaError_t cudaStreamQuery(cudaStream_t st) { return stream_of(st)->q.empty() ? cudaSuccess : cudaErrorNotReady; }
-cudaError_t cudaDeviceSynchronize() { flush_all(); return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { g_counters[3]++; flush_all(); return cudaSuccess; }
 static cudaError_t stream_create(cudaStream_t* out, unsigned flags) {
     stream_of(nullptr);
     Stream* s = new Stream();
@@ -612,6 +613,7 @@ cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t eh, unsigned) {
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t eh) {
     Event* e = (Event*)eh;
+    g_counters[3]++;
     if (e->recorded) run_dep(Dep{e->stream_id, e->seq});
     return cudaSuccess;
 }

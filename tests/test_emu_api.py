@@ -227,6 +227,60 @@ def test_emu_gnn_engine_epoch_equals_op_level_solver():
         assert torch.equal(nbr_after, gnn.inputs["nbr_list"])          # python-visible list = list at the last frame
 
 
+def test_emu_gnn_engine_async_steps_and_overflow_retry(monkeypatch):
+    """The device engine's GNN epochs run their steps without any read-back (pair count consumed on the device, edge buffers sized
+    from the first evaluation); a too-small capacity is latched and the epoch repeated on the synchronous path.  All three ways
+    (asynchronous, forced synchronous, forced overflow -> retry) give the SAME bits."""
+    from nff.nn.models.schnet import SchNet
+    from torchmd.interface import GNNPotentials, PairPotentials, Stack
+    from torchmd.potentials import ExcludedVolume
+    from torchmd.md import NoseHooverChain, Simulations
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms, units
+    from test_schnet import _fixture
+    g, params, sd = _fixture("water")
+    runs = {}
+    for mode in ("async", "sync", "overflow", "async_long"):
+        monkeypatch.delenv("MDG_GNN_SYNC", raising=False)
+        monkeypatch.delenv("MDG_GNN_MARGIN", raising=False)
+        if mode == "sync":
+            monkeypatch.setenv("MDG_GNN_SYNC", "1")
+        if mode == "overflow":
+            monkeypatch.setenv("MDG_GNN_MARGIN", "-40")        # edge buffers 40 pairs SMALLER than the first count
+        system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device="cpu")
+        np.random.seed(0)
+        system.set_temperature(298.0 * units.kB)
+        model = SchNet(params)
+        model.load_state_dict(sd)
+        gnn = GNNPotentials(system, model, cutoff=params["cutoff"])
+        oxy = [int(i) for i in np.nonzero(g["numbers"] == 8)[0]]
+        prior = PairPotentials(system, ExcludedVolume(2.6, 0.015, 12), cutoff=params["cutoff"], index_tuple=(oxy, oxy))
+        integ = NoseHooverChain(Stack({"gnn": gnn, "prior": prior}), system, T=298.0 * units.kB, num_chains=5, Q=50.0, adjoint=True)
+        sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+        real_run = emu_lib.EmuContext.md_run_gnn
+        syncs = []
+
+        def counted(self, *a, **k):
+            c0 = emu_lib.load().cuemu_counter(3)
+            r = real_run(self, *a, **k)
+            syncs.append(emu_lib.load().cuemu_counter(3) - c0)
+            return r
+        monkeypatch.setattr(emu_lib.EmuContext, "md_run_gnn", counted)
+        nst = 10 if mode == "async_long" else 6
+        out = sim.simulate(steps=nst, frequency=nst, dt=0.5 * units.fs)
+        monkeypatch.setattr(emu_lib.EmuContext, "md_run_gnn", real_run)
+        runs[mode] = ([o.detach().clone() for o in out], integ.last_engine_stats["maxrow_or_K"], syncs[0])
+    assert runs["async"][1] == 1 and runs["sync"][1] == 0 and runs["overflow"][1] == 0      # which path completed the epoch
+    # host-blocking synchronisations inside the engine call (counted by the emulator's runtime): two per evaluation on the
+    # synchronous path; on the asynchronous one a constant (first evaluation, one-time buffer growth, end of the epoch) that
+    # does not depend on the number of steps
+    assert runs["sync"][2] >= 2 * 6 and runs["async"][2] < runs["sync"][2], (runs["sync"][2], runs["async"][2])
+    assert runs["async_long"][1] == 1 and runs["async_long"][2] == runs["async"][2], (runs["async_long"][2], runs["async"][2])
+    for mode in ("sync", "overflow"):
+        for a, b in zip(runs["async"][0], runs[mode][0]):
+            assert torch.equal(a, b), mode
+
+
 def test_emu_angle_distribution_vs_live_reference():
     """angle_distribution (native neighbor list -> device-side triple enumeration -> smeared histogram) against the
     unmodified reference observable (authoring container only)"""
