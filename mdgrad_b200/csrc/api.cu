@@ -66,6 +66,8 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
     if (c->h_layers) cudaFreeHost(c->h_layers);
     mdg_i_release_profile(c);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->gnn_stream) cudaStreamDestroy(c->gnn_stream);
+    if (c->ev_gnn) cudaEventDestroy(c->ev_gnn);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     if (c->ev_ke) cudaEventDestroy(c->ev_ke);

@@ -297,6 +297,9 @@ struct mdg_ctx {
     const float* sn_wkey[2 * MDG_SCHNET_MAX_LAYERS] = {nullptr};
     DevBuf sn_wt;             // transposed weight scratch of the tensor-core dense layers (schnet_tc.cuh)
     DevBuf gnn_nbr, gnn_off, gnn_xyz, gnn_f3, gnn_fp3;   // GNN epoch (engine.cu): exported list, xyz / force staging
+    cudaStream_t gnn_stream = nullptr;   // private stream of the graph-replay GNN epochs (capture is illegal on torch's legacy default stream)
+    cudaEvent_t  ev_gnn = nullptr;
+    int64_t stat_graph_replays = 0;
     DevBuf bd_slots, bd_part;  // bonded terms (bonded.cu): per-term gradient slots, block partial sums
     int     g_n = -1;
     int64_t g_edges = 0;

@@ -855,11 +855,13 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
     // evaluation turns out too small during the epoch, the latched flags say so at the end and the epoch is repeated on
     // the synchronous path (inputs are never modified).  MDG_GNN_SYNC=1 forces the synchronous path.
     const bool try_async = getenv("MDG_GNN_SYNC") == nullptr && n_grid > 2;
+    const int64_t replays0 = c->stat_graph_replays;
     if (try_async) {
         int latched = 0;
         MDG_TRY(gnn_run_once(c, p, model, d_z, n, d_mass, d_v0, d_q0, h_pv0, h_tgrid, n_grid, d_traj_v, d_traj_q, h_traj_pv,
                              h_last_energy, true, &latched, (cudaStream_t)stream));
-        if (!latched) { c->stat_maxrow = 1; return MDG_OK; }     // stats slot 3: 1 = the epoch completed on the asynchronous path
+        // stats slot 3: 1 = the epoch completed on the asynchronous path, 2 = with its force evaluations replayed as a graph
+        if (!latched) { c->stat_maxrow = c->stat_graph_replays > replays0 ? 2 : 1; return MDG_OK; }
         c->stat_async_retries++;
     }
     c->stat_maxrow = 0;
@@ -870,7 +872,29 @@ extern "C" int mdg_md_run_gnn(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_
 static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_model* model, const int64_t* d_z, int n,
                         const float* d_mass, const float* d_v0, const float* d_q0, const float* h_pv0, const float* h_tgrid,
                         int n_grid, float* d_traj_v, float* d_traj_q, float* h_traj_pv, float* h_last_energy, bool async,
-                        int* latched, cudaStream_t st) {
+                        int* latched, cudaStream_t st_user) {
+    // MDG_GNN_GRAPH=1 (opt-in until measured on a GPU): on the asynchronous path a force evaluation is a FIXED launch sequence
+    // with fixed arguments (same buffers, capacities, device-side counts), so it is captured once (at the second step, after the
+    // first one has grown every buffer) and replayed as a CUDA graph.  Stream capture is not allowed on the legacy default
+    // stream - which is what PyTorch's current stream usually is - so such an epoch runs on a private stream, ordered after the
+    // caller's stream by an event and synchronised before the call returns.
+    struct GraphGuard {
+        cudaGraphExec_t exec = nullptr;
+        ~GraphGuard() { if (exec) cudaGraphExecDestroy(exec); }
+    } gg;
+    const char* ge = getenv("MDG_GNN_GRAPH");
+    const bool use_graph = async && ge && ge[0] == '1' && n_grid > 3;
+    bool graph_failed = false;
+    cudaStream_t st = st_user;
+    if (use_graph) {
+        if (!c->gnn_stream) {
+            MDG_CUDA(cudaStreamCreateWithFlags(&c->gnn_stream, cudaStreamNonBlocking));
+            MDG_CUDA(cudaEventCreateWithFlags(&c->ev_gnn, cudaEventDisableTiming));
+        }
+        MDG_CUDA(cudaEventRecord(c->ev_gnn, st_user));
+        MDG_CUDA(cudaStreamWaitEvent(c->gnn_stream, c->ev_gnn, 0));
+        st = c->gnn_stream;
+    }
     const int nhc = p->integrator == MDG_INT_NHC;
     const int M = nhc ? p->n_chains : 0;
     const int stride = p->traj_stride < 1 ? 1 : p->traj_stride;
@@ -944,7 +968,29 @@ static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet
             k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, v4, vh4, q4, f4, nullptr, 0, ke_h_cur, c->flags.as<int>());
             c->stat_launches++;
         }
-        MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, cap_pairs, nullptr, st));
+        if (use_graph && g >= 1 && !gg.exec && !graph_failed) {       // capture the evaluation of the second step
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                int64_t dummy = 0;
+                const int r = gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &dummy, cap_pairs, nullptr, st);
+                const cudaError_t e = cudaStreamEndCapture(st, &graph);        // (always: never leave the stream capturing)
+                if (r != MDG_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&gg.exec, graph, 0) != cudaSuccess) {
+                    graph_failed = true;
+                    gg.exec = nullptr;
+                }
+                if (graph) cudaGraphDestroy(graph);
+            } else {
+                graph_failed = true;
+            }
+            if (graph_failed) (void)cudaGetLastError();                        // plain launches from here on
+        }
+        if (gg.exec) {
+            MDG_CUDA(cudaGraphLaunch(gg.exec, st));
+            c->stat_graph_replays++;
+            launches++;
+        } else {
+            MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, cap_pairs, nullptr, st));
+        }
         int gp = g + 1;
         bool keep = (gp % stride) == 0;
         size_t fr = (size_t)(gp / stride);

@@ -194,3 +194,20 @@ def check_pair_tab_through_pair_potentials(dev):
     _close(e.item(), ec.item())
     _close(gq.cpu().numpy(), gqc.numpy())
     _close(gt.cpu().numpy(), gtc.numpy())
+
+
+def check_fold_force_field_graph_replay(dev):
+    """the same epoch with the force evaluations (SchNet + bonds + excluded volume: ~50 launches) replayed as a CUDA graph
+    (MDG_GNN_GRAPH=1, opt-in): bit-identical to the plain asynchronous epoch"""
+    old = os.environ.pop("MDG_GNN_GRAPH", None)
+    try:
+        integ, v, q, pv, g = _fold_sim(dev, engine=True)
+        assert integ.last_engine_stats["maxrow_or_K"] == 1
+        os.environ["MDG_GNN_GRAPH"] = "1"
+        integ2, v2, q2, pv2, _ = _fold_sim(dev, engine=True)
+        assert integ2.last_engine_stats["maxrow_or_K"] == 2, "the force evaluations were not replayed from a graph"
+        assert np.array_equal(q, q2) and np.array_equal(v, v2) and np.array_equal(pv, pv2)
+    finally:
+        os.environ.pop("MDG_GNN_GRAPH", None)
+        if old is not None:
+            os.environ["MDG_GNN_GRAPH"] = old

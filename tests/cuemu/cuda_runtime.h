@@ -302,6 +302,21 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
 cudaError_t cudaEventQuery(cudaEvent_t e);
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
+// stream capture / graphs: ops enqueued on a capturing stream are recorded instead of queued; cudaGraphLaunch queues copies of
+// them (kernel arguments frozen at capture time, as on a GPU).  Calls that are illegal during capture (synchronisations,
+// cudaMalloc / cudaFree, copies that are synchronous with the host, capture on the legacy stream) fail as the driver does
+// and invalidate the capture.
+typedef struct cuemu_graph_st*     cudaGraph_t;
+typedef struct cuemu_graphexec_st* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
+#define cudaErrorStreamCaptureUnsupported 900
+#define cudaErrorStreamCaptureInvalidated 901
+cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode mode);
+cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* graph);
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* exec, cudaGraph_t graph, unsigned long long flags = 0);
+cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t st);
+cudaError_t cudaGraphDestroy(cudaGraph_t graph);
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t exec);
 namespace cuemu {
 cudaError_t func_set_attr(const char* call_text, int attr, int value);
 template <typename F> inline cudaError_t func_set_attr2(const char* call_text, F, int attr, int value) { return func_set_attr(call_text, attr, value); }

@@ -347,6 +347,8 @@ struct Stream {
     bool     nonblocking = false, legacy = false, running = false;
     uint64_t last_seq = 0;         // seq of the last op ever enqueued
     std::deque<Op> q;
+    std::vector<std::function<void()>>* capture = nullptr;   // non-null while the stream is being captured into a graph
+    bool capture_invalid = false;
 };
 struct Event { bool recorded = false; uint64_t stream_id = 0, seq = 0; };
 
@@ -385,7 +387,22 @@ static void run_until(Stream* s, uint64_t seq) {
     }
 }
 
+static int g_capturing = 0;          // number of streams in capture mode
+// a call that is illegal while a capture is in progress (global / thread-local capture modes): fail it and poison the capture
+static bool capture_violation(const char* what) {
+    if (!g_capturing) return false;
+    fprintf(stderr, "cuemu: %s during stream capture: not permitted (the capture is invalidated)\n", what);
+    for (auto& kv : g_streams)
+        if (kv.second->capture) kv.second->capture_invalid = true;
+    g_last_error = cudaErrorStreamCaptureUnsupported;
+    return true;
+}
+
 static void enqueue(Stream* s, std::function<void()> fn, std::vector<Dep> deps = {}) {
+    if (s->capture) {               // recorded into the graph, not executed
+        if (fn) s->capture->push_back(std::move(fn));
+        return;
+    }
     Op op;
     op.seq = g_next_seq++;
     op.deps = std::move(deps);
@@ -480,6 +497,7 @@ cudaError_t cudaGetLastError() { cudaError_t e = g_last_error; g_last_error = cu
 cudaError_t cudaPeekAtLastError() { return g_last_error; }
 
 cudaError_t cudaMalloc(void** p, size_t bytes) {
+    if (capture_violation("cudaMalloc")) return cudaErrorStreamCaptureUnsupported;
     if (!strict()) {
         size_t b = (bytes + 255) & ~(size_t)255;
         *p = aligned_alloc(256, b ? b : 256);
@@ -506,6 +524,7 @@ cudaError_t cudaMalloc(void** p, size_t bytes) {
 }
 cudaError_t cudaFree(void* p) {
     if (!p) return cudaSuccess;
+    if (capture_violation("cudaFree")) return cudaErrorStreamCaptureUnsupported;
     if (!strict()) { free(p); return cudaSuccess; }
     g_counters[3]++;
     flush_all();                                   // cudaFree synchronises the device
@@ -545,13 +564,21 @@ static cudaError_t copy_async(void* d, const void* s, size_t n, cudaMemcpyKind k
     if (k == cudaMemcpyHostToHost) { memmove(d, s, n); return cudaSuccess; }
     const bool src_host = k == cudaMemcpyHostToDevice || (k == cudaMemcpyDefault && is_pinned(s));
     const bool dst_host = k == cudaMemcpyDeviceToHost || (k == cudaMemcpyDefault && is_pinned(d));
+    if (src_host && !is_pinned(s) && st->capture) {
+        capture_violation("cudaMemcpyAsync from pageable host memory");
+        return cudaErrorStreamCaptureUnsupported;
+    }
     if (src_host && !is_pinned(s)) {
         std::vector<char> stage((const char*)s, (const char*)s + n);
         enqueue(st, [d, n, stage = std::move(stage)]() { memcpy(d, stage.data(), n); });
     } else {
         enqueue(st, [d, s, n]() { memmove(d, s, n); });
     }
-    if (blocking || (dst_host && !is_pinned(d))) { g_counters[3]++; run_until(st, st->last_seq); }
+    if (blocking || (dst_host && !is_pinned(d))) {
+        if (capture_violation("a copy that is synchronous with the host")) return cudaErrorStreamCaptureUnsupported;
+        g_counters[3]++;
+        run_until(st, st->last_seq);
+    }
     return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind k) { return copy_async(d, s, n, k, stream_of(nullptr), true); }
@@ -570,9 +597,9 @@ cudaError_t cudaMemset(void* d, int v, size_t n) {
     run_until(s, s->last_seq);
     return cudaSuccess;
 }
-cudaError_t cudaStreamSynchronize(cudaStream_t st) { Stream* s = stream_of(st); g_counters[3]++; run_until(s, s->last_seq); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t st) { if (capture_violation("cudaStreamSynchronize")) return cudaErrorStreamCaptureUnsupported; Stream* s = stream_of(st); g_counters[3]++; run_until(s, s->last_seq); return cudaSuccess; }
 cudaError_t cudaStreamQuery(cudaStream_t st) { return stream_of(st)->q.empty() ? cudaSuccess : cudaErrorNotReady; }
-cudaError_t cudaDeviceSynchronize() { g_counters[3]++; flush_all(); return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { if (capture_violation("cudaDeviceSynchronize")) return cudaErrorStreamCaptureUnsupported; g_counters[3]++; flush_all(); return cudaSuccess; }
 static cudaError_t stream_create(cudaStream_t* out, unsigned flags) {
     stream_of(nullptr);
     Stream* s = new Stream();
@@ -627,6 +654,52 @@ cudaError_t cudaEventQuery(cudaEvent_t eh) {
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
     *ms = 0.f;
     if (cudaEventQuery(a) != cudaSuccess || cudaEventQuery(b) != cudaSuccess) return g_last_error = cudaErrorNotReady;
+    return cudaSuccess;
+}
+
+struct cuemu_graph_st { std::vector<std::function<void()>> ops; };
+struct cuemu_graphexec_st { std::vector<std::function<void()>> ops; };
+
+cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode) {
+    Stream* s = stream_of(st);
+    if (s->legacy) {
+        fprintf(stderr, "cuemu: cudaStreamBeginCapture on the legacy default stream is not supported by CUDA\n");
+        return g_last_error = cudaErrorStreamCaptureUnsupported;
+    }
+    if (s->capture) return g_last_error = cudaErrorInvalidValue;
+    s->capture = new std::vector<std::function<void()>>();
+    s->capture_invalid = false;
+    g_capturing++;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* graph) {
+    Stream* s = stream_of(st);
+    *graph = nullptr;
+    if (!s->capture) return g_last_error = cudaErrorInvalidValue;
+    std::vector<std::function<void()>>* ops = s->capture;
+    s->capture = nullptr;
+    g_capturing--;
+    if (s->capture_invalid) { delete ops; return g_last_error = cudaErrorStreamCaptureInvalidated; }
+    *graph = new cuemu_graph_st{std::move(*ops)};
+    delete ops;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* exec, cudaGraph_t graph, unsigned long long) {
+    if (!graph) return g_last_error = cudaErrorInvalidValue;
+    *exec = new cuemu_graphexec_st{graph->ops};
+    return cudaSuccess;
+}
+cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t st) {
+    if (!exec) return g_last_error = cudaErrorInvalidValue;
+    Stream* s = stream_of(st);
+    for (const auto& fn : exec->ops) enqueue(s, fn);
+    g_counters[0] += 0;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphDestroy(cudaGraph_t graph) { delete graph; return cudaSuccess; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t exec) {
+    flush_all();                    // (queued copies of the ops hold their own state; be conservative)
+    delete exec;
     return cudaSuccess;
 }
 

@@ -117,6 +117,34 @@ int main(int argc, char** argv) {
         k_copy<<<1, 256>>>(d, d2, 256);
         cudaMemcpy(pin, d2, 256 * sizeof(int), cudaMemcpyDeviceToHost);
         puts(ok && pin[0] == 7 ? "caught" : "missed");
+    } else if (!strcmp(c, "graph_ok")) {            // capture two kernels, replay twice: arguments frozen at capture time
+        cudaGraph_t g;
+        cudaGraphExec_t ge;
+        int v = 3;
+        cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal);
+        k_fill<<<1, 256, 0, s1>>>(d, 256, v);
+        k_copy<<<1, 256, 0, s1>>>(d, d2, 256);
+        bool ok = cudaStreamEndCapture(s1, &g) == cudaSuccess && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
+        v = 9;                                      // must not leak into the captured launch
+        cudaMemsetAsync(d2, 0, 1024, s1);
+        cudaStreamSynchronize(s1);
+        cudaMemcpy(pin, d2, 4, cudaMemcpyDeviceToHost);
+        ok = ok && pin[0] == 0;                     // capturing did not execute anything
+        cudaGraphLaunch(ge, s1);
+        cudaMemcpyAsync(pin, d2, 1024, cudaMemcpyDeviceToHost, s1);
+        cudaStreamSynchronize(s1);
+        puts(ok && pin[255] == 3 ? "caught" : "missed");
+    } else if (!strcmp(c, "graph_legacy")) {        // capture on the legacy default stream (torch's default stream!) is an error
+        puts(cudaStreamBeginCapture(nullptr, cudaStreamCaptureModeThreadLocal) == cudaErrorStreamCaptureUnsupported ? "caught" : "missed");
+    } else if (!strcmp(c, "graph_sync_inside")) {   // a synchronisation / allocation inside the captured region invalidates it
+        cudaGraph_t g;
+        cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal);
+        k_fill<<<1, 256, 0, s1>>>(d, 256, 1);
+        bool e1 = cudaStreamSynchronize(s1) != cudaSuccess;
+        int* tmp = nullptr;
+        bool e2 = cudaMalloc(&tmp, 64) != cudaSuccess;
+        bool e3 = cudaStreamEndCapture(s1, &g) == cudaErrorStreamCaptureInvalidated && g == nullptr;
+        puts(e1 && e2 && e3 ? "caught" : "missed");
     } else {
         puts("unknown case");
         return 2;

@@ -230,7 +230,7 @@ def test_emu_gnn_engine_epoch_equals_op_level_solver():
 def test_emu_gnn_engine_async_steps_and_overflow_retry(monkeypatch):
     """The device engine's GNN epochs run their steps without any read-back (pair count consumed on the device, edge buffers sized
     from the first evaluation); a too-small capacity is latched and the epoch repeated on the synchronous path.  All three ways
-    (asynchronous, forced synchronous, forced overflow -> retry) give the SAME bits."""
+    (asynchronous, forced synchronous, forced overflow -> retry) and the opt-in CUDA-graph replay give the SAME bits."""
     from nff.nn.models.schnet import SchNet
     from torchmd.interface import GNNPotentials, PairPotentials, Stack
     from torchmd.potentials import ExcludedVolume
@@ -240,9 +240,12 @@ def test_emu_gnn_engine_async_steps_and_overflow_retry(monkeypatch):
     from test_schnet import _fixture
     g, params, sd = _fixture("water")
     runs = {}
-    for mode in ("async", "sync", "overflow", "async_long"):
+    for mode in ("async", "sync", "overflow", "async_long", "graph"):
         monkeypatch.delenv("MDG_GNN_SYNC", raising=False)
         monkeypatch.delenv("MDG_GNN_MARGIN", raising=False)
+        monkeypatch.delenv("MDG_GNN_GRAPH", raising=False)
+        if mode == "graph":
+            monkeypatch.setenv("MDG_GNN_GRAPH", "1")           # force evaluations captured once, replayed as a CUDA graph
         if mode == "sync":
             monkeypatch.setenv("MDG_GNN_SYNC", "1")
         if mode == "overflow":
@@ -276,7 +279,8 @@ def test_emu_gnn_engine_async_steps_and_overflow_retry(monkeypatch):
     # does not depend on the number of steps
     assert runs["sync"][2] >= 2 * 6 and runs["async"][2] < runs["sync"][2], (runs["sync"][2], runs["async"][2])
     assert runs["async_long"][1] == 1 and runs["async_long"][2] == runs["async"][2], (runs["async_long"][2], runs["async"][2])
-    for mode in ("sync", "overflow"):
+    assert runs["graph"][1] == 2                                 # ... with graph replays (private stream, captured at step 2)
+    for mode in ("sync", "overflow", "graph"):
         for a, b in zip(runs["async"][0], runs[mode][0]):
             assert torch.equal(a, b), mode
 

@@ -26,7 +26,8 @@ def _run(exe, case, **env):
 
 
 @pytest.mark.parametrize("case", ["ok", "pinned_before_sync", "pinned_reuse", "missing_wait", "event_wait_ok", "zero_grid",
-                                  "grid_y", "smem_optin", "legacy_stream"])
+                                  "grid_y", "smem_optin", "legacy_stream", "graph_ok", "graph_legacy",
+                                  "graph_sync_inside"])
 def test_strict_emulator_exposes(exe, case):
     r = _run(exe, case)
     assert r.returncode == 0, r.stderr

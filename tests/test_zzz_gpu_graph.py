@@ -1,0 +1,11 @@
+"""GPU: the opt-in CUDA-graph replay of the device engine's force evaluations (MDG_GNN_GRAPH=1) - first hardware run pending.
+Kept in the file that sorts LAST, so that `-x` reaches every other GPU test first."""
+import pytest
+
+import bonded_checks as B
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_fold_force_field_graph_replay():
+    B.check_fold_force_field_graph_replay("cuda")

@@ -37,6 +37,9 @@ echo "== 5. SchNet MD (configs[2] / configs[4] shapes)" | tee -a gpurun_out/r2_s
 timeout 300 python tools/schnet_md_bench.py --config water --route engine  2>&1 | tail -1 | tee -a gpurun_out/r2_summary.txt
 timeout 300 python tools/schnet_md_bench.py --config water --route oplevel 2>&1 | tail -1 | tee -a gpurun_out/r2_summary.txt
 timeout 600 python tools/schnet_md_bench.py --config si --route engine     2>&1 | tail -1 | tee -a gpurun_out/r2_summary.txt
+echo "== 5b. SchNet MD: synchronous vs asynchronous vs graph-replay steps" | tee -a gpurun_out/r2_summary.txt
+MDG_GNN_SYNC=1 timeout 300 python tools/schnet_md_bench.py --config water --route engine 2>&1 | tail -1 | sed 's/^/sync : /' | tee -a gpurun_out/r2_summary.txt
+MDG_GNN_GRAPH=1 timeout 300 python tools/schnet_md_bench.py --config water --route engine 2>&1 | tail -1 | sed 's/^/graph: /' | tee -a gpurun_out/r2_summary.txt
 echo "== 6. tcgen05 dense layers: first execution ever, under timeouts" | tee -a gpurun_out/r2_summary.txt
 timeout 200 python tools/tc_check.py simt gpurun_out/r2_simt.npz 2>&1 | tail -2 | tee -a gpurun_out/r2_summary.txt
 MDG_SCHNET_TC=1 timeout 120 python tools/tc_check.py tc gpurun_out/r2_tc.npz 2>&1 | tail -4 | tee -a gpurun_out/r2_summary.txt
