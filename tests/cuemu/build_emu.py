@@ -187,6 +187,20 @@ def build(verbose=False):
     return LIB
 
 
+def build_fake_nccl():
+    """tests/cuemu/fake_nccl.cpp -> _build/libfakenccl.so (NCCL over shared memory between emulated ranks, tests/test_emu_dist.py)"""
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "libfakenccl.so")
+    src = os.path.join(HERE, "fake_nccl.cpp")
+    if os.path.exists(lib) and os.path.getmtime(lib) >= os.path.getmtime(src):
+        return lib
+    r = subprocess.run([CXX, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", src, "-o", lib, "-ldl", "-lrt", "-lpthread"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("fake_nccl build failed:\n" + r.stdout + r.stderr)
+    return lib
+
+
 def build_selftest():
     """tests/cuemu/selftest.cu -> _build/selftest (the emulator checking itself, tests/test_emu_selftest.py)"""
     os.makedirs(OUT, exist_ok=True)

@@ -329,6 +329,7 @@ template <typename F> inline cudaError_t func_set_attr2(const char* call_text, F
 extern "C" {
 int  cuemu_api_return(void* user_stream);   // synchronise the caller's stream; returns the number of OTHER streams with pending work
 void cuemu_flush_all();
+void cuemu_enqueue_host_fn(void* stream, void (*fn)(void*), void* arg);
 int  cuemu_strict();
 long cuemu_counter(int which);              // 0 launches run, 1 launches rejected, 2 ops deferred past their enqueue call, 3 host-blocking synchronisations
 }

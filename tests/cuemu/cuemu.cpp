@@ -713,6 +713,10 @@ int cuemu_api_return(void* user_stream) {
     return left;
 }
 void cuemu_flush_all() { flush_all(); }
+// a host function as a stream operation (used by tests/cuemu/fake_nccl.cpp: communication calls are stream-ordered)
+void cuemu_enqueue_host_fn(void* stream, void (*fn)(void*), void* arg) {
+    enqueue(stream_of((cudaStream_t)stream), [fn, arg]() { fn(arg); });
+}
 int  cuemu_strict() { return strict() ? 1 : 0; }
 long cuemu_counter(int which) { return which >= 0 && which < 4 ? g_counters[which] : -1; }
 }

@@ -56,7 +56,7 @@ def load():
     if _emu is None:
         sys.path.insert(0, os.path.join(ROOT, "tests", "cuemu"))
         import build_emu
-        _emu = _AsyncBoundary(L.bind(ctypes.CDLL(build_emu.build())))
+        _emu = _AsyncBoundary(L.bind(ctypes.CDLL(build_emu.build(), mode=ctypes.RTLD_GLOBAL)))   # (global: fake_nccl resolves cuemu_* hooks)
     return _emu
 
 
