@@ -350,6 +350,42 @@ def schnet_energy(sd, z, xyz, nbr, offsets, cell=None, pbc_mode="reference"):
 # ----------------------------------------------------------------------------
 # synthetic systems (SURVEY 8d generators; numpy default_rng(seed))
 # ----------------------------------------------------------------------------
+# ----------------------------------------------------------------------------
+# bonded / electrostatic Stack members  (reference torchmd/interface.py:406-510, :303-361)
+# ----------------------------------------------------------------------------
+def image_offsets(vecs, cell3):
+    """get_offsets (reference torchmd/topology.py:74-80): -(v >= L/2) + (v < -L/2)"""
+    return -vecs.ge(0.5 * cell3).to(F32) + vecs.lt(-0.5 * cell3).to(F32)
+
+
+def bond_energy(xyz, top, cell3, k, ro):
+    """BondPotentials.forward (interface.py:444-451): 0.5 k sum (|v|^2 - ro)^2 - the SQUARED length is compared with ro"""
+    v = xyz[top[:, 0]] - xyz[top[:, 1]]
+    v = v + image_offsets(v, cell3) * cell3
+    return 0.5 * k * (v.pow(2).sum(-1) - ro).pow(2).sum(-1)
+
+
+def angle_energy(xyz, top, cell3, k, theta0):
+    """AnglePotentials.forward (interface.py:497-510)"""
+    v1 = xyz[top[:, 0]] - xyz[top[:, 1]]
+    v2 = xyz[top[:, 2]] - xyz[top[:, 1]]
+    v1 = v1 + image_offsets(v1, cell3) * cell3
+    v2 = v2 + image_offsets(v2, cell3) * cell3
+    cos = (v1 * v2).sum(-1) / (v1.pow(2).sum(-1) * v2.pow(2).sum(-1)).sqrt()
+    return 0.5 * k * (torch.acos(cos) - theta0).pow(2).sum(-1)
+
+
+def coulomb_energy(xyz, charges, cell3, cutoff, conversion, ex_pairs=None):
+    """Electrostatics.forward (interface.py:347-360) INCLUDING its overwritten first charge: U = -conv sum q_j^2 / r over the
+    minimum-image list (rebuilt at the call)"""
+    nbr, dis, _ = neighbor_list(xyz, cutoff, cell3, ex_pairs=ex_pairs, get_dis=True)
+    # differentiable distances over the (constant) list
+    off = neighbor_list(xyz.detach(), cutoff, cell3, ex_pairs=ex_pairs)[1]
+    r = pair_distance(xyz, nbr, off, cell3).squeeze(-1)
+    qj = charges[nbr[:, 1]]
+    return (-conversion * (qj * qj / r)).sum()
+
+
 def fcc_positions(ncell, a):
     """FCC lattice, unit cells in (i outer, j, k inner) order, basis innermost - the ASE
     FaceCenteredCubic ordering."""

@@ -121,3 +121,26 @@ def test_known_answers_fcc500():
     assert abs(e.item() - (-3386.684)) < 2e-3
     ec, _ = C.lj_forces(xyz.numpy(), cell.numpy(), 2.5)
     assert abs(ec - (-3386.684)) < 2e-3
+
+
+def test_bonded_members_vs_reference_fixture():
+    """oracle restatement of BondPotentials / AnglePotentials / Electrostatics against the reference's outputs
+    (tests/golden/bonded_chain.npz, oracle/make_golden.py --bonded)"""
+    from mdgrad_b200._ase_compat import wrap_positions
+    g = _load("bonded_chain.npz")
+    cell = torch.tensor(g["cell"], dtype=torch.float32)
+    kb, ro, ka, th0 = [float(x) for x in g["params"]]
+    bt, at = torch.tensor(g["bond_top"]), torch.tensor(g["angle_top"])
+    raw = torch.tensor(g["positions"], dtype=torch.float32)
+    wrap = torch.tensor(wrap_positions(g["positions"], np.diag(g["cell"])), dtype=torch.float32)
+    for tag, x in (("raw", raw), ("wrap", wrap)):
+        for name, fn, args in (("bond", O.bond_energy, (bt, cell, kb, ro)), ("angle", O.angle_energy, (at, cell, ka, th0))):
+            q = x.clone().requires_grad_(True)
+            e = fn(q, *args)
+            f = -torch.autograd.grad(e, q)[0]
+            assert e.item() == float(g["e_%s_%s" % (name, tag)])                       # same ops, same bits
+            assert np.array_equal(f.numpy(), g["f_%s_%s" % (name, tag)])
+    q = wrap.clone().requires_grad_(True)
+    e = O.coulomb_energy(q, torch.tensor(g["charges"]), cell, 2.5, float(g["coul_conversion"]), ex_pairs=g["bond_top"])
+    np.testing.assert_allclose(e.item(), float(g["e_coul"]), rtol=2e-6)
+    np.testing.assert_allclose((-torch.autograd.grad(e, q)[0]).numpy(), g["f_coul"], rtol=1e-5, atol=1e-5 * np.abs(g["f_coul"]).max())
