@@ -1,5 +1,5 @@
 """One emulated RANK of the slab-decomposed engine (TEST INFRASTRUCTURE, spawned by tests/test_emu_dist.py):
-    python tests/emu_dist_worker.py <rank> <world> <id_file> <out.npz> [nsteps]
+    python tests/emu_dist_worker.py <rank> <world> <id_file> <out.npz> [nsteps [rebuild_every [velocity_scale]]]
 Loads the CPU-emulated library (tests/cuemu), joins the fake NCCL communicator (tests/cuemu/fake_nccl.cpp, shared memory
 between the rank processes) and runs mdg_md_run on the common box; world == 1 runs the single-device engine."""
 import ctypes
@@ -33,8 +33,11 @@ def system(nx=9, nz=14, seed=1):
 def main():
     rank, world, id_file, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
     nsteps = int(sys.argv[5]) if len(sys.argv) > 5 else 12
+    K0 = int(sys.argv[6]) if len(sys.argv) > 6 else 4            # requested rebuild interval
+    vscale = float(sys.argv[7]) if len(sys.argv) > 7 else 1.0
     lib = emu_lib.load()
     pos, vel, L = system()
+    vel = (vel * vscale).astype(np.float32)
     n = pos.shape[0]
     p = _lib.MdParams()
     p.integrator = _lib.INT_NHC
@@ -50,7 +53,7 @@ def main():
     p.T = 1.0
     p.ndof = 3 * n
     p.skin = SKIN
-    p.rebuild_every = 4
+    p.rebuild_every = K0
     p.traj_stride = 3
     t = [float(np.float32(0.002 * i)) for i in range(nsteps + 1)]
     ctx = emu_lib.EmuContext()

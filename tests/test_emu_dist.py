@@ -13,11 +13,12 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(world, tmp, nsteps):
-    idf = os.path.join(tmp, "id_%d" % world)
-    outs = [os.path.join(tmp, "w%d_r%d.npz" % (world, r)) for r in range(world)]
+def _run(world, tmp, nsteps, K=4, vscale=1.0):
+    idf = os.path.join(tmp, "id_%d_%d" % (world, K))
+    outs = [os.path.join(tmp, "w%d_r%d_k%d.npz" % (world, r, K)) for r in range(world)]
     env = dict(os.environ, FAKE_NCCL_TIMEOUT="150")
-    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "emu_dist_worker.py"), str(r), str(world), idf, outs[r], str(nsteps)],
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "emu_dist_worker.py"), str(r), str(world), idf, outs[r], str(nsteps),
+                               str(K), str(vscale)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
     logs = []
     for p in procs:
@@ -57,3 +58,16 @@ def test_emu_slab_engine_matches_single_device(world, tmp_path):
     for r in ranks[1:]:
         assert np.array_equal(r["tpv"], ranks[0]["tpv"]) and float(r["e"]) == float(ranks[0]["e"])
     assert int(ranks[0]["rebuilds"]) >= 2      # the run crossed at least one distributed (local) rebuild
+
+
+def test_emu_slab_engine_skin_retry_is_collective(tmp_path):
+    """A rebuild interval that violates the skin criterion: the violation flag is max-all-reduced, so ALL ranks halve K and
+    repeat the epoch together (a rank deciding alone would deadlock the halo exchange - the fake NCCL would time out)."""
+    nsteps = 16
+    single = _run(1, str(tmp_path), nsteps, K=16, vscale=3.0)[0]
+    ranks = _run(2, str(tmp_path), nsteps, K=16, vscale=3.0)
+    assert int(single["K"]) < 16 and all(int(r["K"]) == int(ranks[0]["K"]) for r in ranks) and int(ranks[0]["K"]) < 16
+    tq = sum(r["tq"] for r in ranks)
+    assert np.abs(tq - single["tq"]).max() / 15.0 < 5e-6
+    for r in ranks[1:]:
+        assert np.array_equal(r["tpv"], ranks[0]["tpv"])
