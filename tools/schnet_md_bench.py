@@ -85,6 +85,8 @@ def main():
     print(json.dumps({"workload": label, "route": args.route, "tc": os.environ.get("MDG_SCHNET_TC") == "1", "steps": steps,
                       "steps_per_s": steps / el, "ns_per_day": steps / el * (dt / units.fs) * 1e-6 * 86400,
                       "edges": int(gnn.inputs["nbr_list"].shape[0]), "launches_per_step": (st.get("launches", 0) or 0) / max(1, steps),
+                      "engine_mode": {0: "synchronous", 1: "asynchronous", 2: "asynchronous + graph replay"}.get(st.get("maxrow_or_K"), None)
+                      if args.route == "engine" else None,
                       "finite": bool(torch.isfinite(q).all())}))
 
 
