@@ -322,3 +322,26 @@ def test_pair_tab_is_the_not_a_knot_cubic_spline():
     with torch.no_grad():
         p.tab.copy_(torch.randn(12))
     torch.testing.assert_close(p(p.x[:, None]).squeeze(-1), p.tab.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_3xtf32_split_reaches_fp32_parity_model():
+    """Numerical model of the tcgen05 dense-layer design (csrc/schnet_tc.cuh): x = hi + lo with hi = tf32(x), lo = tf32(x - hi),
+    A B ~ Ah Bh + Ah Bl + Al Bh accumulated in fp32.  On SchNet-sized layers (K = 512) the result must sit within the 1e-5
+    parity bar of the fp32 product, while a single TF32 product does not - which is why the kernel issues three MMAs."""
+    def tf32(x):                                    # cvt.rna.tf32.f32: round to nearest, ties away, 10 explicit mantissa bits
+        b = x.view(np.uint32).astype(np.uint64)
+        b = (b + 0x1000) & 0xFFFFE000
+        return b.astype(np.uint32).view(np.float32)
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((256, 512)).astype(np.float32)
+    B = (rng.standard_normal((512, 256)) / np.sqrt(512)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    Ah, Bh = tf32(A), tf32(B)
+    Al, Bl = tf32(A - Ah), tf32(B - Bh)
+    one = (Ah @ Bh).astype(np.float32)
+    three = (Ah @ Bh + Ah @ Bl + Al @ Bh).astype(np.float32)
+    scale = np.abs(ref).max()
+    assert np.abs(one - ref).max() / scale > 1e-4                    # a single TF32 pass misses the bar by > 10x
+    assert np.abs(three - ref).max() / scale < 2e-6                  # the 3-pass split is at fp32 accumulation noise
+    fp32 = (A @ B)
+    assert np.abs(three - ref).max() < 4 * np.abs(fp32 - ref).max() + 1e-7 * scale
