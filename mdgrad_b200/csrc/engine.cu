@@ -758,7 +758,7 @@ __global__ void k_gnn_sum_forces(int n, const float* __restrict__ f3, const floa
     f4[i] = make_float4(fx, fy, fz, 0.f);
 }
 
-int mdg_i_nbr_build_async(mdg_ctx* c, const float* d_xyz, int n, const float* h_cell3, double cutoff, const uint8_t* d_sel_a,
+int mdg_i_nbr_build_async(mdg_ctx* c, const float* d_xyz, const float4* d_q4, int n, const float* h_cell3, double cutoff, const uint8_t* d_sel_a,
                           const uint8_t* d_sel_b, const int64_t* d_ex_keys, int n_ex, bool want_export, int64_t cap_pairs,
                           int64_t* d_nbr, float* d_offsets, cudaStream_t st);
 int mdg_i_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, const int64_t* d_z, const float* d_xyz, int n,
@@ -793,7 +793,7 @@ static int gnn_force(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_mo
                                             d_e_gnn, f3, (void*)st));
             if (pairs_out) *pairs_out = P;
         } else {
-            MDG_TRY(mdg_i_nbr_build_async(c, xyz, n, p->cell, p->cutoff, nullptr, nullptr, p->d_ex_keys, p->n_ex, true, cap_pairs,
+            MDG_TRY(mdg_i_nbr_build_async(c, xyz, q4, n, p->cell, p->cutoff, nullptr, nullptr, p->d_ex_keys, p->n_ex, true, cap_pairs,
                                           c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), st));
             MDG_TRY(mdg_i_schnet_energy_force(c, model, d_z, xyz, n, c->gnn_nbr.as<int64_t>(), c->gnn_off.as<float>(), cap_pairs,
                                               c->flags.as<int>() + 4, p->off_scale, d_e_gnn, f3, (void*)st));
@@ -808,7 +808,7 @@ static int gnn_force(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet_mo
             int64_t Pk = 0;
             MDG_TRY(mdg_nbr_build(R.ctx, xyz, n, p->cell, R.cutoff, R.d_sel_a, R.d_sel_b, R.d_ex_keys, R.n_ex, (void*)st, &Pk));
         } else {    // the force kernel streams the member's rows: no export, no count
-            MDG_TRY(mdg_i_nbr_build_async(R.ctx, xyz, n, p->cell, R.cutoff, R.d_sel_a, R.d_sel_b, R.d_ex_keys, R.n_ex, false, 0,
+            MDG_TRY(mdg_i_nbr_build_async(R.ctx, xyz, q4, n, p->cell, R.cutoff, R.d_sel_a, R.d_sel_b, R.d_ex_keys, R.n_ex, false, 0,
                                           nullptr, nullptr, st));
         }
         MDG_TRY(mdg_pair_force(R.ctx, R.kind, R.params, R.n_params, xyz, n, nullptr, fp3 + (size_t)k * 3 * n, nullptr, (void*)st));

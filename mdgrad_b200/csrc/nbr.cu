@@ -54,8 +54,9 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* smem, int& total
     return wbase + x - v;
 }
 
+// single_total != nullptr (one-tile scans only): the grand total is written here and no second kernel is needed
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int* __restrict__ in, int* __restrict__ out,
-                                                            int* __restrict__ tile_tot, int n) {
+                                                            int* __restrict__ tile_tot, int n, int* __restrict__ single_total) {
     __shared__ int sm[32];
     int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
@@ -72,7 +73,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int* __restri
         if (base + k < n) out[base + k] = ex;
         ex += v[k];
     }
-    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+    if (threadIdx.x == 0) {
+        tile_tot[blockIdx.x] = tot;
+        if (single_total) *single_total = tot;
+    }
 }
 
 __global__ void __launch_bounds__(1024) k_scan_totals(int* __restrict__ tile_tot, int ntiles, int* __restrict__ grand) {
@@ -112,10 +116,15 @@ int mdg_i_scan_exclusive(mdg_ctx* c, const int* d_in, int* d_out, int n, int* d_
     int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     MDG_TRY(c->scan_tmp.reserve(sizeof(int) * (size_t)(ntiles + 1)));
     int* tt = c->scan_tmp.as<int>();
-    k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(d_in, d_out, tt, n);
-    k_scan_totals<<<1, 1024, 0, st>>>(tt, ntiles, d_total);
-    if (ntiles > 1) k_scan_add<<<ntiles, SCAN_THREADS, 0, st>>>(d_out, tt, n);
-    c->stat_launches += 2 + (ntiles > 1);
+    if (ntiles == 1) {          // small arrays (SchNet-sized systems): one launch
+        k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(d_in, d_out, tt, n, d_total);
+        c->stat_launches += 1;
+    } else {
+        k_scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(d_in, d_out, tt, n, nullptr);
+        k_scan_totals<<<1, 1024, 0, st>>>(tt, ntiles, d_total);
+        k_scan_add<<<ntiles, SCAN_THREADS, 0, st>>>(d_out, tt, n);
+        c->stat_launches += 3;
+    }
     MDG_KERNEL_CHECK();
     return MDG_OK;
 }
@@ -776,7 +785,8 @@ __global__ void k_latch(int* __restrict__ flags, int check_total, int64_t cap_pa
     }
 }
 
-int mdg_i_nbr_build_async(mdg_ctx* c, const float* d_xyz, int n, const float* h_cell3, double cutoff, const uint8_t* d_sel_a,
+// d_q4 (optional): the same positions already packed as float4 with w = atom id (the engine's state) - saves the pack kernel
+int mdg_i_nbr_build_async(mdg_ctx* c, const float* d_xyz, const float4* d_q4, int n, const float* h_cell3, double cutoff, const uint8_t* d_sel_a,
                           const uint8_t* d_sel_b, const int64_t* d_ex_keys, int n_ex, bool want_export, int64_t cap_pairs,
                           int64_t* d_nbr, float* d_offsets, cudaStream_t st) {
     c->sel_a = d_sel_a;
@@ -786,7 +796,7 @@ int mdg_i_nbr_build_async(mdg_ctx* c, const float* d_xyz, int n, const float* h_
     c->rows_wanted = true;
     c->fast_build = false;       // exact membership, as mdg_nbr_build
     c->stat_launches = 0;
-    MDG_TRY(mdg_i_build_list(c, d_xyz, nullptr, n, h_cell3, cutoff, cutoff, st));
+    MDG_TRY(mdg_i_build_list(c, d_xyz, d_q4, n, h_cell3, cutoff, cutoff, st));
     if (n == 0) return MDG_OK;
     if (want_export) {
         MDG_TRY(c->up_cnt.reserve(sizeof(int) * (size_t)(n + 1)));
