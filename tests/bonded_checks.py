@@ -211,3 +211,19 @@ def check_fold_force_field_graph_replay(dev):
         os.environ.pop("MDG_GNN_GRAPH", None)
         if old is not None:
             os.environ["MDG_GNN_GRAPH"] = old
+
+
+def check_fold_engine_sync_equals_async(dev):
+    """the epoch with a pair-count read-back per list build (MDG_GNN_SYNC=1) and the default asynchronous epoch: same bits"""
+    old = os.environ.pop("MDG_GNN_SYNC", None)
+    try:
+        integ, v, q, pv, g = _fold_sim(dev, engine=True)
+        assert integ.last_engine_stats["maxrow_or_K"] == 1, "the default epoch did not complete on the asynchronous path"
+        os.environ["MDG_GNN_SYNC"] = "1"
+        integ2, v2, q2, pv2, _ = _fold_sim(dev, engine=True)
+        assert integ2.last_engine_stats["maxrow_or_K"] == 0
+        assert np.array_equal(q, q2) and np.array_equal(v, v2) and np.array_equal(pv, pv2)
+    finally:
+        os.environ.pop("MDG_GNN_SYNC", None)
+        if old is not None:
+            os.environ["MDG_GNN_SYNC"] = old
