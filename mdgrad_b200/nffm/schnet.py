@@ -69,24 +69,44 @@ def scatter_add(src, index, dim=-1, out=None, dim_size=None, fill_value=0):
 
 
 class _CfconvAgg(torch.autograd.Function):
-    """agg[k] = sum_{e incident to k} h[other] * W[e]; backward through the same native operator."""
+    """agg[k] = sum_{e incident to k} h[other(e, k)] * W[e]   (bilinear in h and W).
+
+    Differentiable to ANY order on the native kernels: the gradient w.r.t. h is the same operator applied to the upstream
+    gradient, the gradient w.r.t. W is _CfconvEdgeGrad, whose own gradients are this operator again - backward calls
+    `.apply`, so a double-backward graph (the adjoint solver's reverse sweep, sovlers.py:211-293 of the reference) records
+    native ops instead of the gather / multiply / scatter_add chain."""
 
     @staticmethod
     def forward(ctx, h, W, graph):
-        h32, W32 = h.detach().float().contiguous(), W.detach().float().contiguous()
-        out = graph.ctx.cfconv_agg(h32, W32)
-        ctx.save_for_backward(h32, W32)
+        out = graph.ctx.cfconv_agg(h.detach().float().contiguous(), W.detach().float().contiguous())
+        ctx.save_for_backward(h, W)
         ctx.graph = graph
         return out
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         h, W = ctx.saved_tensors
-        g = g.contiguous()
-        gh = ctx.graph.ctx.cfconv_agg(g, W) if ctx.needs_input_grad[0] else None
-        gW = ctx.graph.ctx.cfconv_edge_grad(h, g, W.shape[0]) if ctx.needs_input_grad[1] else None
+        gh = _CfconvAgg.apply(g, W, ctx.graph) if ctx.needs_input_grad[0] else None
+        gW = _CfconvEdgeGrad.apply(h, g, ctx.graph) if ctx.needs_input_grad[1] else None
         return gh, gW, None
+
+
+class _CfconvEdgeGrad(torch.autograd.Function):
+    """gW[e] = h[a0] * g[a1] + h[a1] * g[a0]   (bilinear in h and g); d/dh = agg(g, U), d/dg = agg(h, U)."""
+
+    @staticmethod
+    def forward(ctx, h, g, graph):
+        out = graph.ctx.cfconv_edge_grad(h.detach().float().contiguous(), g.detach().float().contiguous(), graph.nbr.shape[0])
+        ctx.save_for_backward(h, g)
+        ctx.graph = graph
+        return out
+
+    @staticmethod
+    def backward(ctx, U):
+        h, g = ctx.saved_tensors
+        dh = _CfconvAgg.apply(g, U, ctx.graph) if ctx.needs_input_grad[0] else None
+        dg = _CfconvAgg.apply(h, U, ctx.graph) if ctx.needs_input_grad[1] else None
+        return dh, dg, None
 
 
 class NativeGraph:
@@ -245,7 +265,8 @@ class SchNet(nn.Module):
         N = batch["num_atoms"].reshape(-1).tolist()
         a = batch["nbr_list"]
         offsets = batch.get("offsets", 0)
-        native = _lib.on_device(xyz) and not (self.second_order and torch.is_grad_enabled())
+        on_dev = _lib.on_device(xyz)
+        native = on_dev and not (self.second_order and torch.is_grad_enabled())
         if native and torch.is_tensor(offsets):
             # |x_i - x_j - offsets| : the distance kernel with a unit "cell" reproduces the reference's raw subtraction
             from ..topology import _PairDis
@@ -253,7 +274,9 @@ class SchNet(nn.Module):
         else:
             e = (xyz[a[:, 0]] - xyz[a[:, 1]] - offsets).pow(2).sum(1).sqrt()[:, None]
         r = self.atom_embed(r.long()).squeeze()
-        graph = self._graph_for(batch, r.shape[0]) if native else None
+        # the aggregation Functions are differentiable to any order (backward = the same native operators), so the native
+        # graph also serves the second-order route; only the distance op falls back to torch ops there
+        graph = self._graph_for(batch, r.shape[0]) if on_dev else None
         for conv in self.convolutions:
             r = r + conv(r=r, e=e, a=a, graph=graph)
         return r, N, xyz
