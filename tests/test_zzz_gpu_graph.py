@@ -9,3 +9,8 @@ pytestmark = pytest.mark.gpu
 
 def test_gpu_fold_force_field_graph_replay():
     B.check_fold_force_field_graph_replay("cuda")
+
+
+def test_gpu_schnet_second_order_through_native_aggregation():
+    import schnet_checks
+    schnet_checks.check_second_order_through_native_aggregation("cuda")
