@@ -102,7 +102,7 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
-if __name__ == "__main__" and "--schnet" not in sys.argv and "--bonded" not in sys.argv:
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--schnet", "--bonded", "--gnn-adjoint")):
     main()
 
 
@@ -238,7 +238,46 @@ def bonded_golden():
               "outside box:", int(((xyz0 < 0) | (xyz0 > 6.0)).any(1).sum()))
 
 
+def gnn_adjoint_golden():
+    """G6: the defining flow of BASELINE configs[4] at small size - SchNet + ExcludedVolume Stack, NoseHooverChain epoch with
+    adjoint=True, an RDF-based loss on the last frame, `.backward()` through the reference's adjoint solver
+    (torchmd/sovlers.py:196-293): gradients of every SchNet parameter."""
+    from mdgrad_b200._ase_compat import Diamond, units
+    with ref_import.active() as ref:
+        atoms = Diamond("Si", (2, 2, 2), 5.45933)
+        rng = np.random.default_rng(21)
+        atoms.set_positions(atoms.get_positions() + rng.normal(0, 0.08, (len(atoms), 3)))
+        system = ref.system.System(atoms, device="cpu")
+        np.random.seed(5)
+        system.set_temperature(600.0 * units.kB)
+        v0 = system.get_velocities().copy()
+        q0 = system.get_positions(wrap=True).copy()
+        gp = {"n_atom_basis": 24, "n_filters": 24, "n_gaussians": 12, "n_convolutions": 2, "cutoff": 4.9, "trainable_gauss": False}
+        torch.manual_seed(8)
+        schnet = ref.schnet.SchNet(gp)
+        gnn = ref.interface.GNNPotentials(system, schnet, cutoff=gp["cutoff"])
+        prior = ref.interface.PairPotentials(system, ref.potentials.ExcludedVolume(1.9, 0.015, 12), cutoff=4.9)
+        ff = ref.interface.Stack({"gnn": gnn, "prior": prior})
+        integ = ref.md.NoseHooverChain(ff, system, Q=50.0, T=600.0 * units.kB, num_chains=5, adjoint=True)
+        sim = ref.md.Simulations(system, integ, wrap=True, method="NH_verlet")
+        v, q, pv = sim.simulate(steps=6, frequency=6, dt=1.0 * units.fs)
+        obs = ref.observable.rdf(system, 30, (1.8, 4.9))
+        _, bins, g = obs(q[-1:])
+        loss = g.pow(2).sum() + 1e3 * (v[-1] ** 2).sum()
+        loss.backward()
+        out = {"numbers": system.get_atomic_numbers(), "cell": np.diag(system.get_cell()), "q0": q0, "v0": v0,
+               "traj_q": q.detach().numpy(), "traj_v": v.detach().numpy(), "rdf_g": g.detach().numpy(), "loss": loss.detach().numpy()}
+        out.update({("gnnp_" + k): np.array(val) for k, val in gp.items() if k != "trainable_gauss"})
+        out.update({("w_" + k): val.numpy() for k, val in schnet.state_dict().items()})
+        out.update({("g_" + k): p.grad.numpy() for k, p in schnet.named_parameters() if p.grad is not None})
+        np.savez_compressed(os.path.join(OUT, "gnn_adjoint.npz"), **out)
+        gn = float(sum((p.grad ** 2).sum() for p in schnet.parameters() if p.grad is not None) ** 0.5)
+        print("gnn adjoint: loss %.6f |grad| %.6e params with grad: %d" % (loss.item(), gn, sum(p.grad is not None for p in schnet.parameters())))
+
+
 if __name__ == "__main__" and "--schnet" in sys.argv:
     schnet_golden()
+if __name__ == "__main__" and "--gnn-adjoint" in sys.argv:
+    gnn_adjoint_golden()
 if __name__ == "__main__" and "--bonded" in sys.argv:
     bonded_golden()

@@ -49,3 +49,51 @@ def check_second_order_through_native_aggregation(dev):
         assert (a - b).abs().max().item() <= 5e-4 * max(1e-6, b.abs().max().item()), (name, (a - b).abs().max().item(), b.abs().max().item())
 
 
+
+
+def check_gnn_adjoint_fit_vs_reference_fixture(dev):
+    """BASELINE configs[4]'s flow at small size: Stack{SchNet, ExcludedVolume}, NoseHooverChain(adjoint=True) epoch on the device
+    engine, RDF-based loss on the last frame, `.backward()` through the adjoint solver - the gradient of EVERY SchNet parameter
+    against the reference's (tests/golden/gnn_adjoint.npz, oracle/make_golden.py --gnn-adjoint)"""
+    import os
+    import numpy as np
+    from nff.nn.models.schnet import SchNet
+    from torchmd.interface import GNNPotentials, PairPotentials, Stack
+    from torchmd.md import NoseHooverChain, Simulations
+    from torchmd.observable import rdf
+    from torchmd.potentials import ExcludedVolume
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms, units
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gnn_adjoint.npz"))
+    system = System(Atoms(numbers=g["numbers"], positions=g["q0"], cell=g["cell"], pbc=True), device=dev)
+    system.set_velocities(g["v0"])
+    params = {k[5:]: (float(g[k]) if k == "gnnp_cutoff" else int(g[k])) for k in g.files if k.startswith("gnnp_")}
+    params["trainable_gauss"] = False
+    model = SchNet(params)
+    model.load_state_dict({k[2:]: torch.tensor(g[k]) for k in g.files if k.startswith("w_")})
+    model = model.to(dev)
+    gnn = GNNPotentials(system, model, cutoff=params["cutoff"])
+    prior = PairPotentials(system, ExcludedVolume(1.9, 0.015, 12).to(dev), cutoff=4.9)
+    integ = NoseHooverChain(Stack({"gnn": gnn, "prior": prior}), system, Q=50.0, T=600.0 * units.kB, num_chains=5, adjoint=True).to(dev)
+    sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+    v, q, pv = sim.simulate(steps=6, frequency=6, dt=1.0 * units.fs)
+    assert integ.last_engine_stats is not None, "the forward epoch did not run on the device engine"
+    assert np.abs(q.detach().cpu().numpy() - g["traj_q"]).max() < 2e-5
+    assert np.abs(v.detach().cpu().numpy() - g["traj_v"]).max() < 2e-5 * max(1.0, np.abs(g["traj_v"]).max() * 1e2)
+    obs = rdf(system, 30, (1.8, 4.9))
+    _, bins, gr = obs(q[-1:])
+    np.testing.assert_allclose(gr.detach().cpu().numpy(), g["rdf_g"], rtol=2e-4, atol=2e-4 * g["rdf_g"].max())
+    loss = gr.pow(2).sum() + 1e3 * (v[-1] ** 2).sum()
+    assert abs(loss.item() - float(g["loss"])) <= 2e-4 * abs(float(g["loss"]))
+    loss.backward()
+    checked = 0
+    gnorm = float(np.sqrt(sum((g[k].astype(np.float64) ** 2).sum() for k in g.files if k.startswith("g_"))))
+    for name, p in model.named_parameters():
+        key = "g_" + name
+        if key not in g.files:
+            continue
+        assert p.grad is not None, name
+        err = np.abs(p.grad.detach().cpu().numpy() - g[key]).max()
+        assert err <= 1e-4 * max(np.abs(g[key]).max(), 1e-3 * gnorm), (name, err, np.abs(g[key]).max())      # measured: ~3e-7
+        checked += 1
+    assert checked >= 20

@@ -290,6 +290,11 @@ def test_emu_schnet_second_order_through_native_aggregation():
     schnet_checks.check_second_order_through_native_aggregation("cpu")
 
 
+def test_emu_gnn_adjoint_fit_vs_reference_fixture():
+    import schnet_checks
+    schnet_checks.check_gnn_adjoint_fit_vs_reference_fixture("cpu")
+
+
 def test_emu_angle_distribution_vs_live_reference():
     """angle_distribution (native neighbor list -> device-side triple enumeration -> smeared histogram) against the
     unmodified reference observable (authoring container only)"""

@@ -14,3 +14,8 @@ def test_gpu_fold_force_field_graph_replay():
 def test_gpu_schnet_second_order_through_native_aggregation():
     import schnet_checks
     schnet_checks.check_second_order_through_native_aggregation("cuda")
+
+
+def test_gpu_gnn_adjoint_fit_vs_reference_fixture():
+    import schnet_checks
+    schnet_checks.check_gnn_adjoint_fit_vs_reference_fixture("cuda")
