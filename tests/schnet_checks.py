@@ -97,3 +97,29 @@ def check_gnn_adjoint_fit_vs_reference_fixture(dev):
         assert err <= 1e-4 * max(np.abs(g[key]).max(), 1e-3 * gnorm), (name, err, np.abs(g[key]).max())      # measured: ~3e-7
         checked += 1
     assert checked >= 20
+
+
+def check_water_rdf_oo_species_selection(dev):
+    """BASELINE configs[2]'s observable: RDF(O-O) of the 64-water box through `rdf(..., index_tuple=(O, O))` - the RDF kernel's
+    species selection (no-grad path) and the differentiable path - against the oracle's restatement of observable.py:33-76"""
+    import os
+    import numpy as np
+    from oracle import oracle_torch as O
+    from torchmd.observable import rdf
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "schnet_water.npz"))
+    system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device=dev)
+    oxy = [int(i) for i in np.nonzero(g["numbers"] == 8)[0]]
+    hyd = [int(i) for i in np.nonzero(g["numbers"] == 1)[0]]
+    xyz = torch.Tensor(system.get_positions(wrap=True))
+    for sel in ((oxy, oxy), (oxy, hyd), None):
+        obs = rdf(system, 100, (1.8, 5.7), index_tuple=sel)
+        co, bo, go = O.rdf(xyz, [float(x) for x in g["cell"]], 100, (1.8, 5.7), index_tuple=sel)
+        c, b, gr = obs(xyz.to(dev))                                     # kernel path
+        torch.testing.assert_close(gr.cpu(), go, rtol=1e-5, atol=1e-5 * go.max().item())
+        x = xyz.to(dev).clone().requires_grad_(True)                     # differentiable path (fitting loss)
+        c2, _, gr2 = obs(x)
+        torch.testing.assert_close(gr2.detach().cpu(), go, rtol=2e-5, atol=2e-5 * go.max().item())
+        (gr2 ** 2).sum().backward()
+        assert torch.isfinite(x.grad).all() and float(x.grad.abs().max()) > 0

@@ -295,6 +295,11 @@ def test_emu_gnn_adjoint_fit_vs_reference_fixture():
     schnet_checks.check_gnn_adjoint_fit_vs_reference_fixture("cpu")
 
 
+def test_emu_water_rdf_oo_species_selection():
+    import schnet_checks
+    schnet_checks.check_water_rdf_oo_species_selection("cpu")
+
+
 def test_emu_angle_distribution_vs_live_reference():
     """angle_distribution (native neighbor list -> device-side triple enumeration -> smeared histogram) against the
     unmodified reference observable (authoring container only)"""
