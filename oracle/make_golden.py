@@ -102,7 +102,7 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--schnet", "--bonded", "--gnn-adjoint")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--schnet", "--bonded", "--gnn-adjoint", "--generic")):
     main()
 
 
@@ -275,6 +275,35 @@ def gnn_adjoint_golden():
         print("gnn adjoint: loss %.6f |grad| %.6e params with grad: %d" % (loss.item(), gn, sum(p.grad is not None for p in schnet.parameters())))
 
 
+def generic_route_golden():
+    """G7: the configurations that stay on the op-level solver - stale lists (topology_update_freq = 3) and method='rk4' -
+    on the C1 box, through the reference's Simulations.simulate."""
+    with ref_import.active() as ref:
+        out = {}
+        for tag, kw, method, steps, dt in (("freq3", dict(topology_update_freq=3), "NH_verlet", 13, 0.01),
+                                           ("rk4", dict(topology_update_freq=1), "rk4", 9, 0.005)):
+            atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+            system = ref.system.System(atoms, device="cpu")
+            np.random.seed(2)
+            system.set_temperature(1.2)
+            out["v0"] = system.get_velocities().copy()
+            out["q0"] = system.get_positions(wrap=True).copy()
+            lj = ref.potentials.LennardJones(1.0, 1.0)
+            pair = ref.interface.PairPotentials(system, lj, cutoff=2.5)
+            integ = ref.md.NoseHooverChain(pair, system, T=1.0, num_chains=3, Q=50.0, adjoint=True, **kw)
+            sim = ref.md.Simulations(system, integ, wrap=True, method=method)
+            v, q, pv = sim.simulate(steps=steps, frequency=steps, dt=dt)
+            loss = (q[-1] ** 2).sum() + pv[-1].sum()
+            loss.backward()
+            out.update({"v_" + tag: v.detach().numpy(), "q_" + tag: q.detach().numpy(), "pv_" + tag: pv.detach().numpy(),
+                        "dsigma_" + tag: lj.sigma.grad.numpy(), "depsilon_" + tag: lj.epsilon.grad.numpy(),
+                        "update_count_" + tag: np.array(integ.update_count)})
+        np.savez_compressed(os.path.join(OUT, "c1_generic.npz"), **out)
+        print("generic route:", {k: v.shape for k, v in out.items() if k.startswith("q_")}, out["dsigma_freq3"], out["dsigma_rk4"])
+
+
+if __name__ == "__main__" and "--generic" in sys.argv:
+    generic_route_golden()
 if __name__ == "__main__" and "--schnet" in sys.argv:
     schnet_golden()
 if __name__ == "__main__" and "--gnn-adjoint" in sys.argv:

@@ -227,3 +227,34 @@ def check_fold_engine_sync_equals_async(dev):
         os.environ.pop("MDG_GNN_SYNC", None)
         if old is not None:
             os.environ["MDG_GNN_SYNC"] = old
+
+
+def check_generic_route_configs(dev):
+    """The configurations that stay on the op-level solver: stale lists (topology_update_freq = 3: the list is rebuilt at every
+    third EVALUATION, reference md.py:200-204) and method='rk4'; trajectories and adjoint gradients against the reference
+    (tests/golden/c1_generic.npz, oracle/make_golden.py --generic)"""
+    from torchmd.interface import PairPotentials
+    from torchmd.potentials import LennardJones
+    from torchmd.md import NoseHooverChain, Simulations
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    g = np.load(os.path.join(G, "c1_generic.npz"))
+    for tag, kw, method, steps, dt in (("freq3", dict(topology_update_freq=3), "NH_verlet", 13, 0.01),
+                                       ("rk4", dict(topology_update_freq=1), "rk4", 9, 0.005)):
+        system = System(FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True), device=dev)
+        system.set_positions(g["q0"])
+        system.set_velocities(g["v0"])
+        lj = LennardJones(1.0, 1.0).to(dev)
+        integ = NoseHooverChain(PairPotentials(system, lj, cutoff=2.5), system, T=1.0, num_chains=3, Q=50.0, adjoint=True, **kw).to(dev)
+        sim = Simulations(system, integ, wrap=True, method=method)
+        v, q, pv = sim.simulate(steps=steps, frequency=steps, dt=dt)
+        assert np.abs(q.detach().cpu().numpy() - g["q_" + tag]).max() < 2e-5, tag
+        assert np.abs(v.detach().cpu().numpy() - g["v_" + tag]).max() < 2e-4, tag
+        assert np.abs(pv.detach().cpu().numpy() - g["pv_" + tag]).max() < 2e-3, tag
+        loss = (q[-1] ** 2).sum() + pv[-1].sum()
+        loss.backward()
+        for name, got in (("dsigma_", lj.sigma.grad), ("depsilon_", lj.epsilon.grad)):
+            ref = float(g[name + tag][0])
+            assert abs(got.item() - ref) <= 5e-3 * abs(ref), (tag, name, got.item(), ref)
+        # number of force evaluations (and with it the list-rebuild cadence) of forward + reverse sweep, as the reference
+        assert integ.update_count == int(g["update_count_" + tag]), (tag, integ.update_count, int(g["update_count_" + tag]))
