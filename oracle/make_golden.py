@@ -298,6 +298,22 @@ def generic_route_golden():
             out.update({"v_" + tag: v.detach().numpy(), "q_" + tag: q.detach().numpy(), "pv_" + tag: pv.detach().numpy(),
                         "dsigma_" + tag: lj.sigma.grad.numpy(), "depsilon_" + tag: lj.epsilon.grad.numpy(),
                         "update_count_" + tag: np.array(integ.update_count)})
+        # temperature-conditioned learned pair potential (TPairPotentials + TpairMLP, interface.py:139-215, potentials.py:208-217)
+        # and the plain learned one (pairMLP) on the same jittered box: energies, forces, every weight
+        atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+        system = ref.system.System(atoms, device="cpu")
+        rng = np.random.default_rng(13)
+        xyz = torch.tensor(system.get_positions() + rng.normal(0, 0.06, (108, 3)), dtype=torch.float32)
+        torch.manual_seed(6)
+        mlp_args = dict(n_gauss=12, r_start=0.0, r_end=2.5, n_layers=2, n_width=16, nonlinear="ELU")
+        tnet = ref.potentials.TpairMLP(**mlp_args)
+        tp = ref.interface.TPairPotentials(system, tnet, T=1.3, cutoff=2.5)
+        tp._reset_topology(xyz)
+        q = xyz.clone().requires_grad_(True)
+        e = tp(q)
+        out["tpair_xyz"], out["tpair_e"] = xyz.numpy(), e.detach().numpy()
+        out["tpair_f"] = (-torch.autograd.grad(e, q)[0]).numpy()
+        out.update({("tw_" + k): v.numpy() for k, v in tnet.state_dict().items()})
         np.savez_compressed(os.path.join(OUT, "c1_generic.npz"), **out)
         print("generic route:", {k: v.shape for k, v in out.items() if k.startswith("q_")}, out["dsigma_freq3"], out["dsigma_rk4"])
 

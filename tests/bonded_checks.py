@@ -258,3 +258,26 @@ def check_generic_route_configs(dev):
             assert abs(got.item() - ref) <= 5e-3 * abs(ref), (tag, name, got.item(), ref)
         # number of force evaluations (and with it the list-rebuild cadence) of forward + reverse sweep, as the reference
         assert integ.update_count == int(g["update_count_" + tag]), (tag, integ.update_count, int(g["update_count_" + tag]))
+
+
+def check_tpair_potentials_vs_reference_fixture(dev):
+    """TPairPotentials + TpairMLP (temperature-conditioned learned pair potential, reference interface.py:139-215,
+    potentials.py:208-217): the reference's state_dict loads unchanged; energy and forces through the native list and
+    distance op"""
+    from torchmd.interface import TPairPotentials
+    from torchmd.potentials import TpairMLP
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    g = np.load(os.path.join(G, "c1_generic.npz"))
+    system = System(FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True), device=dev)
+    net = TpairMLP(n_gauss=12, r_start=0.0, r_end=2.5, n_layers=2, n_width=16, nonlinear="ELU")
+    missing = net.load_state_dict({k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("tw_")}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    tp = TPairPotentials(system, net.to(dev), T=1.3, cutoff=2.5)
+    xyz = torch.tensor(g["tpair_xyz"]).to(dev)
+    tp._reset_topology(xyz)
+    q = xyz.clone().requires_grad_(True)
+    e = tp(q)
+    f = -torch.autograd.grad(e, q)[0]
+    _close(e.item(), g["tpair_e"], 2e-5)
+    _close(f.cpu().numpy(), g["tpair_f"], 2e-5)
