@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .sovlers import odeint, odeint_adjoint
+from .sovlers import odeint, odeint_adjoint, second_order
 from .system import HAVE_ASE
 
 if HAVE_ASE:  # pragma: no cover
@@ -125,9 +125,13 @@ class Simulations():
             if self.integrator.adjoint:
                 trajs = odeint_adjoint(self.integrator, states, t, method=self.solvemethod)
             else:
+                # adjoint=False: the whole trajectory goes on the autograd tape (reference md.py:84-88) and the forces on it
+                # are differentiated again by .backward() - so every interaction module records its twice-differentiable
+                # form while the epoch is integrated (the fused first-order kernels would cut the parameters off the tape)
                 for var in states:
                     var.requires_grad = True
-                trajs = odeint(self.integrator, tuple(states), t, method=self.solvemethod)
+                with second_order(self.integrator):
+                    trajs = odeint(self.integrator, tuple(states), t, method=self.solvemethod)
             nxt = self._device_check_point(trajs) if self.device_handoff else None
             if nxt is None:                           # reference order of operations, on the host
                 self._flush_log(pending)

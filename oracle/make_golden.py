@@ -276,12 +276,13 @@ def gnn_adjoint_golden():
 
 
 def generic_route_golden():
-    """G7: the configurations that stay on the op-level solver - stale lists (topology_update_freq = 3) and method='rk4' -
-    on the C1 box, through the reference's Simulations.simulate."""
+    """G7: the configurations that stay on the op-level solver - stale lists (topology_update_freq = 3), method='rk4' and
+    adjoint=False (the whole trajectory on the autograd tape) - on the C1 box, through the reference's Simulations.simulate."""
     with ref_import.active() as ref:
         out = {}
         for tag, kw, method, steps, dt in (("freq3", dict(topology_update_freq=3), "NH_verlet", 13, 0.01),
-                                           ("rk4", dict(topology_update_freq=1), "rk4", 9, 0.005)):
+                                           ("rk4", dict(topology_update_freq=1), "rk4", 9, 0.005),
+                                           ("tape", dict(topology_update_freq=1, adjoint=False), "NH_verlet", 7, 0.01)):
             atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
             system = ref.system.System(atoms, device="cpu")
             np.random.seed(2)
@@ -290,7 +291,8 @@ def generic_route_golden():
             out["q0"] = system.get_positions(wrap=True).copy()
             lj = ref.potentials.LennardJones(1.0, 1.0)
             pair = ref.interface.PairPotentials(system, lj, cutoff=2.5)
-            integ = ref.md.NoseHooverChain(pair, system, T=1.0, num_chains=3, Q=50.0, adjoint=True, **kw)
+            kw = dict(adjoint=True, **kw) if "adjoint" not in kw else kw
+            integ = ref.md.NoseHooverChain(pair, system, T=1.0, num_chains=3, Q=50.0, **kw)
             sim = ref.md.Simulations(system, integ, wrap=True, method=method)
             v, q, pv = sim.simulate(steps=steps, frequency=steps, dt=dt)
             loss = (q[-1] ** 2).sum() + pv[-1].sum()

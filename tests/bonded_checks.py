@@ -231,7 +231,8 @@ def check_fold_engine_sync_equals_async(dev):
 
 def check_generic_route_configs(dev):
     """The configurations that stay on the op-level solver: stale lists (topology_update_freq = 3: the list is rebuilt at every
-    third EVALUATION, reference md.py:200-204) and method='rk4'; trajectories and adjoint gradients against the reference
+    third EVALUATION, reference md.py:200-204), method='rk4', and adjoint=False (the whole trajectory on the autograd tape,
+    .backward() differentiates the forces again); trajectories and parameter gradients against the reference
     (tests/golden/c1_generic.npz, oracle/make_golden.py --generic)"""
     from torchmd.interface import PairPotentials
     from torchmd.potentials import LennardJones
@@ -239,13 +240,14 @@ def check_generic_route_configs(dev):
     from torchmd.system import System
     from mdgrad_b200._ase_compat import FaceCenteredCubic
     g = np.load(os.path.join(G, "c1_generic.npz"))
-    for tag, kw, method, steps, dt in (("freq3", dict(topology_update_freq=3), "NH_verlet", 13, 0.01),
-                                       ("rk4", dict(topology_update_freq=1), "rk4", 9, 0.005)):
+    for tag, kw, method, steps, dt in (("freq3", dict(topology_update_freq=3, adjoint=True), "NH_verlet", 13, 0.01),
+                                       ("rk4", dict(topology_update_freq=1, adjoint=True), "rk4", 9, 0.005),
+                                       ("tape", dict(topology_update_freq=1, adjoint=False), "NH_verlet", 7, 0.01)):
         system = System(FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True), device=dev)
         system.set_positions(g["q0"])
         system.set_velocities(g["v0"])
         lj = LennardJones(1.0, 1.0).to(dev)
-        integ = NoseHooverChain(PairPotentials(system, lj, cutoff=2.5), system, T=1.0, num_chains=3, Q=50.0, adjoint=True, **kw).to(dev)
+        integ = NoseHooverChain(PairPotentials(system, lj, cutoff=2.5), system, T=1.0, num_chains=3, Q=50.0, **kw).to(dev)
         sim = Simulations(system, integ, wrap=True, method=method)
         v, q, pv = sim.simulate(steps=steps, frequency=steps, dt=dt)
         assert np.abs(q.detach().cpu().numpy() - g["q_" + tag]).max() < 2e-5, tag
