@@ -87,3 +87,58 @@ def test_emu_simulations_matrix_vs_live_reference(k):
     assert set(ograds) == set(rgrads)
     for name in rgrads:
         assert np.abs(ograds[name] - rgrads[name]).max() <= 2e-3 * max(np.abs(rgrads[name]).max(), 1e-6), (name, ograds[name], rgrads[name])
+
+
+def _fit_case(ns, which, seed):
+    """short differentiable runs whose reverse sweep goes through autograd (no closed-form route): learned pair potential,
+    Stack of pair members; loss = RDF-based + state terms; returns outputs and all parameter gradients"""
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+    rng = np.random.default_rng(seed)
+    atoms.set_positions(atoms.get_positions() + rng.normal(0, 0.04, (108, 3)))
+    system = ns.system.System(atoms, device="cpu")
+    system.set_velocities(rng.standard_normal((108, 3)) * 0.8)
+    torch.manual_seed(seed)
+    if which == "mlp":
+        net = ns.potentials.pairMLP(n_gauss=10, r_start=0.0, r_end=2.5, n_layers=1, n_width=12, nonlinear="ELU")
+        prior = ns.potentials.ExcludedVolume(1.0, 1.0, 12)
+        model = ns.interface.Stack({"mlp": ns.interface.PairPotentials(system, net, cutoff=2.5),
+                                    "prior": ns.interface.PairPotentials(system, prior, cutoff=2.5)})
+        mods = [net, prior]
+    else:
+        a = ns.potentials.LennardJones(1.0, 0.6)
+        b = ns.potentials.ExcludedVolume(0.9, 0.4, 12)
+        A, B = list(range(0, 108, 2)), list(range(1, 108, 2))
+        model = ns.interface.Stack({"aa": ns.interface.PairPotentials(system, a, cutoff=2.5, index_tuple=(A, A)),
+                                    "ab": ns.interface.PairPotentials(system, b, cutoff=2.0, index_tuple=(A, B))})
+        mods = [a, b]
+    integ = ns.md.NoseHooverChain(model, system, T=1.0, num_chains=3, Q=50.0, adjoint=True)
+    sim = ns.md.Simulations(system, integ, wrap=True, method="NH_verlet")
+    v, q, pv = sim.simulate(steps=5, frequency=5, dt=0.005)
+    obs = ns.observable.rdf(system, 40, (0.8, 2.0))
+    _, _, g = obs(q[-1:])
+    loss = (g ** 2).sum() + (v[-1] ** 2).sum() + pv[-1].sum()
+    loss.backward()
+    grads = []
+    for m in mods:
+        grads += [p.grad.detach().numpy().copy() for p in m.parameters()]
+    return [x.detach().numpy() for x in (v, q, pv, g)], loss.item(), grads
+
+
+@pytest.mark.parametrize("which", ["mlp", "stack"])
+def test_emu_fit_flows_vs_live_reference(which):
+    import types
+    import torchmd
+    with ref_import.active() as ref:
+        rout, rloss, rgrads = _fit_case(ref, which, seed=7)
+    ours = types.SimpleNamespace(system=torchmd.system, interface=torchmd.interface, potentials=torchmd.potentials, md=torchmd.md,
+                                 observable=torchmd.observable)
+    oout, oloss, ograds = _fit_case(ours, which, seed=7)
+    for a, b in zip(oout, rout):
+        assert a.shape == b.shape and np.abs(a - b).max() <= 5e-5 * max(1.0, np.abs(b).max())
+    assert abs(oloss - rloss) <= 1e-4 * abs(rloss)
+    assert len(ograds) == len(rgrads) and len(rgrads) >= 4
+    gmax = max(np.abs(g).max() for g in rgrads)
+    for a, b in zip(ograds, rgrads):
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= 2e-3 * max(np.abs(b).max(), 1e-3 * gmax), (np.abs(a - b).max(), np.abs(b).max())
