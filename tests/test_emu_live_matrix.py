@@ -142,3 +142,42 @@ def test_emu_fit_flows_vs_live_reference(which):
     for a, b in zip(ograds, rgrads):
         assert a.shape == b.shape
         assert np.abs(a - b).max() <= 2e-3 * max(np.abs(b).max(), 1e-3 * gmax), (np.abs(a - b).max(), np.abs(b).max())
+
+
+def _optimisation_loop(ns, seed, iters=3):
+    """the loop of scripts/fit_rdf_pair.py in miniature: simulate -> RDF loss -> backward -> optimiser step, the simulation
+    CONTINUING from the log between iterations while the parameters change in place"""
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+    rng = np.random.default_rng(seed)
+    system = ns.system.System(atoms, device="cpu")
+    system.set_velocities(rng.standard_normal((108, 3)) * 0.8)
+    lj = ns.potentials.LennardJones(0.95, 1.1)
+    pair = ns.interface.PairPotentials(system, lj, cutoff=2.5)
+    integ = ns.md.NoseHooverChain(pair, system, T=1.0, num_chains=5, Q=50.0, adjoint=True)
+    sim = ns.md.Simulations(system, integ)
+    obs = ns.observable.rdf(system, 50, (0.8, 2.0))
+    target = torch.linspace(0.0, 1.5, 50)
+    opt = torch.optim.Adam(list(lj.parameters()), lr=0.01)
+    hist = []
+    for _ in range(iters):
+        v, q, pv = sim.simulate(8, dt=0.01, frequency=8)
+        _, _, g = obs(q[-2:])
+        loss = (g - target).pow(2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        hist.append((loss.item(), lj.sigma.item(), lj.epsilon.item()))
+    return np.array(hist), system.get_positions()
+
+
+def test_emu_optimisation_loop_vs_live_reference():
+    import types
+    import torchmd
+    with ref_import.active() as ref:
+        rh, rq = _optimisation_loop(ref, 11)
+    ours = types.SimpleNamespace(system=torchmd.system, interface=torchmd.interface, potentials=torchmd.potentials, md=torchmd.md,
+                                 observable=torchmd.observable)
+    oh, oq = _optimisation_loop(ours, 11)
+    np.testing.assert_allclose(oh, rh, rtol=2e-4)                 # losses and the parameter values after every Adam step
+    np.testing.assert_allclose(oq, rq, atol=1e-4)
