@@ -181,3 +181,50 @@ def test_emu_optimisation_loop_vs_live_reference():
     oh, oq = _optimisation_loop(ours, 11)
     np.testing.assert_allclose(oh, rh, rtol=2e-4)                 # losses and the parameter values after every Adam step
     np.testing.assert_allclose(oq, rq, atol=1e-4)
+
+
+def _gnn_optimisation_loop(ns, schnet_cls, seed, iters=3):
+    """demo/fit_rdf_gnn.py in miniature: SchNet + ExcludedVolume Stack, epochs continuing from the log, Adam steps on the
+    SchNet weights between them (the native weight cache of the engine must follow the in-place updates)"""
+    from mdgrad_b200._ase_compat import Diamond, units
+    atoms = Diamond("Si", (2, 2, 2), 5.45933)
+    rng = np.random.default_rng(seed)
+    atoms.set_positions(atoms.get_positions() + rng.normal(0, 0.08, (len(atoms), 3)))
+    system = ns.system.System(atoms, device="cpu")
+    system.set_velocities(rng.standard_normal((len(atoms), 3)) * 0.02)
+    torch.manual_seed(seed)
+    model = schnet_cls({"n_atom_basis": 16, "n_filters": 16, "n_gaussians": 10, "n_convolutions": 2, "cutoff": 4.9,
+                        "trainable_gauss": False})
+    gnn = ns.interface.GNNPotentials(system, model, cutoff=4.9)
+    prior = ns.interface.PairPotentials(system, ns.potentials.ExcludedVolume(1.9, 0.015, 12), cutoff=4.9)
+    integ = ns.md.NoseHooverChain(ns.interface.Stack({"gnn": gnn, "prior": prior}), system, Q=50.0, T=600.0 * units.kB,
+                                  num_chains=5, adjoint=True)
+    sim = ns.md.Simulations(system, integ)
+    obs = ns.observable.rdf(system, 30, (1.8, 4.9))
+    target = torch.linspace(0.0, 2.0, 30)
+    opt = torch.optim.Adam(list(model.parameters()), lr=3e-3)
+    hist = []
+    for _ in range(iters):
+        v, q, pv = sim.simulate(5, dt=1.0 * units.fs, frequency=5)
+        _, _, g = obs(q[-1:])
+        loss = (g - target).pow(2).mean() + 10.0 * (v[-1] ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        hist.append(loss.item())
+    w = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy()
+    return np.array(hist), w, system.get_positions()
+
+
+def test_emu_gnn_optimisation_loop_vs_live_reference():
+    import types
+    import torchmd
+    from nff.nn.models.schnet import SchNet
+    with ref_import.active() as ref:
+        rh, rw, rq = _gnn_optimisation_loop(ref, ref.schnet.SchNet, 4)
+    ours = types.SimpleNamespace(system=torchmd.system, interface=torchmd.interface, potentials=torchmd.potentials, md=torchmd.md,
+                                 observable=torchmd.observable)
+    oh, ow, oq = _gnn_optimisation_loop(ours, SchNet, 4)
+    np.testing.assert_allclose(oh, rh, rtol=5e-4)                 # loss of every iteration
+    assert np.abs(ow - rw).max() <= 2e-4 * np.abs(rw).max()       # all SchNet weights after the Adam steps
+    np.testing.assert_allclose(oq, rq, atol=2e-4)
