@@ -228,3 +228,42 @@ def test_emu_gnn_optimisation_loop_vs_live_reference():
     np.testing.assert_allclose(oh, rh, rtol=5e-4)                 # loss of every iteration
     assert np.abs(ow - rw).max() <= 2e-4 * np.abs(rw).max()       # all SchNet weights after the Adam steps
     np.testing.assert_allclose(oq, rq, atol=2e-4)
+
+
+def test_emu_topology_and_observable_calls_vs_live_reference():
+    """call-level differential of the remaining public functions against the reference: generate_nbr_list for one frame and for
+    a stack of frames (get_dis on/off, (3,) and (3,3) cells, masks), compute_dis, rdf over several frames with explicit width,
+    vacf, Temperature"""
+    import torchmd
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    rng = np.random.default_rng(2)
+    cell3 = torch.tensor([7.1, 7.9, 6.6])
+    xyz = torch.tensor(rng.uniform(-1.0, 8.0, (150, 3)), dtype=torch.float32)
+    frames = torch.tensor(rng.uniform(0.0, 6.5, (3, 90, 3)), dtype=torch.float32)
+    A, B = list(range(0, 150, 3)), list(range(1, 150, 2))
+    ex = torch.LongTensor(rng.integers(0, 150, (30, 2)))
+    with ref_import.active() as ref:
+        r1 = ref.topology.generate_nbr_list(xyz, 2.6, cell3, get_dis=True)
+        r2 = ref.topology.generate_nbr_list(xyz, 2.6, torch.diag(cell3), index_tuple=(A, B), ex_pairs=ex)
+        r3 = ref.topology.generate_nbr_list(frames, 2.2, cell3)
+        rd = ref.topology.compute_dis(xyz, r1[0], r1[2], torch.diag(cell3))
+        atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+        rsys = ref.system.System(atoms, device="cpu")
+        traj = torch.tensor(rsys.get_positions()[None] + rng.normal(0, 0.05, (4, 108, 3)), dtype=torch.float32)
+        vel = torch.tensor(rng.standard_normal((20, 108, 3)), dtype=torch.float32)
+        rg = ref.observable.rdf(rsys, 60, (0.8, 2.0), width=0.05)(traj)
+        rv = ref.observable.vacf(rsys, t_range=8)(vel)
+    o1 = torchmd.topology.generate_nbr_list(xyz, 2.6, cell3, get_dis=True)
+    o2 = torchmd.topology.generate_nbr_list(xyz, 2.6, torch.diag(cell3), index_tuple=(A, B), ex_pairs=ex)
+    o3 = torchmd.topology.generate_nbr_list(frames, 2.2, cell3)
+    od = torchmd.topology.compute_dis(xyz, o1[0], o1[2], torch.diag(cell3))
+    for a, b in ((o1[0], r1[0]), (o1[2], r1[2]), (o2[0], r2[0]), (o2[1], r2[1]), (o3[0], r3[0])):
+        assert a.dtype == b.dtype and torch.equal(a.cpu(), b), (a.shape, b.shape)            # indices / offsets: bit-exact
+    torch.testing.assert_close(o1[1], r1[1], rtol=2e-6, atol=0)
+    torch.testing.assert_close(od, rd, rtol=2e-6, atol=1e-6)
+    osys = torchmd.system.System(FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True), device="cpu")
+    og = torchmd.observable.rdf(osys, 60, (0.8, 2.0), width=0.05)(traj)
+    for a, b in zip(og, rg):
+        torch.testing.assert_close(torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float(), rtol=2e-5, atol=2e-5 * float(torch.as_tensor(b).abs().max()))
+    ov = torchmd.observable.vacf(osys, t_range=8)(vel)
+    torch.testing.assert_close(ov, rv, rtol=1e-6, atol=1e-6)
