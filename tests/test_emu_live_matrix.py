@@ -267,3 +267,53 @@ def test_emu_topology_and_observable_calls_vs_live_reference():
         torch.testing.assert_close(torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float(), rtol=2e-5, atol=2e-5 * float(torch.as_tensor(b).abs().max()))
     ov = torchmd.observable.vacf(osys, t_range=8)(vel)
     torch.testing.assert_close(ov, rv, rtol=1e-6, atol=1e-6)
+
+
+def _fold_optimisation_loop(ns, schnet_cls, seed, iters=2):
+    """demo/fold.py in miniature: Stack{gnn: SchNet, prior: BondPotentials, pair: ExcludedVolume with the bonds excluded}, a loss on
+    bond lengths and dihedral cosines of the last frame (observable.compute_dihe), adjoint backward, Adam steps"""
+    sys_mod = __import__("sys")
+    sys_mod.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__file__), "..", "oracle"))
+    from make_golden import chain_system
+    atoms, bond_top, angle_top = chain_system(n_beads=16, L=8.0, seed=9)
+    n = len(atoms)
+    system = ns.system.System(atoms, device="cpu")
+    rng = np.random.default_rng(seed)
+    system.set_velocities(rng.standard_normal((n, 3)) * 0.3)
+    torch.manual_seed(seed)
+    model = schnet_cls({"n_atom_basis": 16, "n_filters": 16, "n_gaussians": 8, "n_convolutions": 2, "cutoff": 2.5, "trainable_gauss": False})
+    bt = torch.LongTensor(bond_top)
+    gnn = ns.interface.GNNPotentials(system, model, cutoff=2.5)
+    bond = ns.interface.BondPotentials(system, bt, 3.0, 1.3)
+    pair = ns.interface.PairPotentials(system, ns.potentials.ExcludedVolume(1.0, 0.8, 10), cutoff=2.5, ex_pairs=bt)
+    ff = ns.interface.Stack({"gnn": gnn, "prior": bond, "pair": pair})
+    integ = ns.md.NoseHooverChain(ff, system, Q=50.0, T=0.6, num_chains=5, adjoint=True)
+    sim = ns.md.Simulations(system, integ)
+    dihes = torch.LongTensor([[i, i + 1, i + 2, i + 3] for i in range(n - 3)])
+    opt = torch.optim.Adam(list(model.parameters()), lr=2e-3)
+    hist = []
+    for _ in range(iters):
+        v, q, pv = sim.simulate(6, dt=0.002, frequency=6)
+        cosphi = ns.observable.compute_dihe(q[-2:], dihes)
+        blen = (q[-1][bt[:, 0]] - q[-1][bt[:, 1]]).pow(2).sum(-1)
+        loss = (cosphi - 0.3).pow(2).mean() + (blen - 1.2).pow(2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        hist.append(loss.item())
+    w = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy()
+    return np.array(hist), w, system.get_positions()
+
+
+def test_emu_fold_optimisation_loop_vs_live_reference():
+    import types
+    import torchmd
+    from nff.nn.models.schnet import SchNet
+    with ref_import.active() as ref:
+        rh, rw, rq = _fold_optimisation_loop(ref, ref.schnet.SchNet, 3)
+    ours = types.SimpleNamespace(system=torchmd.system, interface=torchmd.interface, potentials=torchmd.potentials, md=torchmd.md,
+                                 observable=torchmd.observable)
+    oh, ow, oq = _fold_optimisation_loop(ours, SchNet, 3)
+    np.testing.assert_allclose(oh, rh, rtol=5e-4)
+    assert np.abs(ow - rw).max() <= 2e-4 * np.abs(rw).max()
+    np.testing.assert_allclose(oq, rq, atol=2e-4)
