@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 echo "== 1. GPU parity suite" | tee gpurun_out/r2_summary.txt
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 | tee -a gpurun_out/r2_summary.txt
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 | tee -a gpurun_out/r2_summary.txt
 echo "== 2. bench, default build" | tee -a gpurun_out/r2_summary.txt
 timeout 600 python bench.py --steps 1000 --warmup 200 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 tail -c 1500 gpurun_out/r2_bench_default.json | tee -a gpurun_out/r2_summary.txt
