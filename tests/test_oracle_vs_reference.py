@@ -79,3 +79,27 @@ def test_angle_list_and_angles_live():
     cb = Ob.compute_angle(xyz, b, cell, N=n)
     assert torch.equal(ca, cb)
     assert T.generate_angle_list(nbr[:0]).shape == (0, 4)
+
+
+@pytest.mark.parametrize("maker,fname", [("bonded_golden", "bonded_chain.npz"), ("gnn_adjoint_golden", "gnn_adjoint.npz"),
+                                         ("generic_route_golden", "c1_generic.npz")])
+def test_committed_fixtures_are_reproducible_from_the_reference(maker, fname, tmp_path, monkeypatch):
+    """provenance of tests/golden/: re-running oracle/make_golden.py against the reference tree reproduces the committed arrays"""
+    import os
+    import sys
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import make_golden
+    monkeypatch.setattr(make_golden, "OUT", str(tmp_path))
+    getattr(make_golden, maker)()
+    new = np.load(os.path.join(str(tmp_path), fname))
+    old = np.load(os.path.join(os.path.dirname(__file__), "golden", fname))
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        assert new[k].shape == old[k].shape, k
+        if new[k].dtype.kind == "f":
+            np.testing.assert_allclose(new[k], old[k], rtol=1e-6, atol=1e-6 * max(1e-30, float(np.abs(old[k]).max())), err_msg=k)
+        else:
+            assert np.array_equal(new[k], old[k]), k
