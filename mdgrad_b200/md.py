@@ -215,37 +215,50 @@ class _EOM(torch.nn.Module):
     _POWER_LAW = (_lib.POT_LJ, _lib.POT_LJFAM, _lib.POT_LJ69, _lib.POT_EXV, _lib.POT_BUCK, _lib.POT_MORSE)   # kinds with closed-form second order
 
     def _native_second_order(self, q):
-        """The pair model when its force has closed-form second-order products (mdg_pair_hvp), else None."""
-        from .interface import PairPotentials
-        m = self.model
-        if type(m) is not PairPotentials or not _lib.on_device(q) or getattr(self, "disable_native_adjoint", False):
+        """The pair members when every member's force has closed-form second-order products (mdg_pair_hvp): a single
+        PairPotentials or a Stack of PairPotentials over the analytic kinds (e.g. the species-pair members of
+        scripts/fit_2_comp.py:182); else None."""
+        from .interface import PairPotentials, Stack
+        if not _lib.on_device(q) or getattr(self, "disable_native_adjoint", False):
             return None
-        spec = m.native_kind()
-        return m if spec is not None and spec[0] in self._POWER_LAW else None
+        members = list(self.model.models.values()) if type(self.model) is Stack else [self.model]
+        for m in members:
+            if type(m) is not PairPotentials:
+                return None
+            spec = m.native_kind()
+            if spec is None or spec[0] not in self._POWER_LAW:
+                return None
+        return members or None
 
     def native_augmented(self, tt, y_aug, n):
         """Augmented adjoint dynamics (f, vjp_y, vjp_t, vjp_params) at (y, adj) WITHOUT autograd: the reference
         differentiates the autograd force a second time (sovlers.py:216-236); here the force comes from the force
-        kernel, (dF/dq)^T a and (dF/dtheta)^T a from the analytic Hessian-vector kernel, the thermostat algebra is
-        written out.  Returns None when this configuration is not covered (the caller then uses autograd)."""
+        kernel, (dF/dq)^T a and (dF/dtheta)^T a from the analytic Hessian-vector kernel (summed over the members of a
+        Stack, each on its own list), the thermostat algebra is written out.  Returns None when this configuration is
+        not covered (the caller then uses autograd)."""
         y, adj = y_aug[:n], y_aug[n:2 * n]
-        m = self._native_second_order(y[1])
-        if m is None:
+        members = self._native_second_order(y[1])
+        if members is None:
             return None
         with torch.no_grad():
             v, q = y[0], y[1]
             self.update_topology(q)                      # same evaluation count / list refresh as func(t, y)
-            kind, values, ptensors = m.native_kind()
-            F = m.native_force(q)
+            F = None
+            for m in members:
+                Fm = m.native_force(q)
+                F = Fm if F is None else F + Fm
             f = self.derivative(tt, y, F)
             cot = tuple(-a for a in adj)
             a_q, gv, gpv = self._vjp_algebra(y, cot)
-            hv, dth = m._ctx.pair_hvp(kind, values, q, a_q)
+            hv, dtheta = None, {}
+            for m in members:
+                kind, values, ptensors = m.native_kind()
+                hvm, dth = m._ctx.pair_hvp(kind, values, q, a_q)
+                hv = hvm if hv is None else hv + hvm
+                for k, pt in enumerate(ptensors):
+                    dtheta[id(pt)] = dth[k].reshape(-1) + dtheta.get(id(pt), 0.0)
             vjp_y = (gv, hv) + ((gpv,) if gpv is not None else ())
-            parts = []
-            for p_ in self.parameters():
-                hit = [k for k, pt in enumerate(ptensors) if pt is p_]
-                parts.append(dth[hit[0]].reshape(-1) if hit else torch.zeros(p_.numel(), device=q.device))
+            parts = [dtheta[id(p_)] if id(p_) in dtheta else torch.zeros(p_.numel(), device=q.device) for p_ in self.parameters()]
             vjp_p = torch.cat(parts) if parts else torch.tensor(0.).to(q)
             return (*f, *vjp_y, torch.zeros_like(tt), vjp_p)
 
