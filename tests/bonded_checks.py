@@ -283,3 +283,32 @@ def check_tpair_potentials_vs_reference_fixture(dev):
     f = -torch.autograd.grad(e, q)[0]
     _close(e.item(), g["tpair_e"], 2e-5)
     _close(f.cpu().numpy(), g["tpair_f"], 2e-5)
+
+
+def check_stack_adjoint_native_equals_autograd(dev):
+    """Stack of analytic species-pair members (scripts/fit_2_comp.py's force field): the closed-form reverse dynamics
+    (mdg_pair_hvp per member) and the generic double-backward route give the same parameter gradients"""
+    from torchmd.interface import PairPotentials, Stack
+    from torchmd.potentials import ExcludedVolume, LennardJones
+    from torchmd.md import NoseHooverChain, Simulations
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import FaceCenteredCubic
+    res = []
+    for native in (True, False):
+        rng = np.random.default_rng(7)
+        atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+        atoms.set_positions(atoms.get_positions() + rng.normal(0, 0.04, (108, 3)))
+        system = System(atoms, device=dev)
+        system.set_velocities(rng.standard_normal((108, 3)) * 0.8)
+        a, b = LennardJones(1.0, 0.6).to(dev), ExcludedVolume(0.9, 0.4, 12).to(dev)
+        A, B = list(range(0, 108, 2)), list(range(1, 108, 2))
+        model = Stack({"aa": PairPotentials(system, a, cutoff=2.5, index_tuple=(A, A)),
+                       "ab": PairPotentials(system, b, cutoff=2.0, index_tuple=(A, B))})
+        integ = NoseHooverChain(model, system, T=1.0, num_chains=3, Q=50.0, adjoint=True).to(dev)
+        integ.disable_native_adjoint = not native
+        v, q, pv = Simulations(system, integ).simulate(steps=5, frequency=5, dt=0.005)
+        ((q[-1] ** 2).sum() + (v[-1] * v[1]).sum() + pv[-1].sum()).backward()
+        res.append([p.grad.item() for m in (a, b) for p in m.parameters() if p.grad is not None])
+    assert len(res[0]) == len(res[1]) >= 4
+    for x, y in zip(*res):
+        assert abs(x - y) <= 5e-4 * max(1.0, abs(y)), (res[0], res[1])
