@@ -345,3 +345,13 @@ def test_3xtf32_split_reaches_fp32_parity_model():
     assert np.abs(three - ref).max() / scale < 2e-6                  # the 3-pass split is at fp32 accumulation noise
     fp32 = (A @ B)
     assert np.abs(three - ref).max() < 4 * np.abs(fp32 - ref).max() + 1e-7 * scale
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mdgrad_b200.h is the C ABI: it must compile as C99 without any C++ / CUDA / torch type"""
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "mdgrad_b200.h"\nint main(void) { mdg_bonded_terms t; mdg_gnn_md_params p; (void)t; (void)p; return MDG_OK; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
