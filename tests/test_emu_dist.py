@@ -1,5 +1,5 @@
 """The slab-decomposed MULTI-RANK engine (halo send/recv in place, KE / flag / layer-count all-reduces on a side stream
-overlapping the interior forces, local rebuild - engine.cu, nbr.cu, dist.cu) at world size 2 and 3 in the GPU-less container:
+overlapping the interior forces, local rebuild - engine.cu, nbr.cu, dist.cu) at world size 2, 3 and 4 in the GPU-less container:
 every rank is a process running the CPU-emulated library, NCCL is tests/cuemu/fake_nccl.cpp (shared memory, stream-ordered
 through the emulator's queues).  Same assertions as tests/dist_check.py, which does this on real GPUs with real NCCL.
 TEST INFRASTRUCTURE - functional coverage of the distributed host logic and kernels, nothing about NVLink."""
@@ -34,7 +34,7 @@ def _run(world, tmp, nsteps, K=4, vscale=1.0):
     return [np.load(o) for o in outs]
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_emu_slab_engine_matches_single_device(world, tmp_path):
     nsteps = 12
     single = _run(1, str(tmp_path), nsteps)[0]
