@@ -75,9 +75,31 @@ class PairPotentials(GeneralInteraction):
     # the reference keeps nbr_list on the CPU (interface.py:259); materialise that copy lazily
     @property
     def nbr_list(self):
+        self._refresh_if_stale()
         if self._nbr_cpu is None:
             self._nbr_cpu = self._nbr_dev.to("cpu")
         return self._nbr_cpu
+
+    @property
+    def offsets(self):
+        self._refresh_if_stale()
+        return self._offsets
+
+    @offsets.setter
+    def offsets(self, value):
+        self._offsets = value
+
+    # After an epoch on the fused engine (mdg_md_run keeps its own skin list) the Python-visible topology must be the list of
+    # the reference's last evaluation, i.e. the list at the final positions.  Building + exporting it costs a list build per
+    # epoch that nothing reads in a plain MD loop, so it is deferred until somebody looks (nbr_list / offsets / forward).
+    def _mark_stale(self, xyz):
+        self._stale_xyz = xyz.detach().clone()
+
+    def _refresh_if_stale(self):
+        xyz = getattr(self, "_stale_xyz", None)
+        if xyz is not None:
+            self._stale_xyz = None
+            self._reset_topology(xyz)
 
     def native_kind(self):
         return self.model.native_spec() if hasattr(self.model, "native_spec") else None
@@ -85,8 +107,9 @@ class PairPotentials(GeneralInteraction):
     def _reset_topology(self, xyz):
         """Rebuild the list at xyz; returns (nbr_list, pair_dis, offsets) (reference :263-282)."""
         nbr, off, dis = self._ctx.nbr_list(xyz, self._L, self.cutoff, self._sel[0], self._sel[1], self._exk, get_dis=True)
+        self._stale_xyz = None
         self._nbr_dev, self._nbr_cpu = nbr, None
-        self.offsets = off
+        self._offsets = off
         return nbr, dis, off
 
     # -- native force route (no autograd tape) ---------------------------------------------------------------------
@@ -95,11 +118,13 @@ class PairPotentials(GeneralInteraction):
 
     def native_force(self, xyz):
         """-dE/dxyz over the stored list straight from the force kernel (mdg_pair_force)."""
+        self._refresh_if_stale()
         kind, values, _ = self.native_kind()
         return self._ctx.pair_force(kind, values, xyz, want_force=True)[1]
 
     def forward(self, xyz):
         """sum_pairs u(|x_i - x_j - offsets@cell|) over the STORED list (reference :284-300)."""
+        self._refresh_if_stale()
         spec = self.native_kind()
         if spec is not None and not (self.second_order and torch.is_grad_enabled()):
             return _PairEnergy.apply(self, xyz, *spec[2])

@@ -438,6 +438,8 @@ class _EOM(torch.nn.Module):
         self.last_engine_stats = st
         self._engine_K = int(st["maxrow_or_K"]) if skin > 0 else None
         self.update_count += 2 * (len(tl) - 1)       # two evaluations per step in the reference
+        if len(tl) > 1:
+            m._mark_stale(tq[-1])                    # python-visible list = that of the reference's last evaluation (built lazily)
         return (tv, tq, tpv) if tpv is not None else (tv, tq)
 
 
