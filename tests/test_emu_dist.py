@@ -34,10 +34,15 @@ def _run(world, tmp, nsteps, K=4, vscale=1.0):
     return [np.load(o) for o in outs]
 
 
+@pytest.fixture(scope="module")
+def single_device_run(tmp_path_factory):
+    return _run(1, str(tmp_path_factory.mktemp("single")), 12)[0]
+
+
 @pytest.mark.parametrize("world", [2, 3, 4])
-def test_emu_slab_engine_matches_single_device(world, tmp_path):
+def test_emu_slab_engine_matches_single_device(world, tmp_path, single_device_run):
     nsteps = 12
-    single = _run(1, str(tmp_path), nsteps)[0]
+    single = single_device_run
     ranks = _run(world, str(tmp_path), nsteps)
     # frames hold the owned atoms only and are ZERO elsewhere (the caller sums over ranks): no NaN poison may survive
     for r in ranks:
