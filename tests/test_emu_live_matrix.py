@@ -83,6 +83,7 @@ def test_emu_simulations_matrix_vs_live_reference(k):
         assert np.abs(a - b).max() <= 3e-5 * max(1.0, np.abs(b).max())
     np.testing.assert_allclose(os_.get_positions(), rs.get_positions(), atol=3e-5)
     np.testing.assert_allclose(os_.get_velocities(), rs.get_velocities(), atol=3e-4)
+    assert osim.integrator.update_count == rsim.integrator.update_count        # force evaluations counted as the reference does
     # the Python-visible topology of the potential after the run = the list of the reference's last evaluation
     rn, on = rsim.integrator.model.nbr_list, osim.integrator.model.nbr_list
     assert on.shape == rn.shape and torch.equal(on.cpu(), rn.cpu()), (on.shape, rn.shape)
