@@ -324,19 +324,23 @@ __global__ void __launch_bounds__(256) k_sn_gemm(int M, int N, int K, const floa
 
 // MDG_SCHNET_TC=1: route the dense layers through the tcgen05 kernel (experimental, see schnet_tc.cuh)
 static bool sn_tc_enabled() {
+#ifdef MDG_EMU      // the emulated suite switches between the two paths inside one process
+    const char* e = getenv("MDG_SCHNET_TC");
+    return e && e[0] == '1';
+#else
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("MDG_SCHNET_TC");
         on = (e && e[0] == '1') ? 1 : 0;
     }
     return on == 1;
+#endif
 }
 
 template <bool TRANSB, int EPI>
 static int sn_gemm(mdg_ctx* c, int M, int N, int K, const float* A, const float* B, int ldb, const float* bias, float* aux, float* C,
                    cudaStream_t st) {
     if (M <= 0 || N <= 0) return MDG_OK;
-#ifndef MDG_EMU
     if (sn_tc_enabled()) {
         const float* Bt = B;                     // the tensor-core kernel wants B as (N x K) row-major = K-major
         if (!TRANSB) {                           // backward layers multiply by W (K x N): transpose the (small) weight first
@@ -349,7 +353,6 @@ static int sn_gemm(mdg_ctx* c, int M, int N, int K, const float* A, const float*
             if (r != MDG_E_STATE) return r;
         }
     }
-#endif
     dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
     k_sn_gemm<TRANSB, EPI><<<grid, 256, 0, st>>>(M, N, K, A, B, ldb, bias, aux, C);
     MDG_KERNEL_CHECK();

@@ -2,10 +2,12 @@
 //
 //     C (M x N) = epilogue( A (M x K, row-major fp32) * Bt^T ),   Bt = (N x K) row-major = torch Linear weight (out x in)
 //
-// EXPERIMENTAL - opt-in with MDG_SCHNET_TC=1, default OFF: written after the round's GPU budget was spent, it cannot be
-// executed by the CPU emulation harness (tensor-core instructions) and has NOT run on a B200 yet.  The default path
-// stays the SIMT kernel k_sn_gemm of schnet.cu; both share the epilogue codes.  First task of round 2: validate against
-// k_sn_gemm (tests/test_schnet.py::test_tc_gemm_*), then make it the default for the configs[4] layer sizes.
+// EXPERIMENTAL - opt-in with MDG_SCHNET_TC=1, default OFF: written after the round's GPU budget was spent, it has NOT run on
+// a B200 yet.  Its LOGIC (staging layout, descriptors, K loop, guards, epilogue mapping) runs under the CPU emulation through a
+// functional model of the tensor-core primitives (below) and equals the SIMT path there; what only hardware can tell - the
+// descriptor semantics as the model reads them from the CUTLASS headers, the fences, the timing - is the first task of round 2
+// (tests/test_schnet.py::test_tc_gemm_*, tools/tc_check.py), before it becomes the default for the configs[4] layer sizes.
+// The default path stays the SIMT kernel k_sn_gemm of schnet.cu; both share the epilogue codes.
 //
 // Precision: the reference computes these layers in fp32 and the parity bar is 1e-5, so one TF32 product (10-bit
 // mantissa) is not enough.  3xTF32: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  A B ~ Ah Bh + Ah Bl + Al Bh, three
@@ -20,13 +22,23 @@
 //   tcgen05.ld.32x32b.x16, applies bias / ssp / sigmoid-gate / residual and writes 64-byte row segments.
 // Descriptor bit fields: cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor) of the vendored CUTLASS headers.
 #pragma once
-#ifndef MDG_EMU
 
 #define TC_M 128
 #define TC_KB 32
 #define TC_LBO 128u
 #define TC_SBO 1024u
 
+// ---------------------------------------------------------------------------------------------
+// Primitives.  GPU build: thin wrappers around the tcgen05 / mbarrier PTX.  MDG_EMU build (tests/cuemu): a functional model
+// that INTERPRETS the same 64-bit shared-memory descriptors and the 32-bit instruction descriptor (start address, LBO, SBO,
+// M, N per cute/arch/mma_sm100_desc.hpp) on the emulated shared memory and keeps the accumulator in an emulated TMEM, so that
+// the kernel below - staging layout, descriptor arithmetic, K loop / accumulate flags, tile guards, TMEM lane / column ->
+// row / column mapping of the epilogue - runs unchanged on the CPU against the SIMT kernel (tests/test_emu_schnet.py).  The
+// model says nothing about the hardware's timing or about the PTX syntax (ptxas checks the latter at build time).
+// ---------------------------------------------------------------------------------------------
+#ifndef MDG_EMU
+#define TC_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+struct TcBarrier { uint64_t w; };
 __device__ __forceinline__ uint32_t tc_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint32_t tc_tf32(float x) {
@@ -34,6 +46,122 @@ __device__ __forceinline__ uint32_t tc_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ void tc_mbar_init(TcBarrier* b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_addr(b)), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// warp-collective: allocate `cols` TMEM columns, the base address is written to *slot (shared memory)
+__device__ __forceinline__ void tc_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_addr(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t tmem, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the tensor core (async proxy)
+__device__ __forceinline__ void tc_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+// completion of everything issued so far -> one arrival on the mbarrier (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(TcBarrier* b) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(TcBarrier* b, uint32_t parity) {
+    const uint32_t bar = tc_smem_addr(b);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// warp-collective: this thread's TMEM lane (32 * warp + lane), 16 consecutive columns from `col`
+__device__ __forceinline__ void tc_ld16(uint32_t tmem, int warp, int col, uint32_t* r) {
+    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)col;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+#else   // ------------------------------------------------------------------------------------ functional model
+#define TC_DYN_SMEM(name) unsigned char* name = (unsigned char*)cuemu::dyn_smem()
+struct TcBarrier { uint32_t phase; };
+static float    g_tc_tmem[128][512];              // one block at a time in the emulator
+static uint32_t g_tc_next_col;
+static inline uint32_t tc_smem_addr(const void* p) { return (uint32_t)((const unsigned char*)p - (const unsigned char*)cuemu::dyn_smem()); }
+static inline uint32_t tc_tf32(float x) {          // cvt.rna.tf32.f32: nearest, ties away from zero, 10 explicit mantissa bits
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    return (b + 0x1000u) & 0xFFFFE000u;
+}
+static inline void tc_mbar_init(TcBarrier* b) { b->phase = 0; }
+static inline void tc_alloc(uint32_t* slot, uint32_t cols) {
+    if (cuemu::lane_id() == 0) {
+        if (cols < 32 || (cols & (cols - 1)) || cols > 512) { fprintf(stderr, "tc model: tcgen05.alloc of %u columns (power of two in [32, 512] required)\n", cols); abort(); }
+        g_tc_next_col = 0;
+        *slot = g_tc_next_col;                     // lane 0, column 0
+        g_tc_next_col += cols;
+        for (int l = 0; l < 128; ++l)
+            for (uint32_t cidx = 0; cidx < cols; ++cidx) g_tc_tmem[l][cidx] = __int_as_float(0x7fc00000);   // TMEM is not zeroed
+    }
+}
+static inline void tc_dealloc(uint32_t, uint32_t) {}
+static inline void tc_fence_before() {}
+static inline void tc_fence_after() {}
+static inline void tc_fence_smem() {}
+static inline float tc_elem(uint64_t desc, int row, int k) {      // element (row, k) of a K-major no-swizzle operand, k in [0, 8)
+    const uint32_t start = (uint32_t)(desc & 0x3FFFu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3FFFu) << 4,
+                   sbo = (uint32_t)((desc >> 32) & 0x3FFFu) << 4;
+    if (((desc >> 46) & 3u) != 1u || (desc >> 61) != 0u) { fprintf(stderr, "tc model: descriptor version / layout bits not as expected\n"); abort(); }
+    const uint32_t byte = start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 16u + (uint32_t)(k >> 2) * lbo + (uint32_t)(k & 3) * 4u;
+    float v;
+    memcpy(&v, (const unsigned char*)cuemu::dyn_smem() + byte, 4);
+    return v;
+}
+static inline void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
+    if (M != 128 || N < 16 || N > 256 || (N & 15) || ((idesc >> 4) & 3u) != 1u || ((idesc >> 7) & 7u) != 2u || ((idesc >> 10) & 7u) != 2u ||
+        ((idesc >> 15) & 3u) != 0u) {
+        fprintf(stderr, "tc model: instruction descriptor %08x is not F32 += TF32 x TF32, K-major, M128, N%%16\n", idesc);
+        abort();
+    }
+    const int col0 = (int)(tmem_d & 0xFFFFu);
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = accumulate ? g_tc_tmem[m][col0 + n] : 0.f;
+            for (int k = 0; k < 8; ++k) acc += tc_elem(da, m, k) * tc_elem(db, n, k);
+            g_tc_tmem[m][col0 + n] = acc;
+        }
+}
+static inline void tc_commit(TcBarrier* b) { b->phase ^= 1u; }     // the model's MMAs complete at issue
+static inline void tc_mbar_wait(TcBarrier* b, uint32_t parity) {
+    while (b->phase == parity) cuemu::fiber_yield();               // phase bit == parity: that phase has not completed yet
+}
+static inline void tc_ld16(uint32_t tmem, int warp, int col, uint32_t* r) {
+    const int lane = 32 * warp + cuemu::lane_id(), col0 = (int)(tmem & 0xFFFFu) + col;
+    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(g_tc_tmem[lane][col0 + i]);
+}
+#endif
 
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -66,38 +194,11 @@ __device__ __forceinline__ void tc_stage(const float* __restrict__ G, int ld, in
     }
 }
 
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-        "}\n"
-        :
-        : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-
 template <int NT, int EPI>
 __global__ void __launch_bounds__(128) k_sn_gemm_tc(int M, int N, int K, const float* __restrict__ A, const float* __restrict__ Bt,
                                                     const float* __restrict__ bias, float* __restrict__ aux, float* __restrict__ C) {
-    extern __shared__ __align__(1024) unsigned char tc_smem[];
-    __shared__ __align__(8) uint64_t s_bar;
+    TC_DYN_SMEM(tc_smem);
+    __shared__ __align__(8) TcBarrier s_bar;
     __shared__ uint32_t s_tmem;
     unsigned char* sA_hi = tc_smem;
     unsigned char* sA_lo = sA_hi + TC_M * 128;
@@ -105,20 +206,12 @@ __global__ void __launch_bounds__(128) k_sn_gemm_tc(int M, int N, int K, const f
     unsigned char* sB_lo = sB_hi + NT * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * NT;
-    const uint32_t bar = tc_smem_addr(&s_bar);
 
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_addr(&s_tmem)), "r"((uint32_t)NT)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (threadIdx.x == 0) tc_mbar_init(&s_bar);
+    if (warp == 0) tc_alloc(&s_tmem, (uint32_t)NT);
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_fence_after();
     const uint32_t tmem = s_tmem;
 
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = NT, M = 128 (cute UMMA::InstrDescriptor)
@@ -128,10 +221,10 @@ __global__ void __launch_bounds__(128) k_sn_gemm_tc(int M, int N, int K, const f
     for (int kb = 0; kb < nkb; ++kb) {
         tc_stage<TC_M>(A, K, m0, M, kb * TC_KB, K, sA_hi, sA_lo);
         tc_stage<NT>(Bt, K, n0, N, kb * TC_KB, K, sB_hi, sB_lo);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
+        tc_fence_smem();
         __syncthreads();
         if (threadIdx.x == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < TC_KB / 8; ++ks) {
                 const uint32_t off = (uint32_t)ks * 2u * TC_LBO;         // one MMA consumes two 16-byte K chunks
@@ -141,25 +234,18 @@ __global__ void __launch_bounds__(128) k_sn_gemm_tc(int M, int N, int K, const f
                 tc_mma(tmem, dah, dbl, idesc, 1u);
                 tc_mma(tmem, dal, dbh, idesc, 1u);
             }
-            // completion of everything issued so far -> one arrival on the mbarrier (implies fence::before_thread_sync)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            tc_commit(&s_bar);
         }
-        tc_mbar_wait(bar, parity);        // the MMAs have read the staged tiles (and, after the last block, written D)
+        tc_mbar_wait(&s_bar, parity);     // the MMAs have read the staged tiles (and, after the last block, written D)
         parity ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_fence_after();
     }
 
     // epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) = rows m0 + 32 w + lane
     const int m = m0 + 32 * warp + lane;
     for (int c0 = 0; c0 < NT; c0 += 16) {
         uint32_t r[16];
-        const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_ld16(tmem, warp, c0, r);
         if (m < M) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -176,10 +262,9 @@ __global__ void __launch_bounds__(128) k_sn_gemm_tc(int M, int N, int K, const f
             }
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)NT) : "memory");
+    if (warp == 0) tc_dealloc(tmem, (uint32_t)NT);
 }
 
 // Bt: (N x K) row-major.  Returns MDG_E_STATE when the shape is not covered (caller falls back to the SIMT kernel).
@@ -201,4 +286,3 @@ static int sn_gemm_tc(int M, int N, int K, const float* A, const float* Bt, cons
     MDG_KERNEL_CHECK();
     return MDG_OK;
 }
-#endif   // !MDG_EMU

@@ -83,6 +83,7 @@ Coll* coll_enter(unsigned mask, uint64_t value, int pred);
 void  coll_leave(Coll* c);
 void* dyn_smem();
 int   lane_id();
+void  fiber_yield();
 }  // namespace cuemu
 
 #define threadIdx (cuemu::g_cur->tid)

@@ -89,6 +89,14 @@ static void trampoline() {
 }
 
 int lane_id() { return g_cur->lin & 31; }
+// cooperative spin-wait (e.g. a modelled mbarrier wait): let the other threads of the block run.  Counts as progress so that
+// the deadlock detector tolerates a few rounds of spinning, but a wait that never ends is still reported.
+void fiber_yield() {
+    static uint64_t spins = 0;
+    if (++spins % 50000000ull == 0) { fprintf(stderr, "cuemu: a thread has been spinning in fiber_yield() for 5e7 rounds - modelled wait never satisfied?\n"); abort(); }
+    g_progress++;
+    yield();
+}
 void* dyn_smem() { return g_dyn_smem.data(); }
 
 void sync_block() {

@@ -91,3 +91,32 @@ def test_emu_schnet_no_edges_and_single_atom(ectx):
         e, f = ectx.schnet_energy_force(model, z, xyz, nbr, off)
         assert abs(e.item() - e_o.item()) <= 1e-5 * max(1.0, abs(e_o.item()))
         assert float(f.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n,A,F,G,L,R", [
+    (40, 16, 24, 7, 1, 8),            # every tile guard: M, N far below one 128 x 64 tile, K = 16 / 24 (not a multiple of the 32-wide k-block)
+    (150, 64, 64, 29, 2, 32),         # N = 64 -> the 64-column tile exactly
+    (200, 132, 68, 13, 2, 36),        # N = 132 / 68: the 128-column tile with a ragged second tile; M spans two row tiles
+    (64, 512, 256, 33, 3, 256),       # the layer widths of configs[4]
+])
+def test_emu_tc_dense_layers_equal_simt(ectx, monkeypatch, n, A, F, G, L, R):
+    """MDG_SCHNET_TC=1: the dense layers go through k_sn_gemm_tc - the tcgen05 kernel's logic (canonical K-major staging, shared
+    memory / instruction descriptors, 3xTF32 split, K loop, tile guards, TMEM epilogue mapping) executed on a functional model of
+    the tensor-core primitives (csrc/schnet_tc.cuh) - and must reproduce the SIMT path within the parity bar"""
+    rng = np.random.default_rng(n + A)
+    box = 9.0
+    xyz = torch.tensor(rng.uniform(0, box, (n, 3)), dtype=torch.float32)
+    z = torch.tensor(rng.integers(1, 9, n), dtype=torch.long)
+    cell = torch.tensor([box, box * 1.1, box * 0.95])
+    nbr, off = O.neighbor_list(xyz, 3.0, cell)
+    sd = _rand_sd(A, F, G, L, R, 3.0, seed=n)
+    model = _lib.schnet_model_struct(sd, "cpu")
+    monkeypatch.delenv("MDG_SCHNET_TC", raising=False)
+    e0, f0 = ectx.schnet_energy_force(model, z, xyz, nbr, off)
+    l0 = ectx.stats()["launches"]
+    monkeypatch.setenv("MDG_SCHNET_TC", "1")
+    e1, f1 = ectx.schnet_energy_force(model, z, xyz, nbr, off)
+    monkeypatch.delenv("MDG_SCHNET_TC", raising=False)
+    assert abs(e1.item() - e0.item()) <= 1e-5 * max(1.0, abs(e0.item())), (e0.item(), e1.item())
+    assert (f1 - f0).abs().max().item() <= 2e-5 * f0.abs().max().item()
+    assert not torch.equal(f1, f0)                    # (a different arithmetic did run: 3xTF32 is not bit-identical to fp32 FMA)
