@@ -273,7 +273,8 @@ int mdg_schnet_energy_force(mdg_ctx* ctx, const mdg_schnet_model* h_model, const
  *     own cutoff / species selection / exclusions), evaluates SchNet energy+forces (mdg_schnet_energy_force) and
  *     the priors (mdg_pair_force), and applies the fused integrator kernels - all from one host call, no Python
  *     and no autograd inside the loop.  Same trajectory outputs as mdg_md_run.  SYNC: the FIRST evaluation of an
- *     epoch reads its pair counts back (they size the edge buffers, +25%); every later step is enqueued without any
+ *     epoch reads its pair counts back (they size the edge buffers, +25%) unless the previous epoch of the same
+ *     context and atom count completed asynchronously (its capacity is reused); every later step is enqueued without any
  *     read-back - the pair count is consumed on the device, a capacity that turns out too small is latched on the
  *     device, read once at the end of the epoch, and the epoch is then repeated with a read-back per list build
  *     (inputs are never modified; MDG_GNN_SYNC=1 forces that path).  mdg_get_stats slot 3 = 1 if the epoch

@@ -300,6 +300,8 @@ struct mdg_ctx {
     cudaStream_t gnn_stream = nullptr;   // private stream of the graph-replay GNN epochs (capture is illegal on torch's legacy default stream)
     cudaEvent_t  ev_gnn = nullptr;
     int64_t stat_graph_replays = 0;
+    int64_t gnn_last_cap = 0;            // edge capacity a completed asynchronous epoch ran with (0: none) - lets the next epoch
+    int     gnn_last_n = 0;              //   of the same system start without any read-back
     DevBuf bd_slots, bd_part;  // bonded terms (bonded.cu): per-term gradient slots, block partial sums
     int     g_n = -1;
     int64_t g_edges = 0;

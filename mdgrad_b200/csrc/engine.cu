@@ -943,17 +943,29 @@ static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet
     k_gnn_init<<<nb, T, 0, st>>>(n, d_v0, d_q0, d_mass, v4, q4, vh4);
     int ib = nb < 1 ? 1 : (nb > INT_MAX_BLOCKS ? INT_MAX_BLOCKS : nb);
     int64_t launches = 0;
-    // the first evaluation is synchronous: its pair count sizes the edge buffers of the asynchronous steps
+    // The first evaluation of an epoch is synchronous - its pair count sizes the edge buffers of the asynchronous steps -
+    // unless the previous epoch of the same system completed asynchronously: then its capacity is reused and this epoch has no
+    // read-back at all (a capacity that no longer fits is latched like any other overflow and the epoch repeated).
     int64_t P0 = 0, cap_pairs = -1;
-    MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, -1, &P0, st));
-    if (async) {
-        const char* mg = getenv("MDG_GNN_MARGIN");             // (tests force the overflow / retry path with a tiny margin)
-        cap_pairs = P0 + (mg ? (int64_t)atoll(mg) : P0 / 4 + 256);
+    const char* mg = getenv("MDG_GNN_MARGIN");                 // (tests force the overflow / retry path with a tiny margin)
+    if (async && !mg && c->gnn_last_cap > 0 && c->gnn_last_n == n) {
+        cap_pairs = c->gnn_last_cap;
         if (model) {
             MDG_TRY(c->gnn_nbr.reserve(sizeof(int64_t) * 2 * (size_t)(cap_pairs + 1)));
             MDG_TRY(c->gnn_off.reserve(sizeof(float) * 3 * (size_t)(cap_pairs + 1)));
         }
+        MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, cap_pairs, nullptr, st));
+    } else {
+        MDG_TRY(gnn_force(c, p, model, d_z, n, q4, f4, d_e_gnn, &launches, -1, &P0, st));
+        if (async) {
+            cap_pairs = P0 + (mg ? (int64_t)atoll(mg) : P0 / 4 + 256);
+            if (model) {
+                MDG_TRY(c->gnn_nbr.reserve(sizeof(int64_t) * 2 * (size_t)(cap_pairs + 1)));
+                MDG_TRY(c->gnn_off.reserve(sizeof(float) * 3 * (size_t)(cap_pairs + 1)));
+            }
+        }
     }
+    c->gnn_last_cap = 0;                                       // set again below when this epoch completes asynchronously
     if (nhc) k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, v4, ke_v_cur);
     MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
     MDG_CUDA(cudaMemcpyAsync(d_traj_q, d_q0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -1026,6 +1038,7 @@ static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet
         for (int k = 0; k < p->n_priors; ++k) any |= c->h_pinned[9 + k];
         *latched = any;
         if (any & 2) { mdg_set_error("mdg_md_run_gnn: non-finite coordinates or collapsed cell during the epoch"); return MDG_E_NUMERIC; }
+        if (!any && !mg) { c->gnn_last_cap = cap_pairs; c->gnn_last_n = n; }
     }
     if (h_last_energy) *h_last_energy = h_e;      // SchNet energy of the last evaluation (priors not included)
     c->stat_launches += launches;

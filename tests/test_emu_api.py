@@ -280,6 +280,28 @@ def test_emu_gnn_engine_async_steps_and_overflow_retry(monkeypatch):
     assert runs["sync"][2] >= 2 * 5 and runs["async"][2] < runs["sync"][2], (runs["sync"][2], runs["async"][2])
     assert runs["async_long"][1] == 1 and runs["async_long"][2] == runs["async"][2], (runs["async_long"][2], runs["async"][2])
     assert runs["graph"][1] == 2                                 # ... with graph replays (private stream, captured at step 2)
+    # a following epoch of the same system reuses the capacity: no pair-count read-back at all any more
+    system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device="cpu")
+    np.random.seed(0)
+    system.set_temperature(298.0 * units.kB)
+    model = SchNet(params)
+    model.load_state_dict(sd)
+    gnn = GNNPotentials(system, model, cutoff=params["cutoff"])
+    prior = PairPotentials(system, ExcludedVolume(2.6, 0.015, 12), cutoff=params["cutoff"], index_tuple=(oxy, oxy))
+    integ = NoseHooverChain(Stack({"gnn": gnn, "prior": prior}), system, T=298.0 * units.kB, num_chains=5, Q=50.0, adjoint=True)
+    sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+    real_run, per_epoch = emu_lib.EmuContext.md_run_gnn, []
+
+    def counted2(self, *a, **k):
+        c0 = emu_lib.load().cuemu_counter(3)
+        r = real_run(self, *a, **k)
+        per_epoch.append(emu_lib.load().cuemu_counter(3) - c0)
+        return r
+    monkeypatch.setattr(emu_lib.EmuContext, "md_run_gnn", counted2)
+    sim.simulate(steps=15, frequency=5, dt=0.5 * units.fs)       # three epochs
+    monkeypatch.setattr(emu_lib.EmuContext, "md_run_gnn", real_run)
+    assert len(per_epoch) == 3 and per_epoch[1] <= per_epoch[0] - 2 and per_epoch[2] == per_epoch[1], per_epoch
+    assert per_epoch[2] <= 3, per_epoch                          # end-of-epoch synchronisation (+ the host copy of the bath trajectory)
     for mode in ("sync", "overflow", "graph"):
         for a, b in zip(runs["async"][0], runs[mode][0]):
             assert torch.equal(a, b), mode
