@@ -312,3 +312,25 @@ def check_stack_adjoint_native_equals_autograd(dev):
     assert len(res[0]) == len(res[1]) >= 4
     for x, y in zip(*res):
         assert abs(x - y) <= 5e-4 * max(1.0, abs(y)), (res[0], res[1])
+
+
+def check_bonded_edge_cases(dev):
+    """empty topologies (no terms: zero energy, zero forces, no launch with an empty grid), a topology naming a non-existent
+    atom (rejected at construction), duplicate bonds (each listed term counts, as in the reference's sum)"""
+    import pytest
+    from torchmd.interface import AnglePotentials, BondPotentials
+    system, g = _system(dev)
+    n = len(system)
+    x = torch.tensor(g["positions"], dtype=torch.float32).to(dev)
+    for mod in (BondPotentials(system, torch.zeros((0, 2), dtype=torch.long), 3.0, 1.3),
+                AnglePotentials(system, torch.zeros((0, 3), dtype=torch.long), 2.0, 1.9)):
+        q = x.clone().requires_grad_(True)
+        e = mod(q)
+        assert e.item() == 0.0
+        assert float(mod.native_force(x).abs().max()) == 0.0 and mod.native_force(x).shape == (n, 3)
+    with pytest.raises(IndexError):
+        BondPotentials(system, torch.LongTensor([[0, n]]), 3.0, 1.3)
+    one = BondPotentials(system, torch.LongTensor(g["bond_top"][:5]), 3.0, 1.3)
+    two = BondPotentials(system, torch.LongTensor(np.concatenate([g["bond_top"][:5], g["bond_top"][:5]])), 3.0, 1.3)
+    _close(two(x).item(), 2.0 * one(x).item(), 1e-6)
+    _close(two.native_force(x).cpu().numpy(), 2.0 * one.native_force(x).cpu().numpy(), 1e-6)

@@ -11,6 +11,7 @@ from test_emu_api import emulated_backend  # noqa: F401  (autouse fixture: swaps
                                    B.check_electrostatics, B.check_fold_stack_on_device_engine,
                                    B.check_fold_force_field_with_gnn, B.check_pair_tab_through_pair_potentials,
                                    B.check_fold_force_field_graph_replay, B.check_fold_engine_sync_equals_async, B.check_generic_route_configs,
-                                   B.check_tpair_potentials_vs_reference_fixture, B.check_stack_adjoint_native_equals_autograd], ids=lambda f: f.__name__)
+                                   B.check_tpair_potentials_vs_reference_fixture, B.check_stack_adjoint_native_equals_autograd,
+                                   B.check_bonded_edge_cases], ids=lambda f: f.__name__)
 def test_emu_bonded(check):
     check("cpu")

@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
                                    B.check_electrostatics, B.check_fold_stack_on_device_engine,
                                    B.check_fold_force_field_with_gnn, B.check_pair_tab_through_pair_potentials,
                                    B.check_fold_engine_sync_equals_async, B.check_generic_route_configs,
-                                   B.check_tpair_potentials_vs_reference_fixture, B.check_stack_adjoint_native_equals_autograd], ids=lambda f: f.__name__)
+                                   B.check_tpair_potentials_vs_reference_fixture, B.check_stack_adjoint_native_equals_autograd,
+                                   B.check_bonded_edge_cases], ids=lambda f: f.__name__)
 def test_gpu_bonded(check):
     check("cuda")
