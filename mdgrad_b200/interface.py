@@ -26,6 +26,35 @@ class GeneralInteraction(torch.nn.Module):
         self.device = system.device
 
 
+class SpecificInteraction(torch.nn.Module):
+    """Base for interactions over a fixed topology (reference :59-83); nothing in the reference derives from it."""
+
+    def __init__(self, system, topology):
+        super().__init__()
+        self.system = system
+        self.cell = torch.Tensor(np.asarray(system.get_cell())).to(system.device)
+        self.cell.requires_grad = True
+        self.device = system.device
+        self.topology = topology
+
+
+class topology:
+    """Placeholder kept for import compatibility: the reference's class (:513-545) is an unfinished stub whose constructor cannot
+    be called (`def __init__():`)."""
+
+    def __init__(self, top=None):
+        self.top = top
+
+    def _mutate(self, xyz, boundary):
+        pass
+
+    def _get_topology(self):
+        return self.top
+
+    def _stack(self):
+        pass
+
+
 class _PairEnergy(torch.autograd.Function):
     """E(xyz, params) over the context's stored list; backward = the forces / dE/dparam the same
     kernel launch produced (first order only - see PairPotentials.second_order)."""
