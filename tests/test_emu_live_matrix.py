@@ -321,3 +321,41 @@ def test_emu_fold_optimisation_loop_vs_live_reference():
     np.testing.assert_allclose(oh, rh, rtol=5e-4)
     assert np.abs(ow - rw).max() <= 2e-4 * np.abs(rw).max()
     np.testing.assert_allclose(oq, rq, atol=2e-4)
+
+
+def test_emu_gnn_potentials_orthorhombic_and_exclusions_vs_live_reference():
+    """GNNPotentials on an orthorhombic box with atoms outside the cell and an exclusion list: the reference's raw-offset quirk
+    (integer offsets subtracted without the cell, schnet.py:122-127) only cancels on unit cells - energies and forces through
+    the native program and through the op-level route must still equal the reference's"""
+    import torchmd
+    from nff.nn.models.schnet import SchNet
+    from mdgrad_b200._ase_compat import Atoms
+    rng = np.random.default_rng(12)
+    cell = np.array([9.3, 10.4, 8.8])
+    n = 70
+    pos = rng.uniform(-1.0, 1.0, (n, 3)) + rng.uniform(0, 1, (n, 3)) * cell
+    numbers = rng.integers(1, 9, n)
+    ex = torch.LongTensor(rng.integers(0, n, (25, 2)))
+    params = {"n_atom_basis": 20, "n_filters": 24, "n_gaussians": 11, "n_convolutions": 2, "cutoff": 3.6, "trainable_gauss": False}
+    out = {}
+    with ref_import.active() as ref:
+        torch.manual_seed(2)
+        rsys = ref.system.System(Atoms(numbers=numbers, positions=pos, cell=cell, pbc=True), device="cpu")
+        rmodel = ref.schnet.SchNet(params)
+        rg = ref.interface.GNNPotentials(rsys, rmodel, cutoff=3.6, ex_pairs=ex)
+        x = torch.Tensor(rsys.get_positions()).requires_grad_(True)
+        e = rg(x)
+        out["ref"] = (e.detach().reshape(-1), -torch.autograd.grad(e.sum(), x)[0], rg.inputs["nbr_list"].clone(), rg.inputs["offsets"].clone())
+        sd = {k: v.clone() for k, v in rmodel.state_dict().items()}
+    osys = torchmd.system.System(Atoms(numbers=numbers, positions=pos, cell=cell, pbc=True), device="cpu")
+    omodel = SchNet(params)
+    omodel.load_state_dict(sd)
+    og = torchmd.interface.GNNPotentials(osys, omodel, cutoff=3.6, ex_pairs=ex)
+    assert torch.equal(og.inputs["nbr_list"].cpu(), out["ref"][2]) and torch.equal(og.inputs["offsets"].cpu(), out["ref"][3])
+    x = torch.Tensor(osys.get_positions()).requires_grad_(True)
+    e = og(x)                                                           # op-level route
+    f = -torch.autograd.grad(e.sum(), x)[0]
+    en, fn = og.native_energy_force(torch.Tensor(osys.get_positions()))    # native program
+    for ee, ff in ((e.detach().reshape(-1), f), (en.reshape(-1), fn)):
+        assert (ee - out["ref"][0]).abs().max() <= 1e-5 * out["ref"][0].abs().max()
+        assert (ff - out["ref"][1]).abs().max() <= 2e-5 * out["ref"][1].abs().max()
