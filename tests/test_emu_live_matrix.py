@@ -359,3 +359,51 @@ def test_emu_gnn_potentials_orthorhombic_and_exclusions_vs_live_reference():
     for ee, ff in ((e.detach().reshape(-1), f), (en.reshape(-1), fn)):
         assert (ee - out["ref"][0]).abs().max() <= 1e-5 * out["ref"][0].abs().max()
         assert (ff - out["ref"][1]).abs().max() <= 2e-5 * out["ref"][1].abs().max()
+
+
+def test_emu_water_fit_loop_vs_live_reference():
+    """BASELINE configs[2]'s flow (scripts/run_water.py in miniature): water box, SchNet + O-O ExcludedVolume Stack, NHC epochs, a loss on
+    RDF(O-O) through `index_tuple`, adjoint backward, Adam on the SchNet weights - against the reference, same seed"""
+    import types
+    import torchmd
+    from nff.nn.models.schnet import SchNet
+    from mdgrad_b200._ase_compat import Atoms, units
+
+    def loop(ns, schnet_cls):
+        g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "schnet_water.npz"))
+        keep = np.arange(96)                                   # 32 molecules of the 64 (keeps the reference's O(N^2) lists quick)
+        atoms = Atoms(numbers=g["numbers"][keep], positions=g["positions"][keep], cell=g["cell"], pbc=True)
+        system = ns.system.System(atoms, device="cpu")
+        np.random.seed(3)
+        system.set_temperature(298.0 * units.kB)
+        torch.manual_seed(5)
+        model = schnet_cls({"n_atom_basis": 24, "n_filters": 24, "n_gaussians": 12, "n_convolutions": 2, "cutoff": 5.0,
+                            "trainable_gauss": False})
+        oxy = [int(i) for i in np.nonzero(g["numbers"][keep] == 8)[0]]
+        gnn = ns.interface.GNNPotentials(system, model, cutoff=5.0)
+        prior = ns.interface.PairPotentials(system, ns.potentials.ExcludedVolume(2.6, 0.015, 12), cutoff=5.0, index_tuple=(oxy, oxy))
+        integ = ns.md.NoseHooverChain(ns.interface.Stack({"gnn": gnn, "prior": prior}), system, Q=50.0, T=298.0 * units.kB,
+                                      num_chains=5, adjoint=True)
+        sim = ns.md.Simulations(system, integ)
+        obs = ns.observable.rdf(system, 40, (1.8, 5.5), index_tuple=(oxy, oxy))
+        target = torch.linspace(0.0, 1.5, 40)
+        opt = torch.optim.Adam(list(model.parameters()), lr=2e-3)
+        hist = []
+        for _ in range(2):
+            v, q, pv = sim.simulate(5, dt=0.5 * units.fs, frequency=5)
+            _, _, gr = obs(q[-1:])
+            loss = (gr - target).pow(2).mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            hist.append(loss.item())
+        return np.array(hist), torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy(), system.get_positions()
+
+    with ref_import.active() as ref:
+        rh, rw, rq = loop(ref, ref.schnet.SchNet)
+    ours = types.SimpleNamespace(system=torchmd.system, interface=torchmd.interface, potentials=torchmd.potentials, md=torchmd.md,
+                                 observable=torchmd.observable)
+    oh, ow, oq = loop(ours, SchNet)
+    np.testing.assert_allclose(oh, rh, rtol=5e-4)
+    assert np.abs(ow - rw).max() <= 2e-4 * np.abs(rw).max()
+    np.testing.assert_allclose(oq, rq, atol=2e-4)
