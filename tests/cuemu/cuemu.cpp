@@ -701,7 +701,6 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t st) {
     if (!exec) return g_last_error = cudaErrorInvalidValue;
     Stream* s = stream_of(st);
     for (const auto& fn : exec->ops) enqueue(s, fn);
-    g_counters[0] += 0;
     return cudaSuccess;
 }
 cudaError_t cudaGraphDestroy(cudaGraph_t graph) { delete graph; return cudaSuccess; }
