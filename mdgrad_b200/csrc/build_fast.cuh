@@ -19,7 +19,7 @@
 #pragma once
 
 #ifndef FB_WARPS
-#define FB_WARPS 4                // cells (warps) per CTA; build variants fbw2 / fbw8
+#define FB_WARPS 4                // cells (warps) per CTA; build variant fbw2 (8 would exceed the 48 KB static shared-memory limit)
 #endif
 #define FB_BATCH 736             // candidates per batch (23 chunks of 32; a 27-cell stencil holds ~650 at liquid density)
 #define FB_CHUNKS (FB_BATCH / 32)
