@@ -2,6 +2,9 @@
 # First GPU call of the next round (run under gpurun, 1 GPU):  bash tools/round2_first_call.sh
 # Everything written after the round-1 GPU budget ran out gets its first hardware run here, each stage under its own
 # timeout, all output under gpurun_out/.  Order = value of the information per GPU-minute.
+# BEFORE calling gpurun, build the variant libraries in the container (about 5 minutes of nvcc, no GPU needed):
+#     python -c "from mdgrad_b200 import build as b; [b.build(variant=v) for v in b.VARIANTS]"
+# the .so files travel with the snapshot and the stamps turn section 3's build loop into a no-op on the (charged) GPU box.
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 echo "== 1. GPU parity suite" | tee gpurun_out/r2_summary.txt
