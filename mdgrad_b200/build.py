@@ -39,6 +39,8 @@ VARIANTS = {
     # (8 warps per CTA would need 77 KB of STATIC shared memory - over the 48 KB limit; only the 2-warp shape is buildable)
     "fbw2": ["-DFB_WARPS=2"],
     "lean": ["-DMDG_BUILD_LEAN=1"],
+    # SchNet fused filter generator at 3 CTAs per SM (register cap 85 instead of the 100 it takes by itself)
+    "sne3": ["-DSN_EDGE_MINBLOCKS=3"],
     "i8lean": ["-DMDG_BUILD_INT8_SCREEN=1", "-DMDG_BUILD_LEAN=1"],
 }
 

@@ -59,7 +59,12 @@ __global__ void k_sn_transpose(int rows, int cols, const float* __restrict__ W, 
 // FMAs with the same weight; weights come pre-transposed ([in][out]) so that the lanes of a warp (consecutive output
 // index) read one coalesced line per k.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sn_edge_fwd(int64_t E, const int* __restrict__ dE, int G, int F, const float* __restrict__ dis,
+#ifdef SN_EDGE_MINBLOCKS          // build variant sne3: 3 CTAs per SM (77 registers, no spills) for the fused filter generator
+#define SN_EDGE_BOUNDS __launch_bounds__(256, SN_EDGE_MINBLOCKS)
+#else                            // default: 100 registers, 2 CTAs per SM
+#define SN_EDGE_BOUNDS __launch_bounds__(256)
+#endif
+__global__ void SN_EDGE_BOUNDS k_sn_edge_fwd(int64_t E, const int* __restrict__ dE, int G, int F, const float* __restrict__ dis,
                                                      const float* __restrict__ mu, const float* __restrict__ width,
                                                      const float* __restrict__ We1T, const float* __restrict__ be1,
                                                      const float* __restrict__ We2T, const float* __restrict__ be2,

@@ -20,7 +20,7 @@ for v in b.VARIANTS:
         b.build(variant=v)
     except Exception as e:
         print('variant %s does not build: %s' % (v, str(e)[-300:]))" 2>&1 | grep -v "^ptxas info\|bytes stack frame" | tail -6
-for v in pf pfmb6 pfmb4 i8 lean i8lean mb6 mb4 u2mb6 u2mb4 fbw2; do
+for v in pf pfmb6 pfmb4 i8 lean i8lean mb6 mb4 u2mb6 u2mb4 fbw2; do   # (sne3 only matters for SchNet: section 5)
   MDG_LIB_VARIANT=$v timeout 200 python bench.py --steps 600 --warmup 60 --no-e2e --no-cpu-baseline \
       > gpurun_out/r2_ab_$v.json 2> gpurun_out/r2_ab_$v.err
   python - "$v" <<'PY' | tee -a gpurun_out/r2_summary.txt
@@ -47,6 +47,7 @@ timeout 600 python tools/schnet_md_bench.py --config si --route engine     2>&1 
 echo "== 5b. SchNet MD: synchronous vs asynchronous vs graph-replay steps" | tee -a gpurun_out/r2_summary.txt
 MDG_GNN_SYNC=1 timeout 300 python tools/schnet_md_bench.py --config water --route engine 2>&1 | tail -1 | sed 's/^/sync : /' | tee -a gpurun_out/r2_summary.txt
 MDG_GNN_GRAPH=1 timeout 300 python tools/schnet_md_bench.py --config water --route engine 2>&1 | tail -1 | sed 's/^/graph: /' | tee -a gpurun_out/r2_summary.txt
+MDG_LIB_VARIANT=sne3 timeout 600 python tools/schnet_md_bench.py --config si --route engine 2>&1 | tail -1 | sed 's/^/sne3 : /' | tee -a gpurun_out/r2_summary.txt
 echo "== 6. tcgen05 dense layers: first execution ever, under timeouts" | tee -a gpurun_out/r2_summary.txt
 timeout 200 python tools/tc_check.py simt gpurun_out/r2_simt.npz 2>&1 | tail -2 | tee -a gpurun_out/r2_summary.txt
 MDG_SCHNET_TC=1 timeout 120 python tools/tc_check.py tc gpurun_out/r2_tc.npz 2>&1 | tail -4 | tee -a gpurun_out/r2_summary.txt
