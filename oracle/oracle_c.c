@@ -94,6 +94,39 @@ int64_t orc_nbr_list(const float* xyz, int n, const float* cell3, double cutoff,
     return P;
 }
 
+/* Reference rows of SELECTED atoms at any box size (tests/fullsize_checks.py): for every i = sel[r] the pairs (i, j), j > i,
+ * that torchmd/topology.py:59-68 lists (upper triangle, d = x_j - x_i, strict +-0.5 image test, d2 < fl32(cutoff^2) && d2 != 0),
+ * in ascending j like torch.nonzero.  out_j / out_off hold `cap` slots per selected row; out_cnt[r] is the TRUE count (may
+ * exceed cap: the caller re-runs with a larger cap).  O(nsel * N) work, O(nsel * cap) memory. */
+void orc_nbr_rows_upper(const float* xyz, int n, const float* cell3, double cutoff, const int64_t* sel, int nsel,
+                        int64_t* out_j, float* out_off, int* out_cnt, int cap) {
+    float L[3], invL[3];
+    for (int k = 0; k < 3; ++k) { L[k] = cell3[k]; invL[k] = 1.0f / cell3[k]; }
+    const float rc2 = (float)(cutoff * cutoff);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int r = 0; r < nsel; ++r) {
+        const int i = (int)sel[r];
+        int c = 0;
+        for (int j = i + 1; j < n; ++j) {
+            float ox, oy, oz;
+            float dx = axis_min_image(xyz[3 * i], xyz[3 * j], L[0], invL[0], &ox);
+            float dy = axis_min_image(xyz[3 * i + 1], xyz[3 * j + 1], L[1], invL[1], &oy);
+            float dz = axis_min_image(xyz[3 * i + 2], xyz[3 * j + 2], L[2], invL[2], &oz);
+            float d2 = (dx * dx + dy * dy) + dz * dz;
+            if ((d2 < rc2) && (d2 != 0.0f)) {
+                if (c < cap) {
+                    out_j[(size_t)r * cap + c] = j;
+                    out_off[((size_t)r * cap + c) * 3] = ox;
+                    out_off[((size_t)r * cap + c) * 3 + 1] = oy;
+                    out_off[((size_t)r * cap + c) * 3 + 2] = oz;
+                }
+                ++c;
+            }
+        }
+        out_cnt[r] = c;
+    }
+}
+
 /* LJ u(r) = 4 eps ((s/r)^12 - (s/r)^6): e and g = -u'(r)/r from d2 (double precision algebra). */
 static inline void lj_eval(double d2, double sigma, double eps, double* e, double* g) {
     double r2i = 1.0 / d2, s2 = sigma * sigma * r2i, s6 = s2 * s2 * s2, s12 = s6 * s6;

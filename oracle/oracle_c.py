@@ -33,6 +33,9 @@ def load():
         lib.orc_nbr_list.restype = ctypes.c_int64
         lib.orc_nbr_list.argtypes = [f32p, ctypes.c_int, f32p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_int64]
+        lib.orc_nbr_rows_upper.restype = None
+        lib.orc_nbr_rows_upper.argtypes = [f32p, ctypes.c_int, f32p, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         lib.orc_pair_rows.restype = ctypes.c_double
         lib.orc_pair_rows.argtypes = [f32p, ctypes.c_int, f32p, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_int, ctypes.c_int, f32p]
@@ -59,6 +62,24 @@ def nbr_list(xyz, cell3, cutoff, get_dis=True):
     dis = np.empty((P,), dtype=np.float32)
     lib.orc_nbr_list(xyz, n, cell3, float(cutoff), nbr.ctypes.data, off.ctypes.data, dis.ctypes.data, P)
     return nbr, off, dis
+
+
+def nbr_rows_upper(xyz, cell3, cutoff, sel, cap=128):
+    """Reference list rows (i, j > i) of the selected atoms: returns (cnt[nsel], j[nsel, cap], off[nsel, cap, 3]);
+    only the first cnt[r] slots of row r are defined."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    cell3 = np.ascontiguousarray(cell3, dtype=np.float32)
+    sel = np.ascontiguousarray(sel, dtype=np.int64)
+    lib = load()
+    while True:
+        j = np.zeros((len(sel), cap), dtype=np.int64)
+        off = np.zeros((len(sel), cap, 3), dtype=np.float32)
+        cnt = np.zeros((len(sel),), dtype=np.int32)
+        lib.orc_nbr_rows_upper(xyz, xyz.shape[0], cell3, float(cutoff), sel.ctypes.data, len(sel), j.ctypes.data,
+                               off.ctypes.data, cnt.ctypes.data, cap)
+        if len(sel) == 0 or int(cnt.max()) <= cap:
+            return cnt, j, off
+        cap = int(cnt.max())
 
 
 def lj_forces(xyz, cell3, cutoff, sigma=1.0, eps=1.0, rows=None):

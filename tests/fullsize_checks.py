@@ -41,6 +41,34 @@ def check_list_structure(ctx, dev, ncell):
     return P
 
 
+def check_list_rows_bit_exact(ctx, dev, ncell, nrandom=6144, nboundary=6144):
+    """neighbor INDICES, ORDER and image OFFSETS of sampled rows of the exported list, bit-exact against the C restatement of the
+    reference arithmetic (topology.py:59-68) run over the whole box for those rows: random rows plus rows of atoms within
+    one cutoff of a box face (the rows whose pairs carry image shifts), the first and the last atoms.  At 256 000 atoms the
+    sample holds ~330 000 listed pairs; the reference itself cannot allocate this box (70 N^2 bytes)."""
+    pos32, _, L32, xyz, _ = system(ncell, dev)
+    n = xyz.shape[0]
+    nbr, off = ctx.nbr_list(xyz, [L32] * 3, RC)
+    nbr_h, off_h = nbr.cpu().numpy(), off.cpu().numpy()
+    rng = np.random.default_rng(11)
+    near_face = np.nonzero(((pos32 < RC) | (pos32 > L32 - RC)).any(1))[0]
+    sel = np.unique(np.concatenate([rng.choice(n, size=min(nrandom, n), replace=False),
+                                    rng.choice(near_face, size=min(nboundary, len(near_face)), replace=False),
+                                    np.arange(min(64, n)), np.arange(max(0, n - 64), n)]))
+    cnt, jj, oo = OC.nbr_rows_upper(pos32, [L32] * 3, RC, sel, cap=96)
+    lo = np.searchsorted(nbr_h[:, 0], sel, side="left")
+    hi = np.searchsorted(nbr_h[:, 0], sel, side="right")
+    assert np.array_equal(hi - lo, cnt), "row lengths differ from the reference arithmetic at %d rows" % int((hi - lo != cnt).sum())
+    rows = np.repeat(np.arange(len(sel)), cnt)
+    cols = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    flat = np.repeat(lo, cnt) + cols
+    assert np.array_equal(nbr_h[flat, 1], jj[rows, cols]), "neighbor indices differ"
+    assert np.array_equal(off_h[flat], oo[rows, cols]), "image offsets differ"
+    shifted = int((oo[rows, cols] != 0).any(1).sum())
+    assert shifted > 0 or ncell < 4
+    return int(cnt.sum()), shifted
+
+
 def check_forces_against_c_oracle(ctx, dev, ncell, nrows=2048):
     """forces / per-row energy of a block of rows vs the C restatement of the reference (all-pairs over the whole box,
     fp64 accumulation), 1e-5; Newton's third law over the whole box"""

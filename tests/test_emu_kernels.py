@@ -204,6 +204,8 @@ def test_emu_fullsize_property_checks_at_reduced_size(ectx):
     cpu = torch.device("cpu")
     P = F.check_list_structure(ectx, cpu, 10)
     assert 100_000 < P < 120_000
+    pairs, shifted = F.check_list_rows_bit_exact(ectx, cpu, 10, nrandom=1024, nboundary=1024)
+    assert pairs > 40_000 and shifted > 5_000
     F.check_forces_against_c_oracle(ectx, cpu, 10, nrows=512)
     F.check_engine_invariants(ectx, cpu, 10, nsteps=12)
     F.check_rdf_two_paths(ectx, cpu, 10)

@@ -19,6 +19,11 @@ def test_fullsize_list_structure(ctx):
     assert 6_900_000 < P < 7_250_000          # P ~ 7.07 M at 256 000 atoms
 
 
+def test_fullsize_list_rows_bit_exact(ctx):
+    pairs, shifted = F.check_list_rows_bit_exact(ctx, _dev(), NCELL)
+    assert pairs > 250_000 and shifted > 20_000
+
+
 def test_fullsize_forces_vs_c_oracle_rows(ctx):
     F.check_forces_against_c_oracle(ctx, _dev(), NCELL)
 
