@@ -202,7 +202,7 @@ int mdg_md_run(mdg_ctx* ctx, const mdg_md_params* p, int n, const float* d_mass,
 /* Statistics of the last mdg_md_run / mdg_nbr_build on this context (for bench / tests):
  * out[0]=kernels launched, out[1]=list rebuilds, out[2]=directed list entries (last build),
  * out[3]=max row length, out[4]=ncell_x, out[5]=ncell_y, out[6]=ncell_z, out[7]=path
- * (0 = cell list, 1 = all-pairs). */
+ * (0 = cell list, 1 = all-pairs, 2 = cell list in the engine's tile form). */
 int mdg_get_stats(mdg_ctx* ctx, int64_t* h_out8);
 
 /* ------------------------------------------------------------------------------------------

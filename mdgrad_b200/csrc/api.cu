@@ -48,6 +48,10 @@ extern "C" int mdg_create(int device, mdg_ctx** out) {
     cudaMemset(c->flags.p, 0, sizeof(int) * 8);
     const char* fg = getenv("MDG_FORCE_GROUP");
     c->force_group = (fg && (atoi(fg) == 8 || atoi(fg) == 2)) ? atoi(fg) : 4;
+    const char* tl = getenv("MDG_TILES");            // MDG_TILES=0: engine skin list in the round-1 row form (A/B, fallback)
+    c->tiles_off = tl && tl[0] == '0';
+    const char* tw = getenv("MDG_TILE_WARPS");
+    c->tile_warps_env = (tw && atoi(tw) >= 1 && atoi(tw) <= 16) ? atoi(tw) : 0;
     *out = c;
     return MDG_OK;
 }
@@ -56,7 +60,7 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
     if (!c) return MDG_OK;
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->cell_of, &c->slot_of, &c->cell_count, &c->cell_start, &c->perm, &c->perm_tmp, &c->stencil,
-                      &c->qs_buf[0], &c->qs_buf[1], &c->rows, &c->row_len, &c->flags, &c->up_cnt, &c->up_off,
+                      &c->qs_buf[0], &c->qs_buf[1], &c->rows, &c->row_len, &c->tile_rows, &c->tile_len, &c->flags, &c->up_cnt, &c->up_off,
                       &c->scan_tmp, &c->fs, &c->partials, &c->v4, &c->vh4, &c->q4b, &c->f4b, &c->qref,
                       &c->mass_sorted, &c->pvbuf, &c->kebuf, &c->dtbuf, &c->g_off, &c->g_cnt, &c->g_edge,
                       &c->g_other, &c->sn_ws, &c->sn_wt, &c->sn_wcache, &c->gnn_nbr, &c->gnn_off, &c->gnn_xyz, &c->gnn_f3, &c->gnn_fp3,
@@ -145,6 +149,6 @@ extern "C" int mdg_get_stats(mdg_ctx* c, int64_t* o) {
     o[4] = c->nc[0];
     o[5] = c->nc[1];
     o[6] = c->nc[2];
-    o[7] = c->path;
+    o[7] = c->tiles ? 2 : c->path;      // 0 = cell list (rows), 1 = all-pairs, 2 = cell list in tile form (tiles.cuh)
     return MDG_OK;
 }

@@ -224,6 +224,17 @@ __device__ __forceinline__ void pair_eval(const PotParams& P, float d2, float& e
     }
 }
 
+// geometry of the engine's tile list (tiles.cuh)
+struct TileGeom {
+    int ncx, ncy, ncz;
+    int nblk;                      // blocks per x-row (balanced widths <= MDG_TILE_MAXW, each width + 2 <= ncx)
+    int wbase, wrem;               // ncx / nblk, ncx % nblk: block bi spans cells [bi * wbase + min(bi, wrem), ... + wbase + (bi < wrem))
+    int capc;                      // row capacity in chunks
+    int scap;                      // staged-atom capacity (dynamic shared memory = 16 * scap bytes)
+    int g_base;                    // group index of the first stored group (rows are allocated for the own range only)
+    int b_base;                    // block index that group offset counts from
+};
+
 // ---------------------------------------------------------------------------------------------
 // the context
 // ---------------------------------------------------------------------------------------------
@@ -272,6 +283,15 @@ struct mdg_ctx {
     int    force_group = 4;            // lanes per row in k_force_rows (MDG_FORCE_GROUP=2|4|8)
     bool   force_energy = true;        // false: the next force launches skip the per-atom energy (engine inner steps)
     DevBuf flags;             // int[8]: 0 = capacity overflow, 1 = skin violation
+    // tile list (tiles.cuh): the engine's skin list in block-local 16-bit form
+    bool     tiles = false;            // the last build produced tile rows (force launches use k_force_tiles)
+    TileGeom tile;
+    int      tile_warps = 12;          // warps per CTA of k_force_tiles
+    int      tile_warps_env = 0;       // MDG_TILE_WARPS
+    bool     tiles_off = false;        // MDG_TILES=0: keep the row list (k_build_fast / k_force_rows) - A/B and fallback
+    bool     flags_sticky = false;     // mdg_i_build_list must not clear the overflow flags (engine epochs)
+    int      tile_scap_min = 0;        // staged-atom capacity demanded by a previous overflow
+    DevBuf   tile_rows, tile_len;      // uint16 [groups * capc * 128], uint32 [n]
     // export scratch
     DevBuf up_cnt, up_off, scan_tmp;
     int64_t npairs = 0;

@@ -479,6 +479,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     MDG_CUDA(cudaMemcpyAsync(sc, &hs, sizeof(Scalars), cudaMemcpyHostToDevice, st));
     MDG_TRY(c->flags.reserve(sizeof(int) * 8));
     MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 8, st));
+    c->flags_sticky = true;      // the rebuilds of this epoch accumulate into the flags; they are read once at its end
 
     // initial sort + list at q0, state into sorted order (every rank holds the full inputs)
     c->sel_a = c->eng_sel_a; c->sel_b = c->eng_sel_b; c->ex_keys = c->eng_ex_keys; c->n_ex = c->eng_n_ex;
@@ -699,7 +700,12 @@ extern "C" int mdg_md_run(mdg_ctx* c, const mdg_md_params* p, int n, const float
         int s = run_once(c, p, n, d_mass, d_v0, d_q0, h_pv0, h_tgrid, n_grid, d_traj_v, d_traj_q, h_traj_pv,
                          h_last_energy, K, st);
         c->force_energy = true;     // (an error return inside the loop must not leak the force-only mode)
+        c->flags_sticky = false;
         if (s == MDG_E_CAPACITY) {
+            if (c->h_pinned[1] > 0) {          // tile list: a block's stencil did not fit the staged-atom capacity
+                c->tile_scap_min = c->h_pinned[1] + c->h_pinned[1] / 8 + 32;
+                if (c->h_pinned[2] == 0) continue;
+            }
             int need = c->h_pinned[2];
             int cap = ((need + need / 8 + 31) / 32) * 32;
             if (cap <= c->cap) cap = c->cap + 32;

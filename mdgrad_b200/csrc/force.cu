@@ -2,6 +2,7 @@
 // Replaces PairPotentials.forward (reference torchmd/interface.py:284-300: compute_dis
 // topology.py:5-12 -> u(r).sum()) and the autograd force F = -dE/dxyz (torchmd/md.py:227-228).
 #include "common.cuh"
+#include "force_tiles.cuh"
 
 PotParams mdg_make_pot(int kind, const float* h_params, int n_params) {
     PotParams P;
@@ -260,6 +261,12 @@ int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4
 int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, bool with_dp,
                        double* d_dp_partials, cudaStream_t st) {
     if (c->n == 0) return MDG_OK;
+    if (c->tiles) {       // engine skin list in tile form (tiles.cuh): always re-tested, no parameter gradients
+        if (!retest || with_dp) { mdg_set_error("tile list: only the engine's re-tested force evaluation is available"); return MDG_E_STATE; }
+        const int c0 = c->force_s0 >= 0 ? c->force_c0 : c->own_c0, c1 = c->force_s0 >= 0 ? c->force_c1 : c->own_c1;
+        if (c->force_energy) return launch_force_tiles<true>(c, P, d_qs, d_fs, c0, c1, st);
+        return launch_force_tiles<false>(c, P, d_qs, d_fs, c0, c1, st);
+    }
     if (retest) {
         if (with_dp) return launch_force<true, true>(c, P, d_qs, d_fs, d_dp_partials, st);
         return launch_force<true, false>(c, P, d_qs, d_fs, d_dp_partials, st);

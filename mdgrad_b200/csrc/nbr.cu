@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(128) k_build_cells(int s0, int n, const float4
 // ones the reference's single +-1 correction loses (SURVEY 7 "unwrapped positions") and are dropped.
 // ---------------------------------------------------------------------------------------------
 #include "build_fast.cuh"
+#include "build_tiles.cuh"
 
 // written per sorted atom: its cell id (needed by k_build_cells)
 __global__ void k_cell_sorted(int ncell, const int* __restrict__ cell_start, int* __restrict__ cell_sorted) {
@@ -523,8 +524,10 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
     PairFilter F{c->sel_a, c->sel_b, c->ex_keys, c->n_ex, n};
     float4* qs = (qin == c->qs_buf[0].as<float4>()) ? c->qs_buf[1].as<float4>() : c->qs_buf[0].as<float4>();
     c->qs_ptr = qs;
-    MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 3, st));   // [0] overflow, [2] max row count
-    MDG_CUDA(cudaMemsetAsync(c->flags.as<int>() + 6, 0, sizeof(int) * 2, st));   // [6] non-finite, [7] cell overflow
+    if (!c->flags_sticky) {      // (the engine clears the flags once per epoch: an overflow of ANY rebuild must survive to its end)
+        MDG_CUDA(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 3, st));   // [0] overflow, [1] staged-atom demand (tiles), [2] max row count
+        MDG_CUDA(cudaMemsetAsync(c->flags.as<int>() + 6, 0, sizeof(int) * 2, st));   // [6] non-finite, [7] cell overflow
+    }
     if (path == 0) {
         MDG_TRY(c->slot_of.reserve(sizeof(int) * (size_t)n));
         MDG_TRY(c->perm_tmp.reserve(sizeof(int) * (size_t)n));
@@ -635,10 +638,48 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
             c->own_s0 = c->h_layers[c->slab_zlo]; c->own_s1 = c->h_layers[c->slab_zhi];
             c->rows_s0 = c->own_s0;
         }
-        if (c->rows_wanted) {
+        c->tiles = false;
+        bool roomy = g.nc[0] >= 5 && g.nc[1] >= 5 && g.nc[2] >= 5;   // stencil extent < half a box
+        if (c->rows_wanted && c->fast_build && rlist > cutoff && roomy && !c->tiles_off) {
+            // ---- tile list (tiles.cuh): block-local 16-bit rows for k_force_tiles --------------------------------
+            const double occ = (double)n / (double)ncell;
+            int maxw = g.nc[0] - 2 < MDG_TILE_MAXW ? g.nc[0] - 2 : MDG_TILE_MAXW;
+            int scap = 0;
+            for (; maxw >= 1; --maxw) {
+                scap = roundup((int)(9.0 * (maxw + 2) * occ * 1.35) + 96, 64);
+                if (scap < c->tile_scap_min) scap = roundup(c->tile_scap_min, 64);
+                if (scap <= MDG_TILE_MAXSCAP && maxw * occ * 1.1 <= 16.0 * MDG_TILE_GROUP) break;
+            }
+            if (maxw >= 1 && c->cap / MDG_TILE_CHUNK <= 255) {
+                TileGeom& G = c->tile;
+                G.ncx = g.nc[0]; G.ncy = g.nc[1]; G.ncz = g.nc[2];
+                G.nblk = (g.nc[0] + maxw - 1) / maxw;
+                G.wbase = g.nc[0] / G.nblk;
+                G.wrem = g.nc[0] % G.nblk;
+                G.capc = c->cap / MDG_TILE_CHUNK;
+                G.scap = scap;
+                const int xr0 = c->own_c0 / g.nc[0], nxr = (c->own_c1 - c->own_c0) / g.nc[0];
+                G.b_base = xr0 * G.nblk;
+                G.g_base = c->own_s0 >> 3;
+                const int nblocks = nxr * G.nblk;
+                const size_t ngroups = (size_t)((c->own_s1 - c->own_s0) >> 3) + (size_t)nblocks + 2;
+                MDG_TRY(c->tile_rows.reserve(sizeof(uint16_t) * ngroups * (size_t)G.capc * MDG_TILE_GCHUNK));
+                MDG_TRY(c->tile_len.reserve(sizeof(uint32_t) * (size_t)n));
+                if (c->tile_warps_env > 0) c->tile_warps = c->tile_warps_env;
+                else {
+                    int tw = (int)((occ * g.nc[0] / G.nblk * 1.1 + MDG_TILE_GROUP - 1) / MDG_TILE_GROUP);
+                    c->tile_warps = tw < 2 ? 2 : (tw > 16 ? 16 : tw);
+                }
+                if (nblocks > 0)
+                    k_build_tiles<<<dim3(G.nblk, g.nc[1], nxr / g.nc[1]), MDG_TILE_MAXW * 32, 0, st>>>(xr0 / g.nc[1], G, qs, c->cell_start.as<int>(), c->box, c->rlist2, F,
+                                                                         c->tile_rows.as<uint16_t>(), c->tile_len.as<uint32_t>(),
+                                                                         c->flags.as<int>());
+                c->tiles = true;
+            }
+        }
+        if (c->rows_wanted && !c->tiles) {
             MDG_TRY(c->rows.reserve(sizeof(uint32_t) * (size_t)(c->own_s1 - c->own_s0 + 1) * c->cap));
             uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
-            bool roomy = g.nc[0] >= 5 && g.nc[1] >= 5 && g.nc[2] >= 5;   // stencil extent < half a box
             if (c->fast_build && rlist > cutoff && roomy) {
                 int ncl = c->own_c1 - c->own_c0;
                 if (ncl > 0)
@@ -659,6 +700,7 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         MDG_CUDA(cudaMemcpyAsync(qs, qin, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         k_iota<<<nb, T, 0, st>>>(c->perm.as<int>(), n);
         c->own_s0 = 0; c->own_s1 = n; c->own_c0 = 0; c->own_c1 = ncell; c->rows_s0 = 0;
+        c->tiles = false;
         if (c->rows_wanted) MDG_TRY(c->rows.reserve(sizeof(uint32_t) * (size_t)n * c->cap));
         if (c->rows_wanted)
             k_build_allpairs<<<(n + AP_TILE - 1) / AP_TILE, AP_TILE, 0, st>>>(n, qs, c->box, c->rlist2, c->cap, F,
@@ -667,7 +709,7 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
         c->stat_launches += 1 + (c->rows_wanted ? 1 : 0);
     }
     MDG_KERNEL_CHECK();
-    c->built = c->rows_wanted;
+    c->built = c->rows_wanted && !c->tiles;      // (tile rows only serve the engine's force kernel)
     c->stat_rebuilds++;
     return MDG_OK;
 }
