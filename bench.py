@@ -81,6 +81,22 @@ def make_system(ncell, seed=1, zmult=1):
     return pos, vel, ncell * a
 
 
+def ncu_traffic(kernel_substr):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu summary of THIS round (profiles/r02_force_ncu.json,
+    written by tools/ncu_summary.py from an `ncu --set full` capture of the same bench command); None if it does not list
+    the kernel the engine actually ran."""
+    p = os.path.join(ROOT, "profiles", "r02_force_ncu.json")
+    try:
+        for k in json.load(open(p))["kernels"]:
+            if kernel_substr in k["name"]:
+                return float(k["dram_bytes_read"]) + float(k["dram_bytes_write"]), \
+                    "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch (%s, kernel %s)" % (
+                        os.path.relpath(p, ROOT), k["name"])
+    except Exception:
+        pass
+    return None, "no ncu capture of this kernel committed"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -193,6 +209,41 @@ def equilibrate(ctx, _lib, torch, n, L, mass, v, q, skin, log, zmult=1, world=1)
     return v, q
 
 
+def dist_parity(ctx, _lib, torch, dist, dev, rank, world):
+    """UNTIMED multi-GPU parity statement inside the driver-run line: a small box (6912 atoms per rank) runs 40 NHC
+    steps on the slab-decomposed engine of all ranks and, on rank 0, on the single-GPU engine; both sum the forces of a row
+    in the same order, so they agree to the rounding of the kinetic-energy all-reduce.  Returns relative differences."""
+    ncell = 12
+    pos, vel, L = make_system(ncell, seed=7, zmult=world)
+    n = pos.shape[0]
+    L32 = float(np.float32(L))
+    q0 = torch.tensor(pos, dtype=torch.float32, device=dev)
+    v0 = torch.tensor(vel * 0.5, dtype=torch.float32, device=dev)
+    mass = torch.full((n,), MASS, dtype=torch.float32, device=dev)
+    p = md_params(_lib, n, L32, 0.4, 5, world)
+    nsteps = 40
+    p.traj_stride = 10
+    t = tgrid(nsteps, 0.002)
+    tv, tq, tpv, e = ctx.md_run(p, mass, v0, q0, [0.0] * CHAINS, t, want_energy=True)
+    tv, tq = tv.clone(), tq.clone()
+    dist.all_reduce(tv)
+    dist.all_reduce(tq)
+    out = None
+    if rank == 0:
+        sctx = _lib.Context(dev)
+        sv, sq, spv, se = sctx.md_run(p, mass, v0, q0, [0.0] * CHAINS, t, want_energy=True)
+        out = {"atoms": n, "steps": nsteps, "rebuilds": int(ctx.stats()["rebuilds"]),
+               "dv": (tv - sv).abs().max().item() / sv.abs().max().item(),
+               "dq": (tq - sq).abs().max().item() / L,
+               "dpv": (tpv - spv).abs().max().item() / max(1e-9, spv.abs().max().item()),
+               "dE": abs(e - se) / abs(se),
+               "frame0_equal": bool(torch.equal(tq[0], q0) and torch.equal(tv[0], v0)),
+               "what": "world-%d slab engine vs the single-GPU engine on rank 0, relative max differences of v, q (per box edge), "
+                       "bath momenta, potential energy after %d NHC steps" % (world, nsteps)}
+        del sctx
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the C oracle (port of the reference's per-evaluation all-pairs
 # algorithm) on the host cores, on a bounded row sample of the same workload
@@ -201,6 +252,8 @@ def cpu_reference_steps_per_s(ncell, steps, warmup, budget_s, zmult=1):
     from oracle import oracle_c as C
     pos, vel, L = make_system(ncell, zmult=zmult)
     n = pos.shape[0]
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    C.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cores = C.num_threads()
     cell3 = np.array([L, L, L * zmult], dtype=np.float32)
     x = pos.astype(np.float32)
@@ -224,21 +277,24 @@ def cpu_reference_steps_per_s(ncell, steps, warmup, budget_s, zmult=1):
     full_step = (el / steps) * (n / rows) if rows < n else el / steps
     sample = ("C oracle (all-pairs list rebuilt per evaluation, as the reference), %d of %d atom rows per step, "
               "time scaled x%.1f; reference torch path cannot allocate this box (70*N^2 B)" % (rows, n, n / rows))
-    return zmult / full_step, cores, sample, n     # 256k-atom-box equivalents per second (see value_definition)
+    detail = {"extrapolated": rows < n, "rows_measured_per_step": int(rows), "rows_total": int(n), "steps_measured": int(steps),
+              "seconds_measured": el, "scale_factor": float(n) / rows}
+    return zmult / full_step, cores, sample, n, detail     # 256k-atom-box equivalents per second (see value_definition)
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    v, cores, sample, n = cpu_reference_steps_per_s(args.ncell, args.steps, args.warmup, budget_s=90.0, zmult=max(1, args.gpus))
+    v, cores, sample, n, detail = cpu_reference_steps_per_s(args.ncell, args.steps, args.warmup, budget_s=90.0, zmult=max(1, args.gpus))
     line = {
         "impl": "reference", "metric": "MD steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "LJ fluid %d atoms (FCC %d^3, rho 0.845), rc 2.5, NoseHooverChain Q=50*N/256 T=1 M=5, dt 0.005"
                                % (n, args.ncell), "atoms": n},
-        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": dict({"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}, **detail),
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extrapolated": detail["extrapolated"],
     }
     emit(line)
 
@@ -255,6 +311,9 @@ def main():
     ap.add_argument("--rebuild-every", type=int, default=0, help="0 = auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dist-parity", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c1", "c3", "c5"],
+                    help="c2 (default) = BASELINE configs[1], the headline; c1 / c3 / c5 = configs[0] / [2] / [4] through the public API")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -262,6 +321,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.config != "c2":
+        if rank != 0:
+            return
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        r = bench_configs.RUN[args.config](args)
+        line = {"metric": "MD steps/sec", "value": r["value"], "unit": "steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": r["config"], "gpu_launches": r["gpu_launches"],
+                "e2e": {"value": r["value"], "unit": "steps/s", "note": "this configuration is timed through Simulations.simulate "
+                        "with the host state of System: H2D at the start of the epoch, D2H of the last frame at its end"}}
+        emit(line)
         return
 
     import torch
@@ -285,8 +357,12 @@ def main():
     v0 = torch.tensor(vel, dtype=torch.float32, device=dev)
     mass = torch.full((n,), MASS, dtype=torch.float32, device=dev)
     ctx = _lib.Context(dev)
+    parity = None
     if world > 1:
         ctx.dist_init()
+        if not args.no_dist_parity:
+            parity = dist_parity(ctx, _lib, torch, dist, dev, rank, world)
+            log("dist parity: %s" % parity)
 
     p = md_params(_lib, n, L32, args.skin, 4, world)
     log("set-up: equilibrating %d atoms (NVE + rescale, untimed)" % n)
@@ -368,6 +444,7 @@ def main():
         "tau_per_day": box_steps_per_s * DT * 86400.0,
     }
     if world > 1:
+        res["dist_parity"] = parity
         if rank == 0:
             emit(res)
         ctx.dist_finalize()
@@ -390,10 +467,13 @@ def main():
     peak, peak_src = peaks()
     achieved = alg_bytes / (force_ms * 1e-3) / 1e9
     log("pair counts done: P_rc=%d P_list=%d force %.4f ms" % (P_rc, P_list, force_ms))
-    res["roofline"] = {"bound": "hbm", "kernel": "k_force_rows<LJ,RETEST,4 lanes/row> (pair force over the fixed-capacity skin rows)", "achieved": achieved,
-                       "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 104.2e6 + 4.8e6,
-                       "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                         "(profiles/r01_ncu_summary.md, skin 0.45)",
+    tiles = int(stats["path"]) == 2
+    kname = ("k_force_tiles<LJ> (persistent CTA per block of cells, TMA-staged stencil positions in shared memory, 16-bit local skin rows)"
+             if tiles else "k_force_rows<LJ,RETEST,4 lanes/row> (pair force over the fixed-capacity skin rows)")
+    traffic, traffic_src = ncu_traffic("k_force_tiles" if tiles else "k_force_rows")
+    res["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": achieved,
+                       "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                       "traffic_source": traffic_src,
                        "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "pairs_in_cutoff": P_rc,
                        "pairs_in_skin_list": P_list, "streamed_bytes_with_skin": 32.0 * n + 8.0 * P_list,
                        "kernel_ms": force_ms, "kernel_launches_timed": prof["force_launches"],
@@ -446,9 +526,9 @@ def main():
     # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only)
     if not args.no_cpu_baseline:
         log("cpu baseline (C oracle, bounded sample)")
-        v, cores, sample, _ = cpu_reference_steps_per_s(args.ncell, steps=3, warmup=1, budget_s=20.0)
+        v, cores, sample, _, detail = cpu_reference_steps_per_s(args.ncell, steps=3, warmup=1, budget_s=20.0)
         log("cpu baseline done")
-        res["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+        res["cpu_baseline"] = dict({"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}, **detail)
     emit(res)
 
 

@@ -52,6 +52,8 @@ extern "C" int mdg_create(int device, mdg_ctx** out) {
     c->tiles_off = tl && tl[0] == '0';
     const char* tw = getenv("MDG_TILE_WARPS");
     c->tile_warps_env = (tw && atoi(tw) >= 1 && atoi(tw) <= 16) ? atoi(tw) : 0;
+    const char* tc = getenv("MDG_TILE_CTAS");
+    c->tile_ctas_env = (tc && atoi(tc) >= 1 && atoi(tc) <= 16) ? atoi(tc) : 0;
     *out = c;
     return MDG_OK;
 }
@@ -60,7 +62,7 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
     if (!c) return MDG_OK;
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->cell_of, &c->slot_of, &c->cell_count, &c->cell_start, &c->perm, &c->perm_tmp, &c->stencil,
-                      &c->qs_buf[0], &c->qs_buf[1], &c->rows, &c->row_len, &c->tile_rows, &c->tile_len, &c->flags, &c->up_cnt, &c->up_off,
+                      &c->qs_buf[0], &c->qs_buf[1], &c->rows, &c->row_len, &c->tile_rows, &c->tile_len, &c->tile_desc, &c->flags, &c->up_cnt, &c->up_off,
                       &c->scan_tmp, &c->fs, &c->partials, &c->v4, &c->vh4, &c->q4b, &c->f4b, &c->qref,
                       &c->mass_sorted, &c->pvbuf, &c->kebuf, &c->dtbuf, &c->g_off, &c->g_cnt, &c->g_edge,
                       &c->g_other, &c->sn_ws, &c->sn_wt, &c->sn_wcache, &c->gnn_nbr, &c->gnn_off, &c->gnn_xyz, &c->gnn_f3, &c->gnn_fp3,

@@ -288,10 +288,12 @@ struct mdg_ctx {
     TileGeom tile;
     int      tile_warps = 12;          // warps per CTA of k_force_tiles
     int      tile_warps_env = 0;       // MDG_TILE_WARPS
+    int      tile_ctas_env = 0;        // MDG_TILE_CTAS: resident CTAs per SM of the persistent k_force_tiles
     bool     tiles_off = false;        // MDG_TILES=0: keep the row list (k_build_fast / k_force_rows) - A/B and fallback
     bool     flags_sticky = false;     // mdg_i_build_list must not clear the overflow flags (engine epochs)
     int      tile_scap_min = 0;        // staged-atom capacity demanded by a previous overflow
     DevBuf   tile_rows, tile_len;      // uint16 [groups * capc * 128], uint32 [n]
+    DevBuf   tile_desc;                // int [blocks * MDG_TILE_DESC]: block descriptors written by k_build_tiles
     // export scratch
     DevBuf up_cnt, up_off, scan_tmp;
     int64_t npairs = 0;

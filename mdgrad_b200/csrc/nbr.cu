@@ -646,9 +646,9 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
             int maxw = g.nc[0] - 2 < MDG_TILE_MAXW ? g.nc[0] - 2 : MDG_TILE_MAXW;
             int scap = 0;
             for (; maxw >= 1; --maxw) {
-                scap = roundup((int)(9.0 * (maxw + 2) * occ * 1.35) + 96, 64);
+                scap = roundup((int)(9.0 * (maxw + 2) * occ * 1.2) + 64, 32);
                 if (scap < c->tile_scap_min) scap = roundup(c->tile_scap_min, 64);
-                if (scap <= MDG_TILE_MAXSCAP && maxw * occ * 1.1 <= 16.0 * MDG_TILE_GROUP) break;
+                if (scap <= MDG_TILE_MAXSCAP && maxw * occ * 1.1 <= 24.0 * MDG_TILE_GROUP) break;
             }
             if (maxw >= 1 && c->cap / MDG_TILE_CHUNK <= 255) {
                 TileGeom& G = c->tile;
@@ -665,15 +665,16 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
                 const size_t ngroups = (size_t)((c->own_s1 - c->own_s0) >> 3) + (size_t)nblocks + 2;
                 MDG_TRY(c->tile_rows.reserve(sizeof(uint16_t) * ngroups * (size_t)G.capc * MDG_TILE_GCHUNK));
                 MDG_TRY(c->tile_len.reserve(sizeof(uint32_t) * (size_t)n));
-                if (c->tile_warps_env > 0) c->tile_warps = c->tile_warps_env;
+                MDG_TRY(c->tile_desc.reserve(sizeof(int) * (size_t)(nblocks + 1) * MDG_TILE_DESC));
+                if (c->tile_warps_env > 0) c->tile_warps = c->tile_warps_env > 11 ? 11 : c->tile_warps_env;
                 else {
                     int tw = (int)((occ * g.nc[0] / G.nblk * 1.1 + MDG_TILE_GROUP - 1) / MDG_TILE_GROUP);
-                    c->tile_warps = tw < 2 ? 2 : (tw > 16 ? 16 : tw);
+                    c->tile_warps = tw < 2 ? 2 : (tw > 11 ? 11 : tw);      // consumer warps (+ 1 producer warp <= 384 threads)
                 }
                 if (nblocks > 0)
                     k_build_tiles<<<dim3(G.nblk, g.nc[1], nxr / g.nc[1]), MDG_TILE_MAXW * 32, 0, st>>>(xr0 / g.nc[1], G, qs, c->cell_start.as<int>(), c->box, c->rlist2, F,
                                                                          c->tile_rows.as<uint16_t>(), c->tile_len.as<uint32_t>(),
-                                                                         c->flags.as<int>());
+                                                                         c->tile_desc.as<int>(), c->flags.as<int>());
                 c->tiles = true;
             }
         }

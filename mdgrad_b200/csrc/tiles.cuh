@@ -28,6 +28,8 @@
 #define MDG_TILE_MAXW 4             // cells per block along x
 #define MDG_TILE_MAXST (9 * (MDG_TILE_MAXW + 2))            // stencil cells of a block
 #define MDG_TILE_MAXSCAP 4095       // staged atoms: (index << 4) must fit 16 bits
+#define MDG_TILE_DESC 64            // ints per block descriptor: [0] first row, [1] rows, [2] home offset in the stream, [3] staged atoms,
+                                    // [4] pieces, then (source index, stream offset, count) per contiguous piece from [8]
 
 
 __host__ __device__ __forceinline__ int tile_bx0(const TileGeom& G, int bi) { return bi * G.wbase + (bi < G.wrem ? bi : G.wrem); }

@@ -202,6 +202,37 @@ def schnet_golden_configured():
     print("mirror initialisation == reference initialisation for", len(ref_sd), "tensors")
 
 
+def adjoint_short_golden():
+    """G3b (round 2): SHORT-horizon adjoint gradients (5 NH-Verlet steps of the C1 system, dt 0.01): d loss / d sigma,
+    d loss / d epsilon and d loss / d (v0, q0) from the unmodified reference's OdeintAdjointMethod (sovlers.py:211-293).  Over
+    5 steps the dynamics has not amplified rounding differences yet, so the CUDA path is held to 1e-4 here (the 49-step
+    fixture c1_traj.npz only supports ~1e-2)."""
+    with ref_import.active() as ref:
+        atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+        system = ref.system.System(atoms, device="cpu")
+        np.random.seed(0)
+        system.set_temperature(1.0)
+        v0 = system.get_velocities().copy()
+        q0 = system.get_positions(wrap=True).copy()
+        out = {"v0": v0, "q0": q0}
+        for tag, pot in (("lj", ref.potentials.LennardJones(1.1, 0.9)), ("buck", ref.potentials.Buck(1000.0, 3.5, 2.0))):
+            system.set_positions(q0)
+            system.set_velocities(v0)
+            pair = ref.interface.PairPotentials(system, pot, cutoff=2.5)
+            integ = ref.md.NoseHooverChain(pair, system, T=1.0, num_chains=5, Q=50.0, adjoint=True, topology_update_freq=1)
+            sim = ref.md.Simulations(system, integ, wrap=True, method="NH_verlet")
+            v, q, pv = sim.simulate(steps=6, frequency=6, dt=0.01)
+            loss = (q[-1] ** 2).sum() + (v[2] * v[4]).sum() + pv[-1].sum()
+            loss.backward()
+            out["loss_" + tag] = np.array(loss.item())
+            out["v_" + tag] = v.detach().numpy()
+            out["q_" + tag] = q.detach().numpy()
+            for name, prm in pot.named_parameters():
+                out["d%s_%s" % (name, tag)] = prm.grad.numpy().copy()
+            print(tag, "loss", loss.item(), {n: p.grad.item() for n, p in pot.named_parameters()})
+        np.savez_compressed(os.path.join(OUT, "c1_adjoint_short.npz"), **out)
+
+
 def chain_system(n_beads=24, bond_len=1.1, L=6.0, seed=5):
     """a bead chain wound through a periodic box (bonds and angles cross the boundary), fold.py-style (demo/fold.py:116-119)"""
     from mdgrad_b200._ase_compat import Atoms
@@ -387,3 +418,5 @@ if __name__ == "__main__" and "--bonded" in sys.argv:
     bonded_golden()
 if __name__ == "__main__" and "--schnet-configured" in sys.argv:
     schnet_golden_configured()
+if __name__ == "__main__" and "--adjoint-short" in sys.argv:
+    adjoint_short_golden()

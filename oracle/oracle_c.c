@@ -38,6 +38,14 @@ static inline float axis_min_image(float xi, float xj, float L, float invL, floa
     return d + o * L;
 }
 
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

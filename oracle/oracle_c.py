@@ -30,6 +30,8 @@ def load():
         lib = ctypes.CDLL(LIB)
         f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
         lib.orc_num_threads.restype = ctypes.c_int
+        lib.orc_set_threads.restype = None
+        lib.orc_set_threads.argtypes = [ctypes.c_int]
         lib.orc_nbr_list.restype = ctypes.c_int64
         lib.orc_nbr_list.argtypes = [f32p, ctypes.c_int, f32p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_int64]
@@ -49,6 +51,11 @@ def load():
 
 def num_threads():
     return load().orc_num_threads()
+
+
+def set_threads(n):
+    """use n OpenMP threads from now on (bench.py: torchrun exports OMP_NUM_THREADS=1 to every rank)"""
+    load().orc_set_threads(int(n))
 
 
 def nbr_list(xyz, cell3, cutoff, get_dis=True):

@@ -20,6 +20,71 @@ def _fixture(tag):
     return g, params, sd
 
 
+def _configured_fixture(tag):
+    """fixtures at BASELINE's CONFIGURED widths (oracle/make_golden.py --schnet-configured): the weights are rebuilt from the
+    seed with the mirror class (same draws as the reference's initialisation) and pinned by the per-tensor sums in the fixture"""
+    from nff.nn.models.schnet import SchNet
+    g = np.load(os.path.join(G, "schnet_%s.npz" % tag))
+    params = {k: (float(g[k]) if k == "cutoff" else int(g[k])) for k in
+              ("n_atom_basis", "n_filters", "n_gaussians", "n_convolutions", "cutoff")}
+    params["trainable_gauss"] = False
+    torch.manual_seed(int(g["weight_seed"]))
+    model = SchNet(params)
+    sd = model.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["weight_names"]]
+    sums = np.array([float(v.double().sum()) for v in sd.values()])
+    asums = np.array([float(v.double().abs().sum()) for v in sd.values()])
+    np.testing.assert_allclose(sums, g["weight_sums"], rtol=0, atol=1e-9 * max(1.0, np.abs(g["weight_abs_sums"]).max()))
+    np.testing.assert_allclose(asums, g["weight_abs_sums"], rtol=1e-12)
+    return g, params, model
+
+
+@pytest.mark.parametrize("tag", ["water128", "si4096"])
+def test_oracle_schnet_vs_reference_fixture_configured_widths(tag):
+    """the oracle restatement at C3 (A128/F128/G29/L2, 192 atoms) and C5 (A512/F256/G33/L3, 4096 atoms) sizes"""
+    g, params, model = _configured_fixture(tag)
+    xyz = torch.Tensor(g["positions"]).requires_grad_(True)
+    nbr, off = O.neighbor_list(xyz.detach(), params["cutoff"], torch.Tensor(g["cell"]), block=512)
+    assert nbr.shape[0] == int(g["n_edges"])
+    z = torch.tensor(g["numbers"], dtype=torch.long)
+    e = O.schnet_energy(model.state_dict(), z, xyz, nbr, off, pbc_mode="reference")
+    f = -torch.autograd.grad(e, xyz)[0]
+    eref = float(g["energy"].reshape(-1)[0])
+    assert abs(e.item() - eref) <= 2e-6 * abs(eref)
+    assert np.abs(f.numpy() - g["forces"]).max() <= 5e-6 * np.abs(g["forces"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["water128", "si4096"])
+@pytest.mark.parametrize("dense", ["simt", "tc"])
+def test_native_schnet_configured_widths_vs_reference_fixture(tag, dense, monkeypatch):
+    """BOTH native routes (the fused energy+force program - with SIMT and with tcgen05 dense layers - and the op-by-op
+    autograd route over the native list / aggregation kernels) against the reference at the configured sizes and widths."""
+    from torchmd.interface import GNNPotentials
+    from torchmd.system import System
+    from mdgrad_b200._ase_compat import Atoms
+    if dense == "tc":
+        monkeypatch.setenv("MDG_SCHNET_TC", "1")
+    else:
+        monkeypatch.delenv("MDG_SCHNET_TC", raising=False)
+    g, params, model = _configured_fixture(tag)
+    system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device=0)
+    gnn = GNNPotentials(system, model.cuda(), cutoff=params["cutoff"])
+    assert gnn.native_ready()
+    xyz = torch.Tensor(system.get_positions()).cuda()
+    assert gnn.inputs["nbr_list"].shape[0] == int(g["n_edges"])
+    eref, fref = float(g["energy"].reshape(-1)[0]), g["forces"]
+    e, f = gnn.native_energy_force(xyz)
+    assert abs(e.item() - eref) <= 1e-5 * abs(eref), (e.item(), eref)
+    assert np.abs(f.cpu().numpy() - fref).max() <= 1e-5 * np.abs(fref).max()
+    if dense == "simt":                                             # op-by-op route (native list / aggregation + cuBLAS)
+        x = xyz.clone().requires_grad_(True)
+        ea = gnn(x)
+        fa = -torch.autograd.grad(ea.sum(), x)[0]
+        assert abs(ea.item() - eref) <= 1e-5 * abs(eref)
+        assert np.abs(fa.cpu().numpy() - fref).max() <= 1e-5 * np.abs(fref).max()
+
+
 @pytest.mark.parametrize("tag", ["water", "si"])
 def test_oracle_schnet_vs_reference_fixture(tag):
     g, params, sd = _fixture(tag)
