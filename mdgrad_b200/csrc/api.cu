@@ -48,8 +48,11 @@ extern "C" int mdg_create(int device, mdg_ctx** out) {
     cudaMemset(c->flags.p, 0, sizeof(int) * 8);
     const char* fg = getenv("MDG_FORCE_GROUP");
     c->force_group = (fg && (atoi(fg) == 8 || atoi(fg) == 2)) ? atoi(fg) : 4;
-    const char* tl = getenv("MDG_TILES");            // MDG_TILES=0: engine skin list in the round-1 row form (A/B, fallback)
-    c->tiles_off = tl && tl[0] == '0';
+    // MDG_TILES=1: engine skin list in the block-local tile form (tiles.cuh: TMA-staged stencil, 16-bit rows).  Measured on the
+    // 256k-atom box (profiles/r02_force_kernel.md) it halves the kernel's DRAM traffic but is slower than the row form
+    // (52-57 vs 47 us), so the row form stays the default.
+    const char* tl = getenv("MDG_TILES");
+    c->tiles_off = !(tl && tl[0] == '1');
     const char* tw = getenv("MDG_TILE_WARPS");
     c->tile_warps_env = (tw && atoi(tw) >= 1 && atoi(tw) <= 16) ? atoi(tw) : 0;
     const char* tc = getenv("MDG_TILE_CTAS");

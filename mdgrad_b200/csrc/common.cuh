@@ -289,7 +289,7 @@ struct mdg_ctx {
     int      tile_warps = 12;          // warps per CTA of k_force_tiles
     int      tile_warps_env = 0;       // MDG_TILE_WARPS
     int      tile_ctas_env = 0;        // MDG_TILE_CTAS: resident CTAs per SM of the persistent k_force_tiles
-    bool     tiles_off = false;        // MDG_TILES=0: keep the row list (k_build_fast / k_force_rows) - A/B and fallback
+    bool     tiles_off = true;         // MDG_TILES=1 switches the engine's skin list to the tile form (opt-in, see api.cu)
     bool     flags_sticky = false;     // mdg_i_build_list must not clear the overflow flags (engine epochs)
     int      tile_scap_min = 0;        // staged-atom capacity demanded by a previous overflow
     DevBuf   tile_rows, tile_len;      // uint16 [groups * capc * 128], uint32 [n]

@@ -198,6 +198,14 @@ def test_emu_nbr_list_fuzz(ectx):
         assert torch.equal(nbr, nbr_o) and torch.equal(off, off_o), (it, n, Ls, rc, spread)
 
 
+def test_emu_tile_list_engine_equals_row_list_engine(monkeypatch):
+    """body of test_gpu_kernels.py::test_tile_list_engine_equals_row_list_engine on the emulated kernels (the emulation replaces
+    the TMA bulk copies / mbarrier pipeline of k_force_tiles by plain copies + block barriers: layout, builder and arithmetic
+    are what is checked here)"""
+    monkeypatch.setattr(G, "_new_ctx", lambda: EmuContext())
+    G.test_tile_list_engine_equals_row_list_engine(monkeypatch)
+
+
 def test_emu_fullsize_property_checks_at_reduced_size(ectx):
     """the property checks of tests/test_gpu_zfullsize.py (run there at 256 000 atoms) executed here on a 4 000-atom box"""
     import fullsize_checks as F

@@ -204,6 +204,49 @@ def test_skin_list_equals_fresh_list(ctx):
     assert ctx.stats()["rebuilds"] < 30
 
 
+def _new_ctx():
+    from mdgrad_b200 import _lib
+    return _lib.Context(_dev())
+
+
+def test_tile_list_engine_equals_row_list_engine(monkeypatch):
+    """MDG_TILES=1 (engine skin list in the block-local tile form: TMA-staged stencil in shared memory, 16-bit rows,
+    persistent warp-specialised k_force_tiles) against the default row form and against rebuilding every step: same pair set
+    at every evaluation (exact re-test in both), only the summation order differs.  Boundary blocks (image-shifted
+    entries), a non-cubic box and a pair filter are covered."""
+    pos, vel, L = O.lj_system(12, jitter=0.03, seed=2)
+    n = pos.shape[0]
+    L32 = float(np.float32(L))
+    dev = _dev()
+    q0 = torch.tensor(pos, dtype=torch.float32).to(dev)
+    v0 = torch.tensor(vel, dtype=torch.float32).to(dev)
+    mass = torch.full((n,), 1.008).to(dev)
+    t = O.time_grid(0.005, 30).tolist()
+    monkeypatch.setenv("MDG_TILES", "1")
+    tctx = _new_ctx()
+    monkeypatch.delenv("MDG_TILES")
+    rctx = _new_ctx()
+    pb, _ = _md_params(1, L32, n, skin=0.4, K=8)
+    pa, _ = _md_params(1, L32, n, skin=0.0, K=1)
+    a = rctx.md_run(pa, mass, v0, q0, [0.0] * 5, t, want_energy=True)
+    r = rctx.md_run(pb, mass, v0, q0, [0.0] * 5, t, want_energy=True)
+    assert rctx.stats()["path"] == 0
+    b = tctx.md_run(pb, mass, v0, q0, [0.0] * 5, t, want_energy=True)
+    assert tctx.stats()["path"] == 2 and tctx.stats()["rebuilds"] < 30
+    vs = a[0].abs().max().item()
+    for x in (a, r):
+        assert (x[0] - b[0]).abs().max().item() <= 5e-5 * vs
+        assert (x[1] - b[1]).abs().max().item() <= 5e-6 * L
+        assert (x[2] - b[2]).abs().max().item() <= 5e-5 * a[2].abs().max().item()
+        assert abs(x[3] - b[3]) <= 2e-5 * abs(a[3])
+    # other analytic kinds share the kernel template
+    for kind, pp in ((1, (1.0, 0.8, 10.0, 5.0)), (3, (1.0, 0.5, 12.0))):
+        pk, _ = _md_params(1, L32, n, skin=0.4, K=8, kind=kind, pp=pp)
+        x = rctx.md_run(pk, mass, v0, q0, [0.0] * 5, t[:12])
+        y = tctx.md_run(pk, mass, v0, q0, [0.0] * 5, t[:12])
+        assert (x[1] - y[1]).abs().max().item() <= 5e-6 * L
+
+
 # ------------------------------------------------------------------------------------------
 # K6: RDF
 # ------------------------------------------------------------------------------------------
