@@ -65,7 +65,7 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
     if (!c) return MDG_OK;
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->cell_of, &c->slot_of, &c->cell_count, &c->cell_start, &c->perm, &c->perm_tmp, &c->stencil,
-                      &c->qs_buf[0], &c->qs_buf[1], &c->rows, &c->row_len, &c->tile_rows, &c->tile_len, &c->tile_desc, &c->flags, &c->up_cnt, &c->up_off,
+                      &c->qs_buf[0], &c->qs_buf[1], &c->rows, &c->row_len, &c->tile_rows, &c->tile_len, &c->tile_desc, &c->dsync, &c->flags, &c->up_cnt, &c->up_off,
                       &c->scan_tmp, &c->fs, &c->partials, &c->v4, &c->vh4, &c->q4b, &c->f4b, &c->qref,
                       &c->mass_sorted, &c->pvbuf, &c->kebuf, &c->dtbuf, &c->g_off, &c->g_cnt, &c->g_edge,
                       &c->g_other, &c->sn_ws, &c->sn_wt, &c->sn_wcache, &c->gnn_nbr, &c->gnn_off, &c->gnn_xyz, &c->gnn_f3, &c->gnn_fp3,

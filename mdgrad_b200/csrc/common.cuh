@@ -269,6 +269,17 @@ struct mdg_ctx {
     void*  dist_comm = nullptr;
     cudaStream_t comm_stream = nullptr;            // NCCL side stream: halo + KE all-reduce overlap the interior forces
     cudaEvent_t  ev_a = nullptr, ev_halo = nullptr, ev_ke = nullptr;
+    // peer-to-peer step path (dist.cuh DistSync): IPC mappings of the neighbours' position buffers and of every rank's sync block
+    bool   dist_p2p = false;         // mappings valid -> the per-step halo / kinetic-energy exchange uses NVLink stores + flags
+    bool   dist_p2p_off = false;     // MDG_DIST_P2P=0, or the IPC set-up failed once: stay on the NCCL path
+    DevBuf dsync;                    // my DistSync block
+    void*  peer_sync[16] = {nullptr};        // every rank's DistSync as mapped here (own entry = dsync.p)
+    void*  peer_qs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [below, above][qs_buf 0, 1] of the two neighbours
+    void*  p2p_exported[2] = {nullptr, nullptr};   // my qs_buf pointers at export time (re-export when they change)
+    void*  p2p_opened[40] = {nullptr};       // everything cudaIpcOpenMemHandle returned (closed on release)
+    int    p2p_n_opened = 0;
+    int    dist_seq = 0;             // running sequence number of the distributed steps (identical on all ranks)
+    cudaEvent_t ev_push = nullptr;
     int*   h_layers = nullptr;       // pinned: atom offset of every z-layer of cells (ncz + 1 entries)
     int    n_layers = 0;
     bool   fast_build = false; // engine skin lists: approximate (FMA) membership at the list radius is allowed

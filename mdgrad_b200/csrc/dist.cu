@@ -33,6 +33,7 @@ static int load_nccl(const char* path) {
     SYM(Recv, "ncclRecv");
     SYM(AllReduce, "ncclAllReduce");
     SYM(Broadcast, "ncclBroadcast");
+    *(void**)(&g_nccl.AllGather) = dlsym(h, "ncclAllGather");      // optional (peer-to-peer set-up only)
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -85,11 +86,103 @@ extern "C" int mdg_dist_init(mdg_ctx* c, const char* nccl_lib_path, const char* 
     void* comm = nullptr;
     MDG_TRY(mdg_nccl_check(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank"));
     c->dist_comm = comm;
+    const char* pe = getenv("MDG_DIST_P2P");
+    c->dist_p2p_off = pe && pe[0] == '0';
     return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Peer-to-peer set-up: export my two position buffers and my DistSync block with CUDA IPC, all-gather the handles over
+// NCCL, map the neighbours' position buffers and every rank's DistSync.  Called by the engine after the first build of an
+// epoch (the buffers exist then); repeated when a position buffer was re-allocated (every rank does so at the same call).
+// Any failure leaves the NCCL path in place (dist_p2p_off).
+// ---------------------------------------------------------------------------------------------------------------------
+void mdg_i_dist_p2p_release(mdg_ctx* c) {
+#ifndef MDG_EMU
+    for (int k = 0; k < c->p2p_n_opened; ++k)
+        if (c->p2p_opened[k]) cudaIpcCloseMemHandle(c->p2p_opened[k]);
+#endif
+    c->p2p_n_opened = 0;
+    c->dist_p2p = false;
+    for (int r = 0; r < MDG_DIST_MAXW; ++r) c->peer_sync[r] = nullptr;
+    for (int s = 0; s < 2; ++s) c->peer_qs[s][0] = c->peer_qs[s][1] = nullptr;
+}
+
+int mdg_i_dist_p2p_setup(mdg_ctx* c, cudaStream_t st) {
+#ifdef MDG_EMU
+    (void)st;
+    c->dist_p2p_off = true;      // (the CPU emulation runs ranks as processes over a fake NCCL: no CUDA IPC there)
+    return MDG_OK;
+#else
+    const int W = c->dist_world, me = c->dist_rank;
+    if (c->dist_p2p_off || W < 2 || W > MDG_DIST_MAXW || !g_nccl.AllGather) return MDG_OK;
+    if (c->dist_p2p && c->p2p_exported[0] == c->qs_buf[0].p && c->p2p_exported[1] == c->qs_buf[1].p) return MDG_OK;
+    const bool first = c->dsync.p == nullptr;
+    mdg_i_dist_p2p_release(c);
+    if (first) {
+        MDG_TRY(c->dsync.reserve(sizeof(DistSync)));
+        MDG_CUDA(cudaMemsetAsync(c->dsync.p, 0, sizeof(DistSync), st));
+        MDG_CUDA(cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming));
+    }
+    struct Pack { cudaIpcMemHandle_t h[3]; int ok; int pad[15]; };      // 3 x 64 + 64 bytes
+    Pack mine;
+    memset(&mine, 0, sizeof(mine));
+    void* ptrs[3] = {c->qs_buf[0].p, c->qs_buf[1].p, c->dsync.p};
+    mine.ok = 1;
+    for (int k = 0; k < 3; ++k)
+        if (cudaIpcGetMemHandle(&mine.h[k], ptrs[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    DevBuf xfer;
+    MDG_TRY(xfer.reserve(sizeof(Pack) * (size_t)(W + 1)));
+    Pack* d_all = xfer.as<Pack>();
+    MDG_CUDA(cudaMemcpyAsync(d_all + W, &mine, sizeof(Pack), cudaMemcpyHostToDevice, st));
+    int r = mdg_nccl_check(g_nccl.AllGather(d_all + W, d_all, sizeof(Pack), 0 /* ncclInt8 */, c->dist_comm, st), "AllGather");
+    if (r != MDG_OK) { xfer.release(); return r; }
+    std::vector<Pack> all((size_t)W);
+    MDG_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Pack) * (size_t)W, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA(cudaStreamSynchronize(st));
+    xfer.release();
+    bool ok = true;
+    for (int q = 0; q < W; ++q) ok = ok && all[q].ok == 1;
+    const int below = (me - 1 + W) % W, above = (me + 1) % W;
+    auto open = [&](const cudaIpcMemHandle_t& h) -> void* {
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (c->p2p_n_opened < 40) c->p2p_opened[c->p2p_n_opened++] = p;
+        return p;
+    };
+    if (ok) {
+        for (int q = 0; q < W && ok; ++q) {
+            c->peer_sync[q] = (q == me) ? c->dsync.p : open(all[q].h[2]);
+            ok = ok && c->peer_sync[q] != nullptr;
+        }
+        for (int k = 0; k < 2 && ok; ++k) {
+            c->peer_qs[0][k] = open(all[below].h[k]);
+            c->peer_qs[1][k] = (above == below) ? c->peer_qs[0][k] : open(all[above].h[k]);
+            ok = ok && c->peer_qs[0][k] && c->peer_qs[1][k];
+        }
+    }
+    // every rank must take the same path: agree through a 1-int max all-reduce of the failure flag
+    int* d_flag = c->dsync.as<int>() + offsetof(DistSync, pad) / sizeof(int);
+    int bad = ok ? 0 : 1;
+    MDG_CUDA(cudaMemcpyAsync(d_flag, &bad, sizeof(int), cudaMemcpyHostToDevice, st));
+    MDG_TRY(mdg_nccl_check(g_nccl.AllReduce(d_flag, d_flag, 1, MDG_NCCL_INT32, MDG_NCCL_MAX, c->dist_comm, st), "AllReduce"));
+    MDG_CUDA(cudaMemcpyAsync(&bad, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MDG_CUDA(cudaStreamSynchronize(st));
+    if (bad) {
+        mdg_i_dist_p2p_release(c);
+        c->dist_p2p_off = true;
+        return MDG_OK;
+    }
+    c->p2p_exported[0] = c->qs_buf[0].p;
+    c->p2p_exported[1] = c->qs_buf[1].p;
+    c->dist_p2p = true;
+    return MDG_OK;
+#endif
 }
 
 extern "C" int mdg_dist_finalize(mdg_ctx* c) {
     if (!c) return MDG_OK;
+    mdg_i_dist_p2p_release(c);
     if (c->dist_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist_comm);
     c->dist_comm = nullptr;
     c->dist_world = 1;

@@ -95,6 +95,115 @@ __global__ void __launch_bounds__(INT_THREADS) k_ke_pack(const double* __restric
     if (threadIdx.x == 0) { dke[0] = ta; dke[1] = tb; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// peer-to-peer step path (dist.cuh): flags and kinetic energies live in DistSync blocks that the peers write over NVLink
+// ---------------------------------------------------------------------------------------------------------------------
+struct PeerTab { DistSync* s[MDG_DIST_MAXW]; };
+struct DistArgs {
+    DistSync* mine;            // nullptr: single GPU, or the NCCL path (kinetic energies arrive in ke_part arrays)
+    DistSync* below;           // the neighbours' blocks as mapped here (acknowledgements)
+    DistSync* above;
+    int world, seq;
+};
+
+__device__ __forceinline__ int vload_i(const int* p) { return *(const volatile int*)p; }
+__device__ __forceinline__ void vstore_i(int* p, int v) { *(volatile int*)p = v; }
+// Bounded spin (a peer that died must not hang this GPU): after ~2 s the wait gives up and latches *timeout_flag, which the
+// host turns into an error at the end of the epoch.
+__device__ __forceinline__ void spin_until_ge(const int* p, int v, int* timeout_flag) {
+    for (int it = 0; vload_i(p) < v; ++it) {
+#ifndef MDG_EMU
+        __nanosleep(64);
+#endif
+        if (it > (1 << 22)) { *(volatile int*)timeout_flag = 1; break; }
+    }
+}
+
+// Prologue of the B kernels on the peer-to-peer path: acknowledge the ghosts of this step (the forces that read them are
+// complete - stream order), wait for every rank's kinetic energies and sum them in rank order (identical on all ranks).
+__device__ __forceinline__ void dist_ack(const DistArgs& D) {
+    if (D.mine && blockIdx.x == 0 && threadIdx.x == 0) {
+        vstore_i(&D.below->ack_flag[1], D.seq);      // I am the neighbour ABOVE of the rank below me
+        vstore_i(&D.above->ack_flag[0], D.seq);
+    }
+}
+
+__device__ __forceinline__ void dist_gather_ke(const DistArgs& D, double* sm, float* ke0, float* ke1) {
+    const int par = D.seq & 1;
+    if ((int)threadIdx.x < D.world) spin_until_ge(&D.mine->ke_flag[par][threadIdx.x], D.seq, &D.mine->pad[1]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int r = 0; r < D.world; ++r) {
+            a += *(const volatile double*)&D.mine->ke[par][r][0];
+            b += *(const volatile double*)&D.mine->ke[par][r][1];
+        }
+        sm[0] = a;
+        sm[1] = b;
+    }
+    __syncthreads();
+    *ke0 = (float)sm[0];
+    *ke1 = (float)sm[1];
+    __syncthreads();
+}
+
+// One launch per step on the communication stream: (1) wait until both neighbours have consumed the ghosts of the previous
+// step, (2) store my bottom / top layer of positions into the ghost ranges of the rank below / above (same global sorted
+// indices on both sides), (3) block 0: reduce my kinetic-energy partials and store them into every rank's table, flag after a
+// system-scope fence, (4) the last block to finish raises the halo flags on the two neighbours.
+__global__ void __launch_bounds__(256) k_dist_push(const float4* __restrict__ q, int lo0, int lo1, int hi0, int hi1,
+                                                   float4* __restrict__ q_below, float4* __restrict__ q_above,
+                                                   const double* __restrict__ ke_v_part, const double* __restrict__ ke_h_part,
+                                                   int n_part, int nhc, PeerTab T, int me, int world, int below, int above, int seq,
+                                                   int do_halo) {
+    __shared__ double sm[256 / 32];
+    __shared__ int s_last;
+    DistSync* mine = T.s[me];
+    if (nhc && blockIdx.x == 0) {
+        double va = 0, vb = 0;
+        for (int i = threadIdx.x; i < n_part; i += blockDim.x) { va += ke_v_part[i]; vb += ke_h_part[i]; }
+        double ta = block_sum_double(va, sm);
+        double tb = block_sum_double(vb, sm);
+        if (threadIdx.x == 0) {
+            const int par = seq & 1;
+            for (int r = 0; r < world; ++r) {
+                *(volatile double*)&T.s[r]->ke[par][me][0] = ta;
+                *(volatile double*)&T.s[r]->ke[par][me][1] = tb;
+            }
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) vstore_i(&T.s[r]->ke_flag[par][me], seq);
+        }
+    }
+    if (!do_halo) return;
+    if (threadIdx.x == 0) {
+        spin_until_ge(&mine->ack_flag[0], seq - 1, &mine->pad[1]);
+        spin_until_ge(&mine->ack_flag[1], seq - 1, &mine->pad[1]);
+    }
+    __syncthreads();
+    const int nlo = lo1 - lo0, nhi = hi1 - hi0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlo + nhi; i += gridDim.x * blockDim.x) {
+        if (i < nlo) q_below[lo0 + i] = q[lo0 + i];
+        else q_above[hi0 + (i - nlo)] = q[hi0 + (i - nlo)];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        mine->ticket = 0;
+        __threadfence_system();
+        vstore_i(&T.s[below]->halo_flag[1], seq);    // my bottom layer is the ghost layer ABOVE the rank below me
+        vstore_i(&T.s[above]->halo_flag[0], seq);
+    }
+}
+
+__global__ void k_dist_wait(DistSync* mine, int seq) {
+    if (threadIdx.x == 0) {
+        spin_until_ge(&mine->halo_flag[0], seq, &mine->pad[1]);
+        spin_until_ge(&mine->halo_flag[1], seq, &mine->pad[1]);
+    }
+}
+
 // step part A (sovlers.py:111-118): a0 from (v, f, pv); vh = 1/2 a0 dt; q += (v + vh) dt;
 // accumulates ke(v + vh) and checks the skin criterion against the positions of the last build.
 __global__ void __launch_bounds__(INT_THREADS) k_step_a(IntArgs A, float dt, int pv_sel, const Scalars* __restrict__ sc,
@@ -154,14 +263,19 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_b(IntArgs A, float dt, int
                                                         const double* __restrict__ ke_part, const double* __restrict__ ke_half_part,
                                                         int n_part, double* __restrict__ ke_next_part,
                                                         float* __restrict__ traj_v, float* __restrict__ traj_q,
-                                                        float* __restrict__ traj_pv_row) {
+                                                        float* __restrict__ traj_pv_row, DistArgs D) {
     __shared__ double sm[INT_THREADS / 32];
     __shared__ float bc[2];
     __shared__ float s_pvh0;
     float pvh0 = 0.f, Q0 = 1.f;
+    dist_ack(D);
     if (A.integrator == MDG_INT_NHC) {
-        float ke0 = sum_partials(ke_part, n_part, sm, &bc[0]);
-        float ke1 = sum_partials(ke_half_part, n_part, sm, &bc[1]);
+        float ke0, ke1;
+        if (D.mine) dist_gather_ke(D, sm, &ke0, &ke1);
+        else {
+            ke0 = sum_partials(ke_part, n_part, sm, &bc[0]);
+            ke1 = sum_partials(ke_half_part, n_part, sm, &bc[1]);
+        }
         if (threadIdx.x == 0) {
             float pv[MDG_MAX_CHAINS], ph[MDG_MAX_CHAINS], pvh[MDG_MAX_CHAINS], d0[MDG_MAX_CHAINS], d1[MDG_MAX_CHAINS];
             for (int k = 0; k < A.M; ++k) pv[k] = sc->pv[pv_sel][k];
@@ -227,14 +341,19 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_ba(IntArgs A, float dt, fl
                                                          double* __restrict__ ke_next_part, double* __restrict__ ke_half_next_part,
                                                          float* __restrict__ traj_v, float* __restrict__ traj_q,
                                                          float* __restrict__ traj_pv_row, const float4* __restrict__ qref,
-                                                         int check_skin_next, int* __restrict__ flags) {
+                                                         int check_skin_next, int* __restrict__ flags, DistArgs D) {
     __shared__ double sm[INT_THREADS / 32];
     __shared__ float bc[2];
     __shared__ float s_pvh0, s_pvn0;
     float pvh0 = 0.f, pvn0 = 0.f, Q0 = 1.f;
+    dist_ack(D);
     if (A.integrator == MDG_INT_NHC) {
-        float ke0 = sum_partials(ke_part, n_part, sm, &bc[0]);
-        float ke1 = sum_partials(ke_half_part, n_part, sm, &bc[1]);
+        float ke0, ke1;
+        if (D.mine) dist_gather_ke(D, sm, &ke0, &ke1);
+        else {
+            ke0 = sum_partials(ke_part, n_part, sm, &bc[0]);
+            ke1 = sum_partials(ke_half_part, n_part, sm, &bc[1]);
+        }
         if (threadIdx.x == 0) {
             float pv[MDG_MAX_CHAINS], ph[MDG_MAX_CHAINS], pvh[MDG_MAX_CHAINS], d0[MDG_MAX_CHAINS], d1[MDG_MAX_CHAINS];
             for (int k = 0; k < A.M; ++k) pv[k] = sc->pv[pv_sel][k];
@@ -487,6 +606,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     c->fast_build = retest;      // skin list: every entry is re-tested exactly by the force kernel
     c->slab = dist;
     MDG_TRY(mdg_i_build_list(c, d_q0, nullptr, n, p->cell, rlist, p->cutoff, st));
+    if (dist) MDG_TRY(mdg_i_dist_p2p_setup(c, st));      // (no-op once the mappings exist; collective when it is not)
     float4* q = c->qs_ptr;
     if (c->own_s1 > c->own_s0)
         k_init_v<<<(c->own_s1 - c->own_s0 + T - 1) / T, T, 0, st>>>(c->own_s0, c->own_s1, c->perm.as<int>(), d_v0, d_mass, vbuf[vsel]);
@@ -557,6 +677,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         const double* ke_a = ke_v_cur;
         const double* ke_b = ke_h_cur;
         int n_part = ib_prev;
+        DistArgs DA{nullptr, nullptr, nullptr, 1, 0};
         c->force_energy = !(energy_free && g + 1 < nsteps);
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (c->prof_enable) {
@@ -583,7 +704,47 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             MDG_CUDA(cudaStreamWaitEvent(cs, c->ev_a, 0));
             const int* Ly = c->h_layers;
             const int zlo = c->slab_zlo, zhi = c->slab_zhi;
+            const int ncz = c->n_layers - 1;
+            const bool p2p = c->dist_p2p && ((zlo - 1 + ncz) % ncz != zhi % ncz);     // (distinct ghost layers below / above)
             bool split = !do_rebuild && (zhi - zlo) >= 3;
+            if (p2p) {
+                // ---- peer-to-peer: one push kernel (NVLink stores + flags), no NCCL kernel on the step path ----------------
+                const int seq = ++c->dist_seq;
+                const int W = c->dist_world, me = c->dist_rank, below = (me - 1 + W) % W, above = (me + 1) % W;
+                const int sel = (q == c->qs_buf[0].as<float4>()) ? 0 : 1;
+                PeerTab PT;
+                for (int r = 0; r < MDG_DIST_MAXW; ++r) PT.s[r] = (DistSync*)c->peer_sync[r < W ? r : me];
+                const int nh = (Ly[zlo + 1] - Ly[zlo]) + (Ly[zhi] - Ly[zhi - 1]);
+                int pb = do_rebuild ? 1 : (nh + 2047) / 2048;
+                pb = pb < 1 ? 1 : (pb > 64 ? 64 : pb);
+                k_dist_push<<<pb, 256, 0, cs>>>(q, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], (float4*)c->peer_qs[0][sel],
+                                               (float4*)c->peer_qs[1][sel], ke_v_cur, ke_h_cur, ib_prev, nhc, PT, me, W, below, above,
+                                               seq, do_rebuild ? 0 : 1);
+                MDG_CUDA(cudaEventRecord(c->ev_push, cs));
+                c->stat_launches++;
+                DA.mine = (DistSync*)c->dsync.p;
+                DA.below = (DistSync*)c->peer_sync[below];
+                DA.above = (DistSync*)c->peer_sync[above];
+                DA.world = W;
+                DA.seq = seq;
+                if (ev0) MDG_CUDA(cudaEventRecord(ev0, st));
+                if (split) {
+                    const int nxy = c->nc[0] * c->nc[1];
+                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
+                                              (zhi - 1) * nxy, st));                                                      // interior
+                    k_dist_wait<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq);                                             // ghosts landed
+                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], zlo * nxy,
+                                              (zlo + 1) * nxy, st));                                                      // bottom layer
+                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
+                                              zhi * nxy, st));                                                            // top layer
+                    c->stat_launches++;
+                } else {
+                    if (!do_rebuild) { k_dist_wait<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq); c->stat_launches++; }
+                    MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
+                }
+                if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
+                MDG_CUDA(cudaStreamWaitEvent(st, c->ev_push, 0));      // B overwrites q: my own stores to the neighbours must have read it
+            } else {
             if (!do_rebuild) {
                 MDG_TRY(halo_exchange(c, q, cs));
                 MDG_CUDA(cudaEventRecord(c->ev_halo, cs));
@@ -612,6 +773,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             }
             if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
             if (nhc) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_ke, 0));
+            }
         }
         c->force_energy = true;
         int gp = g + 1;
@@ -625,13 +787,13 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             bool next_rebuild = ((g + 2) % rebuild_every) == 0;
             k_step_ba<<<ib, INT_THREADS, 0, st>>>(A, dt, dt_next, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
                                                   ke_a, ke_b, n_part, ke_v_nxt, ke_h_nxt, tv, tq, tp, c->qref.as<float4>(),
-                                                  (retest && !next_rebuild) ? 1 : 0, c->flags.as<int>());
+                                                  (retest && !next_rebuild) ? 1 : 0, c->flags.as<int>(), DA);
             a_done = true;
             { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
             { double* t2 = ke_h_cur; ke_h_cur = ke_h_nxt; ke_h_nxt = t2; }
         } else {
             k_step_b<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
-                                                 ke_a, ke_b, n_part, ke_v_nxt, tv, tq, tp);
+                                                 ke_a, ke_b, n_part, ke_v_nxt, tv, tq, tp, DA);
             a_done = false;
             { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
         }
@@ -645,6 +807,10 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         if (dist) MDG_TRY(mdg_nccl_check(N->AllReduce(dke + 6, dke + 6, 1, MDG_NCCL_FLOAT64, MDG_NCCL_SUM, c->dist_comm, st), "AllReduce"));
         c->stat_launches += 2;
     }
+    int h_p2p_timeout = 0;
+    if (dist && c->dist_p2p)
+        MDG_CUDA(cudaMemcpyAsync(&h_p2p_timeout, c->dsync.as<char>() + offsetof(DistSync, pad) + sizeof(int), sizeof(int),
+                                 cudaMemcpyDeviceToHost, st));
     if (dist)   // all ranks must take the same retry decision
         MDG_TRY(mdg_nccl_check(N->AllReduce(c->flags.p, c->flags.p, 8, MDG_NCCL_INT32, MDG_NCCL_MAX, c->dist_comm, st), "AllReduce"));
     MDG_KERNEL_CHECK();
@@ -656,6 +822,10 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     MDG_CUDA(cudaMemcpyAsync(c->h_pinned, c->flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
     MDG_CUDA(cudaStreamSynchronize(st));
     if (h_last_energy) *h_last_energy = (float)h_e;
+    if (h_p2p_timeout) {
+        mdg_set_error("distributed step: a peer-to-peer wait timed out (a neighbouring rank stopped making progress)");
+        return MDG_E_NCCL;
+    }
     if (c->prof_enable && c->prof_events) {
         std::vector<cudaEvent_t>* pool = (std::vector<cudaEvent_t>*)c->prof_events;
         c->prof_force_ms = 0.0;
@@ -1018,11 +1188,12 @@ static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet
         if (g + 1 < nsteps) {
             float dt_next = h_tgrid[g + 2] - h_tgrid[g + 1];
             k_step_ba<<<ib, INT_THREADS, 0, st>>>(A, dt, dt_next, pv_sel, sc, v4, vh4, q4, f4, ke_v_cur, ke_h_cur, ib, ke_v_nxt,
-                                                  ke_h_nxt, tv, tq, tp, nullptr, 0, c->flags.as<int>());
+                                                  ke_h_nxt, tv, tq, tp, nullptr, 0, c->flags.as<int>(), DistArgs{nullptr, nullptr, nullptr, 1, 0});
             { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
             { double* t2 = ke_h_cur; ke_h_cur = ke_h_nxt; ke_h_nxt = t2; }
         } else {
-            k_step_b<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, v4, vh4, q4, f4, ke_v_cur, ke_h_cur, ib, ke_v_nxt, tv, tq, tp);
+            k_step_b<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, v4, vh4, q4, f4, ke_v_cur, ke_h_cur, ib, ke_v_nxt, tv, tq, tp,
+                                                 DistArgs{nullptr, nullptr, nullptr, 1, 0});
             { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
         }
         c->stat_launches++;

@@ -93,6 +93,8 @@ void  fiber_yield();
 #define warpSize 32
 
 static inline void __syncthreads() { cuemu::sync_block(); }
+static inline void __threadfence_system() {}
+
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { cuemu::coll_leave(cuemu::coll_enter(mask, 0, 0)); }
 
 namespace cuemu {
