@@ -258,6 +258,7 @@ struct mdg_ctx {
     int    own_c0 = 0, own_c1 = 0;   // cell range whose rows are built
     int    force_c0 = 0, force_c1 = 0;    // matching cell sub-range (whole z-layers)
     int    force_s0 = -1, force_s1 = 0;   // >= 0: explicit row sub-range for the next force launch
+    int    force_gap_at = 0, force_gap = 0;   // force_gap > 0: the sub-range skips rows [force_gap_at, force_gap_at + force_gap)
     int    rows_s0 = 0;              // first row held in `rows` (rows are allocated for the own range only)
     bool   slab = false;             // true: own_* are set by the distributed engine after the sort
     bool   slab_local = false;       // rebuild touches own +- 2 layers only (engine refreshed them by a 2-layer exchange)
@@ -363,5 +364,7 @@ int mdg_i_force_sorted(mdg_ctx* c, const PotParams& P, const float4* d_qs, float
                        bool with_dp, double* d_dp_partials, cudaStream_t st);
 int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, int s0, int s1,
                       int c0, int c1, cudaStream_t st);
+int mdg_i_force_range2(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, int s0a, int s1a, int s0b,
+                       int s1b, cudaStream_t st);
 PotParams mdg_make_pot(int kind, const float* h_params, int n_params);
 int mdg_i_check_flags(mdg_ctx* c, cudaStream_t st, bool sync);

@@ -108,14 +108,27 @@ struct DistArgs {
 
 __device__ __forceinline__ int vload_i(const int* p) { return *(const volatile int*)p; }
 __device__ __forceinline__ void vstore_i(int* p, int v) { *(volatile int*)p = v; }
-// Bounded spin (a peer that died must not hang this GPU): after ~2 s the wait gives up and latches *timeout_flag, which the
+// Bounded spin (a peer that died must not hang this GPU): after 60 s the wait gives up and latches *timeout_flag, which the
 // host turns into an error at the end of the epoch.
-__device__ __forceinline__ void spin_until_ge(const int* p, int v, int* timeout_flag) {
-    for (int it = 0; vload_i(p) < v; ++it) {
-#ifndef MDG_EMU
-        __nanosleep(64);
+__device__ __forceinline__ unsigned long long mdg_globaltimer_ns() {
+#ifdef MDG_EMU
+    return 0ull;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 #endif
-        if (it > (1 << 22)) { *(volatile int*)timeout_flag = 1; break; }
+}
+__device__ __forceinline__ void spin_until_ge(const int* p, int v, int* timeout_flag) {
+    if (vload_i(p) >= v) return;
+    const unsigned long long t0 = mdg_globaltimer_ns();
+    unsigned ns = 32;
+    while (vload_i(p) < v) {
+#ifndef MDG_EMU
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+#endif
+        if (mdg_globaltimer_ns() - t0 > 60ull * 1000000000ull) { *(volatile int*)timeout_flag = 1; break; }   // 60 s
     }
 }
 
@@ -194,6 +207,16 @@ __global__ void __launch_bounds__(256) k_dist_push(const float4* __restrict__ q,
         __threadfence_system();
         vstore_i(&T.s[below]->halo_flag[1], seq);    // my bottom layer is the ghost layer ABOVE the rank below me
         vstore_i(&T.s[above]->halo_flag[0], seq);
+    }
+}
+
+// Epoch start: this rank has built its lists and evaluated the initial forces - its ghost ranges may be overwritten now.
+// (Without it a faster neighbour's first push of the epoch could land while this rank still sorts / reads the initial state:
+// the end-of-step acknowledgements only order the steps INSIDE an epoch.)
+__global__ void k_dist_ack(DistSync* below, DistSync* above, int seq) {
+    if (threadIdx.x == 0) {
+        vstore_i(&below->ack_flag[1], seq);
+        vstore_i(&above->ack_flag[0], seq);
     }
 }
 
@@ -622,6 +645,12 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     c->force_energy = !(energy_free && n_grid > 1);
     MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
     c->force_energy = true;
+    if (dist && c->dist_p2p) {
+        const int W = c->dist_world, me = c->dist_rank;
+        ++c->dist_seq;                     // the epoch-start pseudo-step: the first real step waits for THIS acknowledgement
+        k_dist_ack<<<1, 32, 0, st>>>((DistSync*)c->peer_sync[(me - 1 + W) % W], (DistSync*)c->peer_sync[(me + 1) % W], c->dist_seq);
+        c->stat_launches++;
+    }
     if (nhc) { k_ke_init<<<ib, INT_THREADS, 0, st>>>(A, vbuf[vsel], ke_v_cur); c->stat_launches++; }
     if (!dist) {   // frame 0 = the initial state, verbatim
         MDG_CUDA(cudaMemcpyAsync(d_traj_v, d_v0, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -733,10 +762,14 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                     MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
                                               (zhi - 1) * nxy, st));                                                      // interior
                     k_dist_wait<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq);                                             // ghosts landed
-                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], zlo * nxy,
-                                              (zlo + 1) * nxy, st));                                                      // bottom layer
-                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
-                                              zhi * nxy, st));                                                            // top layer
+                    if (!c->tiles) {   // bottom + top layer in one launch
+                        MDG_TRY(mdg_i_force_range2(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], st));
+                    } else {
+                        MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], zlo * nxy,
+                                                  (zlo + 1) * nxy, st));                                                  // bottom layer
+                        MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
+                                                  zhi * nxy, st));                                                        // top layer
+                    }
                     c->stat_launches++;
                 } else {
                     if (!do_rebuild) { k_dist_wait<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq); c->stat_launches++; }
@@ -763,10 +796,14 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                 MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
                                           (zhi - 1) * nxy, st));                                                      // interior
                 MDG_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
-                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], zlo * nxy,
-                                          (zlo + 1) * nxy, st));                                                      // bottom layer
-                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
-                                          zhi * nxy, st));                                                            // top layer
+                if (!c->tiles) {       // bottom + top layer in one launch
+                    MDG_TRY(mdg_i_force_range2(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], st));
+                } else {
+                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], zlo * nxy,
+                                              (zlo + 1) * nxy, st));                                                  // bottom layer
+                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
+                                              zhi * nxy, st));                                                        // top layer
+                }
             } else {
                 if (!do_rebuild) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
                 MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));

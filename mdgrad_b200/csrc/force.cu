@@ -152,13 +152,14 @@ __device__ __forceinline__ void mdg_row_stream(const float4* __restrict__ qs, co
 // WITH_E = false: the per-atom energy (fs.w) is not accumulated (written as 0) - the MD loop only needs it after
 // the last step of an epoch, and the energy costs 3 of the 28 instructions of a pure-row entry.
 template <int KIND, bool RETEST, bool WITH_DP, int GROUP, bool WITH_E>
-__global__ void __launch_bounds__(256, MDG_FORCE_MINBLOCKS) k_force_rows(int s0, int n, const float4* __restrict__ qs,
+__global__ void __launch_bounds__(256, MDG_FORCE_MINBLOCKS) k_force_rows(int s0, int n, int gap_at, int gap, const float4* __restrict__ qs,
                                                                     const uint32_t* __restrict__ rows,
                                                                     const int* __restrict__ row_len, int cap, Box bx, float rc2,
                                                                     PotParams P, float4* __restrict__ fs,
                                                                     double* __restrict__ dp_partials) {
     const int lane_in_group = threadIdx.x % GROUP;
-    const int s = s0 + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+    int s = s0 + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+    if (s >= gap_at) s += gap;       // two row ranges in one launch (multi-GPU: bottom + top boundary layer): [s0, gap_at) and [gap_at + gap, n)
     float fx = 0.f, fy = 0.f, fz = 0.f, en = 0.f;
     float dpa[MDG_MAX_POT_PARAMS] = {0.f, 0.f, 0.f, 0.f};
     if (s < n) {
@@ -211,12 +212,14 @@ template <bool RETEST, bool WITH_DP, int GROUP, bool WITH_E>
 static int launch_force_g(mdg_ctx* c, const PotParams& P, const float4* qs, float4* fs, double* dpp, cudaStream_t st) {
     const int T = 256;
     int s0 = c->force_s0 >= 0 ? c->force_s0 : c->own_s0, n = c->force_s0 >= 0 ? c->force_s1 : c->own_s1;
-    int nb = (int)(((int64_t)(n - s0) * GROUP + T - 1) / T);
+    const int gap_at = (c->force_s0 >= 0 && c->force_gap > 0) ? c->force_gap_at : 0x7fffffff, gap = c->force_gap;
+    const int nrows = (n - s0) - ((c->force_s0 >= 0 && c->force_gap > 0) ? gap : 0);
+    int nb = (int)(((int64_t)nrows * GROUP + T - 1) / T);
     if (nb <= 0) return MDG_OK;
     // rows are allocated for the own range only: address them by the global sorted index
     const uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
 #define LF(K)                                                                                                  \
-    k_force_rows<K, RETEST, WITH_DP, GROUP, WITH_E><<<nb, T, 0, st>>>(s0, n, qs, rows_base, c->row_len.as<int>(),      \
+    k_force_rows<K, RETEST, WITH_DP, GROUP, WITH_E><<<nb, T, 0, st>>>(s0, n, gap_at, gap, qs, rows_base, c->row_len.as<int>(),      \
                                                               c->cap, c->box, c->rc2, P, fs, dpp)
     switch (P.kind) {
         case MDG_POT_LJ: LF(MDG_POT_LJ); break;
@@ -255,6 +258,21 @@ int mdg_i_force_range(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4
     c->force_c1 = c1;
     int r = mdg_i_force_sorted(c, P, d_qs, d_fs, retest, false, nullptr, st);
     c->force_s0 = -1;
+    return r;
+}
+
+// two row ranges [s0a, s1a) and [s0b, s1b) (s1a <= s0b) in ONE launch: the bottom and the top boundary layer of a slab
+int mdg_i_force_range2(mdg_ctx* c, const PotParams& P, const float4* d_qs, float4* d_fs, bool retest, int s0a, int s1a, int s0b,
+                       int s1b, cudaStream_t st) {
+    if (c->tiles || s1a > s0b) { mdg_set_error("mdg_i_force_range2: row-list ranges in ascending order only"); return MDG_E_STATE; }
+    if (s1a <= s0a && s1b <= s0b) return MDG_OK;
+    c->force_s0 = s0a;
+    c->force_s1 = s1b;
+    c->force_gap_at = s1a;
+    c->force_gap = s0b - s1a;
+    int r = mdg_i_force_sorted(c, P, d_qs, d_fs, retest, false, nullptr, st);
+    c->force_s0 = -1;
+    c->force_gap = 0;
     return r;
 }
 

@@ -106,9 +106,7 @@ class Simulations():
             return states
         raise ValueError("No log available")
 
-    def simulate(self, steps=1, dt=1.0 * units.fs, frequency=1):
-        """steps//frequency epochs of frequency-1 integration steps each; returns the stacked
-        trajectory of the LAST epoch (reference md.py:73-96)."""
+    def _simulate(self, steps, dt, frequency):
         if self.log["positions"] == []:
             states = self.integrator.get_inital_states(self.wrap)
         else:
@@ -120,9 +118,25 @@ class Simulations():
         # returns, and the next epoch's start state is a pure function of the last frame, so between epochs the
         # state stays on the device (bit-identical fp64 wrap there) and the host-side log / System are brought up to
         # date in one flush - same log, same System, same trajectory, without a host round trip per epoch.
-        pending = []
+        pending = self._pending
         for epoch in range(sim_epochs):
-            if self.integrator.adjoint:
+            # Only the LAST epoch's stacked trajectory is returned (and can be back-propagated through: the epochs before it
+            # are cut off by the host log in the reference, md.py:92-95).  An earlier epoch is needed for its last frame only,
+            # so the fused engine is asked for just that (first + last frame): no (frequency, N, 3) x 2 allocation and no
+            # per-step frame writes for it.
+            last_only = (self.device_handoff and epoch + 1 < sim_epochs and self.integrator.adjoint and
+                         hasattr(self.integrator, "_native_forward"))
+            trajs = None
+            if last_only:
+                with torch.no_grad():
+                    self.integrator._traj_last_only = True
+                    try:
+                        trajs = self.integrator._native_forward(tuple(states), t, self.solvemethod)
+                    finally:
+                        self.integrator._traj_last_only = False
+            if trajs is not None:
+                pass
+            elif self.integrator.adjoint:
                 trajs = odeint_adjoint(self.integrator, states, t, method=self.solvemethod)
             else:
                 # adjoint=False: the whole trajectory goes on the autograd tape (reference md.py:84-88) and the forces on it
@@ -146,6 +160,17 @@ class Simulations():
         self._flush_log(pending)
         return trajs
 
+    def simulate(self, steps=1, dt=1.0 * units.fs, frequency=1):
+        """steps//frequency epochs of frequency-1 integration steps each; returns the stacked
+        trajectory of the LAST epoch (reference md.py:73-96)."""
+        self._pending = []
+        try:
+            return self._simulate(steps, dt, frequency)
+        finally:
+            # epochs that finished before an exception (capacity / skin / non-finite / OOM / KeyboardInterrupt) are logged,
+            # as in the reference, which logs after every epoch
+            self._flush_log(self._pending)
+
     device_handoff = True     # False: host round trip after every epoch, literally as the reference
 
     def _device_check_point(self, trajs):
@@ -164,9 +189,29 @@ class Simulations():
         """append the deferred last frames to the log (numpy, as update_log) and update the System once"""
         if not pending:
             return
-        for frames in pending:
-            for key, fr in zip(self.keys, frames):
-                self.log[key].append(fr.cpu().numpy())
+        if pending[0][0].is_cuda:
+            # device -> pinned host memory, all frames in flight at once, one synchronisation (pageable `.cpu()` copies cost
+            # ~0.5 ms per MB here and were a quarter of an epoch's wall time at 256k atoms)
+            flat = [fr for frames in pending for fr in frames]
+            total = sum(fr.numel() * fr.element_size() for fr in flat)
+            if getattr(self, "_pin", None) is None or self._pin.numel() < total:
+                self._pin = torch.empty(total + total // 4, dtype=torch.uint8, pin_memory=True)
+            views, off = [], 0
+            for fr in flat:
+                nb = fr.numel() * fr.element_size()
+                v = self._pin[off:off + nb].view(fr.dtype).view(fr.shape)
+                v.copy_(fr, non_blocking=True)
+                views.append(v)
+                off += nb
+            torch.cuda.current_stream(flat[0].device).synchronize()
+            it = iter(views)
+            for frames in pending:
+                for key in self.keys:
+                    self.log[key].append(next(it).numpy().copy())
+        else:
+            for frames in pending:
+                for key, fr in zip(self.keys, frames):
+                    self.log[key].append(fr.cpu().numpy())
         pending.clear()
         self.update_states()
 
@@ -425,7 +470,7 @@ class _EOM(torch.nn.Module):
             vmax = float(v0.detach().norm(dim=1).max()) if n else 0.0
             K = 1 if vmax * dtmax <= 0 else int(max(1, min(64, math.floor(0.5 * skin / (1.1 * vmax * dtmax)))))
         p.rebuild_every = int(K)
-        p.traj_stride = 1
+        p.traj_stride = max(1, len(tl) - 1) if getattr(self, "_traj_last_only", False) else 1
         if self._engine_ctx is None:
             self._engine_ctx = _lib.Context(q0.device)
         ctx = self._engine_ctx
