@@ -153,6 +153,13 @@ int mdg_rdf_accumulate(mdg_ctx* ctx, const float* d_xyz, int n, const float* h_c
                        float* d_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Velocity autocorrelation - replaces vacf.forward (torchmd/observable.py:153-163):
+ * d_vel = (n_frames, n_atoms, dim) fp32; d_out[0] = mean(v * v), d_out[t] = mean(v[t:] * v[:-t]) for t < t_range
+ * (un-normalised means over all elements, exactly what the reference returns).  1 <= t_range <= n_frames.
+ * ------------------------------------------------------------------------------------------ */
+int mdg_vacf(mdg_ctx* ctx, const float* d_vel, int n_frames, int n_atoms, int dim, int t_range, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K4 + driver  fused MD epoch - replaces the hot loop of Simulations.simulate
  *     (torchmd/md.py:73-96) -> odeint (torchmd/sovlers.py:171-193) ->
  *     FixedGridODESolver.integrate (torchmd/tinydiffeq.py:56-76) -> NHverlet_update /

@@ -29,7 +29,7 @@ SYMBOLS = [
     "mdg_get_stats", "mdg_set_pair_filter", "mdg_set_profile", "mdg_get_profile",
     "mdg_slab_plan", "mdg_dist_unique_id", "mdg_dist_init", "mdg_dist_finalize",
     "mdg_graph_build", "mdg_cfconv_agg", "mdg_cfconv_edge_grad", "mdg_schnet_energy_force", "mdg_pair_hvp", "mdg_md_run_gnn",
-    "mdg_bonded_force",
+    "mdg_bonded_force", "mdg_vacf",
 ]
 
 
@@ -168,6 +168,7 @@ def bind(lib):
     lib.mdg_pair_dis_fwd.argtypes = [vp, ip, vp, vp, i64, fp, vp, vp]
     lib.mdg_pair_dis_bwd.argtypes = [vp, ip, vp, vp, i64, fp, vp, vp, vp, vp]
     lib.mdg_rdf_accumulate.argtypes = [vp, vp, ip, fp, dbl, dbl, ip, dbl, vp, vp, vp, vp]
+    lib.mdg_vacf.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp]
     lib.mdg_md_run.argtypes = [vp, ctypes.POINTER(MdParams), ip, vp, vp, vp, fp, fp, ip, vp, vp, fp, fp, vp]
     lib.mdg_get_stats.argtypes = [vp, ctypes.POINTER(i64)]
     lib.mdg_set_pair_filter.argtypes = [vp, vp, vp, vp, ip]
@@ -323,6 +324,19 @@ class Context:
                                             int(nbins), float(width) if width else 0.0, _ptr(sel_a), _ptr(sel_b),
                                             _ptr(count), self._stream(dev)))
         self._keepalive = (xyz, sel_a, sel_b)
+
+    def vacf(self, vel, t_range):
+        """velocity autocorrelation of a (frames, N, dim) trajectory for lags 0 .. t_range - 1 (observable.py:153-163)"""
+        self._require(vel, "vel")
+        vel = vel.detach().to(torch.float32).contiguous()
+        assert vel.dim() == 3
+        dev = vel.device
+        out = torch.empty((int(t_range),), dtype=torch.float32, device=dev)
+        with self._guard(dev):
+            self._check(self._api().mdg_vacf(self._h, _ptr(vel), vel.shape[0], vel.shape[1], vel.shape[2], int(t_range), _ptr(out),
+                                             self._stream(dev)))
+        self._keepalive = (vel,)
+        return out
 
     # -- K4 + driver ------------------------------------------------------------------------
     def md_run(self, params, mass, v0, q0, pv0, tgrid, want_energy=False, out=None):

@@ -32,17 +32,38 @@ __global__ void k_inc_fill(const int64_t* __restrict__ nbr, int64_t E, const int
     if ((unsigned)a1 < (unsigned)n) { int p = off[a1] + atomicAdd(&cursor[a1], 1); inc_edge[p] = (int)e; inc_other[p] = a0; }
 }
 
-// deterministic order: each node's incident entries sorted by edge id (thread per node, short lists)
-__global__ void k_inc_sort(int n, const int* __restrict__ off, int* __restrict__ inc_edge, int* __restrict__ inc_other) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+// deterministic order: each node's incident entries sorted by edge id.  One WARP per node: the entries are staged in shared
+// memory and every lane RANKS its entries (edge ids are unique: rank = number of smaller ids) - O(m^2 / 32) broadcast reads
+// instead of a per-thread insertion sort in global memory (553 us for the 64-water box, m ~ 83: 39% of a SchNet MD step).
+// Nodes with more than INC_SORT_CAP incident edges fall back to the insertion sort on lane 0.
+#define INC_SORT_WARPS 4
+#define INC_SORT_CAP 768
+__global__ void __launch_bounds__(INC_SORT_WARPS * 32) k_inc_sort(int n, const int* __restrict__ off, int* __restrict__ inc_edge,
+                                                                 int* __restrict__ inc_other) {
+    __shared__ int s_e[INC_SORT_WARPS][INC_SORT_CAP], s_o[INC_SORT_WARPS][INC_SORT_CAP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * INC_SORT_WARPS + w;
     if (k >= n) return;
-    int b = off[k], m = off[k + 1] - b;
-    for (int a = 1; a < m; ++a) {
-        int e = inc_edge[b + a], o = inc_other[b + a];
-        int j = a - 1;
-        while (j >= 0 && inc_edge[b + j] > e) { inc_edge[b + j + 1] = inc_edge[b + j]; inc_other[b + j + 1] = inc_other[b + j]; --j; }
-        inc_edge[b + j + 1] = e;
-        inc_other[b + j + 1] = o;
+    const int b = off[k], m = off[k + 1] - b;
+    if (m > INC_SORT_CAP) {
+        if (lane == 0)
+            for (int a = 1; a < m; ++a) {
+                int e = inc_edge[b + a], o = inc_other[b + a];
+                int j = a - 1;
+                while (j >= 0 && inc_edge[b + j] > e) { inc_edge[b + j + 1] = inc_edge[b + j]; inc_other[b + j + 1] = inc_other[b + j]; --j; }
+                inc_edge[b + j + 1] = e;
+                inc_other[b + j + 1] = o;
+            }
+        return;
+    }
+    for (int a = lane; a < m; a += 32) { s_e[w][a] = inc_edge[b + a]; s_o[w][a] = inc_other[b + a]; }
+    __syncwarp();
+    for (int a = lane; a < m; a += 32) {
+        const int e = s_e[w][a];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) rank += (s_e[w][j] < e);
+        inc_edge[b + rank] = e;
+        inc_other[b + rank] = s_o[w][a];
     }
 }
 
@@ -56,16 +77,29 @@ __global__ void __launch_bounds__(256) k_cfconv_agg(int n, int F, const int* __r
     if (k >= n) return;
     int b = off[k], e1 = off[k + 1];
     if (VEC4) {
+        // the (edge, other) indices of 32 entries are fetched by the lanes at once and broadcast with shuffles, so the row
+        // gathers of consecutive entries are independent and overlap (the first version chained index load -> row load per
+        // entry: 45 us for 192 nodes x 83 entries); the summation order over the entries is unchanged
         int F4 = F >> 2;
-        for (int f = lane; f < F4; f += 32) {
+        for (int f0 = 0; f0 < F4; f0 += 32) {
+            const int f = f0 + lane;
+            const bool fa = f < F4;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int p = b; p < e1; ++p) {
-                int e = inc_edge[p], o = inc_other[p];
-                float4 w = reinterpret_cast<const float4*>(W + (size_t)e * F)[f];
-                float4 x = reinterpret_cast<const float4*>(h + (size_t)o * F)[f];
-                acc.x += x.x * w.x; acc.y += x.y * w.y; acc.z += x.z * w.z; acc.w += x.w * w.w;
+            for (int p0 = b; p0 < e1; p0 += 32) {
+                const int mine = p0 + lane;
+                const int my_e = mine < e1 ? inc_edge[mine] : 0, my_o = mine < e1 ? inc_other[mine] : 0;
+                const int cnt = min(32, e1 - p0);
+#pragma unroll 4
+                for (int j = 0; j < cnt; ++j) {
+                    const int e = __shfl_sync(0xffffffffu, my_e, j), o = __shfl_sync(0xffffffffu, my_o, j);
+                    if (fa) {
+                        float4 w = reinterpret_cast<const float4*>(W + (size_t)e * F)[f];
+                        float4 x = reinterpret_cast<const float4*>(h + (size_t)o * F)[f];
+                        acc.x += x.x * w.x; acc.y += x.y * w.y; acc.z += x.z * w.z; acc.w += x.w * w.w;
+                    }
+                }
             }
-            reinterpret_cast<float4*>(out + (size_t)k * F)[f] = acc;
+            if (fa) reinterpret_cast<float4*>(out + (size_t)k * F)[f] = acc;
         }
     } else {
         for (int f = lane; f < F; f += 32) {
@@ -112,7 +146,7 @@ int mdg_i_graph_build(mdg_ctx* c, const int64_t* d_nbr, int64_t n_edges, int n, 
     if (n_edges > 0) {
         k_inc_fill<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(d_nbr, n_edges, d_n_edges, n, c->g_off.as<int>(), c->g_cnt.as<int>(),
                                                                    c->g_edge.as<int>(), c->g_other.as<int>());
-        k_inc_sort<<<(n + 127) / 128, 128, 0, st>>>(n, c->g_off.as<int>(), c->g_edge.as<int>(), c->g_other.as<int>());
+        k_inc_sort<<<(n + INC_SORT_WARPS - 1) / INC_SORT_WARPS, INC_SORT_WARPS * 32, 0, st>>>(n, c->g_off.as<int>(), c->g_edge.as<int>(), c->g_other.as<int>());
     }
     MDG_KERNEL_CHECK();
     return MDG_OK;

@@ -220,14 +220,17 @@ __global__ void __launch_bounds__(256) k_sn_edge_bwd(int64_t E, const int* __res
 
 // F_k = - sum over edges e incident to k of  s * gd[e] * rvec_e / d_e,  s = +1 if k is the first atom of e, else -1;
 // rvec_e = x_i - x_j - off_e * scale  (the reference's raw-offset quirk = scale (1,1,1))
-__global__ void k_sn_edge_force(int n, const int* __restrict__ off, const int* __restrict__ inc_edge,
+// One WARP per atom: lanes stride the atom's incident edges, fixed-tree shuffle reduction (deterministic).  (A thread per atom
+// walked ~83 dependent gathers serially on the water box: 154 us.)
+__global__ void __launch_bounds__(128) k_sn_edge_force(int n, const int* __restrict__ off, const int* __restrict__ inc_edge,
                                 const int64_t* __restrict__ nbr, const float* __restrict__ offsets, float sx, float sy, float sz,
                                 const float* __restrict__ xyz, const float* __restrict__ dis, const float* __restrict__ gd,
                                 float* __restrict__ force) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (k >= n) return;
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    for (int p = off[k]; p < off[k + 1]; ++p) {
+    for (int p = off[k] + lane; p < off[k + 1]; p += 32) {
         int e = inc_edge[p];
         int64_t i = nbr[2 * (int64_t)e], j = nbr[2 * (int64_t)e + 1];
         float rx = (xyz[3 * i] - xyz[3 * j]) - offsets[3 * (int64_t)e] * sx;
@@ -238,7 +241,13 @@ __global__ void k_sn_edge_force(int n, const int* __restrict__ off, const int* _
         if (i != k) w = -w;
         fx -= w * rx; fy -= w * ry; fz -= w * rz;
     }
-    force[3 * k] = fx; force[3 * k + 1] = fy; force[3 * k + 2] = fz;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if (lane == 0) { force[3 * k] = fx; force[3 * k + 1] = fy; force[3 * k + 2] = fz; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -528,7 +537,7 @@ int mdg_i_schnet_energy_force(mdg_ctx* c, const mdg_schnet_model* m, const int64
             MDG_TRY((sn_gemm<false, SN_EPI_ADD>(c, n, A, F, gh, Y.Wn, A, nullptr, nullptr, gr, st)));
         }
     }
-    k_sn_edge_force<<<(n + 127) / 128, 128, 0, st>>>(n, c->g_off.as<int>(), c->g_edge.as<int>(), d_nbr, d_offsets, h_off_scale3[0],
+    k_sn_edge_force<<<(n + 3) / 4, 128, 0, st>>>(n, c->g_off.as<int>(), c->g_edge.as<int>(), d_nbr, d_offsets, h_off_scale3[0],
                                                      h_off_scale3[1], h_off_scale3[2], d_xyz, dis, gd, d_force);
     c->stat_launches += 3 + 5 * L;
     MDG_KERNEL_CHECK();

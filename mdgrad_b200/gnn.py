@@ -37,6 +37,16 @@ class GNNPotentials(GeneralInteraction):
         self._ctx_key = "gnn%d" % id(self)
         self._reset_topology(torch.Tensor(system.get_positions()).to(system.device))
 
+    def __del__(self):
+        # the native context registered under this instance's key dies with the instance (no leak over hyper-parameter
+        # sweeps, and a recycled id() can never inherit a stale context)
+        try:
+            from . import topology
+            for k in [k for k in topology._CTX if k[1] == self._ctx_key]:
+                topology._CTX.pop(k, None)
+        except Exception:
+            pass
+
     def _reset_topology(self, xyz):
         nbr, offsets = generate_nbr_list(xyz, self.cutoff, self.cell, ex_pairs=self.ex_pairs, _ctx_key=self._ctx_key)
         self.inputs["nbr_list"] = nbr

@@ -154,7 +154,7 @@ class Simulations():
                 states = self.get_check_point()
                 continue
             pending.append([tr[-1].detach().clone() for tr in trajs])
-            if len(pending) >= 64:                    # bound the device memory held by un-logged frames
+            if len(pending) >= self._flush_every:     # bound the device / pinned memory held by un-logged frames
                 self._flush_log(pending)
             states = nxt
         self._flush_log(pending)
@@ -172,6 +172,7 @@ class Simulations():
             self._flush_log(self._pending)
 
     device_handoff = True     # False: host round trip after every epoch, literally as the reference
+    _flush_every = 8          # epochs whose last frames wait on the device before one pinned-memory flush
 
     def _device_check_point(self, trajs):
         """The states `get_check_point()` would return after logging `trajs`, computed on the device; None if the
@@ -195,7 +196,9 @@ class Simulations():
             flat = [fr for frames in pending for fr in frames]
             total = sum(fr.numel() * fr.element_size() for fr in flat)
             if getattr(self, "_pin", None) is None or self._pin.numel() < total:
-                self._pin = torch.empty(total + total // 4, dtype=torch.uint8, pin_memory=True)
+                # sized once for a full flush interval (page-locking is ~0.4 ms per MB: it must not recur per call)
+                per_epoch = total // len(pending)
+                self._pin = torch.empty(max(total, per_epoch * self._flush_every), dtype=torch.uint8, pin_memory=True)
             views, off = [], 0
             for fr in flat:
                 nb = fr.numel() * fr.element_size()
@@ -590,3 +593,11 @@ def _needs_graph(model):
     if not mods:
         return True
     return any(m.second_order for m in mods)
+
+
+class Isomerization(torch.nn.Module):
+    """reference md.py `Isomerization` (1-D toy dynamics of the isomerisation demos): outside the MD hot path - importable so that
+    the reference's scripts load, loud when constructed."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("mdgrad_b200: Isomerization is outside the MD hot path this package implements")

@@ -264,6 +264,23 @@ class pairTab(nn.Module):
         return u.reshape(shape) if len(shape) and shape[-1] == 1 else u.unsqueeze(-1)
 
 
+def _out_of_scope(name, why):
+    """Names of the reference's potentials.py that are outside the MD hot path (SURVEY 8 'out of scope'): importable, so that
+    the reference's scripts (`from torchmd.potentials import ..., SplineOverlap, ...` at module top of scripts/data.py) load
+    against this package, and loud when constructed."""
+    def __init__(self, *a, **k):
+        raise NotImplementedError("mdgrad_b200: %s is outside the MD hot path this package implements (%s)" % (name, why))
+    return type(name, (nn.Module,), {"__init__": __init__, "__doc__": "out-of-scope placeholder, see potentials._out_of_scope"})
+
+
+SplineOverlap = _out_of_scope("SplineOverlap", "needs torchcubicspline; reference potentials.py")
+BoltzmannInversionSpline = _out_of_scope("BoltzmannInversionSpline", "needs torchcubicspline; reference potentials.py")
+Harmonic1D = _out_of_scope("Harmonic1D", "toy potential of the isomerisation demos")
+toy2d = _out_of_scope("toy2d", "toy potential of the isomerisation demos")
+leps = _out_of_scope("leps", "toy potential of the isomerisation demos")
+MLP2d = _out_of_scope("MLP2d", "toy potential of the isomerisation demos")
+
+
 def __getattr__(name):
     # `PairPotentials` lives in interface.py in the reference, but BASELINE.json / README name it
     # `torchmd.potentials.PairPotentials` (SURVEY naming trap): export it from both.

@@ -12,6 +12,8 @@ Step algebra restated from the reference:
   rk4 (3/8 rule)     tinydiffeq.py:98-103    grid loop                 tinydiffeq.py:56-76
   adjoint backward   sovlers.py:211-293
 """
+import contextlib
+
 import torch
 from torch import nn
 
@@ -111,16 +113,24 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
     """Integrate over the grid t and return every grid point stacked (reference sovlers.py:171-193)."""
     if method not in STEPPERS:
         raise KeyError(method)
+    module = func if isinstance(func, nn.Module) else None
     tensor_input, func, y0, t = _normalise(func, y0, t)
     assert bool((t[1:] > t[:-1]).all()), "t must be strictly increasing or decrasing"
     t = t.type_as(y0[0]).to(y0[0].device)
     step = STEPPERS[method]
     sol = [y0]
     y = y0
-    for i in range(len(t) - 1):
-        dy = step(func, t[i], t[i + 1] - t[i], y)
-        y = tuple(a + b for a, b in zip(y, dy))
-        sol.append(y)
+    # A direct call with grad enabled and a state that requires grad (the reference's `adjoint=False` usage, e.g.
+    # odeint(NoseHooverChain(..., adjoint=False), states, t, "NH_verlet") followed by loss.backward()) puts the whole
+    # trajectory on the autograd tape, and the forces on it are differentiated AGAIN by backward(): the interaction modules
+    # must then record their twice-differentiable form - the fused first-order kernels would silently cut the parameters and
+    # the force Jacobian off the tape (the reference always uses create_graph=True, nff/utils/scatter.py:18-19).
+    want_graph = torch.is_grad_enabled() and module is not None and any(getattr(v, "requires_grad", False) for v in y0)
+    with (second_order(module) if want_graph else contextlib.nullcontext()):
+        for i in range(len(t) - 1):
+            dy = step(func, t[i], t[i + 1] - t[i], y)
+            y = tuple(a + b for a, b in zip(y, dy))
+            sol.append(y)
     out = tuple(torch.stack(s) for s in zip(*sol))
     return out[0] if tensor_input else out
 

@@ -102,7 +102,7 @@ def main():
     print("wrote", sorted(os.listdir(OUT)))
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--schnet", "--schnet-configured", "--bonded", "--gnn-adjoint", "--generic", "--adjoint-short", "--cpu-table")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--schnet", "--schnet-configured", "--bonded", "--gnn-adjoint", "--generic", "--adjoint-short", "--cpu-table", "--observables")):
     main()
 
 
@@ -231,6 +231,33 @@ def adjoint_short_golden():
                 out["d%s_%s" % (name, tag)] = prm.grad.numpy().copy()
             print(tag, "loss", loss.item(), {n: p.grad.item() for n, p in pot.named_parameters()})
         np.savez_compressed(os.path.join(OUT, "c1_adjoint_short.npz"), **out)
+
+
+def observables_golden():
+    """G5 (round 2): observables of the unmodified reference on seeded inputs - vacf (observable.py:153-163) of the
+    C1 velocity trajectory, angle_distribution (observable.py:112-151, topology.py:83-122) of the O-O-O triples of the water
+    box, Temperature (thermo.py:57-66)."""
+    import re
+    from mdgrad_b200._ase_compat import Atoms
+    g = np.load(os.path.join(OUT, "c1_traj.npz"))
+    w = np.load(os.path.join(OUT, "schnet_water.npz"))
+    with ref_import.active() as ref:
+        atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
+        system = ref.system.System(atoms, device="cpu")
+        vel = torch.tensor(g["v"])
+        vac = ref.observable.vacf(system, t_range=15)(vel)
+        import importlib
+        thermo = importlib.import_module("torchmd.thermo")
+        temp = thermo.Temperature(system)(vel[-1])
+        watoms = Atoms(numbers=w["numbers"], positions=w["positions"], cell=w["cell"], pbc=True)
+        wsys = ref.system.System(watoms, device="cpu")
+        oxy = [int(i) for i in np.nonzero(w["numbers"] == 8)[0]]
+        obs = ref.observable.angle_distribution(wsys, nbins=32, angle_range=(0.0, np.pi), cutoff=3.3, index_tuple=(oxy, oxy))
+        bins, count, angles = obs(torch.Tensor(wsys.get_positions()))
+    np.savez_compressed(os.path.join(OUT, "observables.npz"), vacf=vac.numpy(), vacf_t_range=np.array(15), temperature=np.array(temp.item()),
+                        angle_bins=bins.numpy(), angle_count=count.numpy(), n_angles=np.array(angles.numel()),
+                        angle_sum=np.array(angles.double().sum().item()), angle_sorted_head=np.sort(angles.reshape(-1).numpy())[:64])
+    print("observables: vacf[:3]", vac[:3].tolist(), "T", temp.item(), "angles", angles.numel())
 
 
 def chain_system(n_beads=24, bond_len=1.1, L=6.0, seed=5):
@@ -420,3 +447,5 @@ if __name__ == "__main__" and "--schnet-configured" in sys.argv:
     schnet_golden_configured()
 if __name__ == "__main__" and "--adjoint-short" in sys.argv:
     adjoint_short_golden()
+if __name__ == "__main__" and "--observables" in sys.argv:
+    observables_golden()

@@ -529,3 +529,46 @@ def test_emu_adjoint_gradients_short_horizon_vs_reference_fixture(tag, route):
         ref = float(g["d%s_%s" % (name, tag)].reshape(-1)[0])
         assert prm.grad is not None, name
         assert abs(prm.grad.item() - ref) <= 1e-4 * max(abs(ref), 1e-2 * scale), (name, prm.grad.item(), ref)
+
+
+def test_emu_direct_odeint_without_adjoint_keeps_parameter_gradients():
+    """the public `odeint` called directly with adjoint=False and states that require grad must put the forces'
+    twice-differentiable form on the tape - parameter gradients equal those of the same solve through Simulations
+    (which equal the reference's, test_emu_live_matrix)."""
+    from torchmd.interface import PairPotentials
+    from torchmd.potentials import LennardJones
+    from torchmd.md import NoseHooverChain, Simulations
+    from torchmd.sovlers import odeint
+    g = np.load(os.path.join(G, "c1_traj.npz"))
+
+    def build():
+        system = _fcc_system()
+        system.set_positions(g["q0"])
+        system.set_velocities(g["v0"])
+        lj = LennardJones(1.0, 1.0)
+        integ = NoseHooverChain(PairPotentials(system, lj, cutoff=2.5), system, T=1.0, num_chains=5, Q=50.0, adjoint=False)
+        return system, lj, integ
+
+    system, lj, integ = build()
+    sim = Simulations(system, integ, wrap=True, method="NH_verlet")
+    v, q, pv = sim.simulate(steps=6, frequency=6, dt=0.01)
+    ((q[-1] ** 2).sum() + (v[2] * v[4]).sum()).backward()
+    ref = (lj.sigma.grad.item(), lj.epsilon.grad.item())
+    system, lj, integ = build()
+    y0 = tuple(s.requires_grad_(True) for s in integ.get_inital_states(True))
+    t = torch.Tensor([0.01 * i for i in range(6)])
+    v, q, pv = odeint(integ, y0, t, method="NH_verlet")
+    ((q[-1] ** 2).sum() + (v[2] * v[4]).sum()).backward()
+    assert lj.sigma.grad is not None and lj.epsilon.grad is not None
+    assert abs(lj.sigma.grad.item() - ref[0]) <= 1e-5 * abs(ref[0]) and abs(lj.epsilon.grad.item() - ref[1]) <= 1e-5 * abs(ref[1])
+    assert y0[1].grad is not None and torch.isfinite(y0[1].grad).all()
+
+
+def test_emu_f2_observables_vs_reference_fixture():
+    """bodies of tests/test_gpu_observables.py on the emulated kernels (vacf lag-product kernel, angle distribution over the
+    native list, Temperature / virial Pressure)"""
+    import observable_checks as C
+    cpu = torch.device("cpu")
+    C.check_vacf("cpu", cpu)
+    C.check_angle_distribution("cpu", cpu)
+    C.check_temperature_and_pressure("cpu", cpu)

@@ -115,9 +115,9 @@ def c5(args):
     loss.backward()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    gn = float(sum((p.grad.double() ** 2).sum() for p in gnn.model.parameters() if p.grad is not None) ** 0.5)
+    gn = float(sum((p.grad.double() ** 2).sum() for p in gnn.gnn.parameters() if p.grad is not None) ** 0.5)
     out["config"]["adjoint_20_steps"] = {"forward_s": t1 - t0, "backward_s": t2 - t1, "grad_norm": gn,
-                                         "params_with_grad": int(sum(p.grad is not None for p in gnn.model.parameters())),
+                                         "params_with_grad": int(sum(p.grad is not None for p in gnn.gnn.parameters())),
                                          "what": "Simulations.simulate(20 steps, adjoint=True) -> RDF + velocity loss -> .backward() "
                                                  "through the adjoint solver (torchmd/sovlers.py:211-293)"}
     return out
