@@ -299,6 +299,48 @@ def run_reference_arm(args, rank, world):
     emit(line)
 
 
+def time_config(ctx, _lib, torch, dist, dev, world, ncell, steps, warmup, skin, log):
+    """Device-resident steps/s of an ncell x ncell x (ncell * world) FCC LJ box on the same engine (used for the north_star's
+    configs[3] size, 131 072 atoms per GPU, next to the headline configuration): set-up, warm-up, CUDA-event timing with
+    barrier + synchronize on both sides, max over ranks."""
+    pos, vel, L = make_system(ncell, zmult=world)
+    n = pos.shape[0]
+    L32 = float(np.float32(L))
+    q0 = torch.tensor(pos, dtype=torch.float32, device=dev)
+    v0 = torch.tensor(vel, dtype=torch.float32, device=dev)
+    mass = torch.full((n,), MASS, dtype=torch.float32, device=dev)
+    v0, q0 = equilibrate(ctx, _lib, torch, n, L32, mass, v0, q0, skin, lambda m: None, world, world)
+    vmax = float(v0.norm(dim=1).max())
+    p = md_params(_lib, n, L32, skin, int(max(1, min(64, math.floor(0.5 * skin / (1.1 * vmax * DT))))), world)
+
+    def run(nsteps, vv, qq, pv):
+        p.traj_stride = nsteps
+        tv, tq, tpv, _ = ctx.md_run(p, mass, vv, qq, pv, tgrid(nsteps))
+        return assemble(torch, tv[-1], world), assemble(torch, tq[-1], world), [float(x) for x in tpv[-1]]
+
+    v1, q1, pv1 = run(warmup, v0, q0, [0.0] * CHAINS)
+    p.rebuild_every = int(ctx.stats()["maxrow_or_K"])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    v2, q2, _ = run(steps, v1, q1, pv1)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"atoms": n, "atoms_per_gpu": n // world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+            "box_steps_per_s": steps / (ms / 1000.0), "atom_steps_per_s": n * steps / (ms / 1000.0),
+            "rebuild_every": int(p.rebuild_every), "finite": bool(torch.isfinite(q2).all() and torch.isfinite(v2).all()),
+            "trajectory": "first and last frame only"}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -312,6 +354,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-dist-parity", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the extra 131 072-atoms-per-GPU measurement (configs[3] size)")
     ap.add_argument("--config", default="c2", choices=["c2", "c1", "c3", "c5"],
                     help="c2 (default) = BASELINE configs[1], the headline; c1 / c3 / c5 = configs[0] / [2] / [4] through the public API")
     args = ap.parse_args()
@@ -443,6 +486,12 @@ def main():
         "gpu_launches": launches, "clocks": clocks,
         "tau_per_day": box_steps_per_s * DT * 86400.0,
     }
+    if not args.no_c4:
+        # BASELINE configs[3]: 1 048 576-atom LJ box over 8 GPUs = 131 072 atoms per GPU (FCC 32 x 32 x 32 per GPU); reported at
+        # every N so that the weak scaling of THAT size can be read off the same lines (efficiency = box_steps_per_s(N) / (N=1))
+        res["c4"] = time_config(ctx, _lib, torch, dist, dev, world, 32, min(args.steps, 400), max(3, min(args.warmup, 100)), args.skin, log)
+        res["c4"]["what"] = "configs[3] size: 131 072 atoms per GPU (FCC 32^3 per GPU, box grows along z with the GPU count), same engine / skin / thermostat"
+        log("c4: %s" % res["c4"])
     if world > 1:
         res["dist_parity"] = parity
         if rank == 0:
@@ -513,6 +562,7 @@ def main():
             import pstats
             prof.disable()
             pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(22)
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(14)
         e2e_steps = n_epochs * per_epoch
         state_bytes = n * 3 * 4 * 2 + CHAINS * 4
         res["e2e"] = {"value": e2e_steps / el, "unit": "steps/s",

@@ -267,12 +267,207 @@ __global__ void __launch_bounds__(128) k_sn_gemm_tc(int M, int N, int K, const f
     if (warp == 0) tc_dealloc(tmem, (uint32_t)NT);
 }
 
+// =====================================================================================================================
+// Second version (round 2, after the first hardware runs of the kernel above - profiles/r02_schnet.md):
+//   * staging is COALESCED: 8 consecutive threads read the 128 contiguous bytes of one row's 32-wide k-block (the first
+//     version gave every thread a whole row: 32 different 128-byte lines per warp request, the L1 wavefronts of that made a
+//     k-block ~5x longer than its 12 MMAs);
+//   * two shared-memory stages: the threads stage k-block kb + 1 while the tensor core works on kb (one mbarrier per stage,
+//     armed by tcgen05.commit, waited before the stage is overwritten);
+//   * the accumulation over K is CHUNKED: the tensor core accumulates at most TC_KCH k-blocks (128 k) into one half of a
+//     double-buffered TMEM accumulator, the warps add finished chunks into fp32 registers with round-to-nearest adds while the
+//     next chunk runs.  Measured reason: with one long TMEM accumulation the K = 512 layers of configs[4] miss the 1e-5 parity
+//     bar against the reference (the tensor core's fp32 accumulator does not round to nearest: the error grows with the number
+//     of accumulations), K = 128 passes;
+//   * the epilogue reads / writes rows in float4.
+// Same operand layout, descriptors and 3xTF32 split as the first version (validated on hardware).
+// =====================================================================================================================
+#define TC_KCH 4            // k-blocks per TMEM accumulation chunk
+#define TC_STAGES 2
+
+// Staging of one 32-wide k-block in two halves: tc_load2 requests the rows' float4 (registers), tc_store2 splits them into
+// hi / lo TF32 and stores them in the canonical layout.  Thread mapping (128 threads, warp w, lane l): a warp instruction
+// covers row group g = 4 * it' + w (8 rows), rows r = 8 g + (l & 7), float4 column c = 4 * half + (l >> 3):
+//   * shared memory: the 8 lanes of a quarter-warp write the 8 rows of a core matrix = 8 consecutive 16-byte slots ->
+//     conflict-free (the first coalesced mapping put a row's 8 float4 at stride LBO = 128 B: 8-way bank conflicts, 3084
+//     instead of 384 store wavefronts per k-block - ncu, profiles/r02_schnet.md);
+//   * global memory: a warp reads 64 contiguous bytes of each of 8 rows; the other half of every 128-byte line is read by the
+//     next instruction of the same thread (L1 hit).
+template <int ROWS>
+__device__ __forceinline__ void tc_load2(const float* __restrict__ G, int ld, int row0, int nrows, int k0, int K, float4* v) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int it = 0; it < ROWS / 16; ++it) {
+        const int g = (it >> 1) * 4 + w, half = it & 1;
+        const int r = 8 * g + (lane & 7), c = 4 * half + (lane >> 3);
+        const int row = row0 + r, k = k0 + 4 * c;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < nrows && k < K) v[it] = __ldg(reinterpret_cast<const float4*>(G + (size_t)row * ld + k));   // K % 4 == 0
+    }
+}
+template <int ROWS>
+__device__ __forceinline__ void tc_store2(const float4* v, unsigned char* s_hi, unsigned char* s_lo) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int it = 0; it < ROWS / 16; ++it) {
+        const int g = (it >> 1) * 4 + w, half = it & 1;
+        const int c = 4 * half + (lane >> 3);
+        const uint32_t base = (uint32_t)g * TC_SBO + (uint32_t)(lane & 7) * 16u + (uint32_t)c * TC_LBO;
+        uint4 hi, lo;
+        hi.x = tc_tf32(v[it].x); hi.y = tc_tf32(v[it].y); hi.z = tc_tf32(v[it].z); hi.w = tc_tf32(v[it].w);
+        lo.x = tc_tf32(v[it].x - __uint_as_float(hi.x)); lo.y = tc_tf32(v[it].y - __uint_as_float(hi.y));
+        lo.z = tc_tf32(v[it].z - __uint_as_float(hi.z)); lo.w = tc_tf32(v[it].w - __uint_as_float(hi.w));
+        *reinterpret_cast<uint4*>(s_hi + base) = hi;
+        *reinterpret_cast<uint4*>(s_lo + base) = lo;
+    }
+}
+
+template <int NT, int EPI>
+__global__ void __launch_bounds__(128) k_sn_gemm_tc2(int M, int N, int K, const float* __restrict__ A, const float* __restrict__ Bt,
+                                                     const float* __restrict__ bias, float* __restrict__ aux, float* __restrict__ C) {
+    TC_DYN_SMEM(tc_smem);
+    __shared__ __align__(8) TcBarrier s_done[TC_STAGES];      // the MMAs that read stage s have completed
+    __shared__ __align__(8) TcBarrier s_chunk[2];             // every MMA of the chunk accumulated in TMEM half h has completed
+    __shared__ uint32_t s_tmem;
+    constexpr uint32_t STAGE = (uint32_t)(2 * TC_M + 2 * NT) * 128u;
+    const int warp = threadIdx.x >> 5;
+    const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * NT;
+
+    if (threadIdx.x == 0) { tc_mbar_init(&s_done[0]); tc_mbar_init(&s_done[1]); tc_mbar_init(&s_chunk[0]); tc_mbar_init(&s_chunk[1]); }
+    if (warp == 0) tc_alloc(&s_tmem, (uint32_t)(2 * NT));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+    float racc[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) racc[i] = 0.f;
+    uint32_t done_ph = 0, chunk_ph = 0;                       // bit k = parity of the next wait on barrier k
+    const int nkb = (K + TC_KB - 1) / TC_KB;
+    const int nchunks = (nkb + TC_KCH - 1) / TC_KCH;
+    int drained = 0;
+
+    auto drain = [&](int c) {                                 // add the finished chunk c (TMEM half c & 1) into the registers
+        const int h = c & 1;
+        tc_mbar_wait(&s_chunk[h], (chunk_ph >> h) & 1u);
+        chunk_ph ^= 1u << h;
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t r[16];
+            tc_ld16(tmem + (uint32_t)(h * NT), warp, c0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) racc[c0 + i] += __uint_as_float(r[i]);
+        }
+        tc_fence_before();
+    };
+
+    float4 va[TC_M / 16], vb[NT / 16];                       // the k-block being staged (requested one iteration ahead)
+    tc_load2<TC_M>(A, K, m0, M, 0, K, va);
+    tc_load2<NT>(Bt, K, n0, N, 0, K, vb);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        if (kb >= TC_STAGES) {                                // the MMAs of k-block kb - 2 have read this stage
+            tc_mbar_wait(&s_done[s], (done_ph >> s) & 1u);
+            done_ph ^= 1u << s;
+        }
+        unsigned char* sA_hi = tc_smem + (size_t)s * STAGE;
+        unsigned char* sA_lo = sA_hi + TC_M * 128;
+        unsigned char* sB_hi = sA_lo + TC_M * 128;
+        unsigned char* sB_lo = sB_hi + NT * 128;
+        tc_store2<TC_M>(va, sA_hi, sA_lo);
+        tc_store2<NT>(vb, sB_hi, sB_lo);
+        if (kb + 1 < nkb) {                                   // next k-block's rows in flight behind this block's barrier + MMAs
+            tc_load2<TC_M>(A, K, m0, M, (kb + 1) * TC_KB, K, va);
+            tc_load2<NT>(Bt, K, n0, N, (kb + 1) * TC_KB, K, vb);
+        }
+        tc_fence_smem();
+        // a chunk that ended two k-blocks ago has (almost certainly) completed: fold it in while the tensor core is busy
+        if (kb % TC_KCH == 1 && kb / TC_KCH >= 1 && drained < kb / TC_KCH) { drain(drained); ++drained; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            const int chunk = kb / TC_KCH, h = chunk & 1;
+            const uint32_t d = tmem + (uint32_t)(h * NT);
+#pragma unroll
+            for (int ks = 0; ks < TC_KB / 8; ++ks) {
+                const uint32_t off = (uint32_t)ks * 2u * TC_LBO;         // one MMA consumes two 16-byte K chunks
+                const uint64_t dah = tc_desc(tc_smem_addr(sA_hi) + off), dal = tc_desc(tc_smem_addr(sA_lo) + off);
+                const uint64_t dbh = tc_desc(tc_smem_addr(sB_hi) + off), dbl = tc_desc(tc_smem_addr(sB_lo) + off);
+                tc_mma(d, dah, dbh, idesc, ((kb % TC_KCH) | ks) ? 1u : 0u);
+                tc_mma(d, dah, dbl, idesc, 1u);
+                tc_mma(d, dal, dbh, idesc, 1u);
+            }
+            tc_commit(&s_done[s]);
+            if (kb % TC_KCH == TC_KCH - 1 || kb == nkb - 1) tc_commit(&s_chunk[h]);
+        }
+    }
+    for (; drained < nchunks; ++drained) drain(drained);
+
+    // epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) = rows m0 + 32 w + lane; this thread holds its row's NT sums
+    const int m = m0 + 32 * warp + (threadIdx.x & 31);
+    if (m < M) {
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 4) {
+            const int n = n0 + c0;
+            if (n >= N) break;
+            const size_t o = (size_t)m * N + n;
+            if (n + 3 < N && ((N & 3) == 0)) {
+                float4 v = make_float4(racc[c0], racc[c0 + 1], racc[c0 + 2], racc[c0 + 3]);
+                if (EPI == SN_EPI_BIAS || EPI == SN_EPI_BIAS_SSP || EPI == SN_EPI_BIAS_ADD) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                }
+                if (EPI == SN_EPI_BIAS_SSP) {
+                    *reinterpret_cast<float4*>(aux + o) = v;
+                    v = make_float4(sn_ssp(v.x), sn_ssp(v.y), sn_ssp(v.z), sn_ssp(v.w));
+                } else if (EPI == SN_EPI_BIAS_ADD || EPI == SN_EPI_ADD) {
+                    const float4 c = *reinterpret_cast<const float4*>(C + o);
+                    v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+                } else if (EPI == SN_EPI_MUL_SIG) {
+                    const float4 a = *reinterpret_cast<const float4*>(aux + o);
+                    v.x *= sn_sigmoid(a.x); v.y *= sn_sigmoid(a.y); v.z *= sn_sigmoid(a.z); v.w *= sn_sigmoid(a.w);
+                }
+                *reinterpret_cast<float4*>(C + o) = v;
+            } else {
+                for (int i = 0; i < 4 && n + i < N; ++i) {
+                    const float v = racc[c0 + i];
+                    const size_t oi = o + i;
+                    if (EPI == SN_EPI_STORE) C[oi] = v;
+                    else if (EPI == SN_EPI_BIAS) C[oi] = v + bias[n + i];
+                    else if (EPI == SN_EPI_BIAS_SSP) { float p = v + bias[n + i]; aux[oi] = p; C[oi] = sn_ssp(p); }
+                    else if (EPI == SN_EPI_BIAS_ADD) C[oi] += v + bias[n + i];
+                    else if (EPI == SN_EPI_MUL_SIG) C[oi] = v * sn_sigmoid(aux[oi]);
+                    else C[oi] += v;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tmem, (uint32_t)(2 * NT));
+}
+
 // Bt: (N x K) row-major.  Returns MDG_E_STATE when the shape is not covered (caller falls back to the SIMT kernel).
 template <int EPI>
 static int sn_gemm_tc(int M, int N, int K, const float* A, const float* Bt, const float* bias, float* aux, float* C, cudaStream_t st) {
     if (M <= 0 || N <= 0) return MDG_OK;
     if ((K & 3) || (((uintptr_t)A | (uintptr_t)Bt) & 15)) return MDG_E_STATE;
-    if (N > 64) {
+    // 128-wide tiles only when they still give >= 2 CTAs per SM: the kernel is single-staged (stage -> MMA -> wait), so it is
+    // co-resident CTAs that overlap one tile's staging with another's MMAs; at configs[4] (M 4096, N 256 / 512) the 64-wide
+    // tile gives 128 - 256 CTAs of 48 KB instead of 64 - 128 of 64 KB
+    const bool wide = N > 64 && (int64_t)((N + 127) / 128) * ((M + TC_M - 1) / TC_M) >= 2 * 148;
+    if (getenv("MDG_SCHNET_TC_V1") == nullptr) {            // second version: coalesced 2-stage pipeline, chunked accumulation
+        const size_t smem = (size_t)TC_STAGES * (2 * TC_M + 2 * 64) * 128;
+        MDG_CUDA(cudaFuncSetAttribute(k_sn_gemm_tc2<64, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((N + 63) / 64, (M + TC_M - 1) / TC_M);
+        k_sn_gemm_tc2<64, EPI><<<grid, 128, smem, st>>>(M, N, K, A, Bt, bias, aux, C);
+        MDG_KERNEL_CHECK();
+        return MDG_OK;
+    }
+    if (wide) {
         const size_t smem = (size_t)(2 * TC_M + 2 * 128) * 128;
         MDG_CUDA(cudaFuncSetAttribute(k_sn_gemm_tc<128, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((N + 127) / 128, (M + TC_M - 1) / TC_M);

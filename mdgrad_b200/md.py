@@ -153,7 +153,7 @@ class Simulations():
                 self.update_states()
                 states = self.get_check_point()
                 continue
-            pending.append([tr[-1].detach().clone() for tr in trajs])
+            pending.append(self._stage_frames([tr[-1] for tr in trajs]))
             if len(pending) >= self._flush_every:     # bound the device / pinned memory held by un-logged frames
                 self._flush_log(pending)
             states = nxt
@@ -186,31 +186,49 @@ class Simulations():
             last[k] = wrapped
         return last
 
+    def _stage_frames(self, frames):
+        """Last frames of a finished epoch on their way to the host log.  On CUDA the copy into pinned memory is issued right
+        away on a side stream, so it overlaps the next epoch's kernels; `_flush_log` only waits for that stream and moves the
+        pinned data into the numpy arrays of the log."""
+        if not frames[0].is_cuda:
+            return [fr.detach().clone() for fr in frames]
+        dev = frames[0].device
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(dev)
+            self._pin, self._pin_used = None, 0
+        nb_epoch = sum(fr.numel() * fr.element_size() for fr in frames)
+        if self._pin is None or self._pin_used + nb_epoch > self._pin.numel():
+            if self._pin_used:                       # (frames of another size mid-interval: drain what is staged first)
+                self._flush_log(self._pending)
+            if self._pin is None or nb_epoch > self._pin.numel():
+                # sized once for a full flush interval (page-locking costs ~0.4 ms per MB: it must not recur per call)
+                self._pin = torch.empty(nb_epoch * self._flush_every, dtype=torch.uint8, pin_memory=True)
+            self._pin_used = 0
+        self._side.wait_stream(torch.cuda.current_stream(dev))
+        views = []
+        with torch.cuda.stream(self._side):
+            for fr in frames:
+                fr = fr.detach()
+                nb = fr.numel() * fr.element_size()
+                v = self._pin[self._pin_used:self._pin_used + nb].view(fr.dtype).view(fr.shape)
+                v.copy_(fr, non_blocking=True)
+                fr.record_stream(self._side)         # the trajectory block may be recycled by the next epoch's allocation
+                views.append(v)
+                self._pin_used += nb
+        return views
+
     def _flush_log(self, pending):
         """append the deferred last frames to the log (numpy, as update_log) and update the System once"""
         if not pending:
             return
-        if pending[0][0].is_cuda:
-            # device -> pinned host memory, all frames in flight at once, one synchronisation (pageable `.cpu()` copies cost
-            # ~0.5 ms per MB here and were a quarter of an epoch's wall time at 256k atoms)
-            flat = [fr for frames in pending for fr in frames]
-            total = sum(fr.numel() * fr.element_size() for fr in flat)
-            if getattr(self, "_pin", None) is None or self._pin.numel() < total:
-                # sized once for a full flush interval (page-locking is ~0.4 ms per MB: it must not recur per call)
-                per_epoch = total // len(pending)
-                self._pin = torch.empty(max(total, per_epoch * self._flush_every), dtype=torch.uint8, pin_memory=True)
-            views, off = [], 0
-            for fr in flat:
-                nb = fr.numel() * fr.element_size()
-                v = self._pin[off:off + nb].view(fr.dtype).view(fr.shape)
-                v.copy_(fr, non_blocking=True)
-                views.append(v)
-                off += nb
-            torch.cuda.current_stream(flat[0].device).synchronize()
-            it = iter(views)
+        if getattr(self, "_side", None) is not None and pending[0][0].is_pinned():
+            self._side.synchronize()
             for frames in pending:
-                for key in self.keys:
-                    self.log[key].append(next(it).numpy().copy())
+                for key, v in zip(self.keys, frames):
+                    dst = np.empty(tuple(v.shape), dtype=v.numpy().dtype)
+                    torch.from_numpy(dst).copy_(v)          # torch's multi-threaded host copy (numpy's is one thread: ~3 GB/s)
+                    self.log[key].append(dst)
+            self._pin_used = 0
         else:
             for frames in pending:
                 for key, fr in zip(self.keys, frames):

@@ -63,10 +63,7 @@ def test_native_schnet_configured_widths_vs_reference_fixture(tag, dense, monkey
     from torchmd.interface import GNNPotentials
     from torchmd.system import System
     from mdgrad_b200._ase_compat import Atoms
-    if dense == "tc":
-        monkeypatch.setenv("MDG_SCHNET_TC", "1")
-    else:
-        monkeypatch.delenv("MDG_SCHNET_TC", raising=False)
+    monkeypatch.setenv("MDG_SCHNET_TC", "1" if dense == "tc" else "0")     # (unset = auto: tensor cores for the wide layers)
     g, params, model = _configured_fixture(tag)
     system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device=0)
     gnn = GNNPotentials(system, model.cuda(), cutoff=params["cutoff"])
