@@ -366,12 +366,27 @@ def main():
         run_reference_arm(args, rank, world)
         return
     if args.config != "c2":
-        if rank != 0:
-            return
+        # These configurations are a few hundred / thousand atoms: they do not shard ("replicas only") -
+        # under torchrun every rank runs its own independent replica on its GPU and the values are summed (no collective on
+        # the data path; the sum itself goes over gloo).
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs
         r = bench_configs.RUN[args.config](args)
-        line = {"metric": "MD steps/sec", "value": r["value"], "unit": "steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            dist.init_process_group("gloo")
+            t = torch.tensor([r["value"], r["ms_per_step"]], dtype=torch.float64)
+            tsum, tmax = t.clone(), t.clone()
+            dist.all_reduce(tsum)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            r["config"]["replicas"] = world
+            r["config"]["per_replica_steps_per_s"] = r["value"]
+            r["value"], r["ms_per_step"] = float(tsum[0]), float(tmax[1])
+            dist.destroy_process_group()
+        if rank != 0:
+            return
+        line = {"metric": "MD steps/sec", "value": r["value"], "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": r["config"], "gpu_launches": r["gpu_launches"],
                 "e2e": {"value": r["value"], "unit": "steps/s", "note": "this configuration is timed through Simulations.simulate "

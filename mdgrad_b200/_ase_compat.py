@@ -170,8 +170,8 @@ class Atoms:
         return self._momenta / self._masses[:, None]
 
     def set_velocities(self, v):
-        self.set_momenta(np.array(v, dtype=float).reshape(len(self), 3)
-                         * self._masses[:, None])
+        # one conversion and one product (same values as ASE's set_momenta(v * masses[:, None]); the product is a fresh array)
+        self._momenta = np.asarray(v, dtype=float).reshape(len(self), 3) * self._masses[:, None]
 
     def get_kinetic_energy(self):
         return 0.5 * float(np.sum(self._momenta ** 2 / self._masses[:, None]))

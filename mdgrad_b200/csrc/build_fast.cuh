@@ -66,8 +66,15 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                                                              int* __restrict__ row_len, int* __restrict__ flags,
                                                              unsigned char* __restrict__ cell_local) {
     __shared__ uint32_t s_mask[FB_WARPS][32][FB_CHUNKS + 1];   // [atom][chunk], padded: conflict-free for lane = atom
-    __shared__ uint32_t s_img[FB_WARPS][FB_BATCH];
-    __shared__ int s_t[FB_WARPS][FB_BATCH];                     // sorted index of each staged candidate
+    // Per-candidate state is kept small - 3 bytes instead of 8 - because shared memory per warp is what bounds the occupancy of
+    // this kernel (ncu r02: 27% of the warp slots at 9.75 KB per warp, issue rate 54% with 2.8 "wait" + 2.3 "short scoreboard"
+    // stalls per issue: too few warps to cover its dependent ALU / LDS chains):
+    //   s_tk  = (stencil slot << 11) | index inside that cell      -> sorted index = s_cs[slot] + index
+    //   s_dim = image of the candidate RELATIVE to the pass's reference image I0: 5 bits per axis holding dI + 16, 0xFFFF = outside
+    //           [-16, 15] (a pair is only ever listed for |I_j - I_i| <= 1, so this loses nothing unless two atoms of ONE cell
+    //           are themselves more than 14 box lengths apart in raw coordinates)
+    __shared__ unsigned short s_dim[FB_WARPS][FB_BATCH];
+    __shared__ unsigned short s_tk[FB_WARPS][FB_BATCH];
     __shared__ float4 s_ctr[FB_WARPS][32];                     // local coords of the cell's atoms, w = packed image
 #ifdef MDG_BUILD_INT8_SCREEN
     __shared__ uint32_t s_cq[FB_WARPS][32];                    // the same, quantised (fb_quant)
@@ -102,18 +109,19 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         if (lane < 27) { s_pre[w][lane + 1] = x; s_cs[w][lane] = cs; }
         if (lane == 0) s_pre[w][0] = 0;
         kself_slot = __ffs(__ballot_sync(0xffffffffu, lane < 27 && cc == c)) - 1;
+        if (__any_sync(0xffffffffu, cnt >= 2048)) {        // (s_tk holds 11 bits of in-cell index: such a cell is a collapsed system)
+            if (lane == 0) flags[7] = 2048;
+            for (int a = lane; a < na; a += 32) row_len[a0 + a] = 0;
+            return;
+        }
     }
+    (void)kself_slot;
     __syncwarp();
     const int total = s_pre[w][27];
     // Stream-index form (entries index the cell's 27-cell STENCIL STREAM instead of the global sorted array, for a
     // force kernel that stages the stream in shared memory): measured slower than the gather kernel (124 vs 66 us)
     // and not used - the engine always passes cell_local == nullptr, so entries are global indices.
-#ifdef MDG_BUILD_LEAN      // build variants "lean*": the unused stream-index form is compiled out of the phase-2 loop
-    constexpr bool local_idx = false;
-#else
-    const bool local_idx = (cell_local != nullptr) && (total <= MDG_STREAM_CAP);
-    if (cell_local && lane == 0) cell_local[c] = local_idx ? 1 : 0;
-#endif
+    (void)cell_local;          // (the stream-index row form was measured slower in round 1 and is gone)
     const int cx = c % ncx, cy = (c / ncx) % ncy, cz = c / (ncx * ncy);
     const float ox = (float)cx / (float)ncx, oy = (float)cy / (float)ncy, oz = (float)cz / (float)ncz;
     const bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
@@ -140,15 +148,12 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         // image of the pass: if every atom of the cell and every candidate share it, all codes are "no shift"
         const uint32_t im0 = __shfl_sync(0xffffffffu, imc, 0);
         const bool ctr_uniform = __all_sync(0xffffffffu, !act || imc == im0);
+        const int I0x = __shfl_sync(0xffffffffu, Iix, 0), I0y = __shfl_sync(0xffffffffu, Iiy, 0), I0z = __shfl_sync(0xffffffffu, Iiz, 0);
         uint32_t* row = rows + (size_t)(act ? s : a0) * cap;
         int cnt = 0;
         // a row is PURE when its single batch is uniform: bare indices, flagged in row_len (force kernel skips the
         // index mask and the image-code test)
-#ifdef MDG_BUILD_LEAN
         const bool pure_ok = (total <= FB_BATCH);
-#else
-        const bool pure_ok = (cell_local == nullptr) && (total <= FB_BATCH);
-#endif
         bool row_pure = false;
         for (int B = 0; B < total; B += FB_BATCH) {
             const int nb = min(FB_BATCH, total - B);
@@ -171,8 +176,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     local_coord(qj.y, bx.L[1], bx.invL[1], oy, ly, Iy);
                     local_coord(qj.z, bx.L[2], bx.invL[2], oz, lz, Iz);
                     uint32_t imj = pack_img(Ix, Iy, Iz);
-                    s_img[w][a - B] = imj;
-                    s_t[w][a - B] = t;
+                    const int ex = Ix - I0x + 16, ey = Iy - I0y + 16, ez = Iz - I0z + 16;
+                    s_dim[w][a - B] = ((unsigned)ex | (unsigned)ey | (unsigned)ez) > 31u ? (unsigned short)0xFFFF
+                                                                                     : (unsigned short)(ex | (ey << 5) | (ez << 10));
+                    s_tk[w][a - B] = (unsigned short)((kk << 11) | (a - s_pre[w][kk]));
                     cand_uniform = cand_uniform && (imj == im0);
                 }
 #ifdef MDG_BUILD_INT8_SCREEN
@@ -216,18 +223,20 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     int b = __ffs(m) - 1;
                     m &= m - 1;
                     int al = (ch << 5) + b;                    // index within the batch
-                    int t = s_t[w][al];
+                    const unsigned tk = s_tk[w][al];
+                    const int t = s_cs[w][tk >> 11] + (int)(tk & 2047u);
                     if (t == s) continue;                      // self
-                    const uint32_t ref = local_idx ? (uint32_t)(B + al) : (uint32_t)t;   // stencil-stream index, or global index
+                    const uint32_t ref = (uint32_t)t;
                     if (uniform) {                             // interior cells: no pair crosses a periodic boundary
                         if (cnt < cap) row[fb_slot(cnt)] = ref | uni_code;
                         ++cnt;
                         continue;
                     }
-                    uint32_t im = s_img[w][al];
-                    int mx = (int)(im & 1023u) - 512 - Iix;
-                    int my = (int)((im >> 10) & 1023u) - 512 - Iiy;
-                    int mz = (int)((im >> 20) & 1023u) - 512 - Iiz;
+                    const int dc = s_dim[w][al];
+                    if (dc == 0xFFFF) continue;                // image far outside the window: never a listed pair (see s_dim)
+                    int mx = ((dc & 31) - 16) - (Iix - I0x);
+                    int my = (((dc >> 5) & 31) - 16) - (Iiy - I0y);
+                    int mz = ((dc >> 10) - 16) - (Iiz - I0z);
                     if ((unsigned)(mx + 1) > 2u || (unsigned)(my + 1) > 2u || (unsigned)(mz + 1) > 2u) continue;
                     if (filt && !pair_allowed(F, idi, __float_as_int(qs[t].w))) continue;
                     if (cnt < cap)
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
             {   // length (+ PURE flag) and padding to a whole 32-entry block with self entries (see mdg_pad_row)
                 row_len[s] = cnt | (row_pure ? MDG_ROW_PURE : 0);
                 const uint32_t pad_code = row_pure ? 0u : ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
-                const uint32_t self_ref = local_idx ? (uint32_t)(s_pre[w][kself_slot] + pass + lane) : (uint32_t)s;
+                const uint32_t self_ref = (uint32_t)s;
                 int end = (cnt + 31) & ~31;
                 if (end > cap) end = cap;
                 for (int k = cnt; k < end; ++k) row[fb_slot(k)] = self_ref | pad_code;

@@ -1086,7 +1086,9 @@ static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet
                         const float* d_mass, const float* d_v0, const float* d_q0, const float* h_pv0, const float* h_tgrid,
                         int n_grid, float* d_traj_v, float* d_traj_q, float* h_traj_pv, float* h_last_energy, bool async,
                         int* latched, cudaStream_t st_user) {
-    // MDG_GNN_GRAPH=1 (opt-in until measured on a GPU): on the asynchronous path a force evaluation is a FIXED launch sequence
+    // CUDA-graph replay (default since its first hardware runs in round 2 - bit-identical to the plain asynchronous epoch,
+    // tests/test_zzz_gpu_last.py, and 2540 vs 2196 steps/s on the 64-water SchNet box; MDG_GNN_GRAPH=0 turns it off): on the
+    // asynchronous path a force evaluation is a FIXED launch sequence
     // with fixed arguments (same buffers, capacities, device-side counts), so it is captured once (at the second step, after the
     // first one has grown every buffer) and replayed as a CUDA graph.  Stream capture is not allowed on the legacy default
     // stream - which is what PyTorch's current stream usually is - so such an epoch runs on a private stream, ordered after the
@@ -1096,7 +1098,7 @@ static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet
         ~GraphGuard() { if (exec) cudaGraphExecDestroy(exec); }
     } gg;
     const char* ge = getenv("MDG_GNN_GRAPH");
-    const bool use_graph = async && ge && ge[0] == '1' && n_grid > 3;
+    const bool use_graph = async && !(ge && ge[0] == '0') && n_grid > 3;
     bool graph_failed = false;
     cudaStream_t st = st_user;
     if (use_graph) {

@@ -243,7 +243,7 @@ def test_emu_gnn_engine_async_steps_and_overflow_retry(monkeypatch):
     for mode in ("async", "sync", "overflow", "async_long", "graph"):
         monkeypatch.delenv("MDG_GNN_SYNC", raising=False)
         monkeypatch.delenv("MDG_GNN_MARGIN", raising=False)
-        monkeypatch.delenv("MDG_GNN_GRAPH", raising=False)
+        monkeypatch.setenv("MDG_GNN_GRAPH", "0")               # plain asynchronous launches (graph replay is the default)
         if mode == "graph":
             monkeypatch.setenv("MDG_GNN_GRAPH", "1")           # force evaluations captured once, replayed as a CUDA graph
         if mode == "sync":

@@ -40,7 +40,7 @@ def c1(args):
     from torchmd.md import NoseHooverChain, Simulations
     from mdgrad_b200._ase_compat import FaceCenteredCubic
     atoms = FaceCenteredCubic(symbol="H", size=(3, 3, 3), latticeconstant=1.679, pbc=True)
-    system = System(atoms, device=0)
+    system = System(atoms, device=int(os.environ.get("LOCAL_RANK", "0")))
     system.set_velocities(np.random.default_rng(0).standard_normal((108, 3)) * np.sqrt(1.0 / 1.008))
     pair = PairPotentials(system, LennardJones(1.0, 1.0), cutoff=2.5)
     integ = NoseHooverChain(pair, system, T=1.0, num_chains=5, Q=50.0, adjoint=True)

@@ -32,11 +32,13 @@ def build(config):
     from torchmd.md import NoseHooverChain, Simulations
     from torchmd.system import System
     from mdgrad_b200._ase_compat import Atoms, units
+    dev = int(os.environ.get("LOCAL_RANK", "0"))           # (replica runs under torchrun: one model per GPU)
+    torch.cuda.set_device(dev)
     torch.manual_seed(0)
     np.random.seed(0)
     if config == "water":
         g = np.load(os.path.join(ROOT, "tests", "golden", "schnet_water.npz"))
-        system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device=0)
+        system = System(Atoms(numbers=g["numbers"], positions=g["positions"], cell=g["cell"], pbc=True), device=dev)
         T, dt = 298.0 * units.kB, 0.5 * units.fs
         params = {"n_atom_basis": 128, "n_filters": 128, "n_gaussians": 29, "n_convolutions": 2,
                   "cutoff": 5.847718540914188, "trainable_gauss": False}
@@ -50,7 +52,7 @@ def build(config):
         cells = np.array([[i, j, k] for i in range(nc) for j in range(nc) for k in range(nc)])
         pos = ((cells[:, None, :] + basis[None, :, :]).reshape(-1, 3)) * a
         pos = pos + np.random.default_rng(3).normal(0, 0.05, pos.shape)
-        system = System(Atoms(numbers=[14] * len(pos), positions=pos, cell=[a * nc] * 3, pbc=True), device=0)
+        system = System(Atoms(numbers=[14] * len(pos), positions=pos, cell=[a * nc] * 3, pbc=True), device=dev)
         T, dt = 100.0 * units.kB, 1.0 * units.fs
         params = {"n_atom_basis": 512, "n_filters": 256, "n_gaussians": 33, "n_convolutions": 3, "cutoff": 4.9,
                   "trainable_gauss": False}
