@@ -488,8 +488,10 @@ def main():
                                % (n // world, args.ncell, args.ncell, args.ncell * world),
                    "atoms": n, "atoms_per_gpu": n // world,
                    "parallelism": ("1 GPU" if world == 1 else
-                                   "spatial slabs x%d along z in the global cell-sorted index space; per step: NCCL ghost-layer "
-                                   "halo (2 send + 2 recv) + one 2-double all-reduce; per rebuild: state all-gather" % world),
+                                   "spatial slabs x%d along z in the global cell-sorted index space; per step: one peer-to-peer push "
+                                   "kernel (ghost layers + kinetic energies over NVLink stores, CUDA-IPC mapped; MDG_DIST_P2P=0: NCCL "
+                                   "send/recv + all-reduce), boundary layers on a side stream beside the interior rows; per rebuild: "
+                                   "two-layer state exchange + layer totals over NCCL" % world),
                    "value_definition": "steps/s of the whole box x n_gpus (the box grows with the GPU count: 256000 atoms per GPU), "
                                        "i.e. atom-steps/s / 256000; box_steps_per_s is the raw rate of the %d-atom box" % n,
                    "box_steps_per_s": box_steps_per_s,

@@ -75,6 +75,8 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
     if (c->h_layers) cudaFreeHost(c->h_layers);
     mdg_i_release_profile(c);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->bnd_stream) cudaStreamDestroy(c->bnd_stream);
+    if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     if (c->gnn_stream) cudaStreamDestroy(c->gnn_stream);
     if (c->ev_gnn) cudaEventDestroy(c->ev_gnn);
     if (c->ev_a) cudaEventDestroy(c->ev_a);

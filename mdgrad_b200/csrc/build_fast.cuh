@@ -55,8 +55,68 @@ __device__ __forceinline__ uint32_t fb_quant(float lx, float ly, float lz, float
     return (uint32_t)qx | ((uint32_t)qy << 8) | ((uint32_t)qz << 16);
 }
 
+// Predicated store / opaque pointer: without them nvcc branches around every row store and re-derives the row base (s * cap,
+// 64-bit) per entry - 20 instructions per entry in phase 2 instead of 10.
+__device__ __forceinline__ void fb_store(uint32_t* dst, uint32_t v, bool ok) {
+#ifdef MDG_EMU
+    if (ok) *dst = v;
+#else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(dst), "r"(v), "r"((int)ok) : "memory");
+#endif
+}
+__device__ __forceinline__ void fb_opaque(uint32_t*& p) {
+#ifndef MDG_EMU
+    asm volatile("" : "+l"(p));
+#endif
+}
+
 __device__ __forceinline__ uint32_t pack_img(int Ix, int Iy, int Iz) {
     return (uint32_t)((Ix + 512) & 1023) | ((uint32_t)((Iy + 512) & 1023) << 10) | ((uint32_t)((Iz + 512) & 1023) << 20);
+}
+
+// Phase 2 of k_build_fast for one lane (= one atom): walk the set bits of its mask words in ascending candidate order and
+// append the row entries.  UNIFORM (warp-uniform): every atom of the cell and every candidate share one periodic image, all
+// entries carry `uni_code`; otherwise the image code comes from s_dim and pairs outside +-1 image (or filtered ones) are dropped.
+template <bool UNIFORM>
+__device__ __forceinline__ int fb_walk(uint32_t nz, const uint32_t* mrow, const unsigned short* s_tk, const unsigned short* s_dim,
+                                       const int* s_cs, uint32_t* rowp, int cnt, int cap, uint32_t uni_code, int dIx, int dIy,
+                                       int dIz, bool filt, const PairFilter& F, int idi, const float4* __restrict__ qs) {
+    if (nz == 0u) return cnt;
+    const int ch0 = __ffs(nz) - 1;
+    nz &= nz - 1;
+    uint32_t m = mrow[ch0];
+    const unsigned short* tkp = s_tk + (ch0 << 5);
+    const unsigned short* dmp = s_dim + (ch0 << 5);
+    do {
+        const int b = __ffs(m) - 1;            // candidate b of the current word
+        m &= m - 1;
+        const unsigned tk = tkp[b];
+        unsigned dc = 0;
+        if (!UNIFORM) dc = dmp[b];
+        if (m == 0u && nz != 0u) {             // next non-empty word
+            const int ch = __ffs(nz) - 1;
+            nz &= nz - 1;
+            m = mrow[ch];
+            tkp = s_tk + (ch << 5);
+            dmp = s_dim + (ch << 5);
+        }
+        const uint32_t ref = (uint32_t)(s_cs[tk >> 11] + (int)(tk & 2047u));
+        if (UNIFORM) {
+            fb_store(rowp + fb_slot(cnt), ref | uni_code, cnt < cap);
+            ++cnt;
+        } else {
+            // dc == 0xFFFF: image far outside the window, never a listed pair (see s_dim)
+            const int mx = (int)(dc & 31u) - dIx, my = (int)((dc >> 5) & 31u) - dIy, mz = (int)(dc >> 10) - dIz;
+            bool keep = dc != 0xFFFFu && (unsigned)(mx + 1) <= 2u && (unsigned)(my + 1) <= 2u && (unsigned)(mz + 1) <= 2u;
+            if (filt && keep) keep = pair_allowed(F, idi, __float_as_int(qs[ref].w));
+            if (keep) {
+                const uint32_t code = (uint32_t)((1 - mx) | ((1 - my) << 2) | ((1 - mz) << 4)) << MDG_IDX_BITS;
+                fb_store(rowp + fb_slot(cnt), ref | code, cnt < cap);
+                ++cnt;
+            }
+        }
+    } while (m != 0u);
+    return cnt;
 }
 
 __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int ncell, const float4* __restrict__ qs,
@@ -115,7 +175,6 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
             return;
         }
     }
-    (void)kself_slot;
     __syncwarp();
     const int total = s_pre[w][27];
     // Stream-index form (entries index the cell's 27-cell STENCIL STREAM instead of the global sorted array, for a
@@ -208,41 +267,25 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
             const uint32_t uni_code = row_pure ? 0u : ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
             __syncwarp();
             // ---------------- phase 2: lane = atom ------------------------------------------------
-            // One flattened loop per lane over ALL its set bits of the batch: lanes drift apart across
-            // chunks, but (nearly) every iteration of every active lane emits one entry - instead of all
-            // lanes waiting for the largest popcount of each chunk.
+            // One flattened loop per lane over ALL its set bits of the batch: lanes drift apart across chunks, but every
+            // iteration of every active lane emits one entry.  Empty words are skipped through a bitmask of the non-empty ones
+            // (corner cells of the stencil are mostly empty) and the self pair is cleared up front, so the loop body has no
+            // "nothing to emit" iteration (ncu r02: 58 warp instructions per iteration, one in six of them an empty one).
             if (act) {
-                int ch = 0;
-                uint32_t m = s_mask[w][lane][0];
-                while (true) {
-                    if (m == 0) {
-                        if (++ch >= nch) break;
-                        m = s_mask[w][lane][ch];
-                        continue;
-                    }
-                    int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    int al = (ch << 5) + b;                    // index within the batch
-                    const unsigned tk = s_tk[w][al];
-                    const int t = s_cs[w][tk >> 11] + (int)(tk & 2047u);
-                    if (t == s) continue;                      // self
-                    const uint32_t ref = (uint32_t)t;
-                    if (uniform) {                             // interior cells: no pair crosses a periodic boundary
-                        if (cnt < cap) row[fb_slot(cnt)] = ref | uni_code;
-                        ++cnt;
-                        continue;
-                    }
-                    const int dc = s_dim[w][al];
-                    if (dc == 0xFFFF) continue;                // image far outside the window: never a listed pair (see s_dim)
-                    int mx = ((dc & 31) - 16) - (Iix - I0x);
-                    int my = (((dc >> 5) & 31) - 16) - (Iiy - I0y);
-                    int mz = ((dc >> 10) - 16) - (Iiz - I0z);
-                    if ((unsigned)(mx + 1) > 2u || (unsigned)(my + 1) > 2u || (unsigned)(mz + 1) > 2u) continue;
-                    if (filt && !pair_allowed(F, idi, __float_as_int(qs[t].w))) continue;
-                    if (cnt < cap)
-                        row[fb_slot(cnt)] = ref | ((uint32_t)((1 - mx) | ((1 - my) << 2) | ((1 - mz) << 4)) << MDG_IDX_BITS);
-                    ++cnt;
+                uint32_t* const mrow = &s_mask[w][lane][0];
+                {
+                    const int as = s_pre[w][kself_slot] + pass + lane - B;          // this atom in the candidate stream
+                    if ((unsigned)as < (unsigned)nb) mrow[as >> 5] &= ~(1u << (as & 31));
                 }
+                uint32_t nz = 0;
+                for (int ch = 0; ch < nch; ++ch) nz |= (mrow[ch] != 0u ? 1u : 0u) << ch;
+                const int dIx = Iix - I0x + 16, dIy = Iiy - I0y + 16, dIz = Iiz - I0z + 16;
+                uint32_t* rowp = row;
+                fb_opaque(rowp);                               // (keeps the row base in a register pair: no per-entry s * cap)
+                if (uniform)
+                    cnt = fb_walk<true>(nz, mrow, s_tk[w], s_dim[w], s_cs[w], rowp, cnt, cap, uni_code, dIx, dIy, dIz, false, F, idi, qs);
+                else
+                    cnt = fb_walk<false>(nz, mrow, s_tk[w], s_dim[w], s_cs[w], rowp, cnt, cap, 0u, dIx, dIy, dIz, filt, F, idi, qs);
             }
         }
         if (act) {

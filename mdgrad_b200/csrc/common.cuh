@@ -270,6 +270,8 @@ struct mdg_ctx {
     void*  dist_comm = nullptr;
     cudaStream_t comm_stream = nullptr;            // NCCL side stream: halo + KE all-reduce overlap the interior forces
     cudaEvent_t  ev_a = nullptr, ev_halo = nullptr, ev_ke = nullptr;
+    cudaStream_t bnd_stream = nullptr;             // boundary-layer forces of a slab step: wait for the ghosts + two layers of rows, BESIDE the interior rows
+    cudaEvent_t  ev_bnd = nullptr;
     // peer-to-peer step path (dist.cuh DistSync): IPC mappings of the neighbours' position buffers and of every rank's sync block
     bool   dist_p2p = false;         // mappings valid -> the per-step halo / kinetic-energy exchange uses NVLink stores + flags
     bool   dist_p2p_off = false;     // MDG_DIST_P2P=0, or the IPC set-up failed once: stay on the NCCL path

@@ -581,7 +581,11 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         MDG_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
         MDG_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
         MDG_CUDA(cudaEventCreateWithFlags(&c->ev_ke, cudaEventDisableTiming));
+        MDG_CUDA(cudaStreamCreateWithPriority(&c->bnd_stream, cudaStreamNonBlocking, prio_hi));
+        MDG_CUDA(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
     }
+    const char* bz = getenv("MDG_DIST_BND_STREAM");
+    const bool bnd_side = !(bz && bz[0] == '0');     // boundary layers on their own stream, concurrent with the interior rows
     IntArgs A;
     memset(&A, 0, sizeof(A));
     A.integrator = p->integrator;
@@ -758,17 +762,29 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                 DA.seq = seq;
                 if (ev0) MDG_CUDA(cudaEventRecord(ev0, st));
                 if (split) {
+                    // The two boundary layers need the ghosts, the interior layers do not.  Boundary side stream: wait kernel
+                    // (spins on the halo flags) + one launch over the bottom and top layer; main stream: the interior rows.  The
+                    // boundary CTAs fill in as the interior's last wave drains, so a slab step costs about one full force launch
+                    // (serial wait + small boundary launch behind the interior rows: +10 us per step in the r02 measurements).
                     const int nxy = c->nc[0] * c->nc[1];
-                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
-                                              (zhi - 1) * nxy, st));                                                      // interior
-                    k_dist_wait<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq);                                             // ghosts landed
+                    cudaStream_t bs = bnd_side ? c->bnd_stream : st;
+                    if (bnd_side) MDG_CUDA(cudaStreamWaitEvent(bs, c->ev_a, 0));
+                    else MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
+                                                   (zhi - 1) * nxy, st));                                                 // interior
+                    k_dist_wait<<<1, 32, 0, bs>>>((DistSync*)c->dsync.p, seq);                                             // ghosts landed
                     if (!c->tiles) {   // bottom + top layer in one launch
-                        MDG_TRY(mdg_i_force_range2(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], st));
+                        MDG_TRY(mdg_i_force_range2(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], bs));
                     } else {
                         MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], zlo * nxy,
-                                                  (zlo + 1) * nxy, st));                                                  // bottom layer
+                                                  (zlo + 1) * nxy, bs));                                                  // bottom layer
                         MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
-                                                  zhi * nxy, st));                                                        // top layer
+                                                  zhi * nxy, bs));                                                        // top layer
+                    }
+                    if (bnd_side) {
+                        MDG_CUDA(cudaEventRecord(c->ev_bnd, bs));
+                        MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
+                                                  (zhi - 1) * nxy, st));                                                  // interior
+                        MDG_CUDA(cudaStreamWaitEvent(st, c->ev_bnd, 0));
                     }
                     c->stat_launches++;
                 } else {
@@ -793,16 +809,23 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             if (ev0) MDG_CUDA(cudaEventRecord(ev0, st));
             if (split) {
                 const int nxy = c->nc[0] * c->nc[1];
-                MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
-                                          (zhi - 1) * nxy, st));                                                      // interior
-                MDG_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
+                cudaStream_t bs = bnd_side ? c->bnd_stream : st;
+                if (!bnd_side) MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
+                                                         (zhi - 1) * nxy, st));                                       // interior
+                MDG_CUDA(cudaStreamWaitEvent(bs, c->ev_halo, 0));
                 if (!c->tiles) {       // bottom + top layer in one launch
-                    MDG_TRY(mdg_i_force_range2(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], st));
+                    MDG_TRY(mdg_i_force_range2(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], bs));
                 } else {
                     MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], zlo * nxy,
-                                              (zlo + 1) * nxy, st));                                                  // bottom layer
+                                              (zlo + 1) * nxy, bs));                                                  // bottom layer
                     MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
-                                              zhi * nxy, st));                                                        // top layer
+                                              zhi * nxy, bs));                                                        // top layer
+                }
+                if (bnd_side) {        // (see the peer-to-peer branch: boundary rows beside the interior rows)
+                    MDG_CUDA(cudaEventRecord(c->ev_bnd, bs));
+                    MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
+                                              (zhi - 1) * nxy, st));                                                  // interior
+                    MDG_CUDA(cudaStreamWaitEvent(st, c->ev_bnd, 0));
                 }
             } else {
                 if (!do_rebuild) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
