@@ -278,7 +278,9 @@ struct mdg_ctx {
     DevBuf dsync;                    // my DistSync block
     void*  peer_sync[16] = {nullptr};        // every rank's DistSync as mapped here (own entry = dsync.p)
     void*  peer_qs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [below, above][qs_buf 0, 1] of the two neighbours
-    void*  p2p_exported[2] = {nullptr, nullptr};   // my qs_buf pointers at export time (re-export when they change)
+    void*  peer_v[2] = {nullptr, nullptr}, *peer_vh[2] = {nullptr, nullptr};   // [below, above] v4 / vh4 buffers of the neighbours (rebuild state push)
+    void*  p2p_exported[4] = {nullptr, nullptr, nullptr, nullptr};   // my qs_buf / v4 / vh4 pointers at export time (re-export when they change)
+    int    dist_rebuilds = 0;        // rebuilds of the slab engine so far (parity of the layer-total tables; identical on all ranks)
     void*  p2p_opened[40] = {nullptr};       // everything cudaIpcOpenMemHandle returned (closed on release)
     int    p2p_n_opened = 0;
     int    dist_seq = 0;             // running sequence number of the distributed steps (identical on all ranks)

@@ -105,7 +105,7 @@ void mdg_i_dist_p2p_release(mdg_ctx* c) {
     c->p2p_n_opened = 0;
     c->dist_p2p = false;
     for (int r = 0; r < MDG_DIST_MAXW; ++r) c->peer_sync[r] = nullptr;
-    for (int s = 0; s < 2; ++s) c->peer_qs[s][0] = c->peer_qs[s][1] = nullptr;
+    for (int s = 0; s < 2; ++s) c->peer_qs[s][0] = c->peer_qs[s][1] = c->peer_v[s] = c->peer_vh[s] = nullptr;
 }
 
 int mdg_i_dist_p2p_setup(mdg_ctx* c, cudaStream_t st) {
@@ -116,7 +116,9 @@ int mdg_i_dist_p2p_setup(mdg_ctx* c, cudaStream_t st) {
 #else
     const int W = c->dist_world, me = c->dist_rank;
     if (c->dist_p2p_off || W < 2 || W > MDG_DIST_MAXW || !g_nccl.AllGather) return MDG_OK;
-    if (c->dist_p2p && c->p2p_exported[0] == c->qs_buf[0].p && c->p2p_exported[1] == c->qs_buf[1].p) return MDG_OK;
+    if (c->dist_p2p && c->p2p_exported[0] == c->qs_buf[0].p && c->p2p_exported[1] == c->qs_buf[1].p && c->p2p_exported[2] == c->v4.p &&
+        c->p2p_exported[3] == c->vh4.p)
+        return MDG_OK;
     const bool first = c->dsync.p == nullptr;
     mdg_i_dist_p2p_release(c);
     if (first) {
@@ -124,12 +126,12 @@ int mdg_i_dist_p2p_setup(mdg_ctx* c, cudaStream_t st) {
         MDG_CUDA(cudaMemsetAsync(c->dsync.p, 0, sizeof(DistSync), st));
         MDG_CUDA(cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming));
     }
-    struct Pack { cudaIpcMemHandle_t h[3]; int ok; int pad[15]; };      // 3 x 64 + 64 bytes
+    struct Pack { cudaIpcMemHandle_t h[5]; int ok; int pad[15]; };      // 5 x 64 + 64 bytes
     Pack mine;
     memset(&mine, 0, sizeof(mine));
-    void* ptrs[3] = {c->qs_buf[0].p, c->qs_buf[1].p, c->dsync.p};
+    void* ptrs[5] = {c->qs_buf[0].p, c->qs_buf[1].p, c->dsync.p, c->v4.p, c->vh4.p};     // (v4 / vh4: the rebuild's state push)
     mine.ok = 1;
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 5; ++k)
         if (cudaIpcGetMemHandle(&mine.h[k], ptrs[k]) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
     DevBuf xfer;
     MDG_TRY(xfer.reserve(sizeof(Pack) * (size_t)(W + 1)));
@@ -160,6 +162,13 @@ int mdg_i_dist_p2p_setup(mdg_ctx* c, cudaStream_t st) {
             c->peer_qs[1][k] = (above == below) ? c->peer_qs[0][k] : open(all[above].h[k]);
             ok = ok && c->peer_qs[0][k] && c->peer_qs[1][k];
         }
+        if (ok) {
+            c->peer_v[0] = open(all[below].h[3]);
+            c->peer_vh[0] = open(all[below].h[4]);
+            c->peer_v[1] = (above == below) ? c->peer_v[0] : open(all[above].h[3]);
+            c->peer_vh[1] = (above == below) ? c->peer_vh[0] : open(all[above].h[4]);
+            ok = c->peer_v[0] && c->peer_vh[0] && c->peer_v[1] && c->peer_vh[1];
+        }
     }
     // every rank must take the same path: agree through a 1-int max all-reduce of the failure flag
     int* d_flag = c->dsync.as<int>() + offsetof(DistSync, pad) / sizeof(int);
@@ -175,6 +184,8 @@ int mdg_i_dist_p2p_setup(mdg_ctx* c, cudaStream_t st) {
     }
     c->p2p_exported[0] = c->qs_buf[0].p;
     c->p2p_exported[1] = c->qs_buf[1].p;
+    c->p2p_exported[2] = c->v4.p;
+    c->p2p_exported[3] = c->vh4.p;
     c->dist_p2p = true;
     return MDG_OK;
 #endif

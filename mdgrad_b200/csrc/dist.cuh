@@ -38,14 +38,47 @@ int mdg_nccl_check(int r, const char* what);
 //   ack_flag[s]      the neighbour below / above has finished reading the ghosts I stored for that sequence number
 // ---------------------------------------------------------------------------------------------------------------------
 #define MDG_DIST_MAXW 16
+#define MDG_DIST_MAXLAY 2048
 struct DistSync {
     double ke[2][MDG_DIST_MAXW][2];
     int    ke_flag[2][MDG_DIST_MAXW];
     int    halo_flag[2];
     int    ack_flag[2];
-    int    ticket;             // block counter of k_dist_push (self-resetting)
-    int    pad[3];
+    int    ticket;             // block counter of k_dist_push / k_dist_push_state (self-resetting)
+    int    pad[3];             // [0] set-up agreement, [1] latched spin time-out
+    int    state_flag[2];      // rebuild: the neighbour below / above stored its two boundary layers of (q, v, vh) for this sequence number
+    int    lay_flag[2][MDG_DIST_MAXW];   // rebuild: rank r's per-layer atom totals for the rebuild with parity p have arrived
+    int    lay[2][MDG_DIST_MAXLAY];      // ... the totals, each layer written by its owner into every rank's table
 };
+struct PeerTab { DistSync* s[MDG_DIST_MAXW]; };
 struct mdg_ctx;
 int mdg_i_dist_p2p_setup(mdg_ctx* c, cudaStream_t st);
 void mdg_i_dist_p2p_release(mdg_ctx* c);
+
+#if defined(__CUDACC__) || defined(MDG_EMU)
+__device__ __forceinline__ int vload_i(const int* p) { return *(const volatile int*)p; }
+__device__ __forceinline__ void vstore_i(int* p, int v) { *(volatile int*)p = v; }
+// Bounded spin (a peer that died must not hang this GPU): after 60 s the wait gives up and latches *timeout_flag, which the
+// host turns into an error at the end of the epoch.
+__device__ __forceinline__ unsigned long long mdg_globaltimer_ns() {
+#ifdef MDG_EMU
+    return 0ull;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+__device__ __forceinline__ void spin_until_ge(const int* p, int v, int* timeout_flag) {
+    if (vload_i(p) >= v) return;
+    const unsigned long long t0 = mdg_globaltimer_ns();
+    unsigned ns = 32;
+    while (vload_i(p) < v) {
+#ifndef MDG_EMU
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+#endif
+        if (mdg_globaltimer_ns() - t0 > 60ull * 1000000000ull) { *(volatile int*)timeout_flag = 1; break; }   // 60 s
+    }
+}
+#endif

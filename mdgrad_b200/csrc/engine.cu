@@ -16,6 +16,52 @@
 
 #define PROF_MAX_EVENTS 16384
 
+// ---------------------------------------------------------------------------------------------
+// Development aid (MDG_TIMELINE=<path prefix>): CUDA events at the phase boundaries of a window of steps, on the streams the
+// phases run on, written as "<label> <ms since the first mark>" to <prefix><rank>.txt after the epoch.  Events do not serialise
+// the streams, so this is the pipelined timeline (nsys is not available on the GPU boxes).  Off unless the variable is set.
+// ---------------------------------------------------------------------------------------------
+struct Timeline {
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    std::vector<int> step;
+    const char* prefix = nullptr;
+    int g0 = 20, g1 = 36;
+    bool init = false;
+};
+static Timeline g_tl;
+static inline bool tl_on(int g) {
+    if (!g_tl.init) {
+        g_tl.init = true;
+        g_tl.prefix = getenv("MDG_TIMELINE");
+        const char* w = getenv("MDG_TIMELINE_STEPS");
+        if (w) { int a = 0, b = 0; if (sscanf(w, "%d:%d", &a, &b) == 2 && b > a) { g_tl.g0 = a; g_tl.g1 = b; } }
+    }
+    return g_tl.prefix != nullptr && g >= g_tl.g0 && g < g_tl.g1;
+}
+static inline void tl_mark(int g, const char* label, cudaStream_t st) {
+    if (!tl_on(g)) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_tl.marks.emplace_back(label, e);
+    g_tl.step.push_back(g);
+}
+static void tl_flush(int rank) {
+    if (g_tl.marks.empty()) return;
+    char path[512];
+    snprintf(path, sizeof(path), "%s%d.txt", g_tl.prefix, rank);
+    FILE* f = fopen(path, "a");
+    for (size_t i = 0; i < g_tl.marks.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_tl.marks[0].second, g_tl.marks[i].second);
+        if (f) fprintf(f, "%d %s %.3f\n", g_tl.step[i], g_tl.marks[i].first, 1e3 * ms);
+    }
+    if (f) { fprintf(f, "--\n"); fclose(f); }
+    for (auto& m : g_tl.marks) cudaEventDestroy(m.second);
+    g_tl.marks.clear();
+    g_tl.step.clear();
+}
+
 int mdg_i_force_blocks(mdg_ctx* c);
 
 #define INT_THREADS 256
@@ -98,39 +144,12 @@ __global__ void __launch_bounds__(INT_THREADS) k_ke_pack(const double* __restric
 // ---------------------------------------------------------------------------------------------------------------------
 // peer-to-peer step path (dist.cuh): flags and kinetic energies live in DistSync blocks that the peers write over NVLink
 // ---------------------------------------------------------------------------------------------------------------------
-struct PeerTab { DistSync* s[MDG_DIST_MAXW]; };
 struct DistArgs {
     DistSync* mine;            // nullptr: single GPU, or the NCCL path (kinetic energies arrive in ke_part arrays)
     DistSync* below;           // the neighbours' blocks as mapped here (acknowledgements)
     DistSync* above;
     int world, seq;
 };
-
-__device__ __forceinline__ int vload_i(const int* p) { return *(const volatile int*)p; }
-__device__ __forceinline__ void vstore_i(int* p, int v) { *(volatile int*)p = v; }
-// Bounded spin (a peer that died must not hang this GPU): after 60 s the wait gives up and latches *timeout_flag, which the
-// host turns into an error at the end of the epoch.
-__device__ __forceinline__ unsigned long long mdg_globaltimer_ns() {
-#ifdef MDG_EMU
-    return 0ull;
-#else
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-#endif
-}
-__device__ __forceinline__ void spin_until_ge(const int* p, int v, int* timeout_flag) {
-    if (vload_i(p) >= v) return;
-    const unsigned long long t0 = mdg_globaltimer_ns();
-    unsigned ns = 32;
-    while (vload_i(p) < v) {
-#ifndef MDG_EMU
-        __nanosleep(ns);
-        if (ns < 1024) ns <<= 1;
-#endif
-        if (mdg_globaltimer_ns() - t0 > 60ull * 1000000000ull) { *(volatile int*)timeout_flag = 1; break; }   // 60 s
-    }
-}
 
 // Prologue of the B kernels on the peer-to-peer path: acknowledge the ghosts of this step (the forces that read them are
 // complete - stream order), wait for every rank's kinetic energies and sum them in rank order (identical on all ranks).
@@ -220,6 +239,49 @@ __global__ void k_dist_ack(DistSync* below, DistSync* above, int seq) {
     }
 }
 
+// Rebuild on the peer-to-peer path: my bottom two layers of (q, v, vh) go to the rank below, my top two to the rank above, into
+// the SAME global index ranges of their arrays (what state_exchange does with 12 NCCL send / recv: ~50-60 us per rebuild in the r02
+// timeline, launch and handshake latency rather than bytes).  Same write-after-read rule as the ghost push: the neighbours read
+// these ranges last in the forces of the previous step, acknowledged by their B kernel.
+__global__ void __launch_bounds__(256) k_dist_push_state(const float4* __restrict__ q, const float4* __restrict__ v,
+                                                         const float4* __restrict__ vh, int lo0, int lo1, int hi0, int hi1,
+                                                         float4* __restrict__ q_below, float4* __restrict__ v_below,
+                                                         float4* __restrict__ vh_below, float4* __restrict__ q_above,
+                                                         float4* __restrict__ v_above, float4* __restrict__ vh_above, DistSync* mine,
+                                                         DistSync* below, DistSync* above, int seq) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        spin_until_ge(&mine->ack_flag[0], seq - 1, &mine->pad[1]);
+        spin_until_ge(&mine->ack_flag[1], seq - 1, &mine->pad[1]);
+    }
+    __syncthreads();
+    const int nlo = lo1 - lo0, nhi = hi1 - hi0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlo + nhi; i += gridDim.x * blockDim.x) {
+        if (i < nlo) {
+            const int k = lo0 + i;
+            q_below[k] = q[k]; v_below[k] = v[k]; vh_below[k] = vh[k];
+        } else {
+            const int k = hi0 + (i - nlo);
+            q_above[k] = q[k]; v_above[k] = v[k]; vh_above[k] = vh[k];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        mine->ticket = 0;
+        __threadfence_system();
+        vstore_i(&below->state_flag[1], seq);        // I am the neighbour ABOVE of the rank below me
+        vstore_i(&above->state_flag[0], seq);
+    }
+}
+__global__ void k_dist_wait_state(DistSync* mine, int seq) {
+    if (threadIdx.x == 0) {
+        spin_until_ge(&mine->state_flag[0], seq, &mine->pad[1]);
+        spin_until_ge(&mine->state_flag[1], seq, &mine->pad[1]);
+    }
+}
 __global__ void k_dist_wait(DistSync* mine, int seq) {
     if (threadIdx.x == 0) {
         spin_until_ge(&mine->halo_flag[0], seq, &mine->pad[1]);
@@ -585,6 +647,8 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         MDG_CUDA(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
     }
     const char* bz = getenv("MDG_DIST_BND_STREAM");
+    const char* pz = getenv("MDG_DIST_PUSH_SIDE");
+    const bool push_side = pz && pz[0] == '1';        // (A/B: the peer-to-peer push on the communication stream, as measured first)
     const bool bnd_side = !(bz && bz[0] == '0');     // boundary layers on their own stream, concurrent with the interior rows
     IntArgs A;
     memset(&A, 0, sizeof(A));
@@ -681,11 +745,32 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                                                  c->flags.as<int>());
             c->stat_launches++;
         }
+        tl_mark(g, "step_begin", st);
         if (do_rebuild) {
-            if (dist) MDG_TRY(state_exchange(c, q, vbuf[vsel], hbuf[vsel], st));
+            if (dist && c->dist_p2p && c->peer_v[0]) {
+                // peer-to-peer: one push kernel + one wait kernel (dist.cu maps the neighbours' v / vh arrays as well)
+                const int* Ly = c->h_layers;
+                const int zlo = c->slab_zlo, zhi = c->slab_zhi;
+                const int W = c->dist_world, me = c->dist_rank, below = (me - 1 + W) % W, above = (me + 1) % W;
+                if (zhi - zlo < 2) { mdg_set_error("distributed run: every rank needs >= 2 cell layers"); return MDG_E_BADARG; }
+                const int sel = (q == c->qs_buf[0].as<float4>()) ? 0 : 1;
+                const size_t voff = (size_t)(vbuf[vsel] - c->v4.as<float4>()), hoff = (size_t)(hbuf[vsel] - c->vh4.as<float4>());
+                const int nst = (Ly[zlo + 2] - Ly[zlo]) + (Ly[zhi] - Ly[zhi - 2]);
+                int pb = (nst + 1023) / 1024;
+                pb = pb < 1 ? 1 : (pb > 96 ? 96 : pb);
+                const int rseq = c->dist_seq + 1;                  // the sequence number this step's push will carry
+                k_dist_push_state<<<pb, 256, 0, st>>>(q, vbuf[vsel], hbuf[vsel], Ly[zlo], Ly[zlo + 2], Ly[zhi - 2], Ly[zhi],
+                                                     (float4*)c->peer_qs[0][sel], (float4*)c->peer_v[0] + voff, (float4*)c->peer_vh[0] + hoff,
+                                                     (float4*)c->peer_qs[1][sel], (float4*)c->peer_v[1] + voff, (float4*)c->peer_vh[1] + hoff,
+                                                     (DistSync*)c->dsync.p, (DistSync*)c->peer_sync[below], (DistSync*)c->peer_sync[above], rseq);
+                k_dist_wait_state<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, rseq);
+                c->stat_launches += 2;
+            } else if (dist) MDG_TRY(state_exchange(c, q, vbuf[vsel], hbuf[vsel], st));
+            tl_mark(g, "rb_xchg_end", st);
             c->slab_local = dist;
             MDG_TRY(mdg_i_build_list(c, nullptr, q, n, p->cell, rlist, p->cutoff, st));
             c->slab_local = false;
+            tl_mark(g, "rb_build_end", st);
             q = c->qs_ptr;
             A.s0 = c->own_s0; A.s1 = c->own_s1;
             nown = A.s1 - A.s0;
@@ -734,7 +819,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         } else {
             cudaStream_t cs = c->comm_stream;
             MDG_CUDA(cudaEventRecord(c->ev_a, st));                    // positions + KE partials of this step are ready
-            MDG_CUDA(cudaStreamWaitEvent(cs, c->ev_a, 0));
+            if (!(c->dist_p2p && !push_side)) MDG_CUDA(cudaStreamWaitEvent(cs, c->ev_a, 0));
             const int* Ly = c->h_layers;
             const int zlo = c->slab_zlo, zhi = c->slab_zhi;
             const int ncz = c->n_layers - 1;
@@ -750,10 +835,16 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                 const int nh = (Ly[zlo + 1] - Ly[zlo]) + (Ly[zhi] - Ly[zhi - 1]);
                 int pb = do_rebuild ? 1 : (nh + 2047) / 2048;
                 pb = pb < 1 ? 1 : (pb > 64 ? 64 : pb);
-                k_dist_push<<<pb, 256, 0, cs>>>(q, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], (float4*)c->peer_qs[0][sel],
+                // The push runs on the MAIN stream, ahead of the interior rows (r02 timeline: on the side stream it only got SM slots
+                // when the first wave of the interior force retired - the ghosts landed after the interior rows were done and the
+                // boundary launch ran alone: 54 us of forces per step instead of ~35 at 131 072 atoms per GPU).  It is short: wait for
+                // last step's acknowledgements, ~0.2 MB of NVLink stores, flags.
+                cudaStream_t ps = push_side ? cs : st;
+                k_dist_push<<<pb, 256, 0, ps>>>(q, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], (float4*)c->peer_qs[0][sel],
                                                (float4*)c->peer_qs[1][sel], ke_v_cur, ke_h_cur, ib_prev, nhc, PT, me, W, below, above,
                                                seq, do_rebuild ? 0 : 1);
-                MDG_CUDA(cudaEventRecord(c->ev_push, cs));
+                if (push_side) MDG_CUDA(cudaEventRecord(c->ev_push, cs));
+                tl_mark(g, "push_end", ps);
                 c->stat_launches++;
                 DA.mine = (DistSync*)c->dsync.p;
                 DA.below = (DistSync*)c->peer_sync[below];
@@ -772,6 +863,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                     else MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
                                                    (zhi - 1) * nxy, st));                                                 // interior
                     k_dist_wait<<<1, 32, 0, bs>>>((DistSync*)c->dsync.p, seq);                                             // ghosts landed
+                    tl_mark(g, "wait_end", bs);
                     if (!c->tiles) {   // bottom + top layer in one launch
                         MDG_TRY(mdg_i_force_range2(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], bs));
                     } else {
@@ -780,10 +872,12 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                         MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zhi - 1], Ly[zhi], (zhi - 1) * nxy,
                                                   zhi * nxy, bs));                                                        // top layer
                     }
+                    tl_mark(g, "bnd_force_end", bs);
                     if (bnd_side) {
                         MDG_CUDA(cudaEventRecord(c->ev_bnd, bs));
                         MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
                                                   (zhi - 1) * nxy, st));                                                  // interior
+                        tl_mark(g, "int_force_end", st);
                         MDG_CUDA(cudaStreamWaitEvent(st, c->ev_bnd, 0));
                     }
                     c->stat_launches++;
@@ -792,7 +886,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                     MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
                 }
                 if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
-                MDG_CUDA(cudaStreamWaitEvent(st, c->ev_push, 0));      // B overwrites q: my own stores to the neighbours must have read it
+                if (push_side) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_push, 0));      // B overwrites q: my own stores to the neighbours must have read it
             } else {
             if (!do_rebuild) {
                 MDG_TRY(halo_exchange(c, q, cs));
@@ -835,6 +929,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             if (nhc) MDG_CUDA(cudaStreamWaitEvent(st, c->ev_ke, 0));
             }
         }
+        tl_mark(g, "force_end", st);
         c->force_energy = true;
         int gp = g + 1;
         bool keep = (gp % stride) == 0;
@@ -858,6 +953,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
             { double* t1 = ke_v_cur; ke_v_cur = ke_v_nxt; ke_v_nxt = t1; }
         }
         c->stat_launches++;
+        tl_mark(g, "step_end", st);
         pv_sel ^= 1;
         ib_prev = ib;
     }
@@ -882,6 +978,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     MDG_CUDA(cudaMemcpyAsync(c->h_pinned, c->flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
     MDG_CUDA(cudaStreamSynchronize(st));
     if (h_last_energy) *h_last_energy = (float)h_e;
+    tl_flush(c->dist_world > 1 ? c->dist_rank : 0);
     if (h_p2p_timeout) {
         mdg_set_error("distributed step: a peer-to-peer wait timed out (a neighbouring rank stopped making progress)");
         return MDG_E_NCCL;

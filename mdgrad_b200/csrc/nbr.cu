@@ -225,6 +225,32 @@ __global__ void k_layer_offsets(const int* __restrict__ tot, int ncz, int* __res
     }
 }
 
+// Peer-to-peer form of "all-reduce the layer totals" (dist.cuh): every layer has ONE owner, which stores its total into every
+// rank's table, then raises its flag there; the reader waits for all flags and prefix-sums the table.  Replaces a latency-bound
+// NCCL all-reduce of ncz ints on the rebuild path.  Tables are double-buffered by the parity of the rebuild counter.
+__global__ void __launch_bounds__(256) k_dist_layers_push(const int* __restrict__ lay_tot, int zlo, int zhi, PeerTab T, int me, int world,
+                                                          int par, int seq) {
+    for (int k = threadIdx.x; k < (zhi - zlo) * world; k += blockDim.x) {
+        const int r = k / (zhi - zlo), z = zlo + k % (zhi - zlo);
+        vstore_i(&T.s[r]->lay[par][z], lay_tot[z]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        vstore_i(&T.s[threadIdx.x]->lay_flag[par][me], seq);
+    }
+}
+__global__ void k_layer_offsets_p2p(DistSync* mine, int world, int par, int seq, int ncz, int* __restrict__ off) {
+    if ((int)threadIdx.x < world) spin_until_ge(&mine->lay_flag[par][threadIdx.x], seq, &mine->pad[1]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int z = 0; z < ncz; ++z) { off[z] = acc; acc += vload_i(&mine->lay[par][z]); }
+        off[ncz] = acc;
+    }
+}
+
 // cell_start of the cells of layer (zwin0 + blockIdx.x) % ncz = layer offset + exclusive scan of the cell counts
 __global__ void __launch_bounds__(SCAN_THREADS) k_cellstart_layer(const int* __restrict__ cell_count, const int* __restrict__ lay_off,
                                                                  int nxy, int ncz, int zwin0, int* __restrict__ cell_start) {
@@ -657,8 +683,16 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
             int* lay_tot = c->lay_tot.as<int>();
             int* lay_off = lay_tot + ncz + 1;
             k_layer_totals<<<ncz, SCAN_THREADS, 0, st>>>(c->cell_count.as<int>(), nxy, ncz, zlo, zhi, lay_tot);
-            MDG_TRY(mdg_nccl_check(N->AllReduce(lay_tot, lay_tot, (size_t)ncz, MDG_NCCL_INT32, MDG_NCCL_SUM, c->dist_comm, st), "AllReduce"));
-            k_layer_offsets<<<1, 32, 0, st>>>(lay_tot, ncz, lay_off);
+            if (c->dist_p2p && ncz <= MDG_DIST_MAXLAY) {
+                const int par = c->dist_rebuilds & 1, rs = ++c->dist_rebuilds;
+                PeerTab PT;
+                for (int r = 0; r < MDG_DIST_MAXW; ++r) PT.s[r] = (DistSync*)c->peer_sync[r < c->dist_world ? r : c->dist_rank];
+                k_dist_layers_push<<<1, 256, 0, st>>>(lay_tot, zlo, zhi, PT, c->dist_rank, c->dist_world, par, rs);
+                k_layer_offsets_p2p<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, c->dist_world, par, rs, ncz, lay_off);
+            } else {
+                MDG_TRY(mdg_nccl_check(N->AllReduce(lay_tot, lay_tot, (size_t)ncz, MDG_NCCL_INT32, MDG_NCCL_SUM, c->dist_comm, st), "AllReduce"));
+                k_layer_offsets<<<1, 32, 0, st>>>(lay_tot, ncz, lay_off);
+            }
             const int zwin0 = (zlo - 1 + ncz) % ncz, zwin_n = zhi - zlo + 2;
             k_cellstart_layer<<<zwin_n, SCAN_THREADS, 0, st>>>(c->cell_count.as<int>(), lay_off, nxy, ncz, zwin0, c->cell_start.as<int>());
             for (int k = 0; k < np; ++k) {

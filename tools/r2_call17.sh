@@ -7,7 +7,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 
 line() { python -c "
 import json,sys
 r=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=r.get('e2e') or {}; c4=r.get('c4') or {}
-print('value %.1f raw %.1f steps/s, %.1f us/step, launches %d, e2e %s, force %s us, c4 %s, parity %s' % (r['value'], r['config']['box_steps_per_s'], 1e3*r['ms_per_step'], r['gpu_launches'], e.get('value'), (r.get('roofline') or {}).get('kernel_us'), c4.get('value'), r.get('dist_parity')))"; }
+print('value %.1f raw %.1f steps/s, %.1f us/step, launches %d, e2e %s, force %s us, c4 %s, parity %s' % (r['value'], r['config']['box_steps_per_s'], 1e3*r['ms_per_step'], r['gpu_launches'], e.get('value'), 1e3*((r.get('roofline') or {}).get('kernel_ms') or 0), c4.get('value'), r.get('dist_parity')))"; }
 echo "== engine GPU tests" | tee $S
 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_api.py -x -q -m gpu 2>&1 | tail -3 | tee -a $S
 echo "== N=1 1000 steps" | tee -a $S
