@@ -46,6 +46,8 @@ struct DistSync {
     int    ack_flag[2];
     int    ticket;             // block counter of k_dist_push / k_dist_push_state (self-resetting)
     int    pad[3];             // [0] set-up agreement, [1] latched spin time-out
+    int    push_started;       // (local) sequence number of the push kernel that has started on this GPU - gates the interior force launch
+    int    pad3;
     int    state_flag[2];      // rebuild: the neighbour below / above stored its two boundary layers of (q, v, vh) for this sequence number
     int    lay_flag[2][MDG_DIST_MAXW];   // rebuild: rank r's per-layer atom totals for the rebuild with parity p have arrived
     int    lay[2][MDG_DIST_MAXLAY];      // ... the totals, each layer written by its owner into every rank's table
@@ -76,7 +78,7 @@ __device__ __forceinline__ void spin_until_ge(const int* p, int v, int* timeout_
     while (vload_i(p) < v) {
 #ifndef MDG_EMU
         __nanosleep(ns);
-        if (ns < 1024) ns <<= 1;
+        if (ns < 256) ns <<= 1;
 #endif
         if (mdg_globaltimer_ns() - t0 > 60ull * 1000000000ull) { *(volatile int*)timeout_flag = 1; break; }   // 60 s
     }

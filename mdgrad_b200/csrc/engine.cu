@@ -187,39 +187,42 @@ __global__ void __launch_bounds__(256) k_dist_push(const float4* __restrict__ q,
                                                    float4* __restrict__ q_below, float4* __restrict__ q_above,
                                                    const double* __restrict__ ke_v_part, const double* __restrict__ ke_h_part,
                                                    int n_part, int nhc, PeerTab T, int me, int world, int below, int above, int seq,
-                                                   int do_halo) {
+                                                   int halo_blocks) {
+    // blocks [0, halo_blocks): ghost layers; block halo_blocks (present when nhc): the kinetic energies.  The two paths end in
+    // their own system-scope fence + flags, side by side (one after the other they cost ~8 us more per step: r02 timeline).
     __shared__ double sm[256 / 32];
     __shared__ int s_last;
     DistSync* mine = T.s[me];
-    if (nhc && blockIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) vstore_i(&mine->push_started, seq);
+    if ((int)blockIdx.x >= halo_blocks) {
+        if (!nhc) return;
         double va = 0, vb = 0;
         for (int i = threadIdx.x; i < n_part; i += blockDim.x) { va += ke_v_part[i]; vb += ke_h_part[i]; }
         double ta = block_sum_double(va, sm);
         double tb = block_sum_double(vb, sm);
-        if (threadIdx.x == 0) {
-            const int par = seq & 1;
-            for (int r = 0; r < world; ++r) {
-                *(volatile double*)&T.s[r]->ke[par][me][0] = ta;
-                *(volatile double*)&T.s[r]->ke[par][me][1] = tb;
-            }
+        const int par = seq & 1;
+        if ((int)threadIdx.x < world) {
+            const int r = threadIdx.x;
+            *(volatile double*)&T.s[r]->ke[par][me][0] = ta;
+            *(volatile double*)&T.s[r]->ke[par][me][1] = tb;
             __threadfence_system();
-            for (int r = 0; r < world; ++r) vstore_i(&T.s[r]->ke_flag[par][me], seq);
+            vstore_i(&T.s[r]->ke_flag[par][me], seq);
         }
+        return;
     }
-    if (!do_halo) return;
     if (threadIdx.x == 0) {
         spin_until_ge(&mine->ack_flag[0], seq - 1, &mine->pad[1]);
         spin_until_ge(&mine->ack_flag[1], seq - 1, &mine->pad[1]);
     }
     __syncthreads();
     const int nlo = lo1 - lo0, nhi = hi1 - hi0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlo + nhi; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlo + nhi; i += halo_blocks * blockDim.x) {
         if (i < nlo) q_below[lo0 + i] = q[lo0 + i];
         else q_above[hi0 + (i - nlo)] = q[hi0 + (i - nlo)];
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->ticket, 1) == halo_blocks - 1) ? 1 : 0;
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         mine->ticket = 0;
@@ -228,10 +231,12 @@ __global__ void __launch_bounds__(256) k_dist_push(const float4* __restrict__ q,
         vstore_i(&T.s[above]->halo_flag[0], seq);
     }
 }
-
-// Epoch start: this rank has built its lists and evaluated the initial forces - its ghost ranges may be overwritten now.
-// (Without it a faster neighbour's first push of the epoch could land while this rank still sorts / reads the initial state:
-// the end-of-step acknowledgements only order the steps INSIDE an epoch.)
+// Gate on the main stream in front of the interior rows: returns once this step's push kernel is RUNNING (it then holds its few
+// CTA slots).  Without it the interior force - which has no dependency to resolve - takes every CTA slot first and the push only
+// starts when the first wave retires, ~15 us into the step: the ghosts land after the interior rows are done.
+__global__ void k_dist_wait_started(DistSync* mine, int seq) {
+    if (threadIdx.x == 0) spin_until_ge(&mine->push_started, seq, &mine->pad[1]);
+}
 __global__ void k_dist_ack(DistSync* below, DistSync* above, int seq) {
     if (threadIdx.x == 0) {
         vstore_i(&below->ack_flag[1], seq);
@@ -648,7 +653,9 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     }
     const char* bz = getenv("MDG_DIST_BND_STREAM");
     const char* pz = getenv("MDG_DIST_PUSH_SIDE");
-    const bool push_side = pz && pz[0] == '1';        // (A/B: the peer-to-peer push on the communication stream, as measured first)
+    const bool push_side = !(pz && pz[0] == '0');     // peer-to-peer push on the communication stream (0: main stream, ahead of the forces)
+    const char* gz = getenv("MDG_DIST_GATE");
+    const bool gate = !(gz && gz[0] == '0');          // interior rows wait until the push kernel has started
     const bool bnd_side = !(bz && bz[0] == '0');     // boundary layers on their own stream, concurrent with the interior rows
     IntArgs A;
     memset(&A, 0, sizeof(A));
@@ -833,16 +840,17 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                 PeerTab PT;
                 for (int r = 0; r < MDG_DIST_MAXW; ++r) PT.s[r] = (DistSync*)c->peer_sync[r < W ? r : me];
                 const int nh = (Ly[zlo + 1] - Ly[zlo]) + (Ly[zhi] - Ly[zhi - 1]);
-                int pb = do_rebuild ? 1 : (nh + 2047) / 2048;
-                pb = pb < 1 ? 1 : (pb > 64 ? 64 : pb);
-                // The push runs on the MAIN stream, ahead of the interior rows (r02 timeline: on the side stream it only got SM slots
-                // when the first wave of the interior force retired - the ghosts landed after the interior rows were done and the
-                // boundary launch ran alone: 54 us of forces per step instead of ~35 at 131 072 atoms per GPU).  It is short: wait for
-                // last step's acknowledgements, ~0.2 MB of NVLink stores, flags.
+                int hb = do_rebuild ? 0 : (nh + 511) / 512;          // blocks that copy ghost layers
+                hb = do_rebuild ? 0 : (hb < 1 ? 1 : (hb > 48 ? 48 : hb));
+                // The push runs on the communication stream beside the interior rows; MDG_DIST_PUSH_SIDE=0 puts it on the main
+                // stream ahead of them (measured: 8 us per step slower - the push is ~15 us of fence / flag latency, not bytes).
                 cudaStream_t ps = push_side ? cs : st;
-                k_dist_push<<<pb, 256, 0, ps>>>(q, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], (float4*)c->peer_qs[0][sel],
-                                               (float4*)c->peer_qs[1][sel], ke_v_cur, ke_h_cur, ib_prev, nhc, PT, me, W, below, above,
-                                               seq, do_rebuild ? 0 : 1);
+                if (hb + (nhc ? 1 : 0) > 0) {
+                    k_dist_push<<<hb + (nhc ? 1 : 0), 256, 0, ps>>>(q, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], (float4*)c->peer_qs[0][sel],
+                                                                   (float4*)c->peer_qs[1][sel], ke_v_cur, ke_h_cur, ib_prev, nhc, PT, me, W, below,
+                                                                   above, seq, hb);
+                    if (push_side && split && gate) { k_dist_wait_started<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq); c->stat_launches++; }
+                }
                 if (push_side) MDG_CUDA(cudaEventRecord(c->ev_push, cs));
                 tl_mark(g, "push_end", ps);
                 c->stat_launches++;
