@@ -46,11 +46,15 @@ struct DistSync {
     int    ack_flag[2];
     int    ticket;             // block counter of k_dist_push / k_dist_push_state (self-resetting)
     int    pad[3];             // [0] set-up agreement, [1] latched spin time-out
+    int    pos_flag[2];        // pull path: the positions of the neighbour below / above are final for the step with this sequence number
+    int    pull_flag[2];       // pull path: the neighbour below / above has copied MY boundary layer of that step (I may overwrite positions)
+    int    ba_ticket, pull_ticket;   // block counters of the integrator kernels / k_dist_pull (self-resetting)
     int    push_started;       // (local) sequence number of the push kernel that has started on this GPU - gates the interior force launch
     int    pad3;
     int    state_flag[2];      // rebuild: the neighbour below / above stored its two boundary layers of (q, v, vh) for this sequence number
     int    lay_flag[2][MDG_DIST_MAXW];   // rebuild: rank r's per-layer atom totals for the rebuild with parity p have arrived
     int    lay[2][MDG_DIST_MAXLAY];      // ... the totals, each layer written by its owner into every rank's table
+    unsigned long long dbg[16];          // (MDG_TIMELINE) %globaltimer stamps of the last push / wait kernels on this GPU
 };
 struct PeerTab { DistSync* s[MDG_DIST_MAXW]; };
 struct mdg_ctx;
@@ -58,6 +62,14 @@ int mdg_i_dist_p2p_setup(mdg_ctx* c, cudaStream_t st);
 void mdg_i_dist_p2p_release(mdg_ctx* c);
 
 #if defined(__CUDACC__) || defined(MDG_EMU)
+// load from a peer's memory that a remote kernel has just written: never from a stale L1 line
+__device__ __forceinline__ float4 mdg_ld_peer(const float4* p) {
+#ifdef MDG_EMU
+    return *p;
+#else
+    return __ldcv(p);
+#endif
+}
 __device__ __forceinline__ int vload_i(const int* p) { return *(const volatile int*)p; }
 __device__ __forceinline__ void vstore_i(int* p, int v) { *(volatile int*)p = v; }
 // Bounded spin (a peer that died must not hang this GPU): after 60 s the wait gives up and latches *timeout_flag, which the

@@ -149,6 +149,8 @@ struct DistArgs {
     DistSync* below;           // the neighbours' blocks as mapped here (acknowledgements)
     DistSync* above;
     int world, seq;
+    int pos_seq;               // pull path: > 0 -> once ALL blocks have stored their positions, raise pos_flag = pos_seq at both neighbours
+    int wait_pull;             // pull path: > 0 -> both neighbours must have copied my boundary layers of that step before q is overwritten
 };
 
 // Prologue of the B kernels on the peer-to-peer path: acknowledge the ghosts of this step (the forces that read them are
@@ -157,6 +159,35 @@ __device__ __forceinline__ void dist_ack(const DistArgs& D) {
     if (D.mine && blockIdx.x == 0 && threadIdx.x == 0) {
         vstore_i(&D.below->ack_flag[1], D.seq);      // I am the neighbour ABOVE of the rank below me
         vstore_i(&D.above->ack_flag[0], D.seq);
+        D.mine->dbg[8] = mdg_globaltimer_ns();
+    }
+}
+
+// Pull path (default): nothing is stored into a neighbour's arrays on the step path.  A rank raises pos_flag at its neighbours when
+// its integrator kernel has stored the new positions (grid-wide ticket; only LOCAL stores to fence), the neighbours copy its
+// boundary layer with NVLink loads (k_dist_pull) and answer with pull_flag, which this rank's next integrator kernel awaits
+// before it overwrites the positions.  r02 stamps of the push form: 11 us from kernel start to flag (system-scope fences behind
+// remote stores: 3-8 us, ticket + second fence + flag: 3 us) plus the stream hop - the ghosts arrived 16-20 us into the step.
+__device__ __forceinline__ void dist_wait_pulled(const DistArgs& D) {
+    if (D.mine && D.wait_pull > 0) {
+        if (threadIdx.x == 0) {
+            spin_until_ge(&D.mine->pull_flag[0], D.wait_pull, &D.mine->pad[1]);
+            spin_until_ge(&D.mine->pull_flag[1], D.wait_pull, &D.mine->pad[1]);
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void dist_raise_pos(const DistArgs& D) {
+    if (D.mine && D.pos_seq > 0) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&D.mine->ba_ticket, 1) == (int)gridDim.x - 1) {
+            D.mine->ba_ticket = 0;
+            __threadfence_system();
+            vstore_i(&D.below->pos_flag[1], D.pos_seq);      // I am the neighbour ABOVE of the rank below me
+            vstore_i(&D.above->pos_flag[0], D.pos_seq);
+            D.mine->dbg[9] = mdg_globaltimer_ns();
+        }
     }
 }
 
@@ -193,13 +224,17 @@ __global__ void __launch_bounds__(256) k_dist_push(const float4* __restrict__ q,
     __shared__ double sm[256 / 32];
     __shared__ int s_last;
     DistSync* mine = T.s[me];
-    if (blockIdx.x == 0 && threadIdx.x == 0) vstore_i(&mine->push_started, seq);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { vstore_i(&mine->push_started, seq); mine->dbg[0] = mdg_globaltimer_ns(); }
     if ((int)blockIdx.x >= halo_blocks) {
         if (!nhc) return;
         double va = 0, vb = 0;
         for (int i = threadIdx.x; i < n_part; i += blockDim.x) { va += ke_v_part[i]; vb += ke_h_part[i]; }
+        __shared__ double s_t[2];
         double ta = block_sum_double(va, sm);
-        double tb = block_sum_double(vb, sm);
+        double tb = block_sum_double(vb, sm);        // (totals are valid in thread 0 only)
+        if (threadIdx.x == 0) { s_t[0] = ta; s_t[1] = tb; }
+        __syncthreads();
+        ta = s_t[0]; tb = s_t[1];
         const int par = seq & 1;
         if ((int)threadIdx.x < world) {
             const int r = threadIdx.x;
@@ -207,12 +242,14 @@ __global__ void __launch_bounds__(256) k_dist_push(const float4* __restrict__ q,
             *(volatile double*)&T.s[r]->ke[par][me][1] = tb;
             __threadfence_system();
             vstore_i(&T.s[r]->ke_flag[par][me], seq);
+            if (r == 0) mine->dbg[5] = mdg_globaltimer_ns();
         }
         return;
     }
     if (threadIdx.x == 0) {
         spin_until_ge(&mine->ack_flag[0], seq - 1, &mine->pad[1]);
         spin_until_ge(&mine->ack_flag[1], seq - 1, &mine->pad[1]);
+        if (blockIdx.x == 0) mine->dbg[1] = mdg_globaltimer_ns();
     }
     __syncthreads();
     const int nlo = lo1 - lo0, nhi = hi1 - hi0;
@@ -220,7 +257,9 @@ __global__ void __launch_bounds__(256) k_dist_push(const float4* __restrict__ q,
         if (i < nlo) q_below[lo0 + i] = q[lo0 + i];
         else q_above[hi0 + (i - nlo)] = q[hi0 + (i - nlo)];
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) mine->dbg[2] = mdg_globaltimer_ns();
     __threadfence_system();
+    if (blockIdx.x == 0 && threadIdx.x == 0) mine->dbg[3] = mdg_globaltimer_ns();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&mine->ticket, 1) == halo_blocks - 1) ? 1 : 0;
     __syncthreads();
@@ -229,6 +268,7 @@ __global__ void __launch_bounds__(256) k_dist_push(const float4* __restrict__ q,
         __threadfence_system();
         vstore_i(&T.s[below]->halo_flag[1], seq);    // my bottom layer is the ghost layer ABOVE the rank below me
         vstore_i(&T.s[above]->halo_flag[0], seq);
+        mine->dbg[4] = mdg_globaltimer_ns();
     }
 }
 // Gate on the main stream in front of the interior rows: returns once this step's push kernel is RUNNING (it then holds its few
@@ -241,6 +281,36 @@ __global__ void k_dist_ack(DistSync* below, DistSync* above, int seq) {
     if (threadIdx.x == 0) {
         vstore_i(&below->ack_flag[1], seq);
         vstore_i(&above->ack_flag[0], seq);
+    }
+}
+
+// Pull path: copy the ghost layers (the top layer of the rank below, the bottom layer of the rank above - same global index
+// ranges there) out of the neighbours' position arrays once they are final, then tell the neighbours.
+__global__ void __launch_bounds__(256) k_dist_pull(float4* __restrict__ q, const float4* q_below, const float4* q_above, int gl0, int gl1,
+                                                   int gu0, int gu1, DistSync* mine, DistSync* below, DistSync* above, int seq) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) mine->dbg[6] = mdg_globaltimer_ns();
+        spin_until_ge(&mine->pos_flag[0], seq, &mine->pad[1]);
+        spin_until_ge(&mine->pos_flag[1], seq, &mine->pad[1]);
+        if (blockIdx.x == 0) mine->dbg[7] = mdg_globaltimer_ns();
+    }
+    __syncthreads();
+    const int nl = gl1 - gl0, nu = gu1 - gu0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nl + nu; i += gridDim.x * blockDim.x) {
+        if (i < nl) q[gl0 + i] = mdg_ld_peer(q_below + gl0 + i);
+        else q[gu0 + (i - nl)] = mdg_ld_peer(q_above + gu0 + (i - nl));
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&mine->pull_ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        mine->pull_ticket = 0;
+        __threadfence_system();
+        vstore_i(&below->pull_flag[1], seq);         // I am the neighbour ABOVE of the rank below me
+        vstore_i(&above->pull_flag[0], seq);
+        mine->dbg[10] = mdg_globaltimer_ns();
     }
 }
 
@@ -289,8 +359,10 @@ __global__ void k_dist_wait_state(DistSync* mine, int seq) {
 }
 __global__ void k_dist_wait(DistSync* mine, int seq) {
     if (threadIdx.x == 0) {
+        mine->dbg[6] = mdg_globaltimer_ns();
         spin_until_ge(&mine->halo_flag[0], seq, &mine->pad[1]);
         spin_until_ge(&mine->halo_flag[1], seq, &mine->pad[1]);
+        mine->dbg[7] = mdg_globaltimer_ns();
     }
 }
 
@@ -300,9 +372,10 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_a(IntArgs A, float dt, int
                                                         const float4* __restrict__ v4, float4* __restrict__ vh4,
                                                         float4* __restrict__ q4, const float4* __restrict__ f4,
                                                         const float4* __restrict__ qref, int check_skin,
-                                                        double* __restrict__ ke_half_part, int* __restrict__ flags) {
+                                                        double* __restrict__ ke_half_part, int* __restrict__ flags, DistArgs D) {
     __shared__ double sm[INT_THREADS / 32];
     float pv0 = 0.f, Q0 = 1.f;
+    dist_wait_pulled(D);
     if (A.integrator == MDG_INT_NHC) { pv0 = sc->pv[pv_sel][0]; Q0 = A.Q[0]; }
     double acc = 0;
     bool viol = false;
@@ -342,6 +415,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_a(IntArgs A, float dt, int
         double t = block_sum_double(acc, sm);
         if (threadIdx.x == 0) ke_half_part[blockIdx.x] = 0.5 * t;
     }
+    dist_raise_pos(D);
 }
 
 // step part B (sovlers.py:120-127 + tinydiffeq.py:69): a1 from (v + vh, f_new, pv + ph);
@@ -437,6 +511,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_ba(IntArgs A, float dt, fl
     __shared__ float s_pvh0, s_pvn0;
     float pvh0 = 0.f, pvn0 = 0.f, Q0 = 1.f;
     dist_ack(D);
+    dist_wait_pulled(D);
     if (A.integrator == MDG_INT_NHC) {
         float ke0, ke1;
         if (D.mine) dist_gather_ke(D, sm, &ke0, &ke1);
@@ -526,6 +601,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_step_ba(IntArgs A, float dt, fl
         double t2 = block_sum_double(acc_h, sm);
         if (threadIdx.x == 0) ke_half_next_part[blockIdx.x] = 0.5 * t2;
     }
+    dist_raise_pos(D);
 }
 
 // state (re)ordering ---------------------------------------------------------------------------
@@ -654,9 +730,13 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     const char* bz = getenv("MDG_DIST_BND_STREAM");
     const char* pz = getenv("MDG_DIST_PUSH_SIDE");
     const bool push_side = !(pz && pz[0] == '0');     // peer-to-peer push on the communication stream (0: main stream, ahead of the forces)
+    const char* plz = getenv("MDG_DIST_PULL");
+    const char* pbz = getenv("MDG_DIST_PUSH_BLOCKS");
+    const int push_blocks_env = pbz ? atoi(pbz) : 0;
     const char* gz = getenv("MDG_DIST_GATE");
     const bool gate = !(gz && gz[0] == '0');          // interior rows wait until the push kernel has started
     const bool bnd_side = !(bz && bz[0] == '0');     // boundary layers on their own stream, concurrent with the interior rows
+    const bool pull = !(plz && plz[0] == '0') && bnd_side;   // ghosts are PULLED by the consumer (default); 0: pushed by the producer
     IntArgs A;
     memset(&A, 0, sizeof(A));
     A.integrator = p->integrator;
@@ -743,13 +823,25 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     int ib_prev = ib;                       // block count of the launch(es) that wrote the *_cur partial arrays
     const int nsteps = n_grid - 1;
     bool a_done = false;                    // A(g) already executed by the previous fused kernel
+    int last_pull_seq = 0;                  // pull path: sequence number of the last step whose ghosts were pulled (0: none pending)
     for (int g = 0; g < nsteps; ++g) {
         float dt = h_tgrid[g + 1] - h_tgrid[g];          // fp32 subtraction, like t1 - t0 in tinydiffeq.py:67-68
         bool do_rebuild = ((g + 1) % rebuild_every) == 0;
         if (!a_done) {
+            DistArgs DAa{};
+            if (dist && c->dist_p2p && pull) {      // pull path: A overwrites positions the neighbours copy, and produces the next ones
+                const int W = c->dist_world, me = c->dist_rank;
+                DAa.mine = (DistSync*)c->dsync.p;
+                DAa.below = (DistSync*)c->peer_sync[(me - 1 + W) % W];
+                DAa.above = (DistSync*)c->peer_sync[(me + 1) % W];
+                DAa.world = W;
+                DAa.pos_seq = c->dist_seq + 1;
+                DAa.wait_pull = last_pull_seq;
+            }
             k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
                                                  c->qref.as<float4>(), (retest && !do_rebuild) ? 1 : 0, ke_h_cur,
-                                                 c->flags.as<int>());
+                                                 c->flags.as<int>(), DAa);
+            last_pull_seq = 0;
             c->stat_launches++;
         }
         tl_mark(g, "step_begin", st);
@@ -841,7 +933,8 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                 for (int r = 0; r < MDG_DIST_MAXW; ++r) PT.s[r] = (DistSync*)c->peer_sync[r < W ? r : me];
                 const int nh = (Ly[zlo + 1] - Ly[zlo]) + (Ly[zhi] - Ly[zhi - 1]);
                 int hb = do_rebuild ? 0 : (nh + 511) / 512;          // blocks that copy ghost layers
-                hb = do_rebuild ? 0 : (hb < 1 ? 1 : (hb > 48 ? 48 : hb));
+                hb = (do_rebuild || pull) ? 0 : (hb < 1 ? 1 : (hb > 48 ? 48 : hb));
+                if (push_blocks_env > 0 && hb > 0) hb = push_blocks_env;
                 // The push runs on the communication stream beside the interior rows; MDG_DIST_PUSH_SIDE=0 puts it on the main
                 // stream ahead of them (measured: 8 us per step slower - the push is ~15 us of fence / flag latency, not bytes).
                 cudaStream_t ps = push_side ? cs : st;
@@ -849,7 +942,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                     k_dist_push<<<hb + (nhc ? 1 : 0), 256, 0, ps>>>(q, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], (float4*)c->peer_qs[0][sel],
                                                                    (float4*)c->peer_qs[1][sel], ke_v_cur, ke_h_cur, ib_prev, nhc, PT, me, W, below,
                                                                    above, seq, hb);
-                    if (push_side && split && gate) { k_dist_wait_started<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq); c->stat_launches++; }
+                    if (push_side && split && gate && !pull && (Ly[zhi - 1] - Ly[zlo + 1]) < 160000) { k_dist_wait_started<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq); c->stat_launches++; }
                 }
                 if (push_side) MDG_CUDA(cudaEventRecord(c->ev_push, cs));
                 tl_mark(g, "push_end", ps);
@@ -870,7 +963,17 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                     if (bnd_side) MDG_CUDA(cudaStreamWaitEvent(bs, c->ev_a, 0));
                     else MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
                                                    (zhi - 1) * nxy, st));                                                 // interior
-                    k_dist_wait<<<1, 32, 0, bs>>>((DistSync*)c->dsync.p, seq);                                             // ghosts landed
+                    if (pull) {
+                        const int zl = (zlo - 1 + ncz) % ncz, zu = zhi % ncz;
+                        const int ng = (Ly[zl + 1] - Ly[zl]) + (Ly[zu + 1] - Ly[zu]);
+                        int pk = (ng + 511) / 512;
+                        pk = pk < 1 ? 1 : (pk > 48 ? 48 : pk);
+                        k_dist_pull<<<pk, 256, 0, bs>>>(q, (const float4*)c->peer_qs[0][sel], (const float4*)c->peer_qs[1][sel], Ly[zl], Ly[zl + 1],
+                                                       Ly[zu], Ly[zu + 1], (DistSync*)c->dsync.p, (DistSync*)c->peer_sync[below],
+                                                       (DistSync*)c->peer_sync[above], seq);
+                        last_pull_seq = seq;
+                    } else
+                        k_dist_wait<<<1, 32, 0, bs>>>((DistSync*)c->dsync.p, seq);                                         // ghosts landed
                     tl_mark(g, "wait_end", bs);
                     if (!c->tiles) {   // bottom + top layer in one launch
                         MDG_TRY(mdg_i_force_range2(c, P, q, c->fs.as<float4>(), retest, Ly[zlo], Ly[zlo + 1], Ly[zhi - 1], Ly[zhi], bs));
@@ -890,7 +993,17 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                     }
                     c->stat_launches++;
                 } else {
-                    if (!do_rebuild) { k_dist_wait<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq); c->stat_launches++; }
+                    if (!do_rebuild && pull) {
+                        const int zl = (zlo - 1 + ncz) % ncz, zu = zhi % ncz;
+                        const int ng = (Ly[zl + 1] - Ly[zl]) + (Ly[zu + 1] - Ly[zu]);
+                        int pk = (ng + 511) / 512;
+                        pk = pk < 1 ? 1 : (pk > 48 ? 48 : pk);
+                        k_dist_pull<<<pk, 256, 0, st>>>(q, (const float4*)c->peer_qs[0][sel], (const float4*)c->peer_qs[1][sel], Ly[zl], Ly[zl + 1],
+                                                       Ly[zu], Ly[zu + 1], (DistSync*)c->dsync.p, (DistSync*)c->peer_sync[below],
+                                                       (DistSync*)c->peer_sync[above], seq);
+                        last_pull_seq = seq;
+                        c->stat_launches++;
+                    } else if (!do_rebuild) { k_dist_wait<<<1, 32, 0, st>>>((DistSync*)c->dsync.p, seq); c->stat_launches++; }
                     MDG_TRY(mdg_i_force_sorted(c, P, q, c->fs.as<float4>(), retest, false, nullptr, st));
                 }
                 if (ev1) MDG_CUDA(cudaEventRecord(ev1, st));
@@ -948,6 +1061,11 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         if (fused && g + 1 < nsteps) {
             float dt_next = h_tgrid[g + 2] - h_tgrid[g + 1];
             bool next_rebuild = ((g + 2) % rebuild_every) == 0;
+            if (DA.mine && pull) {             // B + A: overwrites the positions the neighbours pulled in this step, produces the next ones
+                DA.pos_seq = DA.seq + 1;
+                DA.wait_pull = last_pull_seq;
+                last_pull_seq = 0;
+            }
             k_step_ba<<<ib, INT_THREADS, 0, st>>>(A, dt, dt_next, pv_sel, sc, vbuf[vsel], hbuf[vsel], q, c->fs.as<float4>(),
                                                   ke_a, ke_b, n_part, ke_v_nxt, ke_h_nxt, tv, tq, tp, c->qref.as<float4>(),
                                                   (retest && !next_rebuild) ? 1 : 0, c->flags.as<int>(), DA);
@@ -986,6 +1104,21 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     MDG_CUDA(cudaMemcpyAsync(c->h_pinned, c->flags.p, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
     MDG_CUDA(cudaStreamSynchronize(st));
     if (h_last_energy) *h_last_energy = (float)h_e;
+    if (g_tl.prefix && dist && c->dist_p2p) {      // stamps of the LAST step's push / wait kernels (ns, relative to the push start)
+        unsigned long long h[16];
+        if (cudaMemcpy(h, c->dsync.as<char>() + offsetof(DistSync, dbg), sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            char path[512];
+            snprintf(path, sizeof(path), "%s%d.txt", g_tl.prefix, c->dist_rank);
+            FILE* f = fopen(path, "a");
+            if (f) {
+                fprintf(f, "# push: start 0 ack_seen %lld copied %lld fenced %lld halo_flag %lld ke_flag %lld | wait / pull kernel: start %lld seen %lld pulled %lld | B prologue(ack sent) %lld pos raised %lld\n",
+                        (long long)(h[1] - h[0]), (long long)(h[2] - h[0]), (long long)(h[3] - h[0]), (long long)(h[4] - h[0]),
+                        (long long)(h[5] - h[0]), (long long)(h[6] - h[0]), (long long)(h[7] - h[0]), (long long)(h[10] - h[0]), (long long)(h[8] - h[0]),
+                        (long long)(h[9] - h[0]));
+                fclose(f);
+            }
+        }
+    }
     tl_flush(c->dist_world > 1 ? c->dist_rank : 0);
     if (h_p2p_timeout) {
         mdg_set_error("distributed step: a peer-to-peer wait timed out (a neighbouring rank stopped making progress)");
@@ -1320,7 +1453,7 @@ static int gnn_run_once(mdg_ctx* c, const mdg_gnn_md_params* p, const mdg_schnet
     for (int g = 0; g < nsteps; ++g) {
         float dt = h_tgrid[g + 1] - h_tgrid[g];
         if (g == 0) {
-            k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, v4, vh4, q4, f4, nullptr, 0, ke_h_cur, c->flags.as<int>());
+            k_step_a<<<ib, INT_THREADS, 0, st>>>(A, dt, pv_sel, sc, v4, vh4, q4, f4, nullptr, 0, ke_h_cur, c->flags.as<int>(), DistArgs{});
             c->stat_launches++;
         }
         if (use_graph && g >= 1 && !gg.exec && !graph_failed) {       // capture the evaluation of the second step

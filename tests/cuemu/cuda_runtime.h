@@ -94,6 +94,7 @@ void  fiber_yield();
 
 static inline void __syncthreads() { cuemu::sync_block(); }
 static inline void __threadfence_system() {}
+static inline void __threadfence() {}
 
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { cuemu::coll_leave(cuemu::coll_enter(mask, 0, 0)); }
 
