@@ -823,6 +823,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     int ib_prev = ib;                       // block count of the launch(es) that wrote the *_cur partial arrays
     const int nsteps = n_grid - 1;
     bool a_done = false;                    // A(g) already executed by the previous fused kernel
+    bool prev_split_pull = false;           // pull path: the previous step pulled its ghosts on the boundary stream (split step)
     int last_pull_seq = 0;                  // pull path: sequence number of the last step whose ghosts were pulled (0: none pending)
     for (int g = 0; g < nsteps; ++g) {
         float dt = h_tgrid[g + 1] - h_tgrid[g];          // fp32 subtraction, like t1 - t0 in tinydiffeq.py:67-68
@@ -895,6 +896,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         const double* ke_b = ke_h_cur;
         int n_part = ib_prev;
         DistArgs DA{nullptr, nullptr, nullptr, 1, 0};
+        bool split_pull_now = false;
         c->force_energy = !(energy_free && g + 1 < nsteps);
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (c->prof_enable) {
@@ -960,18 +962,26 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
                     // (serial wait + small boundary launch behind the interior rows: +10 us per step in the r02 measurements).
                     const int nxy = c->nc[0] * c->nc[1];
                     cudaStream_t bs = bnd_side ? c->bnd_stream : st;
-                    if (bnd_side) MDG_CUDA(cudaStreamWaitEvent(bs, c->ev_a, 0));
-                    else MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
-                                                   (zhi - 1) * nxy, st));                                                 // interior
+                    // Pull path: the copy kernel does NOT wait for this rank's own integrator kernel - it is enqueued behind the
+                    // previous step's boundary rows (the last readers of the ghost ranges, same stream) and spins until the
+                    // neighbours' positions are final, so the ghosts are here ~one NVLink round trip after the neighbours' B + A
+                    // kernels end instead of a stream hop (5-13 us in the r02 stamps) + kernel later.  After a rebuild step (or at
+                    // the start of an epoch) the last reader was the full force launch on the main stream: wait for ev_a then.
+                    const bool early_pull = pull && prev_split_pull;
+                    if (bnd_side && !early_pull) MDG_CUDA(cudaStreamWaitEvent(bs, c->ev_a, 0));
+                    if (!bnd_side) MDG_TRY(mdg_i_force_range(c, P, q, c->fs.as<float4>(), retest, Ly[zlo + 1], Ly[zhi - 1], (zlo + 1) * nxy,
+                                                             (zhi - 1) * nxy, st));                                       // interior
                     if (pull) {
                         const int zl = (zlo - 1 + ncz) % ncz, zu = zhi % ncz;
                         const int ng = (Ly[zl + 1] - Ly[zl]) + (Ly[zu + 1] - Ly[zu]);
-                        int pk = (ng + 511) / 512;
-                        pk = pk < 1 ? 1 : (pk > 48 ? 48 : pk);
+                        int pk = (ng + 255) / 256;                       // one NVLink load per thread: one round trip
+                        pk = pk < 1 ? 1 : (pk > 96 ? 96 : pk);
                         k_dist_pull<<<pk, 256, 0, bs>>>(q, (const float4*)c->peer_qs[0][sel], (const float4*)c->peer_qs[1][sel], Ly[zl], Ly[zl + 1],
                                                        Ly[zu], Ly[zu + 1], (DistSync*)c->dsync.p, (DistSync*)c->peer_sync[below],
                                                        (DistSync*)c->peer_sync[above], seq);
                         last_pull_seq = seq;
+                        if (early_pull) MDG_CUDA(cudaStreamWaitEvent(bs, c->ev_a, 0));      // the boundary rows need MY positions too
+                        split_pull_now = true;
                     } else
                         k_dist_wait<<<1, 32, 0, bs>>>((DistSync*)c->dsync.p, seq);                                         // ghosts landed
                     tl_mark(g, "wait_end", bs);
@@ -1080,6 +1090,7 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
         }
         c->stat_launches++;
         tl_mark(g, "step_end", st);
+        prev_split_pull = split_pull_now;
         pv_sel ^= 1;
         ib_prev = ib;
     }
