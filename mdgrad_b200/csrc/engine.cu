@@ -736,7 +736,13 @@ static int run_once(mdg_ctx* c, const mdg_md_params* p, int n, const float* d_ma
     const char* gz = getenv("MDG_DIST_GATE");
     const bool gate = !(gz && gz[0] == '0');          // interior rows wait until the push kernel has started
     const bool bnd_side = !(bz && bz[0] == '0');     // boundary layers on their own stream, concurrent with the interior rows
-    const bool pull = !(plz && plz[0] == '0') && bnd_side;   // ghosts are PULLED by the consumer (default); 0: pushed by the producer
+    // Ghost layers: PULLED by the consumer (NVLink loads once the neighbour's positions are final) for slabs below ~190 000 atoms per
+    // rank, PUSHED by the producer above - measured on 2 x B200: 131 072 atoms per GPU 83.5 (pull) vs 86.3 us per step (push),
+    // 256 000 per GPU 122.3 vs 116.1 (the longer interior launch hides the push; the pull's spinning CTAs and the ticket in the
+    // integrator kernel then only cost).  n and the world size are the same on every rank, so all ranks take the same path.
+    // MDG_DIST_PULL=1 / 0 forces one.
+    const bool pull_auto = dist && (n / (c->dist_world > 0 ? c->dist_world : 1)) < 190000;
+    const bool pull = (plz ? plz[0] != '0' : pull_auto) && bnd_side;
     IntArgs A;
     memset(&A, 0, sizeof(A));
     A.integrator = p->integrator;
