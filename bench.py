@@ -129,10 +129,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: only rows that arrive from here on are used (nvidia-smi needs > 150 ms to come up on an
+        8-GPU box, so it is started before the warm-up)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        first = getattr(self, "first", 0)
+        t_end = time.time() + 3.0
         time.sleep(0.15)
+        while len(self.rows) <= first and time.time() < t_end:      # at least one sample taken after the start of the timed region
+            time.sleep(0.02)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -140,7 +149,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[first:]:
             c = [x.strip() for x in r.split(",")]
             if len(c) < 7:
                 continue
@@ -440,6 +449,8 @@ def main():
         return tv, tq, tpv
 
     log("system ready: n=%d L=%.3f K=%d skin=%.2f world=%d; warm-up %d steps" % (n, L, K, args.skin, world, args.warmup))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     tv, tq, tpv = run(args.warmup, v0, q0, [0.0] * CHAINS)
     log("warm-up done: %s" % ctx.stats())
     p.rebuild_every = int(ctx.stats()["maxrow_or_K"])
@@ -447,13 +458,12 @@ def main():
     del tv, tq
 
     # ---- timed: device-resident K steps, CUDA events on the launch stream, barrier + sync both sides
-    sampler = ClockSampler(local_rank)
     nfr = args.steps + 1 if full_traj else 2
     out = (torch.zeros((nfr, n, 3), dtype=torch.float32, device=dev), torch.zeros((nfr, n, 3), dtype=torch.float32, device=dev))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     tv, tq, tpv = run(args.steps, v1, q1, pv1, out=out)

@@ -38,6 +38,10 @@ VARIANTS = {
     "pfmb4": ["-DMDG_FORCE_PREFETCH=1", "-DMDG_FORCE_MINBLOCKS=4"],
     # (8 warps per CTA would need 77 KB of STATIC shared memory - over the 48 KB limit; only the 2-warp shape is buildable)
     "fbw2": ["-DFB_WARPS=2"],
+    # list builder phase 1 with two candidates per lane (half the LDS.128 per distance test)
+    "fbp": ["-DFB_PAIR=1"],
+    # list builder with the static cell assignment (cell = f(blockIdx, warp)) instead of the global work counter
+    "fbst": ["-DFB_DYNAMIC=0"],
     "lean": ["-DMDG_BUILD_LEAN=1"],
     # SchNet fused filter generator at 3 CTAs per SM (register cap 85 instead of the 100 it takes by itself)
     "sne3": ["-DSN_EDGE_MINBLOCKS=3"],

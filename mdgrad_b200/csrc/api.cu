@@ -69,7 +69,7 @@ extern "C" int mdg_destroy(mdg_ctx* c) {
                       &c->scan_tmp, &c->fs, &c->partials, &c->v4, &c->vh4, &c->q4b, &c->f4b, &c->qref,
                       &c->mass_sorted, &c->pvbuf, &c->kebuf, &c->dtbuf, &c->g_off, &c->g_cnt, &c->g_edge,
                       &c->g_other, &c->sn_ws, &c->sn_wt, &c->sn_wcache, &c->gnn_nbr, &c->gnn_off, &c->gnn_xyz, &c->gnn_f3, &c->gnn_fp3,
-                      &c->bd_slots, &c->bd_part};
+                      &c->bd_slots, &c->bd_part, &c->work_ctr};
     for (DevBuf* b : bufs) b->release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_layers) cudaFreeHost(c->h_layers);

@@ -21,6 +21,12 @@
 #ifndef FB_WARPS
 #define FB_WARPS 4                // cells (warps) per CTA; build variant fbw2 (8 would exceed the 48 KB static shared-memory limit)
 #endif
+#ifndef FB_DYNAMIC
+#define FB_DYNAMIC 1            // warps take cells from a global counter (0: cell = f(blockIdx, warp), build variant fbst)
+#endif
+#ifndef FB_PAIR
+#define FB_PAIR 0               // build variant fbp: two candidates per lane in phase 1
+#endif
 #define FB_BATCH 736             // candidates per batch (23 chunks of 32; a 27-cell stencil holds ~650 at liquid density)
 #define FB_CHUNKS (FB_BATCH / 32)
 
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                                                              Box bx, int ncx, int ncy, int ncz, float r2list, int cap,
                                                              PairFilter F, uint32_t* __restrict__ rows,
                                                              int* __restrict__ row_len, int* __restrict__ flags,
-                                                             unsigned char* __restrict__ cell_local) {
+                                                             int* __restrict__ work) {
     __shared__ uint32_t s_mask[FB_WARPS][32][FB_CHUNKS + 1];   // [atom][chunk], padded: conflict-free for lane = atom
     // Per-candidate state is kept small - 3 bytes instead of 8 - because shared memory per warp is what bounds the occupancy of
     // this kernel (ncu r02: 27% of the warp slots at 9.75 KB per warp, issue rate 54% with 2.8 "wait" + 2.3 "short scoreboard"
@@ -146,13 +152,26 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
     __shared__ int s_pre[FB_WARPS][28];                        // candidate-index prefix over the 27 stencil cells
     __shared__ int s_cs[FB_WARPS][27];                         // cell_start of the stencil cells
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Cells are handed out by a global counter: a warp that finishes a cheap cell takes the next one, and CTAs that start late
+    // find the counter exhausted.  The static form (cell = f(blockIdx, warp)) ran 2.25 waves of CTAs whose four warps end at
+    // different times: 40 % of the warp slots active against 50 % theoretical in the r02 capture.
+#if FB_DYNAMIC
+  for (;;) {
+    int c = 0;
+    if (lane == 0) c = cell0 + atomicAdd(work, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= ncell) return;
+#else
+  for (int once = 0; once < 1; ++once) {
+    (void)work;
     const int c = cell0 + blockIdx.x * FB_WARPS + w;          // cells [cell0, ncell) (ncell = end of this rank's range)
     if (c >= ncell) return;
+#endif
     const int a0 = cell_start[c], na = cell_start[c + 1] - a0;
-    if (na == 0) return;
+    if (na == 0) continue;
     if (flags[6] | flags[7]) {
         for (int a = lane; a < na; a += 32) row_len[a0 + a] = 0;
-        return;
+        continue;
     }
     // stencil prefix (warp scan over 27 counts) and the stencil slot of the cell itself
     int kself_slot = 0;
@@ -172,15 +191,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         if (__any_sync(0xffffffffu, cnt >= 2048)) {        // (s_tk holds 11 bits of in-cell index: such a cell is a collapsed system)
             if (lane == 0) flags[7] = 2048;
             for (int a = lane; a < na; a += 32) row_len[a0 + a] = 0;
-            return;
+            continue;
         }
     }
     __syncwarp();
     const int total = s_pre[w][27];
-    // Stream-index form (entries index the cell's 27-cell STENCIL STREAM instead of the global sorted array, for a
-    // force kernel that stages the stream in shared memory): measured slower than the gather kernel (124 vs 66 us)
-    // and not used - the engine always passes cell_local == nullptr, so entries are global indices.
-    (void)cell_local;          // (the stream-index row form was measured slower in round 1 and is gone)
     const int cx = c % ncx, cy = (c / ncx) % ncy, cz = c / (ncx * ncy);
     const float ox = (float)cx / (float)ncx, oy = (float)cy / (float)ncy, oz = (float)cz / (float)ncz;
     const bool filt = (F.sel_a != nullptr) || (F.n_ex > 0);
@@ -219,17 +234,97 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
             const int nch = (nb + 31) >> 5;
             __syncwarp();
             // ---------------- phase 1: lane = candidate -------------------------------------------
-            int kk = 0;
+#if FB_PAIR && !defined(MDG_BUILD_INT8_SCREEN)
+            // ---- build variant FB_PAIR: TWO candidates per lane (chunks ch and ch + 1), so that every LDS.128 of an atom's
+            // coordinates feeds two distance tests (half the shared-memory loads and half as many exposed load latencies).
             bool cand_uniform = true;
-            for (int ch = 0; ch < nch; ++ch) {
-                const int a = B + (ch << 5) + lane;
-                const bool valid = a < B + nb;
-                float lx = 1e30f, ly = 1e30f, lz = 1e30f;
-                int t = -1;
+            int kk_run = 0;
+            auto fetch = [&](int chx, int& a, bool& valid, int& kk, float4& q) {
+                a = B + (chx << 5) + lane;
+                valid = (chx < nch) && (a < B + nb);
                 if (valid) {
-                    while (a >= s_pre[w][kk + 1]) ++kk;
-                    t = s_cs[w][kk] + (a - s_pre[w][kk]);
-                    float4 qj = qs[t];
+                    while (a >= s_pre[w][kk_run + 1]) ++kk_run;
+                    q = qs[s_cs[w][kk_run] + (a - s_pre[w][kk_run])];
+                }
+                kk = kk_run;
+            };
+            auto stage = [&](int a, bool valid, int kk, const float4& qj, float& lx, float& ly, float& lz) {
+                lx = 1e30f; ly = 1e30f; lz = 1e30f;
+                if (valid) {
+                    int Ix, Iy, Iz;
+                    local_coord(qj.x, bx.L[0], bx.invL[0], ox, lx, Ix);
+                    local_coord(qj.y, bx.L[1], bx.invL[1], oy, ly, Iy);
+                    local_coord(qj.z, bx.L[2], bx.invL[2], oz, lz, Iz);
+                    uint32_t imj = pack_img(Ix, Iy, Iz);
+                    const int ex = Ix - I0x + 16, ey = Iy - I0y + 16, ez = Iz - I0z + 16;
+                    s_dim[w][a - B] = ((unsigned)ex | (unsigned)ey | (unsigned)ez) > 31u ? (unsigned short)0xFFFF
+                                                                                     : (unsigned short)(ex | (ey << 5) | (ez << 10));
+                    s_tk[w][a - B] = (unsigned short)((kk << 11) | (a - s_pre[w][kk]));
+                    cand_uniform = cand_uniform && (imj == im0);
+                }
+            };
+            int aA_n, aB_n, kA_n, kB_n;
+            bool vA_n, vB_n;
+            float4 qA_n = make_float4(0.f, 0.f, 0.f, 0.f), qB_n = qA_n;
+            fetch(0, aA_n, vA_n, kA_n, qA_n);
+            fetch(1, aB_n, vB_n, kB_n, qB_n);
+            for (int ch = 0; ch < nch; ch += 2) {
+                const int aA = aA_n, aB = aB_n, kA = kA_n, kB = kB_n;
+                const bool vA = vA_n, vB = vB_n;
+                const float4 qA = qA_n, qB = qB_n;
+                fetch(ch + 2, aA_n, vA_n, kA_n, qA_n);
+                fetch(ch + 3, aB_n, vB_n, kB_n, qB_n);
+                float ax, ay, az, bx_, by_, bz_;
+                stage(aA, vA, kA, qA, ax, ay, az);
+                stage(aB, vB, kB, qB, bx_, by_, bz_);
+                int i = 0;
+                for (; i + 2 <= np; i += 2) {           // (the self pair passes here and is dropped in phase 2)
+                    const float4 c0 = s_ctr[w][i], c1 = s_ctr[w][i + 1];
+                    const float x0 = ax - c0.x, y0 = ay - c0.y, z0 = az - c0.z, x1 = ax - c1.x, y1 = ay - c1.y, z1 = az - c1.z;
+                    const float u0 = bx_ - c0.x, v0 = by_ - c0.y, w0 = bz_ - c0.z, u1 = bx_ - c1.x, v1 = by_ - c1.y, w1 = bz_ - c1.z;
+                    const float dA0 = fmaf(z0, z0, fmaf(y0, y0, x0 * x0)), dA1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
+                    const float dB0 = fmaf(w0, w0, fmaf(v0, v0, u0 * u0)), dB1 = fmaf(w1, w1, fmaf(v1, v1, u1 * u1));
+                    const uint32_t mA0 = __ballot_sync(0xffffffffu, dA0 < r2list), mA1 = __ballot_sync(0xffffffffu, dA1 < r2list);
+                    const uint32_t mB0 = __ballot_sync(0xffffffffu, dB0 < r2list), mB1 = __ballot_sync(0xffffffffu, dB1 < r2list);
+                    if (lane == 0) {
+                        s_mask[w][i][ch] = mA0; s_mask[w][i][ch + 1] = mB0; s_mask[w][i + 1][ch] = mA1; s_mask[w][i + 1][ch + 1] = mB1;
+                    }
+                }
+                for (; i < np; ++i) {
+                    const float4 ci = s_ctr[w][i];
+                    const float x0 = ax - ci.x, y0 = ay - ci.y, z0 = az - ci.z, u0 = bx_ - ci.x, v0 = by_ - ci.y, w0 = bz_ - ci.z;
+                    const uint32_t mA = __ballot_sync(0xffffffffu, fmaf(z0, z0, fmaf(y0, y0, x0 * x0)) < r2list);
+                    const uint32_t mB = __ballot_sync(0xffffffffu, fmaf(w0, w0, fmaf(v0, v0, u0 * u0)) < r2list);
+                    if (lane == 0) { s_mask[w][i][ch] = mA; s_mask[w][i][ch + 1] = mB; }
+                }
+            }
+#else
+            bool cand_uniform = true;
+            // The candidate of the NEXT chunk is fetched while this chunk is screened (the global load was an exposed long-scoreboard
+            // stall once per chunk: 5.6 % of the samples in the r02 capture).
+            int a_n = B + lane, kk_n = 0, t_n = 0;
+            bool valid_n = a_n < B + nb;
+            float4 q_n = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid_n) {
+                while (a_n >= s_pre[w][kk_n + 1]) ++kk_n;
+                t_n = s_cs[w][kk_n] + (a_n - s_pre[w][kk_n]);
+                q_n = qs[t_n];
+            }
+            for (int ch = 0; ch < nch; ++ch) {
+                const int a = a_n, kk = kk_n;
+                const bool valid = valid_n;
+                const float4 qj = q_n;
+                if (ch + 1 < nch) {
+                    a_n = B + ((ch + 1) << 5) + lane;
+                    valid_n = a_n < B + nb;
+                    if (valid_n) {
+                        while (a_n >= s_pre[w][kk_n + 1]) ++kk_n;
+                        t_n = s_cs[w][kk_n] + (a_n - s_pre[w][kk_n]);
+                        q_n = qs[t_n];
+                    }
+                }
+                float lx = 1e30f, ly = 1e30f, lz = 1e30f;
+                if (valid) {
                     int Ix, Iy, Iz;
                     local_coord(qj.x, bx.L[0], bx.invL[0], ox, lx, Ix);
                     local_coord(qj.y, bx.L[1], bx.invL[1], oy, ly, Iy);
@@ -252,16 +347,33 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                     if (lane == 0) s_mask[w][i][ch] = m;
                 }
 #else
-#pragma unroll 4
-                for (int i = 0; i < np; ++i) {          // (the self pair passes here and is dropped in phase 2)
-                    float4 ci = s_ctr[w][i];
-                    float dx = lx - ci.x, dy = ly - ci.y, dz = lz - ci.z;
-                    float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    uint32_t m = __ballot_sync(0xffffffffu, d2 < r2list);
+                // Four atoms per trip, their coordinates loaded BEFORE the first use: as one-atom iterations every LDS.128 was
+                // followed by its dependent FADD (short-scoreboard stall per atom: 22 % of the samples in the r02 capture).
+                int i = 0;
+                for (; i + 4 <= np; i += 4) {           // (the self pair passes here and is dropped in phase 2)
+                    const float4 c0 = s_ctr[w][i], c1 = s_ctr[w][i + 1], c2 = s_ctr[w][i + 2], c3 = s_ctr[w][i + 3];
+                    const float x0 = lx - c0.x, y0 = ly - c0.y, z0 = lz - c0.z;
+                    const float x1 = lx - c1.x, y1 = ly - c1.y, z1 = lz - c1.z;
+                    const float x2 = lx - c2.x, y2 = ly - c2.y, z2 = lz - c2.z;
+                    const float x3 = lx - c3.x, y3 = ly - c3.y, z3 = lz - c3.z;
+                    const float d0 = fmaf(z0, z0, fmaf(y0, y0, x0 * x0)), d1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
+                    const float d2 = fmaf(z2, z2, fmaf(y2, y2, x2 * x2)), d3 = fmaf(z3, z3, fmaf(y3, y3, x3 * x3));
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, d0 < r2list), m1 = __ballot_sync(0xffffffffu, d1 < r2list);
+                    const uint32_t m2 = __ballot_sync(0xffffffffu, d2 < r2list), m3 = __ballot_sync(0xffffffffu, d3 < r2list);
+                    if (lane == 0) {
+                        s_mask[w][i][ch] = m0; s_mask[w][i + 1][ch] = m1; s_mask[w][i + 2][ch] = m2; s_mask[w][i + 3][ch] = m3;
+                    }
+                }
+                for (; i < np; ++i) {
+                    const float4 ci = s_ctr[w][i];
+                    const float dx = lx - ci.x, dy = ly - ci.y, dz = lz - ci.z;
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const uint32_t m = __ballot_sync(0xffffffffu, d2 < r2list);
                     if (lane == 0) s_mask[w][i][ch] = m;
                 }
 #endif
             }
+#endif
             const bool uniform = ctr_uniform && __all_sync(0xffffffffu, cand_uniform) && !filt;
             row_pure = pure_ok && uniform;
             const uint32_t uni_code = row_pure ? 0u : ((1u | (1u << 2) | (1u << 4)) << MDG_IDX_BITS);
@@ -301,4 +413,5 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
         }
         __syncwarp();
     }
+  }
 }

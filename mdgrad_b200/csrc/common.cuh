@@ -298,6 +298,7 @@ struct mdg_ctx {
     DevBuf rows, row_len;     // uint32 [n*cap], int [n]
     int    force_group = 4;            // lanes per row in k_force_rows (MDG_FORCE_GROUP=2|4|8)
     bool   force_energy = true;        // false: the next force launches skip the per-atom energy (engine inner steps)
+    DevBuf work_ctr;          // int: cell counter of k_build_fast
     DevBuf flags;             // int[8]: 0 = capacity overflow, 1 = skin violation
     // tile list (tiles.cuh): the engine's skin list in block-local 16-bit form
     bool     tiles = false;            // the last build produced tile rows (force launches use k_force_tiles)

@@ -795,11 +795,14 @@ int mdg_i_build_list(mdg_ctx* c, const float* d_xyz, const float4* d_q4_in, int 
             uint32_t* rows_base = c->rows.as<uint32_t>() - (size_t)c->rows_s0 * c->cap;
             if (c->fast_build && rlist > cutoff && roomy) {
                 int ncl = c->own_c1 - c->own_c0;
-                if (ncl > 0)
+                if (ncl > 0) {
+                    MDG_TRY(c->work_ctr.reserve(sizeof(int) * 4));
+                    MDG_CUDA(cudaMemsetAsync(c->work_ctr.p, 0, sizeof(int), st));          // (k_build_fast hands out cells through it)
                     k_build_fast<<<(ncl + FB_WARPS - 1) / FB_WARPS, FB_WARPS * 32, 0, st>>>(
                         c->own_c0, c->own_c1, qs, c->cell_start.as<int>(), c->stencil.as<int>(), c->box, g.nc[0], g.nc[1], g.nc[2],
                         c->rlist2, c->cap, F, rows_base, c->row_len.as<int>(), c->flags.as<int>(),
-                        nullptr);
+                        c->work_ctr.as<int>());
+                }
             } else {
                 int nl = c->own_s1 - c->own_s0;
                 if (nl > 0 && nl <= 65536)       // small systems: a warp per atom (the thread-per-atom scan is latency-bound there)
