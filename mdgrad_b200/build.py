@@ -39,7 +39,10 @@ VARIANTS = {
     # (8 warps per CTA would need 77 KB of STATIC shared memory - over the 48 KB limit; only the 2-warp shape is buildable)
     "fbw2": ["-DFB_WARPS=2"],
     # list builder phase 1 with two candidates per lane (half the LDS.128 per distance test)
-    "fbp": ["-DFB_PAIR=1"],
+    "fbp0": ["-DFB_PAIR=0"],
+    "fbp4": ["-DFB_TRIP=4"],
+    "fbp64": ["-DFB_MINBLOCKS=8"],
+    "fbp4w2": ["-DFB_TRIP=4", "-DFB_WARPS=2"],
     # list builder with the static cell assignment (cell = f(blockIdx, warp)) instead of the global work counter
     "fbst": ["-DFB_DYNAMIC=0"],
     "lean": ["-DMDG_BUILD_LEAN=1"],

@@ -25,7 +25,7 @@
 #define FB_DYNAMIC 1            // warps take cells from a global counter (0: cell = f(blockIdx, warp), build variant fbst)
 #endif
 #ifndef FB_PAIR
-#define FB_PAIR 0               // build variant fbp: two candidates per lane in phase 1
+#define FB_PAIR 1               // two candidates per lane in phase 1 (0: one, build variant fbp0): 246 -> 228 us per rebuild
 #endif
 #define FB_BATCH 736             // candidates per batch (23 chunks of 32; a 27-cell stencil holds ~650 at liquid density)
 #define FB_CHUNKS (FB_BATCH / 32)
@@ -125,7 +125,15 @@ __device__ __forceinline__ int fb_walk(uint32_t nz, const uint32_t* mrow, const 
     return cnt;
 }
 
-__global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int ncell, const float4* __restrict__ qs,
+#ifdef FB_MINBLOCKS
+#define FB_BOUNDS __launch_bounds__(FB_WARPS * 32, FB_MINBLOCKS)
+#else
+#define FB_BOUNDS __launch_bounds__(FB_WARPS * 32)
+#endif
+#ifndef FB_TRIP
+#define FB_TRIP 2                 // atoms per trip of the paired phase-1 loop (build variant fbp4: 4)
+#endif
+__global__ void FB_BOUNDS k_build_fast(int cell0, int ncell, const float4* __restrict__ qs,
                                                              const int* __restrict__ cell_start, const int* __restrict__ stencil,
                                                              Box bx, int ncx, int ncy, int ncz, float r2list, int cap,
                                                              PairFilter F, uint32_t* __restrict__ rows,
@@ -278,6 +286,24 @@ __global__ void __launch_bounds__(FB_WARPS * 32) k_build_fast(int cell0, int nce
                 stage(aA, vA, kA, qA, ax, ay, az);
                 stage(aB, vB, kB, qB, bx_, by_, bz_);
                 int i = 0;
+#if FB_TRIP == 4
+                for (; i + 4 <= np; i += 4) {
+                    const float4 c0 = s_ctr[w][i], c1 = s_ctr[w][i + 1], c2 = s_ctr[w][i + 2], c3 = s_ctr[w][i + 3];
+                    uint32_t mA[4], mB[4];
+#define FB_T(k, cc)                                                                                                         \
+    {                                                                                                                       \
+        const float x = ax - cc.x, y = ay - cc.y, z = az - cc.z, u = bx_ - cc.x, v = by_ - cc.y, t = bz_ - cc.z;             \
+        mA[k] = __ballot_sync(0xffffffffu, fmaf(z, z, fmaf(y, y, x * x)) < r2list);                                         \
+        mB[k] = __ballot_sync(0xffffffffu, fmaf(t, t, fmaf(v, v, u * u)) < r2list);                                         \
+    }
+                    FB_T(0, c0) FB_T(1, c1) FB_T(2, c2) FB_T(3, c3)
+#undef FB_T
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { s_mask[w][i + k][ch] = mA[k]; s_mask[w][i + k][ch + 1] = mB[k]; }
+                    }
+                }
+#endif
                 for (; i + 2 <= np; i += 2) {           // (the self pair passes here and is dropped in phase 2)
                     const float4 c0 = s_ctr[w][i], c1 = s_ctr[w][i + 1];
                     const float x0 = ax - c0.x, y0 = ay - c0.y, z0 = az - c0.z, x1 = ax - c1.x, y1 = ay - c1.y, z1 = az - c1.z;
