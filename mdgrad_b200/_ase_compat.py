@@ -106,6 +106,42 @@ class Atoms:
         if velocities is not None:
             self.set_velocities(velocities)
 
+    # -- lazily converted state -------------------------------------------
+    # `positions` / `_momenta` are fp64 (n, 3) arrays, as in ase.Atoms.  set_positions / set_velocities with an array that is
+    # not fp64 already (the fp32 log frame Simulations.update_states hands over after every epoch, reference md.py:54-58) keep
+    # a reference to it and convert at the first READ: the same values as the eager np.array(..., dtype=float), without two
+    # 6 MB single-threaded conversions per epoch at 256 000 atoms (5 ms of a 19 ms simulate() call in the r02 e2e profile).
+    # The source arrays are log entries, which nobody mutates.
+    @property
+    def positions(self):
+        src = self.__dict__.get("_pos_src")
+        if src is not None:
+            self.__dict__["_pos"] = np.array(src, dtype=float).reshape(len(self.numbers), 3)
+            self.__dict__["_pos_src"] = None
+        return self.__dict__["_pos"]
+
+    @positions.setter
+    def positions(self, value):
+        self.__dict__["_pos"] = value
+        self.__dict__["_pos_src"] = None
+
+    @property
+    def _momenta(self):
+        src = self.__dict__.get("_vel_src")
+        if src is not None:
+            self.__dict__["_mom"] = np.asarray(src, dtype=float).reshape(len(self.numbers), 3) * self._masses[:, None]
+            self.__dict__["_vel_src"] = None
+        return self.__dict__["_mom"]
+
+    @_momenta.setter
+    def _momenta(self, value):
+        self.__dict__["_mom"] = value
+        self.__dict__["_vel_src"] = None
+
+    @staticmethod
+    def _deferrable(a, n):
+        return isinstance(a, np.ndarray) and a.dtype == np.float32 and a.size == 3 * n
+
     # -- geometry ----------------------------------------------------------
     def set_cell(self, cell):
         cell = np.array(cell, dtype=float)
@@ -148,6 +184,7 @@ class Atoms:
         return self._masses.copy()
 
     def set_masses(self, masses):
+        _ = self._momenta                                # (pending velocities are momenta with the masses of THEIR call)
         self._masses = np.array(masses, dtype=float).reshape(len(self))
 
     def get_positions(self, wrap=False, **wrap_kw):
@@ -158,6 +195,9 @@ class Atoms:
         return self.positions.copy()
 
     def set_positions(self, pos):
+        if self._deferrable(pos, len(self)):
+            self.__dict__["_pos_src"] = pos              # converted at the first read (see `positions`)
+            return
         self.positions = np.array(pos, dtype=float).reshape(len(self), 3)
 
     def get_momenta(self):
@@ -171,6 +211,9 @@ class Atoms:
 
     def set_velocities(self, v):
         # one conversion and one product (same values as ASE's set_momenta(v * masses[:, None]); the product is a fresh array)
+        if self._deferrable(v, len(self)):
+            self.__dict__["_vel_src"] = v                # converted at the first read (see `_momenta`); masses as of that read
+            return
         self._momenta = np.asarray(v, dtype=float).reshape(len(self), 3) * self._masses[:, None]
 
     def get_kinetic_energy(self):

@@ -71,6 +71,34 @@ def test_system_and_ase_compat():
     assert abs(units.fs - 0.09822694788) < 1e-9
 
 
+def test_atoms_defers_the_fp64_conversion_of_logged_frames():
+    """set_positions / set_velocities with an fp32 frame (what Simulations.update_states hands over, reference md.py:54-58) keep
+    a reference and convert at the first read; every reader sees exactly the eager values."""
+    from mdgrad_b200._ase_compat import Atoms
+    rng = np.random.default_rng(3)
+    a = Atoms(numbers=[1, 8, 1, 8, 1], positions=rng.random((5, 3)), cell=[3.0, 3.0, 3.0], pbc=True)
+    eager = Atoms(a)
+    p32, v32 = (rng.random((5, 3)) * 7 - 2).astype(np.float32), rng.standard_normal((5, 3)).astype(np.float32)
+    a.set_positions(p32)
+    a.set_velocities(v32)
+    assert a.__dict__["_pos_src"] is p32 and a.__dict__["_vel_src"] is v32          # nothing converted yet
+    eager.positions = np.array(p32, dtype=float)
+    eager._momenta = np.asarray(v32, dtype=float) * eager.get_masses()[:, None]
+    assert a.get_positions().dtype == np.float64 and np.array_equal(a.get_positions(), eager.get_positions())
+    assert a.__dict__["_pos_src"] is None
+    assert np.array_equal(a.get_momenta(), eager.get_momenta()) and np.array_equal(a.get_velocities(), eager.get_velocities())
+    assert a.get_kinetic_energy() == eager.get_kinetic_energy()
+    a.set_positions(p32)
+    assert np.array_equal(a.get_positions(wrap=True), eager.get_positions(wrap=True))
+    a.set_positions(p32)
+    assert np.array_equal(Atoms(a).positions, eager.positions)                        # the copy constructor reads through it
+    a.set_velocities(v32)
+    a.set_masses([2.0] * 5)                                                            # momenta were defined with the OLD masses
+    assert np.array_equal(a.get_momenta(), eager.get_momenta())
+    a.set_positions([[0.0, 0.0, 0.0]] * 5)                                             # anything else converts eagerly, as before
+    assert a.__dict__["_pos_src"] is None and a.get_positions().sum() == 0.0
+
+
 def test_time_grid_and_simulate_bookkeeping():
     """frequency grid points -> frequency-1 steps; fp32 grid; log keeps the last frame per epoch."""
     from torchmd.md import Simulations
