@@ -553,6 +553,9 @@ def main():
                        "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "pairs_in_cutoff": P_rc,
                        "pairs_in_skin_list": P_list, "streamed_bytes_with_skin": 32.0 * n + 8.0 * P_list,
                        "kernel_ms": force_ms, "kernel_launches_timed": prof["force_launches"],
+                       "limiter": "not HBM: L1TEX / LSU wavefronts 83 % and instruction issue 63 % in the ncu capture (one 16-byte gather per "
+                                  "list entry, >= 23 instructions per entry with the reference's exact membership arithmetic) - "
+                                  "profiles/r02_force_kernel.md",
                        "share_of_step": force_ms / (ms / args.steps)}
 
     # ---- e2e through the public API with HOST state (numpy in System, H2D per epoch, D2H last frame per epoch)
