@@ -152,7 +152,10 @@ class Simulations():
                     var.requires_grad = True
                 with second_order(self.integrator):
                     trajs = odeint(self.integrator, tuple(states), t, method=self.solvemethod)
-            nxt = self._device_check_point(trajs) if self.device_handoff else None
+            if self.device_handoff and epoch + 1 == sim_epochs and self._device_wrap_possible():
+                nxt = ()                              # last epoch: nobody consumes a next start state - only its frames are logged
+            else:
+                nxt = self._device_check_point(trajs) if self.device_handoff else None
             if nxt is None:                           # reference order of operations, on the host
                 self._flush_log(pending)
                 self.update_log(trajs)
@@ -179,6 +182,15 @@ class Simulations():
 
     device_handoff = True     # False: host round trip after every epoch, literally as the reference
     _flush_every = 8          # epochs whose last frames wait on the device before one pinned-memory flush
+
+    def _device_wrap_possible(self):
+        """True when `_device_check_point` would succeed (no wrap requested, or an orthorhombic cell)."""
+        if not (self.wrap and "positions" in self.keys):
+            return True
+        c = np.asarray(self.system.get_cell(), dtype=float)
+        if c.shape == (3,):
+            c = np.diag(c)
+        return bool(c.shape == (3, 3) and not (c - np.diag(np.diag(c))).any() and np.all(np.diag(c) != 0))
 
     def _device_check_point(self, trajs):
         """The states `get_check_point()` would return after logging `trajs`, computed on the device; None if the
